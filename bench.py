@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- synthesized target px/s (and patch-distance evals/s) of the synthesis hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+  python bench.py --impl reference --gpus N ...            # the reference's CPU engine (oracle/_ref)
+
+One "step" = one complete synthesis job (all passes) of the workload on each rank.  Default workload is
+BASELINE.json configs[1]: render-texture, a 1024x1024 target synthesised from a 256x256 synthetic corpus
+tile, no context matching (matchContextType 0, no tiling), the render-texture script's 9 neighbours / 200
+probes (PluginScripts/plugin-render-texture.py:175), through the full API engine().
+
+  value  = target px/s with inputs resident in HBM: n_targets / CUDA-event time from "upload complete" to
+           "last pass done" on the job's stream (whole job: N ranks x K steps, max over ranks).
+  e2e    = the same metric through the reference-facing C-ABI call engine() with HOST buffers: host prep,
+           H2D, passes, D2H, write-back all inside the timed region.
+Multi-GPU: independent jobs per rank (a job does not shard), no data-path collective, "scaling": "weak".
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from resynthesizer_b200 import abi  # noqa: E402
+from resynthesizer_b200.synthetic import G, centered_mask  # noqa: E402
+
+METRIC = "synthesized target px/s"
+UNIT = "px/s"
+
+
+# ------------------------------------------------------------------------------------------ workloads
+def workload(name, seed_shift=0, scale=1.0):
+    """Returns dict(params, fi_args, target pixmap builder inputs, n_color...)."""
+    if name == "cfg2":      # render-texture 1024^2 from 256^2 corpus, ctx 0, 9/200
+        t = int(1024 * scale)
+        cor = G(256, 256, 3, 1 + seed_shift)
+        tgt = np.full((t, t, 3), 255, np.uint8)
+        return dict(name="cfg2 render-texture %dx%d from 256x256 corpus, ctx0, patch 9, probes 200" % (t, t),
+                    params=abi.make_params(0, 0, 0, 0.5, 0.117, 9, 200), n_color=3, n_map=0, alpha=False,
+                    tmask=np.full((t, t), 255, np.uint8), tgt=tgt, cmask=np.full((256, 256), 255, np.uint8), cor=cor,
+                    bpp=4)
+    if name == "cfg1":      # heal 64^2 hole in 512^2, defaults 30/200
+        s = int(512 * scale)
+        img = G(s, s, 3, 12345 + seed_shift)
+        m = centered_mask(s, s, s // 8, s // 8)
+        return dict(name="cfg1 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
+                    params=abi.default_params(), n_color=3, n_map=0, alpha=False,
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+    if name == "cfg5":      # one heal job of the batch config: 2048^2, 256^2 hole, 30/200
+        s = int(2048 * scale)
+        img = G(s, s, 3, 100 + seed_shift)
+        m = centered_mask(s, s, s // 8, s // 8)
+        return dict(name="cfg5 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
+                    params=abi.default_params(), n_color=3, n_map=0, alpha=False,
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+    raise SystemExit("unknown workload %s" % name)
+
+
+def pixmaps(w):
+    tp = np.ascontiguousarray(np.concatenate([w["tmask"][:, :, None], w["tgt"]], axis=2))
+    cp = np.ascontiguousarray(np.concatenate([w["cmask"][:, :, None], w["cor"]], axis=2))
+    return tp, cp
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    libname, wname, scale, seed_shift, steps = args
+    from oracle import refdriver as R
+    lib = R.load(libname)
+    w = workload(wname, seed_shift, scale)
+    fi = R.format_indices(lib, w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
+    times = []
+    n = int((w["tmask"] != 0).sum())
+    for _ in range(steps):
+        tp, cp = pixmaps(w)
+        t0 = time.perf_counter()
+        err = R.engine(lib, w["params"], fi, tp, cp)
+        times.append(time.perf_counter() - t0)
+        assert err == 0
+    return n, times
+
+
+def cpu_reference_run(wname, scale, steps, warmup, procs, libname="ref_rand_1t"):
+    """Runs `procs` independent sample jobs per step on the host cores with the compiled reference."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        if warmup:
+            pool.map(_ref_worker, [(libname, wname, scale, i, 1) for i in range(procs)])
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(libname, wname, scale, i, steps) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    n = res[0][0]
+    return dict(px_per_s=procs * steps * n / wall, wall=wall, n=n, per_job_s=float(np.mean([np.mean(r[1]) for r in res])))
+
+
+def reference_sample_scale(wname):
+    return {"cfg2": 0.25, "cfg1": 1.0, "cfg5": 0.25}[wname]
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_rand_1t.so")):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return
+    procs = max(1, min(os.cpu_count() or 1, 64))
+    scale = reference_sample_scale(a.workload)
+    w = workload(a.workload, 0, scale)
+    r = cpu_reference_run(a.workload, scale, a.steps, min(a.warmup, 1), procs)
+    sample = "%s; %d independent jobs (one per host core) x %d steps, unthreaded reference build (libref_rand_1t)" % (w["name"], procs, a.steps)
+    line = {"metric": METRIC, "value": r["px_per_s"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1000.0 * r["wall"] / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer",
+            "data": "synthetic", "config": {"workload": workload(a.workload)["name"], "sample": sample},
+            "cpu_baseline": {"value": r["px_per_s"], "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
+            "e2e": {"value": r["px_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "per_job_seconds": r["per_job_s"]}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+KERNELS_PER_JOB = 4 + 6 + 5 + 1   # init x4, pass x6, prober copy x5, extract
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from resynthesizer_b200 import api, build
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU path")
+    torch.cuda.set_device(local)
+    api.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = workload(a.workload, seed_shift=rank)
+    fi = api.format_indices(w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
+    n = int((w["tmask"] != 0).sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def one_step(seed):
+        tp, cp = pixmaps(w)
+        api.set_seed(seed)
+        flush.fill_(seed & 0xFF)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        err = api.engine(w["params"], fi, tp, cp)
+        wall = time.perf_counter() - t0
+        assert err == 0
+        return wall, api.last_stats(), tp, cp
+
+    for i in range(a.warmup):
+        one_step(1000 + i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t_begin = time.perf_counter()
+    walls, stats = [], []
+    h2d = d2h = 0
+    for i in range(a.steps):
+        wall, st, tp, cp = one_step(1198472 + i)
+        walls.append(wall); stats.append(st)
+        h2d = tp.nbytes + cp.nbytes + 4 * n + 4 * st["n_corpus"]  # + offsets table, counted below
+        d2h = 4 * n
+    barrier()
+    t_total = time.perf_counter() - t_begin
+    clocks = sampler.stop() if rank == 0 else None
+
+    kern_s = sum(s["ms_kernels"] for s in stats) / 1000.0
+    e2e_s = sum(walls)
+    agg = torch.tensor([kern_s, e2e_s, t_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    kern_s, e2e_s, t_total = [float(x) for x in agg.tolist()]
+    total_px = world * a.steps * n
+    evals = sum(s["evals"] for s in stats); issued = sum(s["evals_issued"] for s in stats)
+    compares = sum(s["compares"] for s in stats); visits = sum(s["visits"] for s in stats)
+    scans = sum(s["offset_scans"] for s in stats)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (k_synth_pass): algorithmic bytes per SURVEY.md section 8d
+    bpp = w["bpp"]
+    K = max(2, w["params"].patchSize)
+    P = w["params"].maxProbeCount
+    fixed = scans * (4 + 4) + visits * (K * (8 + (4 if w["n_map"] else 0)) + K * 8 + P * 4 + 8 + 4)
+    algo_bytes = compares * bpp + fixed
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    launches_pass = 6 * a.steps
+    achieved = algo_bytes / (sum(s["ms_kernels"] for s in stats) / 1000.0) / 1e9
+    traffic = None
+    tp_path = os.path.join(ROOT, "profiles", "traffic_%s.json" % a.workload)
+    if os.path.exists(tp_path):
+        traffic = json.load(open(tp_path)).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "k_synth_pass", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes / launches_pass,
+                "avg_launch_ms": sum(s["ms_kernels"] for s in stats) / launches_pass,
+                "note": "bytes = neighbour-compares x %d B corpus pixel + per-visit fixed part; gathers are 4-8 B "
+                        "from 32 B sectors, so the L2 sector traffic is up to 8x the algorithmic bytes" % bpp}
+
+    # ---- CPU baseline beside it: the compiled reference on a bounded sample of the same workload
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_rand_1t.so")):
+            scale = reference_sample_scale(a.workload)
+            r1 = cpu_reference_run(a.workload, scale, 1, 0, 1, "ref_rand_1t")
+            r8 = cpu_reference_run(a.workload, scale, 1, 0, 1, "ref_rand_8t")
+            best, cores, which = (r1, 1, "unthreaded") if r1["px_per_s"] >= r8["px_per_s"] else (r8, 8, "8-thread refiner")
+            cpu = {"value": best["px_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": "%s, one job, reference %s build; unthreaded %.0f px/s, threaded(8) %.0f px/s" %
+                             (workload(a.workload, 0, scale)["name"], which, r1["px_per_s"], r8["px_per_s"])}
+        else:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+
+    line = {"metric": METRIC, "value": total_px / kern_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000.0 * t_total / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
+            "config": {"workload": w["name"], "parallelism": "independent jobs, %d GPU(s)" % world,
+                       "l2": "256 MiB flush between steps", "api": "engine() full API"},
+            "evals_per_s": world * evals / kern_s, "evals_issued_per_s": world * issued / kern_s,
+            "compares_per_s": world * compares / kern_s, "compares_per_eval_issued": compares / max(issued, 1),
+            "passes_run": stats[-1]["passes_run"], "visits_per_step": visits / a.steps,
+            "e2e": {"value": total_px / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_prep": float(np.mean([s["ms_prep"] for s in stats])), "ms_h2d": float(np.mean([s["ms_h2d"] for s in stats])),
+                    "ms_kernels": float(np.mean([s["ms_kernels"] for s in stats])), "ms_d2h": float(np.mean([s["ms_d2h"] for s in stats]))},
+            "gpu_launches": KERNELS_PER_JOB * a.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg5"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

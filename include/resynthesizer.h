@@ -1,0 +1,143 @@
+/*
+ * resynthesizer.h -- the drop-in boundary of libresynthesizer_b200.so.
+ *
+ * These are the entry points and ABI types a caller of the reference library
+ * binds.  Layouts are binary-compatible with the
+ * reference so that its callers (src/testSynth.c:77,168; the GIMP engine
+ * plug-in src/resynthesizer/resynthesizer.c:505) relink unchanged.  Behind
+ * them the synthesis passes run as sm_100a CUDA kernels (include/rs_cuda.h);
+ * there is no CPU fallback: without a usable CUDA device every synthesis call
+ * returns RS_ERROR_CUDA.
+ */
+#ifndef RESYNTHESIZER_B200_H
+#define RESYNTHESIZER_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* replaces lib/imageBuffer.h:12-19 -- interleaved pixels, rows padded to rowBytes */
+typedef struct _ImageBuffer {
+  unsigned char *data;
+  unsigned int width;
+  unsigned int height;
+  size_t rowBytes;
+} ImageBuffer;
+
+/* replaces lib/imageFormat.h:36-42 */
+typedef enum ImageFormat { T_RGB, T_RGBA, T_Gray, T_GrayA } TImageFormat;
+
+/* replaces lib/engineParams.h:13-28 */
+typedef enum ImageSynthError {
+  IMAGE_SYNTH_SUCCESS,
+  IMAGE_SYNTH_ERROR_INVALID_IMAGE_FORMAT,
+  IMAGE_SYNTH_ERROR_IMAGE_MASK_MISMATCH,
+  IMAGE_SYNTH_ERROR_PATCH_SIZE_EXCEEDED,
+  IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE,
+  IMAGE_SYNTH_ERROR_EMPTY_TARGET,
+  IMAGE_SYNTH_ERROR_EMPTY_CORPUS
+} TImageSynthError;
+
+/* Outside the reference's enum range: the CUDA layer failed (no device, out of
+ * memory, launch error).  rs_last_error() holds the text.  (SURVEY.md section 5:
+ * "map CUDA failure to a non-zero code outside the enum range".) */
+#define RS_ERROR_CUDA 100
+
+/* replaces lib/engineParams.h:31-86 (field order and types fixed by the ABI) */
+typedef struct ImageSynthParametersStruct {
+  int isMakeSeamlesslyTileableHorizontally;
+  int isMakeSeamlesslyTileableVertically;
+  int matchContextType;          /* 0..8, selects orderTarget mode (lib/orderTarget.h:268-343) */
+  double mapWeight;
+  double sensitivityToOutliers;
+  unsigned int patchSize;        /* <= 64 */
+  unsigned int maxProbeCount;
+} TImageSynthParameters;
+
+/* replaces lib/imageFormatIndicies.h:46-58 -- byte positions inside the internal pixel
+ * [mask][colour x1..3][alpha?][map x0..3] */
+typedef unsigned char TPixelelIndex;
+typedef struct indicesStruct {
+  TPixelelIndex colorEndBip;
+  TPixelelIndex alpha_bip;
+  TPixelelIndex map_start_bip;
+  TPixelelIndex map_end_bip;
+  TPixelelIndex img_match_bpp;
+  TPixelelIndex map_match_bpp;
+  TPixelelIndex total_bpp;
+  int isAlphaTarget;
+  int isAlphaSource;
+} TFormatIndices;
+
+/* replaces lib/glibProxy.h:86-92 / GLib's public GArray head; lib/map.h:28-46 */
+#ifndef RS_NO_GLIB_NAMES
+typedef struct _GArray { char *data; unsigned int len; } GArray;
+#endif
+typedef struct {
+  unsigned int width;
+  unsigned int height;
+  unsigned int depth;
+  GArray *data;
+} Map;
+typedef struct { int x; int y; } Coordinates;
+typedef unsigned char Pixelel;
+
+/* ---- simple API: replaces lib/imageSynth.h:31-52 (impl lib/imageSynth.c:61-216) ---- */
+int imageSynth(ImageBuffer *imageBuffer, ImageBuffer *mask, TImageFormat imageFormat,
+               TImageSynthParameters *parameters, /* NULL -> defaults */
+               void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag);
+int imageSynth2(ImageBuffer *imageBuffer, ImageBuffer *mask, ImageBuffer *mask2, TImageFormat imageFormat,
+                TImageSynthParameters *parameters,
+                void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag);
+
+/* ---- full API: replaces lib/engine.h:3-12 (impl lib/engine.c:539-690) ---- */
+int engine(TImageSynthParameters parameters, TFormatIndices *indices, Map *targetMap, Map *corpusMap,
+           void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag);
+
+/* replaces lib/engineParams.h:91-94 */
+void setDefaultParams(TImageSynthParameters *param);
+
+/* replaces lib/imageFormatIndicies.h:60-84 */
+unsigned int countPixelelsPerPixelForFormat(TImageFormat format);
+int prepareImageFormatIndicesFromFormatType(TFormatIndices *indices, TImageFormat format);
+void prepareImageFormatIndices(TFormatIndices *indices, unsigned int count_color_channels_target,
+                               unsigned int count_color_channels_map, int is_alpha_target,
+                               int is_alpha_source, int isMap);
+void prepareDefaultFormatIndices(TFormatIndices *formatIndices);
+
+/* replaces lib/map.h:49-99 (used by the GIMP adapter, src/resynthesizer/adaptGimp.h:190-276) */
+void free_map(Map *map);
+void new_pixmap(Map *map, unsigned int width, unsigned int height, unsigned int depth);
+void new_bytemap(Map *map, unsigned int width, unsigned int height);
+void new_intmap(Map *map, unsigned int width, unsigned int height);
+void new_coordmap(Map *map, unsigned int width, unsigned int height);
+void set_bytemap(Map *map, unsigned char value);
+void invert_bytemap(Map *map);
+void interleave_mask(Map *pixmap, Map *mask);
+
+/* ---- additions (not in the reference) ---- */
+/* Text of the last CUDA-layer failure on this thread ("" if none). */
+const char *rs_last_error(void);
+/* Select the CUDA device subsequent calls on this thread use (default: RESYNTH_CUDA_DEVICE or 0). */
+int rs_set_device(int ordinal);
+
+/* Counters of the most recent engine()/imageSynth() call on this thread. */
+typedef struct {
+  unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
+  unsigned long long betters[6], pass_visits[6], sum_best[6];
+  unsigned int passes_run, n_targets, n_corpus;
+  float ms_prep, ms_h2d, ms_kernels, ms_d2h, ms_total; /* host prep / copies / device passes (CUDA events) */
+} RsStats;
+void rs_get_stats(RsStats *out);
+/* Visit order and final source (best corpus point) of each target point of the last engine() call on this
+ * thread, packed x | y << 16 (0xFFFFFFFF = no source).  Returns the number of target points. */
+unsigned int rs_get_last_result(unsigned int *targets_out, unsigned int *sources_out, unsigned int cap);
+/* Seed of the per-probe counter hash (default 1198472, the reference's PRNG seed, lib/engine.c:643). */
+void rs_set_seed(unsigned int seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+/*
+ * rs_cuda.h -- the thin C-ABI between the C/C++ host (imageSynth/engine, host
+ * prep) and the sm_100a kernels.  Plain pointers and sizes only; no C++ types,
+ * no exceptions cross it; every function returns 0 or a non-zero code with the
+ * text available from rs_cuda_last_error().
+ *
+ * What each entry point replaces in the reference:
+ *   rs_job_run            the pass loop            lib/refiner.h:75-121, lib/refinerThreaded.h:318-358
+ *     (kernel k_synth_pass)  per-target loop       lib/synthesize.h:426-642
+ *                            neighbour gathering   lib/synthesize.h:189-241
+ *                            candidates + probes   lib/synthesize.h:537-604, lib/engine.c:434-443
+ *                            patch distance        lib/synthesize.h:266-400
+ *                            commit                lib/synthesize.h:620-639
+ *   rs_bestfit_batch      computeBestFit alone on caller-given patches and candidate lists
+ *   rs_job_create/upload  state preparation        lib/engine.c:207-224,314-327,338-431
+ *   rs_job_download       result write-back        (engine() mutates targetMap in place)
+ */
+#ifndef RS_CUDA_H
+#define RS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct RsJob RsJob; /* opaque */
+
+typedef struct {
+  int32_t tw, th, cw, ch;        /* target / corpus image dimensions */
+  int32_t bpp;                   /* bytes per pixel of the raw internal pixmaps (TFormatIndices.total_bpp) */
+  int32_t n_color;               /* img_match_bpp: 1 or 3; colours start at byte 1 */
+  int32_t n_map;                 /* map_match_bpp: 0..3 */
+  int32_t map_bip;               /* map_start_bip */
+  int32_t alpha_bip;             /* byte index of alpha, or -1 */
+  int32_t alpha_target;          /* isAlphaTarget */
+  int32_t htile, vtile;          /* wrap neighbour coordinates in x / y */
+  int32_t use_context;           /* matchContextType != 0 */
+  uint32_t patch_size;           /* as passed by the caller (<= 64) */
+  uint32_t max_probes;
+  uint32_t seed;                 /* key of the per-probe counter hash */
+  uint32_t pass_end[6];          /* prefix length of each pass (lib/passes.h:67-93) */
+  uint32_t n_passes;             /* <= 6 */
+  double terminate_fraction;     /* stop after a pass when (float)betters/n, widened to double, is below this (0.1) */
+} RsJobDesc;
+
+typedef struct {
+  uint64_t visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
+  uint64_t betters[6], pass_visits[6], sum_best[6];
+  uint32_t passes_run;
+  float ms_passes;               /* CUDA-event time of all pass kernels of the last run */
+} RsJobCounters;
+
+/* Called on the host, in order, for every (pass, index) with (index & 4095) == 0 that the device
+ * has started (lib/synthesize.h:493-497).  Return non-zero to cancel the job. */
+typedef int (*RsTickFn)(void *ctx, uint32_t pass, uint32_t index);
+
+const char *rs_cuda_last_error(void);
+int rs_cuda_set_device(int ordinal);
+int rs_cuda_device_count(void);
+
+int rs_job_create(const RsJobDesc *desc, RsJob **out);
+/* Host -> device.  target_raw/corpus_raw: tw*th*bpp and cw*ch*bpp bytes, pixel = [mask][colours][alpha?][maps].
+ * targets: n points packed x | y<<16 in visit order.  corpus_points: C points packed likewise.
+ * offsets: n_offsets neighbour offsets packed (int16 x | int16 y << 16), ascending distance, entry 0 = (0,0).
+ * color_lut[256], map_lut[256]: metric by absolute difference; map_lut_max = mapsMetric[0]. */
+int rs_job_upload(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_raw,
+                  const uint32_t *targets, uint32_t n_targets,
+                  const uint32_t *corpus_points, uint32_t n_corpus,
+                  const uint32_t *offsets, uint32_t n_offsets,
+                  const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max);
+/* Runs all passes (early termination decided on the device), calling tick from the waiting host thread. */
+int rs_job_run(RsJob *job, RsTickFn tick, void *tick_ctx);
+/* colours_out: n_targets entries, c0 | c1<<8 | c2<<16 of each target point in visit order;
+ * sources_out (may be NULL): packed best corpus point of each, 0xFFFFFFFF if none. */
+int rs_job_download(RsJob *job, uint32_t *colours_out, uint32_t *sources_out);
+int rs_job_counters(RsJob *job, RsJobCounters *out);
+void rs_job_destroy(RsJob *job);
+
+/* computeBestFit over explicit inputs, for bit-exact kernel tests (lib/synthesize.h:266-400).
+ * corpus_raw: cw*ch*bpp bytes.  For visit v in [0,n_visits): patch entries [nb_begin[v], nb_begin[v+1]) of
+ * nb_offsets (packed int16 pairs) / nb_pixels (8 raw pixel bytes each); candidates
+ * [cand_begin[v], cand_begin[v+1]) of cands (packed x|y<<16).  Outputs per visit: best sum (0xFFFFFFFF if no
+ * candidate), index of the winning candidate within the visit's list (-1 if none). */
+int rs_bestfit_batch(const RsJobDesc *desc, const uint8_t *corpus_raw,
+                     const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max,
+                     uint32_t n_visits, const uint32_t *nb_begin, const uint32_t *nb_offsets,
+                     const uint8_t *nb_pixels, const uint32_t *cand_begin, const uint32_t *cands,
+                     uint32_t *best_sum_out, int32_t *best_index_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

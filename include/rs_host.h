@@ -1,0 +1,22 @@
+/*
+ * rs_host.h -- host-preparation pieces of libresynthesizer_b200.so exported so that parity tests can compare
+ * them with the oracle array by array.  They run on the CPU only (no CUDA call).
+ */
+#ifndef RS_HOST_H
+#define RS_HOST_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* replaces quantizeMetricFuncs (lib/matchWeighting.h:194-204): tables indexed 256 + signed difference */
+void rs_host_metric_tables(double sensitivity, double map_weight, uint16_t *color512, uint32_t *map512);
+/* replaces prepareSortedOffsets (lib/engine.c:465-497); writes min(cap, n) x,y pairs, returns n */
+uint32_t rs_host_sorted_offsets(int tw, int th, int cw, int ch, int32_t *xy, uint32_t cap);
+/* replaces orderTargetPoints (lib/orderTarget.h:268-343) over n x,y pairs given in row-major scan order */
+int rs_host_order_targets(int match_context_type, int32_t *xy, uint32_t n, uint32_t seed);
+/* replaces prepare_repetition_parameters (lib/passes.h:67-93) */
+uint32_t rs_host_pass_schedule(uint32_t n_targets, uint32_t *ends6);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -89,3 +89,77 @@ def engine(lib, params, fi, target_pixmap, corpus_pixmap, progress=None):
     cm, _k2 = abi.make_map(corpus_pixmap)
     pr = progress or Progress()
     return lib.engine(params, C.byref(fi), C.byref(tm), C.byref(cm), pr.cb, None, C.byref(pr.cancel))
+
+
+# ---------------------------------------------------------------- helpers for the C restatement (port)
+class PortStats(C.Structure):
+    _fields_ = [(n, C.c_ulonglong) for n in ("visits", "evals", "compares", "offset_scans", "heur_evals",
+                                             "heur_skips", "perfect")] + \
+               [("betters", C.c_ulonglong * 6), ("pass_visits", C.c_ulonglong * 6), ("sum_best", C.c_ulonglong * 6),
+                ("passes_run", C.c_uint), ("n_targets", C.c_uint), ("n_corpus", C.c_uint)]
+
+
+REF_MODE = (0, 0)      # GLib MT19937 stream, live recentProber: the reference product build
+RAND_MODE = (1, 0)     # libc rand() proxy: the reference standalone build
+GPU_MODE = (2, 1)      # counter hash + pass-snapshot recentProber: sequential definition of the CUDA engine
+
+
+def load_port(mode=REF_MODE, seed=1198472):
+    lib = load("port")
+    lib.port_set_mode.argtypes = [C.c_int, C.c_int]
+    lib.port_set_seed.argtypes = [C.c_uint]
+    lib.port_get_stats.argtypes = [C.POINTER(PortStats)]
+    lib.port_trace_enable.argtypes = [C.c_uint, C.c_uint]
+    lib.port_trace_size.restype = C.c_size_t
+    lib.port_trace_count.restype = C.c_uint
+    lib.port_trace_copy.argtypes = [C.c_void_p]
+    lib.port_luts.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    lib.port_offsets.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint]
+    lib.port_offsets.restype = C.c_uint
+    lib.port_order.argtypes = [C.c_int, C.c_void_p, C.c_uint, C.c_uint]
+    lib.port_set_mode(*mode)
+    lib.port_set_seed(seed)
+    return lib
+
+
+def port_stats(lib):
+    s = PortStats()
+    lib.port_get_stats(C.byref(s))
+    d = {}
+    for name, _t in s._fields_:
+        v = getattr(s, name)
+        d[name] = list(v) if hasattr(v, "__len__") else v
+    return d
+
+
+def port_trace(lib):
+    """Parses the per-visit dump (see resynth_port.c 'trace') into a list of dicts."""
+    n = lib.port_trace_size()
+    buf = np.zeros(n, np.uint8)
+    if n:
+        lib.port_trace_copy(buf.ctypes.data)
+    out, pos = [], 0
+    while pos < n:
+        hd = buf[pos:pos + 44].view(np.uint32)
+        pos += 44
+        K, nc = int(hd[4]), int(hd[5])
+        nb = buf[pos:pos + 24 * K].reshape(K, 24)
+        pos += 24 * K
+        cands = buf[pos:pos + 8 * nc].view(np.int32).reshape(nc, 2).copy()
+        pos += 8 * nc
+        out.append(dict(pass_=int(hd[0]), index=int(hd[1]), x=int(hd[2]), y=int(hd[3]), K=K, best=int(hd[6]),
+                        best_xy=(int(np.int32(hd[7])), int(np.int32(hd[8]))), bettered=int(hd[9]), n_heur=int(hd[10]),
+                        offsets=nb[:, 0:8].copy().view(np.int32).reshape(K, 2),
+                        pixels=nb[:, 8:16].copy(),
+                        sources=nb[:, 16:24].copy().view(np.int32).reshape(K, 2),
+                        cands=cands))
+    return out
+
+
+def port_last_result(lib):
+    lib.port_last_result.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+    lib.port_last_result.restype = C.c_uint
+    n = lib.port_last_result(None, None, 0)
+    t = np.zeros((n, 2), np.int32); s = np.zeros((n, 2), np.int32)
+    lib.port_last_result(t.ctypes.data, s.ctypes.data, n)
+    return t, s

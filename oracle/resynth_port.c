@@ -57,6 +57,15 @@ typedef struct {
 } PortStats;
 static PortStats g_stats;
 
+/* visit order + final sourceOf of the last engine() call (test instrumentation) */
+static int *g_last_xy; static int *g_last_src; static unsigned int g_last_n;
+unsigned int port_last_result(int *target_xy, int *source_xy, unsigned int cap) {
+  for (unsigned int i = 0; i < g_last_n && i < cap; i++) {
+    target_xy[2 * i] = g_last_xy[2 * i]; target_xy[2 * i + 1] = g_last_xy[2 * i + 1];
+    source_xy[2 * i] = g_last_src[2 * i]; source_xy[2 * i + 1] = g_last_src[2 * i + 1];
+  }
+  return g_last_n;
+}
 void port_set_mode(int rng_mode, int prober_mode) { g_rng_mode = rng_mode; g_prober_mode = prober_mode; }
 void port_set_seed(unsigned int seed) { g_seed = seed; }
 void port_get_stats(PortStats *out) { *out = g_stats; }
@@ -424,6 +433,11 @@ int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *targetMap, Map *c
       if ((float)b / e.nT < 0.1) break;
     }
     free(e.prober); free(e.proberNext);
+    g_last_xy = (int *)realloc(g_last_xy, (size_t)e.nT * 8); g_last_src = (int *)realloc(g_last_src, (size_t)e.nT * 8); g_last_n = e.nT;
+    for (unsigned int i = 0; i < e.nT; i++) {
+      Pt t = e.targets[i], so = e.sourceOf[(size_t)t.y * e.tw + t.x];
+      g_last_xy[2 * i] = t.x; g_last_xy[2 * i + 1] = t.y; g_last_src[2 * i] = so.x; g_last_src[2 * i + 1] = so.y;
+    }
   }
   free(e.hasValue); free(e.targets); free(e.corpus); free(e.sourceOf); free(e.offsets);
   return err;

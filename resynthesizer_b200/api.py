@@ -1,0 +1,161 @@
+"""Python mirror of the reference library's API over libresynthesizer_b200.so (ctypes).
+
+Same names, argument meaning and error codes as the reference's C API
+(lib/imageSynth.h:31-52, lib/engine.h:3-12): image_synth() / image_synth2() /
+engine().  The shared library is the product; this module only marshals numpy
+arrays.  If the library is missing or no CUDA device is usable the calls fail
+loudly -- there is no CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libresynthesizer_b200.so")
+_lib = None
+
+
+class ResynthError(RuntimeError):
+    pass
+
+
+class RsStats(C.Structure):
+    _fields_ = [(n, C.c_ulonglong) for n in ("visits", "evals", "evals_issued", "compares", "offset_scans",
+                                             "heur_evals", "heur_skips", "perfect")] + \
+               [("betters", C.c_ulonglong * 6), ("pass_visits", C.c_ulonglong * 6), ("sum_best", C.c_ulonglong * 6),
+                ("passes_run", C.c_uint), ("n_targets", C.c_uint), ("n_corpus", C.c_uint),
+                ("ms_prep", C.c_float), ("ms_h2d", C.c_float), ("ms_kernels", C.c_float),
+                ("ms_d2h", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        d = {}
+        for name, _t in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
+
+
+class RsJobDesc(C.Structure):
+    _fields_ = [("tw", C.c_int32), ("th", C.c_int32), ("cw", C.c_int32), ("ch", C.c_int32), ("bpp", C.c_int32),
+                ("n_color", C.c_int32), ("n_map", C.c_int32), ("map_bip", C.c_int32), ("alpha_bip", C.c_int32),
+                ("alpha_target", C.c_int32), ("htile", C.c_int32), ("vtile", C.c_int32), ("use_context", C.c_int32),
+                ("patch_size", C.c_uint32), ("max_probes", C.c_uint32), ("seed", C.c_uint32),
+                ("pass_end", C.c_uint32 * 6), ("n_passes", C.c_uint32), ("terminate_fraction", C.c_double)]
+
+
+def lib():
+    """Loads the CUDA library (once). Raises if it has not been built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ResynthError("%s is missing: run `python -m resynthesizer_b200.build` (nvcc, sm_100a)" % LIB_PATH)
+        L = abi.bind(C.CDLL(LIB_PATH))
+        L.rs_last_error.restype = C.c_char_p
+        L.rs_cuda_last_error.restype = C.c_char_p
+        L.rs_get_stats.argtypes = [C.POINTER(RsStats)]
+        L.rs_set_seed.argtypes = [C.c_uint]
+        L.rs_set_device.argtypes = [C.c_int]
+        L.rs_cuda_device_count.restype = C.c_int
+        L.rs_host_metric_tables.argtypes = [C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.rs_host_sorted_offsets.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
+        L.rs_host_sorted_offsets.restype = C.c_uint32
+        L.rs_host_order_targets.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.rs_host_pass_schedule.argtypes = [C.c_uint32, C.c_void_p]
+        L.rs_host_pass_schedule.restype = C.c_uint32
+        L.rs_bestfit_batch.argtypes = [C.POINTER(RsJobDesc)] + [C.c_void_p] * 3 + [C.c_uint32, C.c_uint32] + \
+                                      [C.c_void_p] * 7
+        _lib = L
+    return _lib
+
+
+def _check(err):
+    if err >= 100:
+        raise ResynthError("CUDA layer failed (code %d): %s" % (err, lib().rs_last_error().decode()))
+    return err
+
+
+def set_device(ordinal):
+    _check(lib().rs_set_device(int(ordinal)))
+
+
+def set_seed(seed):
+    lib().rs_set_seed(int(seed) & 0xFFFFFFFF)
+
+
+def last_stats():
+    s = RsStats()
+    lib().rs_get_stats(C.byref(s))
+    return s.as_dict()
+
+
+class _Progress:
+    def __init__(self, callback, cancel_after):
+        self.percents = []
+        self.cancel = C.c_int(0)
+
+        def cb(percent, _ctx):
+            self.percents.append(percent)
+            if callback is not None:
+                callback(percent)
+            if cancel_after is not None and len(self.percents) >= cancel_after:
+                self.cancel.value = 1
+        self.cb = abi.PROGRESS_CB(cb)
+
+
+def image_synth(image, mask, fmt, params=None, progress=None, cancel_after=None, mask2=None, return_progress=False):
+    """imageSynth()/imageSynth2(): heal the masked part of `image` (h,w,c uint8) in place.
+
+    Returns the reference's error code (0 = success).  `progress(percent)` is
+    the reference's progress callback; `cancel_after=k` raises the cancel flag
+    inside the k-th callback.
+    """
+    L = lib()
+    assert image.dtype == np.uint8 and image.ndim == 3 and image.flags["C_CONTIGUOUS"]
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    h, w, c = image.shape
+    ib = abi.ImageBuffer(image.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, w * c)
+    mb = abi.ImageBuffer(mask.ctypes.data_as(C.POINTER(C.c_ubyte)), mask.shape[1], mask.shape[0], mask.shape[1])
+    pr = _Progress(progress, cancel_after)
+    pp = C.byref(params) if params is not None else None
+    if mask2 is None:
+        err = L.imageSynth(C.byref(ib), C.byref(mb), fmt, pp, pr.cb, None, C.byref(pr.cancel))
+    else:
+        mask2 = np.ascontiguousarray(mask2, dtype=np.uint8)
+        mb2 = abi.ImageBuffer(mask2.ctypes.data_as(C.POINTER(C.c_ubyte)), mask2.shape[1], mask2.shape[0], mask2.shape[1])
+        err = L.imageSynth2(C.byref(ib), C.byref(mb), C.byref(mb2), fmt, pp, pr.cb, None, C.byref(pr.cancel))
+    _check(err)
+    return (err, pr.percents) if return_progress else err
+
+
+def format_indices(n_color, n_map=0, alpha_target=False, alpha_source=False, is_map=False):
+    fi = abi.TFormatIndices()
+    lib().prepareImageFormatIndices(C.byref(fi), n_color, n_map, int(alpha_target), int(alpha_source), int(is_map))
+    return fi
+
+
+def engine(params, fi, target_pixmap, corpus_pixmap, progress=None, cancel_after=None, return_progress=False):
+    """engine(): full API over internal pixmaps [mask][colours][alpha?][maps]; target_pixmap changes in place."""
+    L = lib()
+    tm, _k1 = abi.make_map(target_pixmap)
+    cm, _k2 = abi.make_map(corpus_pixmap)
+    pr = _Progress(progress, cancel_after)
+    err = L.engine(params, C.byref(fi), C.byref(tm), C.byref(cm), pr.cb, None, C.byref(pr.cancel))
+    _check(err)
+    return (err, pr.percents) if return_progress else err
+
+
+def last_result():
+    """(targets, sources) of the last engine() call: (n,2) int32 arrays in visit order; source (-1,-1) = none."""
+    L = lib()
+    L.rs_get_last_result.argtypes = [C.c_void_p, C.c_void_p, C.c_uint]
+    L.rs_get_last_result.restype = C.c_uint
+    n = L.rs_get_last_result(None, None, 0)
+    t = np.zeros(n, np.uint32); s = np.zeros(n, np.uint32)
+    L.rs_get_last_result(t.ctypes.data, s.ctypes.data, n)
+    txy = np.stack([t & 0xFFFF, t >> 16], axis=1).astype(np.int32)
+    sxy = np.stack([s & 0xFFFF, s >> 16], axis=1).astype(np.int32)
+    sxy[s == 0xFFFFFFFF] = -1
+    return txy, sxy

@@ -1,0 +1,327 @@
+// The reference-facing host layer: imageSynth()/imageSynth2()/engine() with the reference's signatures,
+// error codes, progress and cancel behaviour (include/resynthesizer.h), driving the CUDA passes through
+// include/rs_cuda.h.  There is no CPU synthesis path in this library.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/resynthesizer.h"
+#include "../../include/rs_cuda.h"
+#include "host_prep.h"
+
+namespace {
+
+thread_local std::string t_err;
+thread_local RsStats t_stats;
+thread_local uint32_t t_seed = 1198472u;  // lib/engine.c:643
+thread_local bool t_device_chosen = false;
+thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+int ensure_device() {
+  if (t_device_chosen) return 0;
+  int ordinal = 0;
+  if (const char *e = std::getenv("RESYNTH_CUDA_DEVICE")) ordinal = std::atoi(e);
+  if (rs_cuda_device_count() <= 0) { t_err = "no CUDA device available (this library has no CPU path)"; return RS_ERROR_CUDA; }
+  if (rs_cuda_set_device(ordinal)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
+  t_device_chosen = true;
+  return 0;
+}
+
+// Progress bookkeeping of lib/progress.c:53-65 driven by device ticks.
+struct TickState {
+  void (*cb)(int, void *);
+  void *ctx;
+  int *cancel;
+  uint32_t completed, estimated, prior_percent;
+};
+
+int on_tick(void *p, uint32_t /*pass*/, uint32_t /*index*/) {
+  TickState *t = static_cast<TickState *>(p);
+  t->completed += 4095u;  // IMAGE_SYNTH_CALLBACK_COUNT
+  const uint32_t percent = (uint32_t)(((float)t->completed / t->estimated) * 100);
+  if (percent > t->prior_percent) {
+    t->cb((int)percent, t->ctx);
+    t->prior_percent = percent;
+  }
+  return *t->cancel ? 1 : 0;  // polled right after the callback (lib/synthesize.h:493-497)
+}
+
+}  // namespace
+
+extern "C" const char *rs_last_error(void) { return t_err.c_str(); }
+extern "C" void rs_get_stats(RsStats *out) { *out = t_stats; }
+extern "C" void rs_set_seed(unsigned int seed) { t_seed = seed; }
+extern "C" int rs_set_device(int ordinal) {
+  if (rs_cuda_set_device(ordinal)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
+  t_device_chosen = true;
+  return 0;
+}
+
+// replaces lib/engineParams.c:8-19
+extern "C" void setDefaultParams(TImageSynthParameters *p) {
+  p->isMakeSeamlesslyTileableHorizontally = 0;
+  p->isMakeSeamlesslyTileableVertically = 0;
+  p->matchContextType = 1;
+  p->mapWeight = 0.5;
+  p->sensitivityToOutliers = 0.117;
+  p->patchSize = 30;
+  p->maxProbeCount = 200;
+}
+
+// replaces lib/imageFormat.c:39-56
+extern "C" unsigned int countPixelelsPerPixelForFormat(TImageFormat f) {
+  switch (f) {
+    case T_RGB: return 3;
+    case T_RGBA: return 4;
+    case T_Gray: return 1;
+    case T_GrayA: return 2;
+    default: return 0;
+  }
+}
+
+// replaces lib/imageFormat.c:116-207: [mask][colours][alpha if either image has one][map channels]
+extern "C" void prepareImageFormatIndices(TFormatIndices *o, unsigned int n_color, unsigned int n_map, int alpha_target,
+                                          int alpha_source, int is_map) {
+  o->img_match_bpp = (TPixelelIndex)n_color;
+  o->colorEndBip = (TPixelelIndex)(1 + n_color);
+  if (alpha_target || alpha_source) {
+    o->alpha_bip = o->colorEndBip;
+    o->map_start_bip = (TPixelelIndex)(o->colorEndBip + 1);
+  } else {
+    o->map_start_bip = o->colorEndBip;  // alpha_bip stays undefined, as in the reference
+  }
+  o->map_match_bpp = (TPixelelIndex)(is_map ? n_map : 0);
+  o->map_end_bip = (TPixelelIndex)(o->map_start_bip + o->map_match_bpp);
+  o->total_bpp = o->map_end_bip;
+  o->isAlphaTarget = alpha_target;
+  o->isAlphaSource = alpha_source;
+}
+
+// replaces lib/imageFormat.c:65-113
+extern "C" int prepareImageFormatIndicesFromFormatType(TFormatIndices *o, TImageFormat f) {
+  switch (f) {
+    case T_RGB: prepareImageFormatIndices(o, 3, 0, 0, 0, 0); return 0;
+    case T_RGBA: prepareImageFormatIndices(o, 3, 0, 1, 1, 0); return 0;
+    case T_Gray: prepareImageFormatIndices(o, 1, 0, 0, 0, 0); return 0;
+    case T_GrayA: prepareImageFormatIndices(o, 1, 0, 1, 1, 0); return 0;
+    default: return IMAGE_SYNTH_ERROR_INVALID_IMAGE_FORMAT;
+  }
+}
+
+// replaces lib/imageFormat.c:210-241 (test default: M R G B A)
+extern "C" void prepareDefaultFormatIndices(TFormatIndices *o) {
+  prepareImageFormatIndices(o, 3, 0, 1, 1, 0);
+}
+
+// ------------------------------------------------------------------------------------------ engine()
+extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *targetMap, Map *corpusMap,
+                      void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag) {
+  const double t0 = now_ms();
+  std::memset(&t_stats, 0, sizeof t_stats);
+  t_err.clear();
+  if (prm.patchSize > 64) return IMAGE_SYNTH_ERROR_PATCH_SIZE_EXCEEDED;  // lib/engine.c:591
+
+  const int tw = (int)targetMap->width, th = (int)targetMap->height;
+  const int cw = (int)corpusMap->width, ch = (int)corpusMap->height;
+  const int bpp = fi->total_bpp;
+  uint8_t *tpix = reinterpret_cast<uint8_t *>(targetMap->data->data);
+  const uint8_t *cpix = reinterpret_cast<const uint8_t *>(corpusMap->data->data);
+
+  std::vector<rs::Point> targets, corpus;
+  rs::collect_target_points(tpix, tw, th, bpp, targets);
+  if (targets.empty()) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;  // lib/engine.c:605-610
+  rs::collect_corpus_points(cpix, cw, ch, bpp, *fi, corpus);
+  if (corpus.empty()) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;   // lib/engine.c:620-627
+
+  std::vector<uint32_t> offsets;
+  rs::build_sorted_offsets(tw, th, cw, ch, offsets);
+  uint16_t c512[512];
+  uint32_t m512[512];
+  rs::build_metric_tables(prm.sensitivityToOutliers, prm.mapWeight, c512, m512);
+  rs::GRandMT prng(t_seed);
+  const int oerr = rs::order_target_points(prm.matchContextType, targets, prng);
+  if (oerr) return oerr;  // lib/engine.c:645-647
+
+  if (tw > 65535 || th > 65535 || cw > 65535 || ch > 65535) {
+    t_err = "image dimensions above 65535 are not supported by the packed device layout";
+    return RS_ERROR_CUDA;
+  }
+  if (int e = ensure_device()) return e;
+
+  // metric by |difference| (both functions are even: matchWeighting.h:56-58,176)
+  uint32_t c256[256], m256[256];
+  for (int d = 0; d < 256; d++) { c256[d] = c512[256 + d]; m256[d] = m512[256 + d]; }
+
+  RsJobDesc desc;
+  std::memset(&desc, 0, sizeof desc);
+  desc.tw = tw; desc.th = th; desc.cw = cw; desc.ch = ch; desc.bpp = bpp;
+  desc.n_color = fi->img_match_bpp; desc.n_map = fi->map_match_bpp; desc.map_bip = fi->map_start_bip;
+  desc.alpha_bip = (fi->isAlphaTarget || fi->isAlphaSource) ? fi->alpha_bip : -1;
+  desc.alpha_target = fi->isAlphaTarget ? 1 : 0;
+  desc.htile = prm.isMakeSeamlesslyTileableHorizontally ? 1 : 0;
+  desc.vtile = prm.isMakeSeamlesslyTileableVertically ? 1 : 0;
+  desc.use_context = prm.matchContextType != 0;
+  desc.patch_size = prm.patchSize; desc.max_probes = prm.maxProbeCount; desc.seed = t_seed;
+  const uint32_t n = (uint32_t)targets.size();
+  const uint32_t estimated = rs::pass_schedule(n, desc.pass_end);
+  desc.n_passes = 6;
+  desc.terminate_fraction = 0.1;  // IMAGE_SYNTH_TERMINATE_FRACTION, a double (lib/refiner.h:111)
+
+  std::vector<uint32_t> tpk(n), cpk(corpus.size());
+  for (uint32_t i = 0; i < n; i++) tpk[i] = (uint32_t)targets[i].x | ((uint32_t)targets[i].y << 16);
+  for (size_t i = 0; i < corpus.size(); i++) cpk[i] = (uint32_t)corpus[i].x | ((uint32_t)corpus[i].y << 16);
+  const double t1 = now_ms();
+
+  RsJob *job = nullptr;
+  if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
+  int rc = rs_job_upload(job, tpix, cpix, tpk.data(), n, cpk.data(), (uint32_t)cpk.size(), offsets.data(),
+                         (uint32_t)offsets.size(), c256, m256, m512[0]);
+  const double t2 = now_ms();
+  TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
+  if (!rc) rc = rs_job_run(job, on_tick, &ts);
+  const double t3 = now_ms();
+  std::vector<uint32_t> colours(n);
+  t_last_sources.assign(n, 0xFFFFFFFFu);
+  t_last_targets = tpk;
+  if (!rc) rc = rs_job_download(job, colours.data(), t_last_sources.data());
+  if (rc) {
+    t_err = rs_cuda_last_error();
+    rs_job_destroy(job);
+    return RS_ERROR_CUDA;
+  }
+  // engine() mutates the colour bytes of targetMap in place (lib/synthesize.h:403-419); alpha and maps untouched
+  const int nc = fi->img_match_bpp;
+  for (uint32_t i = 0; i < n; i++) {
+    uint8_t *p = tpix + ((size_t)targets[i].y * tw + targets[i].x) * bpp;
+    for (int c = 0; c < nc; c++) p[1 + c] = (uint8_t)(colours[i] >> (8 * c));
+  }
+  RsJobCounters jc;
+  rs_job_counters(job, &jc);
+  rs_job_destroy(job);
+  const double t4 = now_ms();
+  t_stats.visits = jc.visits; t_stats.evals = jc.evals; t_stats.evals_issued = jc.evals_issued;
+  t_stats.compares = jc.compares; t_stats.offset_scans = jc.offset_scans; t_stats.heur_evals = jc.heur_evals;
+  t_stats.heur_skips = jc.heur_skips; t_stats.perfect = jc.perfect;
+  for (int p = 0; p < 6; p++) { t_stats.betters[p] = jc.betters[p]; t_stats.pass_visits[p] = jc.pass_visits[p]; t_stats.sum_best[p] = jc.sum_best[p]; }
+  t_stats.passes_run = jc.passes_run; t_stats.n_targets = n; t_stats.n_corpus = (unsigned)cpk.size();
+  t_stats.ms_prep = (float)(t1 - t0); t_stats.ms_h2d = (float)(t2 - t1); t_stats.ms_kernels = jc.ms_passes;
+  t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
+  (void)t2;
+  return 0;  // success, also when cancelled (lib/engine.c:689)
+}
+
+// ------------------------------------------------------------------------------- simple API (one image)
+namespace {
+// lib/adaptSimple.h:47-96,260-358: unpadded internal pixmaps [mask][channels], corpus mask inverted or explicit
+int simple_api(ImageBuffer *img, ImageBuffer *mask, ImageBuffer *mask2, TImageFormat fmt, TImageSynthParameters *prm,
+               void (*cb)(int, void *), void *ctx, int *cancel) {
+  if (img->width != mask->width || img->height != mask->height) return IMAGE_SYNTH_ERROR_IMAGE_MASK_MISMATCH;
+  static TImageSynthParameters defaults;  // function-static like lib/imageSynth.c:82-86
+  if (!prm) { setDefaultParams(&defaults); prm = &defaults; }
+  TFormatIndices fi;
+  if (int e = prepareImageFormatIndicesFromFormatType(&fi, fmt)) return e;
+  const unsigned nc = countPixelelsPerPixelForFormat(fmt), depth = nc + 1, w = img->width, h = img->height;
+  std::vector<uint8_t> t((size_t)w * h * depth), c((size_t)w * h * depth);
+  for (unsigned y = 0; y < h; y++) {
+    const uint8_t *srow = img->data + (size_t)y * img->rowBytes, *mrow = mask->data + (size_t)y * mask->rowBytes;
+    const uint8_t *m2row = mask2 ? mask2->data + (size_t)y * mask2->rowBytes : nullptr;
+    for (unsigned x = 0; x < w; x++) {
+      const size_t o = ((size_t)y * w + x) * depth;
+      t[o] = mrow[x];
+      c[o] = m2row ? m2row[x] : (uint8_t)~mrow[x];
+      for (unsigned k = 0; k < nc; k++) t[o + 1 + k] = c[o + 1 + k] = srow[(size_t)x * nc + k];
+    }
+  }
+  GArray ta{reinterpret_cast<char *>(t.data()), w * h}, ca{reinterpret_cast<char *>(c.data()), w * h};
+  Map tm{w, h, depth, &ta}, cm{w, h, depth, &ca};
+  const int err = engine(*prm, &fi, &tm, &cm, cb, ctx, cancel);
+  if (!err && !*cancel) {  // lib/imageSynth.c:108-124: all channels (alpha unchanged) of all pixels go back
+    for (unsigned y = 0; y < h; y++) {
+      uint8_t *drow = img->data + (size_t)y * img->rowBytes;
+      for (unsigned x = 0; x < w; x++)
+        for (unsigned k = 0; k < nc; k++) drow[(size_t)x * nc + k] = t[((size_t)y * w + x) * depth + 1 + k];
+    }
+  }
+  return err;
+}
+}  // namespace
+
+extern "C" int imageSynth(ImageBuffer *img, ImageBuffer *mask, TImageFormat fmt, TImageSynthParameters *prm,
+                          void (*cb)(int, void *), void *ctx, int *cancel) {
+  return simple_api(img, mask, nullptr, fmt, prm, cb, ctx, cancel);
+}
+extern "C" int imageSynth2(ImageBuffer *img, ImageBuffer *mask, ImageBuffer *mask2, TImageFormat fmt,
+                           TImageSynthParameters *prm, void (*cb)(int, void *), void *ctx, int *cancel) {
+  return simple_api(img, mask, mask2, fmt, prm, cb, ctx, cancel);
+}
+
+// ------------------------------------------------------------------- Map helpers (lib/mapOps.h:38-168)
+namespace {
+struct ArrayBox { GArray head; };  // GArray head followed by nothing: data owned separately
+void alloc_map(Map *m, unsigned w, unsigned h, unsigned depth, unsigned elt) {
+  m->width = w; m->height = h; m->depth = depth;
+  ArrayBox *b = static_cast<ArrayBox *>(std::calloc(1, sizeof(ArrayBox)));
+  b->head.data = static_cast<char *>(std::calloc((size_t)w * h, elt));
+  b->head.len = 0;  // the reference never appends to map arrays either (g_array_sized_new reserves only)
+  m->data = &b->head;
+}
+}  // namespace
+extern "C" void free_map(Map *m) {
+  if (!m || !m->data) return;
+  std::free(m->data->data);
+  std::free(m->data);
+  m->data = nullptr;
+}
+extern "C" void new_pixmap(Map *m, unsigned w, unsigned h, unsigned depth) { alloc_map(m, w, h, depth, depth); }
+extern "C" void new_bytemap(Map *m, unsigned w, unsigned h) { alloc_map(m, w, h, 1, 1); }
+extern "C" void new_intmap(Map *m, unsigned w, unsigned h) { alloc_map(m, w, h, sizeof(unsigned), sizeof(unsigned)); }
+extern "C" void new_coordmap(Map *m, unsigned w, unsigned h) { alloc_map(m, w, h, sizeof(Coordinates), sizeof(Coordinates)); }
+extern "C" void set_bytemap(Map *m, unsigned char v) { std::memset(m->data->data, v, (size_t)m->width * m->height); }
+extern "C" void invert_bytemap(Map *m) {
+  unsigned char *p = reinterpret_cast<unsigned char *>(m->data->data);
+  for (size_t i = 0, n = (size_t)m->width * m->height; i < n; i++) p[i] = (unsigned char)~p[i];
+}
+extern "C" void interleave_mask(Map *pixmap, Map *mask) {
+  unsigned char *d = reinterpret_cast<unsigned char *>(pixmap->data->data);
+  const unsigned char *s = reinterpret_cast<const unsigned char *>(mask->data->data);
+  for (size_t i = 0, n = (size_t)pixmap->width * pixmap->height; i < n; i++) d[i * pixmap->depth] = s[i * mask->depth];
+}
+
+// Visit order and final best corpus point of every target of the last engine() call on this thread
+// (packed x | y << 16; 0xFFFFFFFF = none).  Returns the number of targets.
+extern "C" uint32_t rs_get_last_result(uint32_t *targets_out, uint32_t *sources_out, uint32_t cap) {
+  const uint32_t n = (uint32_t)t_last_sources.size();
+  for (uint32_t i = 0; i < n && i < cap; i++) {
+    if (targets_out) targets_out[i] = t_last_targets[i];
+    if (sources_out) sources_out[i] = t_last_sources[i];
+  }
+  return n;
+}
+
+// ------------------------------------------------ host-prep pieces exported for parity tests (include/rs_host.h)
+extern "C" void rs_host_metric_tables(double sensitivity, double map_weight, uint16_t *color512, uint32_t *map512) {
+  rs::build_metric_tables(sensitivity, map_weight, color512, map512);
+}
+extern "C" uint32_t rs_host_sorted_offsets(int tw, int th, int cw, int ch, int32_t *xy, uint32_t cap) {
+  std::vector<uint32_t> o;
+  rs::build_sorted_offsets(tw, th, cw, ch, o);
+  const uint32_t n = (uint32_t)o.size() < cap ? (uint32_t)o.size() : cap;
+  for (uint32_t i = 0; i < n; i++) { xy[2 * i] = (int16_t)(o[i] & 0xFFFFu); xy[2 * i + 1] = ((int32_t)o[i]) >> 16; }
+  return (uint32_t)o.size();
+}
+extern "C" int rs_host_order_targets(int mode, int32_t *xy, uint32_t n, uint32_t seed) {
+  std::vector<rs::Point> p(n);
+  for (uint32_t i = 0; i < n; i++) p[i] = rs::Point{xy[2 * i], xy[2 * i + 1]};
+  rs::GRandMT prng(seed);
+  const int e = rs::order_target_points(mode, p, prng);
+  for (uint32_t i = 0; i < n; i++) { xy[2 * i] = p[i].x; xy[2 * i + 1] = p[i].y; }
+  return e;
+}
+extern "C" uint32_t rs_host_pass_schedule(uint32_t n, uint32_t *ends6) { return rs::pass_schedule(n, ends6); }

@@ -1,0 +1,43 @@
+// Host-side preparation of one synthesis job: everything lib/engine.c:539-655 does before it calls
+// refiner(), restated over flat vectors.  The outputs are the kernel's schedule (visit order), its
+// neighbour-offset table and its two metric tables, so they must equal the reference's arrays exactly;
+// tests/test_host_prep.py compares them with the oracle.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "../../include/resynthesizer.h"
+
+namespace rs {
+
+struct Point { int x, y; };
+
+// GLib GRand (MT19937) as the reference's product build draws it (lib/engine.c:643, lib/orderTarget.h:44,76).
+class GRandMT {
+ public:
+  explicit GRandMT(uint32_t seed);
+  uint32_t next32();
+  uint32_t int_range(uint32_t n);  // g_rand_int_range(0, n)
+ private:
+  uint32_t mt_[624];
+  int mti_;
+};
+
+// lib/matchWeighting.h:142-204.  Tables over the signed difference, index 256+d, like the reference.
+void build_metric_tables(double sensitivity, double map_weight, uint16_t color512[512], uint32_t map512[512]);
+
+// lib/engine.c:465-497 with glibc's merge-sort tie order (ascending x^2+y^2, ties in reverse row-major order).
+// Packed int16 pairs (x | y << 16).
+void build_sorted_offsets(int target_w, int target_h, int corpus_w, int corpus_h, std::vector<uint32_t> &out);
+
+// lib/engine.c:338-431.  Points in row-major scan order.
+void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<Point> &out);
+void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<Point> &out);
+
+// lib/orderTarget.h:268-343 (+ brushfire.h, engineTypes.h).  Returns 0 or IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE.
+int order_target_points(int match_context_type, std::vector<Point> &pts, GRandMT &prng);
+
+// lib/passes.h:67-93.  Returns the estimated total visit count.
+uint32_t pass_schedule(uint32_t n_targets, uint32_t ends[6]);
+
+}  // namespace rs
