@@ -62,7 +62,8 @@ int rs_cuda_device_count(void);
 int rs_job_create(const RsJobDesc *desc, RsJob **out);
 /* Host -> device.  target_raw/corpus_raw: tw*th*bpp and cw*ch*bpp bytes, pixel = [mask][colours][alpha?][maps].
  * targets: n points packed x | y<<16 in visit order.  corpus_points: C points packed likewise.
- * offsets: n_offsets neighbour offsets packed (int16 x | int16 y << 16), ascending distance, entry 0 = (0,0).
+ * offsets: n_offsets neighbour offsets packed (int16 x | int16 y << 16), ascending distance, entry 0 = (0,0);
+ *          NULL = build the reference's full table for these image sizes on the device (cached per workspace).
  * color_lut[256], map_lut[256]: metric by absolute difference; map_lut_max = mapsMetric[0]. */
 int rs_job_upload(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_raw,
                   const uint32_t *targets, uint32_t n_targets,
@@ -76,6 +77,10 @@ int rs_job_run(RsJob *job, RsTickFn tick, void *tick_ctx);
 int rs_job_download(RsJob *job, uint32_t *colours_out, uint32_t *sources_out);
 int rs_job_counters(RsJob *job, RsJobCounters *out);
 void rs_job_destroy(RsJob *job);
+/* Copies the job's neighbour-offset table back (parity tests of the device-side build). */
+int rs_job_read_offsets(RsJob *job, uint32_t *out, uint32_t cap);
+/* Frees the pooled workspaces (device buffers, pinned staging, streams) that jobs leave behind for reuse. */
+void rs_cuda_release_cached(void);
 
 /* computeBestFit over explicit inputs, for bit-exact kernel tests (lib/synthesize.h:266-400).
  * corpus_raw: cw*ch*bpp bytes.  For visit v in [0,n_visits): patch entries [nb_begin[v], nb_begin[v+1]) of

@@ -159,3 +159,38 @@ def last_result():
     sxy = np.stack([s & 0xFFFF, s >> 16], axis=1).astype(np.int32)
     sxy[s == 0xFFFFFFFF] = -1
     return txy, sxy
+
+
+def device_sorted_offsets(tw, th, cw, ch):
+    """The neighbour-offset table exactly as the CUDA layer builds it on the device ((n,2) int32), for tests."""
+    L = lib()
+    d = RsJobDesc()
+    d.tw, d.th, d.cw, d.ch, d.bpp, d.n_color, d.n_map, d.map_bip, d.alpha_bip = tw, th, cw, ch, 4, 3, 0, 4, -1
+    d.patch_size, d.max_probes, d.n_passes = 4, 1, 1
+    d.pass_end[0] = 1
+    d.terminate_fraction = 0.1
+    job = C.c_void_p()
+    L.rs_job_create.argtypes = [C.POINTER(RsJobDesc), C.POINTER(C.c_void_p)]
+    L.rs_job_upload.argtypes = [C.c_void_p] + [C.c_void_p] * 3 + [C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                                  C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.rs_job_read_offsets.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.rs_job_destroy.argtypes = [C.c_void_p]
+    if L.rs_job_create(C.byref(d), C.byref(job)):
+        raise ResynthError(L.rs_cuda_last_error().decode())
+    try:
+        t = np.zeros((th, tw, 4), np.uint8); t[0, 0, 0] = 255
+        c = np.zeros((ch, cw, 4), np.uint8); c[:, :, 0] = 255
+        tg = np.zeros(1, np.uint32); cp = np.zeros(1, np.uint32); lut = np.zeros(256, np.uint32)
+        if L.rs_job_upload(job, t.ctypes.data, c.ctypes.data, tg.ctypes.data, 1, cp.ctypes.data, 1, None, 0,
+                           lut.ctypes.data, lut.ctypes.data, 0):
+            raise ResynthError(L.rs_cuda_last_error().decode())
+        w, h = min(tw, cw), min(th, ch)
+        n = (2 * w - 1) * (2 * h - 1)
+        out = np.zeros(n, np.uint32)
+        if L.rs_job_read_offsets(job, out.ctypes.data, n):
+            raise ResynthError(L.rs_cuda_last_error().decode())
+    finally:
+        L.rs_job_destroy(job)
+    x = (out & 0xFFFF).astype(np.int16).astype(np.int32)
+    y = (out >> 16).astype(np.int16).astype(np.int32)
+    return np.stack([x, y], axis=1)

@@ -140,8 +140,6 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   rs::collect_corpus_points(cpix, cw, ch, bpp, *fi, corpus);
   if (corpus.empty()) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;   // lib/engine.c:620-627
 
-  std::vector<uint32_t> offsets;
-  rs::build_sorted_offsets(tw, th, cw, ch, offsets);
   uint16_t c512[512];
   uint32_t m512[512];
   rs::build_metric_tables(prm.sensitivityToOutliers, prm.mapWeight, c512, m512);
@@ -149,8 +147,8 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   const int oerr = rs::order_target_points(prm.matchContextType, targets, prng);
   if (oerr) return oerr;  // lib/engine.c:645-647
 
-  if (tw > 65535 || th > 65535 || cw > 65535 || ch > 65535) {
-    t_err = "image dimensions above 65535 are not supported by the packed device layout";
+  if (tw > 32767 || th > 32767 || cw > 32767 || ch > 32767) {
+    t_err = "image dimensions above 32767 are not supported by the packed device layout";
     return RS_ERROR_CUDA;
   }
   if (int e = ensure_device()) return e;
@@ -181,8 +179,8 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
 
   RsJob *job = nullptr;
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
-  int rc = rs_job_upload(job, tpix, cpix, tpk.data(), n, cpk.data(), (uint32_t)cpk.size(), offsets.data(),
-                         (uint32_t)offsets.size(), c256, m256, m512[0]);
+  int rc = rs_job_upload(job, tpix, cpix, tpk.data(), n, cpk.data(), (uint32_t)cpk.size(), nullptr, 0,
+                         c256, m256, m512[0]);  // offsets table: built and cached on the device
   const double t2 = now_ms();
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
   if (!rc) rc = rs_job_run(job, on_tick, &ts);

@@ -48,6 +48,8 @@ struct RsDev {              // kernel argument (by value)
   const uint32_t *lut_rep;  // [2][256][32] colour then map metric, replicated per lane (bank-conflict free)
   const uint32_t *proberA;  // snapshot at pass start
   uint32_t *proberB;        // being built by this pass
+  const uint2 *nb_lists;    // pass-0 patches gathered up front by k_gather_pass0: [nT][kmax-1]
+  const uint8_t *nb_counts; // [nT] patch size of each pass-0 visit
   RsCtrl *ctrl;
   volatile unsigned int *host_ticks;  // mapped pinned: [6] highest tick index started per pass (+1)
   const volatile int *host_cancel;    // mapped pinned

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/rs_cuda.h"
 #include "rs_device.cuh"
 
@@ -116,6 +118,64 @@ __global__ void k_extract(const unsigned long long *__restrict__ W, const uint32
   sources[i] = (uint32_t)(w >> 32);
 }
 
+// ------------------------------------------------------------------------------ pass-0 patch precompute
+// In pass 0 a target point may only use context pixels and target points visited BEFORE it (hasValue is set
+// after the visit, lib/synthesize.h:639), so which pixels form the patch of visit v depends on the visit order
+// alone, not on any synthesised colour.  All pass-0 patches are therefore gathered up front by a kernel with no
+// dependencies at all; the (long, deep-hole) offset scans leave the critical path of the ordered pass.
+// Output per visit: count-1 entries {packed offset, pixel index | target flag << 31}.
+#define RS_TARGET_FLAG 0x80000000u
+__global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__restrict__ lists, uint8_t *__restrict__ counts,
+                                                      unsigned int *__restrict__ claim) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t stride = J.kmax - 1u;
+  unsigned long long scans = 0;
+  while (true) {
+    uint32_t v = 0;
+    if (lane == 0) v = atomicAdd(claim, 1u);
+    v = __shfl_sync(RS_FULL, v, 0);
+    if (v >= J.nT) break;
+    const uint32_t tpos = __ldg(J.targets + v);
+    const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
+    uint2 *out = lists + (size_t)v * stride;
+    uint32_t count = 1;
+    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 128) {
+      uint32_t o[4], q[4], m[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t j = base + 32u * u + lane;
+        ok[u] = false; o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
+        if (j < J.nOff) {
+          o[u] = __ldg(J.offsets + j);
+          int x = px + rs_off_x(o[u]), y = py + rs_off_y(o[u]);
+          bool in = true;
+          if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+          else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+          if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+          else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+          if (in) {
+            q[u] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+            m[u] = __ldg(J.meta + q[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        ok[u] = (m[u] == RS_CTX_VALUED) || (m[u] < v);
+        const unsigned b = __ballot_sync(RS_FULL, ok[u]);
+        const uint32_t slot = count + __popc(b & lt);
+        if (ok[u] && slot < J.kmax) out[slot - 1u] = make_uint2(o[u], q[u] | (m[u] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+        count += __popc(b);
+      }
+      scans += 128;
+    }
+    if (lane == 0) counts[v] = (uint8_t)min(count, J.kmax);
+  }
+  if (lane == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
+}
+
 // --------------------------------------------------------------------------------------- the pass kernel
 #define RS_WARPS_PER_CTA 16
 #define RS_THREADS (RS_WARPS_PER_CTA * 32)
@@ -190,34 +250,46 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
       S.aux[0] = v;
     }
     uint32_t count = 1;
-    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
-      const uint32_t j = base + lane;
-      bool ok = false;
-      uint32_t o = 0, q = 0, m = 0;
-      if (j < J.nOff) {
-        o = __ldg(J.offsets + j);
-        int x = px + rs_off_x(o), y = py + rs_off_y(o);
-        bool in = true;  // wrap when tiling, else clip (lib/synthesize.h:81-113); |offset| < image size
-        if (x < 0) { if (J.htile) x += J.tw; else in = false; }
-        else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
-        if (y < 0) { if (J.vtile) y += J.th; else in = false; }
-        else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
-        if (in) {
-          q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
-          m = __ldg(J.meta + q);
-          // valued: usable context, or a target point already synthesised (in pass 0: visited before me)
-          ok = (pass == 0u) ? (m == RS_CTX_VALUED || m < v) : (m != RS_NEVER);
+    if (pass == 0u && J.nb_lists != nullptr) {
+      // precomputed by k_gather_pass0; aux := 0 (< v+1) marks "target visited before me", else context
+      count = J.nb_counts[v];
+      const uint2 *lst = J.nb_lists + (size_t)v * (J.kmax - 1u);
+      for (uint32_t k = 1u + lane; k < count; k += 32) {
+        const uint2 e = __ldg(lst + (k - 1u));
+        S.off[k] = e.x;
+        S.q[k] = e.y & ~RS_TARGET_FLAG;
+        S.aux[k] = (e.y & RS_TARGET_FLAG) ? 0u : RS_CTX_VALUED;
+      }
+    } else {
+      for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
+        const uint32_t j = base + lane;
+        bool ok = false;
+        uint32_t o = 0, q = 0, m = 0;
+        if (j < J.nOff) {
+          o = __ldg(J.offsets + j);
+          int x = px + rs_off_x(o), y = py + rs_off_y(o);
+          bool in = true;  // wrap when tiling, else clip (lib/synthesize.h:81-113); |offset| < image size
+          if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+          else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+          if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+          else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+          if (in) {
+            q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+            m = __ldg(J.meta + q);
+            // valued: usable context, or a target point already synthesised (in pass 0: visited before me)
+            ok = (pass == 0u) ? (m == RS_CTX_VALUED || m < v) : (m != RS_NEVER);
+          }
         }
+        const unsigned b = __ballot_sync(RS_FULL, ok);
+        const uint32_t slot = count + __popc(b & lt);
+        if (ok && slot < J.kmax) {
+          S.off[slot] = o;
+          S.q[slot] = q;
+          S.aux[slot] = m;
+        }
+        count += __popc(b);
+        st_scans += (lane == 0) ? min(32u, J.nOff - base) : 0u;
       }
-      const unsigned b = __ballot_sync(RS_FULL, ok);
-      const uint32_t slot = count + __popc(b & lt);
-      if (ok && slot < J.kmax) {
-        S.off[slot] = o;
-        S.q[slot] = q;
-        S.aux[slot] = m;
-      }
-      count += __popc(b);
-      st_scans += (lane == 0) ? min(32u, J.nOff - base) : 0u;
     }
     const uint32_t K = min(count, J.kmax);
     __syncwarp();
@@ -417,101 +489,191 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   }
 }
 
-// ------------------------------------------------------------------------------------------------ the job
-struct RsJob {
-  RsJobDesc d;
+// ------------------------------------------------------------------------------------------- workspaces
+// Device buffers, pinned staging, stream and events are expensive to create (cudaFree synchronises the
+// device); they live in pooled workspaces that outlive jobs and only ever grow.  A workspace also keeps the
+// sorted neighbour-offset table of the last image size it served, which batches of equal-sized jobs reuse.
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;
-  bool maps = false;
-  // device buffers
-  uint8_t *d_target_raw = nullptr, *d_corpus_raw = nullptr;
-  uint32_t *d_corpus4 = nullptr;
-  uint2 *d_corpus8 = nullptr;
-  unsigned long long *d_W = nullptr;
-  uint32_t *d_meta = nullptr, *d_tmaps = nullptr, *d_targets = nullptr, *d_cpts = nullptr, *d_offsets = nullptr;
-  uint32_t *d_lut256 = nullptr, *d_lut_rep = nullptr, *d_prober[2] = {nullptr, nullptr};
-  uint32_t *d_colours = nullptr, *d_sources = nullptr;
-  RsCtrl *d_ctrl = nullptr;
-  // mapped pinned host words
-  unsigned int *h_ticks = nullptr;  // [6]
-  int *h_cancel = nullptr;
-  RsCtrl *h_ctrl = nullptr;         // pinned copy of the control block, read back after the run
-  uint32_t nT = 0, nC = 0, nOff = 0, penalty = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evDone = nullptr;
-  float ms_passes = 0.f;
-  int grid = 0;
-  size_t smem = 0;
+  DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, colours,
+      sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts;
+  void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
+  size_t pin_cap = 0;
+  unsigned int *h_ticks = nullptr;
+  int *h_cancel = nullptr;
+  RsCtrl *h_ctrl = nullptr;
+  int off_w = 0, off_h = 0;  // dimensions the resident offsets table was built for
+  uint32_t off_n = 0;
+  int grid[2] = {0, 0};      // persistent grid of k_synth_pass<false/true>
 };
+static std::mutex g_pool_mutex;
+static std::vector<Workspace *> g_pool;
+
+static int ws_ensure(DevBuf &b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+  const size_t want = bytes + bytes / 8 + 256;
+  RS_CHECK(cudaMalloc(&b.p, want));
+  b.cap = want;
+  return 0;
+}
+static int ws_ensure_pinned(Workspace *w, size_t bytes) {
+  if (bytes <= w->pin_cap) return 0;
+  if (w->pin) cudaFreeHost(w->pin);
+  w->pin = nullptr;
+  w->pin_cap = 0;
+  const size_t want = bytes + bytes / 8 + 4096;
+  RS_CHECK(cudaHostAlloc(&w->pin, want, cudaHostAllocDefault));
+  w->pin_cap = want;
+  return 0;
+}
+static void ws_free(Workspace *w) {
+  cudaSetDevice(w->device);
+  DevBuf *all[] = {&w->raw_t, &w->raw_c, &w->corpus, &w->W, &w->meta, &w->tmaps, &w->targets, &w->cpts, &w->offsets,
+                   &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->colours, &w->sources, &w->ctrl,
+                   &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts};
+  for (DevBuf *b : all) if (b->p) cudaFree(b->p);
+  if (w->pin) cudaFreeHost(w->pin);
+  if (w->h_ticks) cudaFreeHost(w->h_ticks);
+  if (w->h_cancel) cudaFreeHost(w->h_cancel);
+  if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
+  if (w->ev0) cudaEventDestroy(w->ev0);
+  if (w->ev1) cudaEventDestroy(w->ev1);
+  if (w->evDone) cudaEventDestroy(w->evDone);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  delete w;
+}
 
 static size_t pass_smem(bool maps) {
   return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + sizeof(WarpScratch) * RS_WARPS_PER_CTA + 16;
 }
-
 template <bool MAPS>
-static int configure_pass_kernel(RsJob *j) {
-  size_t smem = pass_smem(MAPS);
+static int configure_pass_kernel(Workspace *w) {
+  const size_t smem = pass_smem(MAPS);
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0, sms = 0;
   RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS>, RS_THREADS, smem));
-  RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, j->device));
+  RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
   if (per_sm < 1) { g_err = "k_synth_pass does not fit on an SM"; return 100; }
-  j->grid = per_sm * sms;
-  j->smem = smem;
+  w->grid[MAPS ? 1 : 0] = per_sm * sms;
   return 0;
 }
 
+static int ws_acquire(Workspace **out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { g_err = "no CUDA device"; return 100; }
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (size_t i = 0; i < g_pool.size(); i++)
+      if (g_pool[i]->device == dev) {
+        *out = g_pool[i];
+        g_pool.erase(g_pool.begin() + i);
+        return 0;
+      }
+  }
+  Workspace *w = new Workspace();
+  w->device = dev;
+  int rc = configure_pass_kernel<false>(w);
+  if (!rc) rc = configure_pass_kernel<true>(w);
+  if (rc) { delete w; return rc; }
+#define WCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ws_free(w); return 100; } } while (0)
+  WCHK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  WCHK(cudaEventCreate(&w->ev0));
+  WCHK(cudaEventCreate(&w->ev1));
+  WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming));
+  WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
+  WCHK(cudaHostAlloc(&w->h_cancel, sizeof(int), cudaHostAllocMapped));
+  WCHK(cudaHostAlloc(&w->h_ctrl, sizeof(RsCtrl), cudaHostAllocDefault));
+#undef WCHK
+  *out = w;
+  return 0;
+}
+static void ws_release(Workspace *w) {
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  g_pool.push_back(w);
+}
+extern "C" void rs_cuda_release_cached(void) {
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  for (Workspace *w : g_pool) ws_free(w);
+  g_pool.clear();
+}
+
+// ---- sorted neighbour offsets on the device (replaces prepareSortedOffsets, lib/engine.c:465-497) ----
+// All (x,y), |x|<w, |y|<h, ascending x^2+y^2, equal distances in reverse row-major order (what glibc's merge
+// sort makes of the reference's never-equal comparator).  Generated in reverse row-major order and sorted
+// by distance with a stable radix sort.
+__global__ void k_gen_offsets(int w, int h, uint32_t n, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t row = i / (uint32_t)(2 * w - 1), col = i % (uint32_t)(2 * w - 1);
+  const int y = (h - 1) - (int)row, x = (w - 1) - (int)col;
+  keys[i] = (uint32_t)(x * x + y * y);
+  vals[i] = ((uint32_t)x & 0xFFFFu) | ((uint32_t)y << 16);
+}
+
+// ------------------------------------------------------------------------------------------------ the job
+struct RsJob {
+  RsJobDesc d;
+  Workspace *ws = nullptr;
+  bool maps = false;
+  uint32_t nT = 0, nC = 0, nOff = 0, penalty = 0;
+  float ms_passes = 0.f;
+};
+
 extern "C" void rs_job_destroy(RsJob *j) {
   if (!j) return;
-  cudaSetDevice(j->device);
-  if (j->stream) cudaStreamSynchronize(j->stream);
-  cudaFree(j->d_target_raw); cudaFree(j->d_corpus_raw); cudaFree(j->d_corpus4); cudaFree(j->d_corpus8);
-  cudaFree(j->d_W); cudaFree(j->d_meta); cudaFree(j->d_tmaps); cudaFree(j->d_targets); cudaFree(j->d_cpts);
-  cudaFree(j->d_offsets); cudaFree(j->d_lut256); cudaFree(j->d_lut_rep); cudaFree(j->d_prober[0]);
-  cudaFree(j->d_prober[1]); cudaFree(j->d_colours); cudaFree(j->d_sources); cudaFree(j->d_ctrl);
-  if (j->h_ticks) cudaFreeHost(j->h_ticks);
-  if (j->h_cancel) cudaFreeHost(j->h_cancel);
-  if (j->h_ctrl) cudaFreeHost(j->h_ctrl);
-  if (j->ev0) cudaEventDestroy(j->ev0);
-  if (j->ev1) cudaEventDestroy(j->ev1);
-  if (j->evDone) cudaEventDestroy(j->evDone);
-  if (j->stream) cudaStreamDestroy(j->stream);
+  if (j->ws) {
+    cudaSetDevice(j->ws->device);
+    cudaStreamSynchronize(j->ws->stream);
+    ws_release(j->ws);
+  }
   delete j;
 }
 
 extern "C" int rs_job_create(const RsJobDesc *desc, RsJob **out) {
   *out = nullptr;
-  if (desc->tw <= 0 || desc->th <= 0 || desc->cw <= 0 || desc->ch <= 0 || desc->tw > 65535 || desc->th > 65535 ||
-      desc->cw > 65535 || desc->ch > 65535 || desc->bpp < 2 || desc->bpp > 8 || desc->n_color < 1 || desc->n_color > 3 ||
+  if (desc->tw <= 0 || desc->th <= 0 || desc->cw <= 0 || desc->ch <= 0 || desc->tw > 32767 || desc->th > 32767 ||
+      desc->cw > 32767 || desc->ch > 32767 || desc->bpp < 2 || desc->bpp > 8 || desc->n_color < 1 || desc->n_color > 3 ||
       desc->n_map < 0 || desc->n_map > 3 || desc->n_passes < 1 || desc->n_passes > 6) {
     g_err = "rs_job_create: descriptor out of range";
     return 100;
   }
+  Workspace *w = nullptr;
+  if (int rc = ws_acquire(&w)) return rc;
   RsJob *j = new RsJob();
   j->d = *desc;
   j->maps = desc->n_map > 0;
-  if (cudaGetDevice(&j->device) != cudaSuccess) { g_err = "no CUDA device"; delete j; return 100; }
-  int rc = j->maps ? configure_pass_kernel<true>(j) : configure_pass_kernel<false>(j);
-  if (rc) { delete j; return rc; }
-#define JCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); rs_job_destroy(j); return 100; } } while (0)
-  JCHK(cudaStreamCreateWithFlags(&j->stream, cudaStreamNonBlocking));
-  JCHK(cudaEventCreate(&j->ev0)); JCHK(cudaEventCreate(&j->ev1));
-  JCHK(cudaEventCreateWithFlags(&j->evDone, cudaEventDisableTiming));
-  const size_t tn = (size_t)desc->tw * desc->th, cn = (size_t)desc->cw * desc->ch;
-  JCHK(cudaMalloc(&j->d_target_raw, tn * desc->bpp));
-  JCHK(cudaMalloc(&j->d_corpus_raw, cn * desc->bpp));
-  if (j->maps) JCHK(cudaMalloc(&j->d_corpus8, cn * sizeof(uint2))); else JCHK(cudaMalloc(&j->d_corpus4, cn * 4));
-  JCHK(cudaMalloc(&j->d_W, tn * 16));
-  JCHK(cudaMalloc(&j->d_meta, tn * 4));
-  if (j->maps) JCHK(cudaMalloc(&j->d_tmaps, tn * 4));
-  JCHK(cudaMalloc(&j->d_lut256, 512 * 4));
-  JCHK(cudaMalloc(&j->d_lut_rep, 2 * RS_LUT_WORDS * 4));
-  JCHK(cudaMalloc(&j->d_prober[0], cn * 4)); JCHK(cudaMalloc(&j->d_prober[1], cn * 4));
-  JCHK(cudaMalloc(&j->d_ctrl, sizeof(RsCtrl)));
-  JCHK(cudaHostAlloc(&j->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
-  JCHK(cudaHostAlloc(&j->h_cancel, sizeof(int), cudaHostAllocMapped));
-  JCHK(cudaHostAlloc(&j->h_ctrl, sizeof(RsCtrl), cudaHostAllocDefault));
-#undef JCHK
+  j->ws = w;
   *out = j;
+  return 0;
+}
+
+static int build_offsets_on_device(Workspace *w, int ow, int oh, uint32_t n) {
+  cudaStream_t s = w->stream;
+  if (int rc = ws_ensure(w->sort_keys_in, (size_t)n * 4)) return rc;
+  if (int rc = ws_ensure(w->sort_keys_out, (size_t)n * 4)) return rc;
+  if (int rc = ws_ensure(w->sort_vals_in, (size_t)n * 4)) return rc;
+  if (int rc = ws_ensure(w->offsets, (size_t)n * 4)) return rc;
+  k_gen_offsets<<<(n + 255) / 256, 256, 0, s>>>(ow, oh, n, (uint32_t *)w->sort_keys_in.p, (uint32_t *)w->sort_vals_in.p);
+  const uint32_t maxd = (uint32_t)((ow - 1) * (ow - 1) + (oh - 1) * (oh - 1));
+  int bits = 1;
+  while (bits < 32 && (maxd >> bits)) bits++;
+  size_t tmp = 0;
+  RS_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const uint32_t *)w->sort_keys_in.p, (uint32_t *)w->sort_keys_out.p,
+                                           (const uint32_t *)w->sort_vals_in.p, (uint32_t *)w->offsets.p, (int)n, 0, bits, s));
+  if (int rc = ws_ensure(w->sort_tmp, tmp)) return rc;
+  RS_CHECK(cub::DeviceRadixSort::SortPairs(w->sort_tmp.p, tmp, (const uint32_t *)w->sort_keys_in.p,
+                                           (uint32_t *)w->sort_keys_out.p, (const uint32_t *)w->sort_vals_in.p,
+                                           (uint32_t *)w->offsets.p, (int)n, 0, bits, s));
+  w->off_w = ow; w->off_h = oh; w->off_n = n;
   return 0;
 }
 
@@ -519,44 +681,83 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
                              uint32_t n_targets, const uint32_t *corpus_points, uint32_t n_corpus,
                              const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
                              const uint32_t *map_lut256, uint32_t map_lut_max) {
-  RS_CHECK(cudaSetDevice(j->device));
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
   const RsJobDesc &d = j->d;
-  if (n_targets == 0 || n_corpus == 0 || n_offsets == 0 || n_targets >= RS_IDX_MASK) {
+  if (n_targets == 0 || n_corpus == 0 || n_targets >= RS_IDX_MASK) {
     g_err = "rs_job_upload: empty or oversized point list";
     return 100;
   }
   const size_t tn = (size_t)d.tw * d.th, cn = (size_t)d.cw * d.ch;
-  cudaStream_t s = j->stream;
-  j->nT = n_targets; j->nC = n_corpus; j->nOff = n_offsets;
+  cudaStream_t s = w->stream;
+  j->nT = n_targets; j->nC = n_corpus;
   j->penalty = 65535u * (uint32_t)d.n_color + map_lut_max * (uint32_t)d.n_map;
-  cudaFree(j->d_targets); cudaFree(j->d_cpts); cudaFree(j->d_offsets); cudaFree(j->d_colours); cudaFree(j->d_sources);
-  j->d_targets = j->d_cpts = j->d_offsets = j->d_colours = j->d_sources = nullptr;
-  RS_CHECK(cudaMalloc(&j->d_targets, (size_t)n_targets * 4));
-  RS_CHECK(cudaMalloc(&j->d_cpts, (size_t)n_corpus * 4));
-  RS_CHECK(cudaMalloc(&j->d_offsets, (size_t)n_offsets * 4));
-  RS_CHECK(cudaMalloc(&j->d_colours, (size_t)n_targets * 4));
-  RS_CHECK(cudaMalloc(&j->d_sources, (size_t)n_targets * 4));
-  RS_CHECK(cudaMemcpyAsync(j->d_target_raw, target_raw, tn * d.bpp, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(j->d_corpus_raw, corpus_raw, cn * d.bpp, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(j->d_targets, targets, (size_t)n_targets * 4, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(j->d_cpts, corpus_points, (size_t)n_corpus * 4, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(j->d_offsets, offsets, (size_t)n_offsets * 4, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(j->d_lut256, color_lut256, 256 * 4, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(j->d_lut256 + 256, map_lut256, 256 * 4, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemsetAsync(j->d_ctrl, 0, sizeof(RsCtrl), s));
-  RS_CHECK(cudaMemsetAsync(j->d_prober[0], 0, cn * 4, s));
-  RS_CHECK(cudaMemsetAsync(j->d_prober[1], 0, cn * 4, s));
+  int rc = 0;
+  if ((rc = ws_ensure(w->raw_t, tn * d.bpp)) || (rc = ws_ensure(w->raw_c, cn * d.bpp)) ||
+      (rc = ws_ensure(w->corpus, cn * (j->maps ? 8 : 4))) || (rc = ws_ensure(w->W, tn * 16)) ||
+      (rc = ws_ensure(w->meta, tn * 4)) || (rc = ws_ensure(w->tmaps, j->maps ? tn * 4 : 4)) ||
+      (rc = ws_ensure(w->targets, (size_t)n_targets * 4)) || (rc = ws_ensure(w->cpts, (size_t)n_corpus * 4)) ||
+      (rc = ws_ensure(w->lut256, 512 * 4)) || (rc = ws_ensure(w->lut_rep, 2 * RS_LUT_WORDS * 4)) ||
+      (rc = ws_ensure(w->prober0, cn * 4)) || (rc = ws_ensure(w->prober1, cn * 4)) ||
+      (rc = ws_ensure(w->colours, (size_t)n_targets * 4)) || (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) ||
+      (rc = ws_ensure(w->ctrl, sizeof(RsCtrl) + 64)))
+    return rc;
+  {
+    uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
+    if (kmax > RS_MAX_NB) kmax = RS_MAX_NB;
+    if ((rc = ws_ensure(w->nb_lists, (size_t)n_targets * (kmax - 1) * sizeof(uint2))) || (rc = ws_ensure(w->nb_counts, n_targets))) return rc;
+  }
+  // neighbour offsets: caller-provided table, or built (and kept) on the device
+  const int ow = d.tw < d.cw ? d.tw : d.cw, oh = d.th < d.ch ? d.th : d.ch;
+  const uint32_t full_n = (uint32_t)(2 * ow - 1) * (uint32_t)(2 * oh - 1);
+  // stage all host inputs through pinned memory so the copies are truly asynchronous
+  const size_t sz_t = tn * d.bpp, sz_c = cn * d.bpp, sz_tp = (size_t)n_targets * 4, sz_cp = (size_t)n_corpus * 4,
+               sz_off = offsets ? (size_t)n_offsets * 4 : 0, sz_lut = 512 * 4;
+  auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t o_t = 0, o_c = o_t + up(sz_t), o_tp = o_c + up(sz_c), o_cp = o_tp + up(sz_tp), o_off = o_cp + up(sz_cp),
+               o_lut = o_off + up(sz_off), total = o_lut + up(sz_lut);
+  const size_t need_pin = total > (size_t)n_targets * 8 ? total : (size_t)n_targets * 8;
+  if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
+  uint8_t *pin = (uint8_t *)w->pin;
+  memcpy(pin + o_t, target_raw, sz_t);
+  memcpy(pin + o_c, corpus_raw, sz_c);
+  memcpy(pin + o_tp, targets, sz_tp);
+  memcpy(pin + o_cp, corpus_points, sz_cp);
+  if (offsets) memcpy(pin + o_off, offsets, sz_off);
+  memcpy(pin + o_lut, color_lut256, 256 * 4);
+  memcpy(pin + o_lut + 256 * 4, map_lut256, 256 * 4);
+  RS_CHECK(cudaMemcpyAsync(w->raw_t.p, pin + o_t, sz_t, cudaMemcpyHostToDevice, s));
+  RS_CHECK(cudaMemcpyAsync(w->raw_c.p, pin + o_c, sz_c, cudaMemcpyHostToDevice, s));
+  RS_CHECK(cudaMemcpyAsync(w->targets.p, pin + o_tp, sz_tp, cudaMemcpyHostToDevice, s));
+  RS_CHECK(cudaMemcpyAsync(w->cpts.p, pin + o_cp, sz_cp, cudaMemcpyHostToDevice, s));
+  RS_CHECK(cudaMemcpyAsync(w->lut256.p, pin + o_lut, sz_lut, cudaMemcpyHostToDevice, s));
+  if (offsets) {
+    if ((rc = ws_ensure(w->offsets, sz_off))) return rc;
+    RS_CHECK(cudaMemcpyAsync(w->offsets.p, pin + o_off, sz_off, cudaMemcpyHostToDevice, s));
+    w->off_w = w->off_h = 0; w->off_n = 0;  // not a cached full table
+    j->nOff = n_offsets;
+  } else {
+    if (!(w->off_w == ow && w->off_h == oh && w->off_n == full_n))
+      if ((rc = build_offsets_on_device(w, ow, oh, full_n))) return rc;
+    j->nOff = full_n;
+  }
+  RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl) + 64, s));
+  RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 4, s));
+  RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 4, s));
   const int T = 256;
-  k_canon_corpus<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>(j->d_corpus_raw, (int)cn, d.bpp, d.n_color, d.n_map, d.map_bip,
-                                                          j->d_corpus4, j->d_corpus8);
-  k_init_target<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>(j->d_target_raw, (int)tn, d.bpp, d.n_color, d.n_map, d.map_bip,
-                                                         d.alpha_bip, d.alpha_target, d.use_context, j->d_W, j->d_meta,
-                                                         j->d_tmaps);
-  k_scatter_order<<<(n_targets + T - 1) / T, T, 0, s>>>(j->d_targets, n_targets, d.tw, j->d_meta);
-  k_replicate_lut<<<(RS_LUT_WORDS + T - 1) / T, T, 0, s>>>(j->d_lut256, j->d_lut256 + 256, j->d_lut_rep);
+  k_canon_corpus<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
+                                                          d.map_bip, j->maps ? nullptr : (uint32_t *)w->corpus.p,
+                                                          j->maps ? (uint2 *)w->corpus.p : nullptr);
+  k_init_target<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_t.p, (int)tn, d.bpp, d.n_color, d.n_map,
+                                                         d.map_bip, d.alpha_bip, d.alpha_target, d.use_context,
+                                                         (unsigned long long *)w->W.p, (uint32_t *)w->meta.p,
+                                                         j->maps ? (uint32_t *)w->tmaps.p : nullptr);
+  k_scatter_order<<<(n_targets + T - 1) / T, T, 0, s>>>((const uint32_t *)w->targets.p, n_targets, d.tw, (uint32_t *)w->meta.p);
+  k_replicate_lut<<<(RS_LUT_WORDS + T - 1) / T, T, 0, s>>>((const uint32_t *)w->lut256.p, (const uint32_t *)w->lut256.p + 256,
+                                                         (uint32_t *)w->lut_rep.p);
   RS_CHECK(cudaGetLastError());
-  for (int p = 0; p < 6; p++) j->h_ticks[p] = 0;
-  *j->h_cancel = 0;
+  for (int p = 0; p < 6; p++) w->h_ticks[p] = 0;
+  *w->h_cancel = 0;
   return 0;
 }
 
@@ -564,10 +765,17 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   RsDev D;
   memset(&D, 0, sizeof D);
   const RsJobDesc &d = j->d;
-  D.corpus4 = j->d_corpus4; D.corpus8 = j->d_corpus8; D.W = j->d_W; D.meta = j->d_meta; D.tmaps = j->d_tmaps;
-  D.targets = j->d_targets; D.corpus_pts = j->d_cpts; D.offsets = j->d_offsets; D.lut_rep = j->d_lut_rep;
-  D.proberA = j->d_prober[pass & 1]; D.proberB = j->d_prober[(pass + 1) & 1];
-  D.ctrl = j->d_ctrl; D.host_ticks = j->h_ticks; D.host_cancel = j->h_cancel;
+  const Workspace *w = j->ws;
+  D.corpus4 = j->maps ? nullptr : (const uint32_t *)w->corpus.p;
+  D.corpus8 = j->maps ? (const uint2 *)w->corpus.p : nullptr;
+  D.W = (unsigned long long *)w->W.p; D.meta = (const uint32_t *)w->meta.p;
+  D.tmaps = j->maps ? (const uint32_t *)w->tmaps.p : nullptr;
+  D.targets = (const uint32_t *)w->targets.p; D.corpus_pts = (const uint32_t *)w->cpts.p;
+  D.offsets = (const uint32_t *)w->offsets.p; D.lut_rep = (const uint32_t *)w->lut_rep.p;
+  uint32_t *pr[2] = {(uint32_t *)w->prober0.p, (uint32_t *)w->prober1.p};
+  D.proberA = pr[pass & 1]; D.proberB = pr[(pass + 1) & 1];
+  D.nb_lists = (const uint2 *)w->nb_lists.p; D.nb_counts = (const uint8_t *)w->nb_counts.p;
+  D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
   D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch;
   D.nT = j->nT; D.nC = j->nC; D.nOff = j->nOff;
   uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;  // the size test follows the append (synthesize.h:222-224)
@@ -580,63 +788,79 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
 }
 
 extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
-  RS_CHECK(cudaSetDevice(j->device));
-  cudaStream_t s = j->stream;
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
+  cudaStream_t s = w->stream;
   const size_t cn = (size_t)j->d.cw * j->d.ch;
-  RS_CHECK(cudaEventRecord(j->ev0, s));
+  const int grid = w->grid[j->maps ? 1 : 0];
+  const size_t smem = pass_smem(j->maps);
+  uint32_t *pr[2] = {(uint32_t *)w->prober0.p, (uint32_t *)w->prober1.p};
+  RS_CHECK(cudaEventRecord(w->ev0, s));
+  {  // all pass-0 patches, dependency-free
+    RsDev D0 = make_dev(j, 0);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+    k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p,
+                                          (unsigned int *)((uint8_t *)w->ctrl.p + sizeof(RsCtrl)));
+  }
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     if (p > 0)  // B := A before the pass stamps into B (pass-snapshot semantics of heuristic 2)
-      k_copy_u32<<<1184, 256, 0, s>>>(j->d_prober[p & 1], j->d_prober[(p + 1) & 1], cn, j->d_ctrl);
+      k_copy_u32<<<1184, 256, 0, s>>>(pr[p & 1], pr[(p + 1) & 1], cn, (const RsCtrl *)w->ctrl.p);
     RsDev D = make_dev(j, p);
-    if (j->maps) k_synth_pass<true><<<j->grid, RS_THREADS, j->smem, s>>>(D);
-    else k_synth_pass<false><<<j->grid, RS_THREADS, j->smem, s>>>(D);
+    if (j->maps) k_synth_pass<true><<<grid, RS_THREADS, smem, s>>>(D);
+    else k_synth_pass<false><<<grid, RS_THREADS, smem, s>>>(D);
   }
   RS_CHECK(cudaGetLastError());
-  RS_CHECK(cudaEventRecord(j->ev1, s));
-  k_extract<<<(j->nT + 255) / 256, 256, 0, s>>>(j->d_W, j->d_targets, j->nT, j->d.tw, j->d_colours, j->d_sources);
-  RS_CHECK(cudaMemcpyAsync(j->h_ctrl, j->d_ctrl, sizeof(RsCtrl), cudaMemcpyDeviceToHost, s));
-  RS_CHECK(cudaEventRecord(j->evDone, s));
+  RS_CHECK(cudaEventRecord(w->ev1, s));
+  k_extract<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, (const uint32_t *)w->targets.p, j->nT,
+                                               j->d.tw, (uint32_t *)w->colours.p, (uint32_t *)w->sources.p);
+  // results land in pinned memory behind the same event
+  RS_CHECK(cudaMemcpyAsync(w->pin, w->colours.p, (size_t)j->nT * 4, cudaMemcpyDeviceToHost, s));
+  RS_CHECK(cudaMemcpyAsync((uint8_t *)w->pin + (size_t)j->nT * 4, w->sources.p, (size_t)j->nT * 4, cudaMemcpyDeviceToHost, s));
+  RS_CHECK(cudaMemcpyAsync(w->h_ctrl, w->ctrl.p, sizeof(RsCtrl), cudaMemcpyDeviceToHost, s));
+  RS_CHECK(cudaEventRecord(w->evDone, s));
   // Host side of the progress/cancel contract: replay ticks in order while the device runs.
-  uint32_t emitted[6] = {0, 0, 0, 0, 0, 0};  // number of ticks already forwarded per pass
+  uint32_t emitted[6] = {0, 0, 0, 0, 0, 0};  // ticks already forwarded per pass
   bool cancelled = false;
-  auto drain = [&](bool final_) {
-    for (uint32_t p = 0; p < j->d.n_passes; p++) {
-      const unsigned int seen = ((volatile unsigned int *)j->h_ticks)[p];  // highest started tick index + 1
-      if (seen == 0) { if (!final_) break; else continue; }
-      const uint32_t upto = (seen - 1u) / 4096u + 1u;  // ticks 0..upto-1 have started
-      while (emitted[p] < upto) {
-        const uint32_t idx = emitted[p] * 4096u;
-        emitted[p]++;
-        if (tick && !cancelled && tick(tick_ctx, p, idx)) {
-          cancelled = true;
-          *(volatile int *)j->h_cancel = 1;
-        }
+  auto emit_upto = [&](uint32_t p, uint32_t upto) {
+    while (emitted[p] < upto) {
+      const uint32_t idx = emitted[p] * 4096u;
+      emitted[p]++;
+      if (tick && !cancelled && tick(tick_ctx, p, idx)) {
+        cancelled = true;
+        *(volatile int *)w->h_cancel = 1;
       }
     }
   };
   while (true) {
-    cudaError_t q = cudaEventQuery(j->evDone);
+    cudaError_t q = cudaEventQuery(w->evDone);
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) { g_err = std::string("rs_job_run: ") + cudaGetErrorString(q); return 100; }
-    drain(false);
+    for (uint32_t p = 0; p < j->d.n_passes; p++) {
+      const unsigned int seen = ((volatile unsigned int *)w->h_ticks)[p];  // a started tick index + 1 (not monotone)
+      if (seen == 0) break;
+      emit_upto(p, (seen - 1u) / 4096u + 1u);
+    }
   }
-  drain(true);
   RS_CHECK(cudaStreamSynchronize(s));
-  RS_CHECK(cudaEventElapsedTime(&j->ms_passes, j->ev0, j->ev1));
+  // final, exact replay from the device's own counters: visits [0, pass_visits) of each pass were started
+  for (uint32_t p = 0; p < j->d.n_passes; p++) {
+    const unsigned long long started = w->h_ctrl->pass_visits[p];
+    if (started) emit_upto(p, (uint32_t)((started - 1ull) / 4096ull + 1ull));
+  }
+  RS_CHECK(cudaEventElapsedTime(&j->ms_passes, w->ev0, w->ev1));
   return 0;
 }
 
 extern "C" int rs_job_download(RsJob *j, uint32_t *colours_out, uint32_t *sources_out) {
-  RS_CHECK(cudaSetDevice(j->device));
-  RS_CHECK(cudaMemcpyAsync(colours_out, j->d_colours, (size_t)j->nT * 4, cudaMemcpyDeviceToHost, j->stream));
-  if (sources_out)
-    RS_CHECK(cudaMemcpyAsync(sources_out, j->d_sources, (size_t)j->nT * 4, cudaMemcpyDeviceToHost, j->stream));
-  RS_CHECK(cudaStreamSynchronize(j->stream));
+  const Workspace *w = j->ws;  // rs_job_run left both arrays in pinned memory
+  memcpy(colours_out, w->pin, (size_t)j->nT * 4);
+  if (sources_out) memcpy(sources_out, (const uint8_t *)w->pin + (size_t)j->nT * 4, (size_t)j->nT * 4);
   return 0;
 }
 
 extern "C" int rs_job_counters(RsJob *j, RsJobCounters *out) {
-  const RsCtrl &c = *j->h_ctrl;
+  const RsCtrl &c = *j->ws->h_ctrl;
   memset(out, 0, sizeof *out);
   out->visits = c.visits; out->evals = c.evals; out->evals_issued = c.evals_issued; out->compares = c.compares;
   out->offset_scans = c.offset_scans; out->heur_evals = c.heur_evals; out->heur_skips = c.heur_skips;
@@ -644,6 +868,16 @@ extern "C" int rs_job_counters(RsJob *j, RsJobCounters *out) {
   for (int p = 0; p < 6; p++) { out->betters[p] = c.betters[p]; out->pass_visits[p] = c.pass_visits[p]; out->sum_best[p] = c.sum_best[p]; }
   out->passes_run = c.passes_run;
   out->ms_passes = j->ms_passes;
+  return 0;
+}
+
+// Device-built offsets table of a job, for parity tests against the host/oracle table.
+extern "C" int rs_job_read_offsets(RsJob *j, uint32_t *out, uint32_t cap) {
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
+  const uint32_t n = j->nOff < cap ? j->nOff : cap;
+  RS_CHECK(cudaStreamSynchronize(w->stream));
+  RS_CHECK(cudaMemcpy(out, w->offsets.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
 }
 
