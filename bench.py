@@ -171,7 +171,7 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-KERNELS_PER_JOB = 4 + 6 + 5 + 1   # init x4, pass x6, prober copy x5, extract
+KERNELS_PER_JOB = 6 + 4 + 2 + 6 + 1   # offsets gen+sort (first job of a size), init x4, pass-0 gather x2, pass x6, write-back
 
 
 def run_ours(a):

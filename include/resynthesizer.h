@@ -131,6 +131,8 @@ typedef struct {
   float ms_prep, ms_h2d, ms_kernels, ms_d2h, ms_total; /* host prep / copies / device passes (CUDA events) */
 } RsStats;
 void rs_get_stats(RsStats *out);
+/* rs_keep_result(1): engine() calls on this thread also fetch what rs_get_last_result() returns (off by default). */
+void rs_keep_result(int yes);
 /* Visit order and final source (best corpus point) of each target point of the last engine() call on this
  * thread, packed x | y << 16 (0xFFFFFFFF = no source).  Returns the number of target points. */
 unsigned int rs_get_last_result(unsigned int *targets_out, unsigned int *sources_out, unsigned int cap);

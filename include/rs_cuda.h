@@ -72,9 +72,12 @@ int rs_job_upload(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_r
                   const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max);
 /* Runs all passes (early termination decided on the device), calling tick from the waiting host thread. */
 int rs_job_run(RsJob *job, RsTickFn tick, void *tick_ctx);
-/* colours_out: n_targets entries, c0 | c1<<8 | c2<<16 of each target point in visit order;
- * sources_out (may be NULL): packed best corpus point of each, 0xFFFFFFFF if none. */
-int rs_job_download(RsJob *job, uint32_t *colours_out, uint32_t *sources_out);
+/* target_raw_out: the caller's tw*th*bpp pixmap; the rows containing target points are overwritten with the
+ * device's copy, which differs from the uploaded one only in the colour bytes of target points.
+ * sources_out (may be NULL; needs rs_job_want_sources(job,1) before rs_job_run): packed best corpus point of
+ * each target point in visit order, 0xFFFFFFFF if none. */
+int rs_job_download(RsJob *job, uint8_t *target_raw_out, uint32_t *sources_out);
+void rs_job_want_sources(RsJob *job, int yes);
 int rs_job_counters(RsJob *job, RsJobCounters *out);
 void rs_job_destroy(RsJob *job);
 /* Copies the job's neighbour-offset table back (parity tests of the device-side build). */

@@ -101,7 +101,7 @@ class PortStats(C.Structure):
 
 REF_MODE = (0, 0)      # GLib MT19937 stream, live recentProber: the reference product build
 RAND_MODE = (1, 0)     # libc rand() proxy: the reference standalone build
-GPU_MODE = (2, 1)      # counter hash + pass-snapshot recentProber: sequential definition of the CUDA engine
+GPU_MODE = (2, 2)      # counter hash + epoch-snapshot recentProber: sequential definition of the CUDA engine
 
 
 def load_port(mode=REF_MODE, seed=1198472):

@@ -15,8 +15,10 @@
  *         1  libc rand() formula of glibProxy.c:36-49        -- reference standalone build
  *         2  counter-based hash keyed (seed,pass,index,probe) -- what the CUDA engine draws
  *   prober 0 live recentProber map (synthesize.h:556,577)     -- reference
- *          1 pass-snapshot recentProber                       -- what the CUDA engine does
- * Mode (2,1) is the sequential definition of the GPU engine's semantics: the
+ *          1 snapshot per epoch of port_set_epoch_len() visits (0 = per pass) -- experiments
+ *          2 lagged epochs of max(64, ceil(n/32)) visits -- what the CUDA engine does: a visit of epoch e
+ *            sees the stamps of earlier passes and of epochs <= e-2 of its pass (and its own visit's)
+ * Mode (2,2) is the sequential definition of the GPU engine's semantics: the
  * CUDA path must equal it bit for bit on whole images.
  */
 #include <limits.h>
@@ -49,6 +51,8 @@ enum { ERR_FORMAT = 1, ERR_MASK_MISMATCH = 2, ERR_PATCH = 3, ERR_CTX = 4, ERR_EM
 /* ------------------------------------------------------------ mode + stats */
 static int g_rng_mode = 0, g_prober_mode = 0;
 static unsigned int g_seed = 1198472u; /* engine.c:643 */
+static unsigned int g_epoch_len = 0;    /* prober mode 1: visits per snapshot epoch (0 = one epoch per pass) */
+void port_set_epoch_len(unsigned int n) { g_epoch_len = n; }
 
 typedef struct {
   unsigned long long visits, evals, compares, offset_scans, heur_evals, heur_skips, perfect;
@@ -152,6 +156,8 @@ typedef struct {
   Pt *offsets; unsigned int nOff;
   unsigned short cLUT[512]; unsigned int mLUT[512];
   MT mt;
+  unsigned int epoch_len;       /* prober modes 1,2: visits per snapshot epoch (0 = whole pass) */
+  unsigned int *proberPrev;     /* prober mode 2: stamps of the previous epoch, not yet visible (0xFFFFFFFF = none) */
 } Eng;
 
 typedef struct { Pt off; unsigned char px[8]; Pt src; } Nb; /* synthesize.h:120-125 */
@@ -306,11 +312,29 @@ static int eval_candidate(Eng *e, Pt cand, const Nb *nb, unsigned int K, unsigne
   return sum == 0;
 }
 
+/* prober mode 1: proberNext collects the current epoch, merged into prober at the epoch boundary.
+ * prober mode 2: proberNext = current epoch, proberPrev = previous epoch, prober = everything older (visible). */
 static void prober_begin_pass(Eng *e) {
-  if (g_prober_mode == 1) memcpy(e->proberNext, e->prober, (size_t)e->cw * e->ch * sizeof(unsigned int));
+  size_t n = (size_t)e->cw * e->ch;
+  if (g_prober_mode == 1) memcpy(e->proberNext, e->prober, n * sizeof(unsigned int));
+  if (g_prober_mode == 2) { memset(e->proberNext, 0xFF, n * sizeof(unsigned int)); memset(e->proberPrev, 0xFF, n * sizeof(unsigned int)); }
+}
+static void prober_advance_epoch(Eng *e) {
+  size_t n = (size_t)e->cw * e->ch;
+  if (g_prober_mode == 1) { unsigned int *t = e->prober; e->prober = e->proberNext; e->proberNext = t; memcpy(e->proberNext, e->prober, n * sizeof(unsigned int)); }
+  if (g_prober_mode == 2) {
+    for (size_t i = 0; i < n; i++) if (e->proberPrev[i] != 0xFFFFFFFFu) e->prober[i] = e->proberPrev[i];
+    unsigned int *t = e->proberPrev; e->proberPrev = e->proberNext; e->proberNext = t;
+    memset(e->proberNext, 0xFF, n * sizeof(unsigned int));
+  }
 }
 static void prober_end_pass(Eng *e) {
+  size_t n = (size_t)e->cw * e->ch;
   if (g_prober_mode == 1) { unsigned int *t = e->prober; e->prober = e->proberNext; e->proberNext = t; }
+  if (g_prober_mode == 2) {  /* a pass boundary makes everything visible */
+    for (size_t i = 0; i < n; i++) if (e->proberPrev[i] != 0xFFFFFFFFu) e->prober[i] = e->proberPrev[i];
+    for (size_t i = 0; i < n; i++) if (e->proberNext[i] != 0xFFFFFFFFu) e->prober[i] = e->proberNext[i];
+  }
 }
 
 /* synthesize.h:426-642 */
@@ -326,6 +350,7 @@ static unsigned int run_pass(Eng *e, unsigned int pass, unsigned int end, Progre
       if (pct > *prior_pct) { tick_cb((int)pct, tick_ctx); *prior_pct = pct; }
       if (*cancel) break;
     }
+    if (g_prober_mode >= 1 && e->epoch_len && ti && (ti % e->epoch_len) == 0) prober_advance_epoch(e);
     Pt pos = e->targets[ti];
     unsigned int K = gather_patch(e, pos, nb);
     unsigned int best = UINT_MAX; int bettered = 0, perfect = 0;
@@ -420,7 +445,9 @@ int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *targetMap, Map *c
   int err = order_targets(&e);
   if (!err) {
     e.prober = (unsigned int *)malloc(cn * sizeof(unsigned int)); memset(e.prober, 0xFF, cn * sizeof(unsigned int));
-    if (g_prober_mode == 1) e.proberNext = (unsigned int *)malloc(cn * sizeof(unsigned int));
+    if (g_prober_mode >= 1) e.proberNext = (unsigned int *)malloc(cn * sizeof(unsigned int));
+    if (g_prober_mode == 2) e.proberPrev = (unsigned int *)malloc(cn * sizeof(unsigned int));
+    e.epoch_len = g_prober_mode == 1 ? g_epoch_len : (g_prober_mode == 2 ? ((e.nT + 31u) / 32u < 64u ? 64u : (e.nT + 31u) / 32u) : 0u);
     /* refiner.h:42-122, passes.h:67-93 */
     unsigned int ends[MAX_PASSES], est = 0, n = e.nT;
     ends[0] = n; est = n;
@@ -432,7 +459,7 @@ int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *targetMap, Map *c
       g_stats.betters[p] = b; g_stats.passes_run = p + 1;
       if ((float)b / e.nT < 0.1) break;
     }
-    free(e.prober); free(e.proberNext);
+    free(e.prober); free(e.proberNext); free(e.proberPrev);
     g_last_xy = (int *)realloc(g_last_xy, (size_t)e.nT * 8); g_last_src = (int *)realloc(g_last_src, (size_t)e.nT * 8); g_last_n = e.nT;
     for (unsigned int i = 0; i < e.nT; i++) {
       Pt t = e.targets[i], so = e.sourceOf[(size_t)t.y * e.tw + t.x];

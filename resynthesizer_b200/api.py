@@ -147,6 +147,11 @@ def engine(params, fi, target_pixmap, corpus_pixmap, progress=None, cancel_after
     return (err, pr.percents) if return_progress else err
 
 
+def keep_result(yes=True):
+    """Make later engine() calls also fetch per-target sources (see last_result())."""
+    lib().rs_keep_result(1 if yes else 0)
+
+
 def last_result():
     """(targets, sources) of the last engine() call: (n,2) int32 arrays in visit order; source (-1,-1) = none."""
     L = lib()

@@ -17,6 +17,7 @@ thread_local std::string t_err;
 thread_local RsStats t_stats;
 thread_local uint32_t t_seed = 1198472u;  // lib/engine.c:643
 thread_local bool t_device_chosen = false;
+thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-target sources (tests, quality metrics)
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
 
 double now_ms() {
@@ -58,6 +59,7 @@ int on_tick(void *p, uint32_t /*pass*/, uint32_t /*index*/) {
 extern "C" const char *rs_last_error(void) { return t_err.c_str(); }
 extern "C" void rs_get_stats(RsStats *out) { *out = t_stats; }
 extern "C" void rs_set_seed(unsigned int seed) { t_seed = seed; }
+extern "C" void rs_keep_result(int yes) { t_keep_result = yes != 0; }
 extern "C" int rs_set_device(int ordinal) {
   if (rs_cuda_set_device(ordinal)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
   t_device_chosen = true;
@@ -134,7 +136,7 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   uint8_t *tpix = reinterpret_cast<uint8_t *>(targetMap->data->data);
   const uint8_t *cpix = reinterpret_cast<const uint8_t *>(corpusMap->data->data);
 
-  std::vector<rs::Point> targets, corpus;
+  static thread_local std::vector<uint32_t> targets, corpus;  // reused across calls: no page faults per job
   rs::collect_target_points(tpix, tw, th, bpp, targets);
   if (targets.empty()) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;  // lib/engine.c:605-610
   rs::collect_corpus_points(cpix, cw, ch, bpp, *fi, corpus);
@@ -172,9 +174,7 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   desc.n_passes = 6;
   desc.terminate_fraction = 0.1;  // IMAGE_SYNTH_TERMINATE_FRACTION, a double (lib/refiner.h:111)
 
-  std::vector<uint32_t> tpk(n), cpk(corpus.size());
-  for (uint32_t i = 0; i < n; i++) tpk[i] = (uint32_t)targets[i].x | ((uint32_t)targets[i].y << 16);
-  for (size_t i = 0; i < corpus.size(); i++) cpk[i] = (uint32_t)corpus[i].x | ((uint32_t)corpus[i].y << 16);
+  const std::vector<uint32_t> &tpk = targets, &cpk = corpus;
   const double t1 = now_ms();
 
   RsJob *job = nullptr;
@@ -183,22 +183,22 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
                          c256, m256, m512[0]);  // offsets table: built and cached on the device
   const double t2 = now_ms();
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
-  if (!rc) rc = rs_job_run(job, on_tick, &ts);
+  if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, on_tick, &ts); }
   const double t3 = now_ms();
-  std::vector<uint32_t> colours(n);
-  t_last_sources.assign(n, 0xFFFFFFFFu);
-  t_last_targets = tpk;
-  if (!rc) rc = rs_job_download(job, colours.data(), t_last_sources.data());
+  if (!rc) {
+    // engine() mutates the colour bytes of targetMap in place (lib/synthesize.h:403-419); alpha and maps untouched
+    if (t_keep_result) {
+      t_last_sources.assign(n, 0xFFFFFFFFu);
+      t_last_targets = tpk;
+      rc = rs_job_download(job, tpix, t_last_sources.data());
+    } else {
+      rc = rs_job_download(job, tpix, nullptr);
+    }
+  }
   if (rc) {
     t_err = rs_cuda_last_error();
     rs_job_destroy(job);
     return RS_ERROR_CUDA;
-  }
-  // engine() mutates the colour bytes of targetMap in place (lib/synthesize.h:403-419); alpha and maps untouched
-  const int nc = fi->img_match_bpp;
-  for (uint32_t i = 0; i < n; i++) {
-    uint8_t *p = tpix + ((size_t)targets[i].y * tw + targets[i].x) * bpp;
-    for (int c = 0; c < nc; c++) p[1 + c] = (uint8_t)(colours[i] >> (8 * c));
   }
   RsJobCounters jc;
   rs_job_counters(job, &jc);
@@ -315,11 +315,11 @@ extern "C" uint32_t rs_host_sorted_offsets(int tw, int th, int cw, int ch, int32
   return (uint32_t)o.size();
 }
 extern "C" int rs_host_order_targets(int mode, int32_t *xy, uint32_t n, uint32_t seed) {
-  std::vector<rs::Point> p(n);
-  for (uint32_t i = 0; i < n; i++) p[i] = rs::Point{xy[2 * i], xy[2 * i + 1]};
+  std::vector<uint32_t> p(n);
+  for (uint32_t i = 0; i < n; i++) p[i] = rs::pack_xy(xy[2 * i], xy[2 * i + 1]);
   rs::GRandMT prng(seed);
   const int e = rs::order_target_points(mode, p, prng);
-  for (uint32_t i = 0; i < n; i++) { xy[2 * i] = p[i].x; xy[2 * i + 1] = p[i].y; }
+  for (uint32_t i = 0; i < n; i++) { xy[2 * i] = rs::unpack_x(p[i]); xy[2 * i + 1] = rs::unpack_y(p[i]); }
   return e;
 }
 extern "C" uint32_t rs_host_pass_schedule(uint32_t n, uint32_t *ends6) { return rs::pass_schedule(n, ends6); }

@@ -78,86 +78,171 @@ void build_sorted_offsets(int tw, int th, int cw, int ch, std::vector<uint32_t> 
 }
 
 // ------------------------------------------------------------------------------------------ points
-void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<Point> &out) {
+void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<uint32_t> &out) {
   out.clear();
-  const size_t n = (size_t)w * h;
-  for (size_t i = 0; i < n; i++)
-    if (pix[i * bpp] != 0) out.push_back(Point{(int)(i % w), (int)(i / w)});
+  for (int y = 0; y < h; y++) {
+    const uint8_t *row = pix + (size_t)y * w * bpp;
+    for (int x = 0; x < w; x++)
+      if (row[(size_t)x * bpp] != 0) out.push_back(pack_xy(x, y));
+  }
 }
 
-void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<Point> &out) {
+void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<uint32_t> &out) {
   out.clear();
-  const size_t n = (size_t)w * h;
-  for (size_t i = 0; i < n; i++) {
-    const uint8_t *p = pix + i * bpp;
-    if (p[0] == 0xFF && (fi.isAlphaSource ? p[fi.alpha_bip] != 0 : true)) out.push_back(Point{(int)(i % w), (int)(i / w)});
+  const bool alpha = fi.isAlphaSource != 0;
+  const int ab = fi.alpha_bip;
+  for (int y = 0; y < h; y++) {
+    const uint8_t *row = pix + (size_t)y * w * bpp;
+    for (int x = 0; x < w; x++) {
+      const uint8_t *p = row + (size_t)x * bpp;
+      if (p[0] == 0xFF && (!alpha || p[ab] != 0)) out.push_back(pack_xy(x, y));
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------- ordering
-static void shuffle_bands(std::vector<Point> &p, GRandMT &prng) {
-  const int last = (int)p.size() - 1;
-  const int half = (int)(p.size() * 0.1);  // IMAGE_SYNTH_BAND_FRACTION
-  for (int i = 0; i <= last; i++) {
-    const int lo = std::max(i - half, 0), hi = std::min(i + half, last);
-    const int j = lo + (int)prng.int_range((uint32_t)(hi - lo));
-    std::swap(p[i], p[j]);
+// v % n for a fixed n without a division per draw (Lemire, "Faster remainder by direct computation", 2019)
+struct FastMod {
+  uint64_t M;
+  uint32_t n;
+  explicit FastMod(uint32_t n_) : M(~0ull / n_ + 1ull), n(n_) {}
+  uint32_t mod(uint32_t v) const {
+    const uint64_t low = M * v;
+    return (uint32_t)(((__uint128_t)low * n) >> 64);
+  }
+};
+
+void GRandMT::fill_int_range(uint32_t n, uint32_t *out, size_t count) {
+  if (n == 0) { for (size_t i = 0; i < count; i++) out[i] = 0; return; }
+  uint32_t leftover = (0x80000000u % n) * 2u;
+  if (leftover >= n) leftover -= n;
+  const uint32_t maxvalue = (n <= 0x80000000u) ? 0xffffffffu - leftover : n - 1u;
+  const FastMod fm(n);
+  for (size_t i = 0; i < count; i++) {
+    uint32_t v;
+    do v = next32(); while (v > maxvalue);
+    out[i] = fm.mod(v);
   }
 }
 
-static unsigned ray_index(const Point &a) {
-  return (unsigned)(std::atan2((double)(float)a.y, (double)(float)a.x) * 200 /
+static void shuffle_bands(std::vector<uint32_t> &p, GRandMT &prng) {
+  const int last = (int)p.size() - 1;
+  const int half = (int)(p.size() * 0.1);  // IMAGE_SYNTH_BAND_FRACTION
+  uint32_t *a = p.data();
+  // draws first (the band is 2*half wide except within `half` of either end: that run is drawn in bulk) ...
+  std::vector<uint32_t> js((size_t)last + 1);
+  int i = 0;
+  while (i <= last) {
+    const int lo = std::max(i - half, 0), hi = std::min(i + half, last);
+    if (i >= half && i + half <= last && hi - lo == 2 * half) {
+      const int run_end = last - half;  // inclusive: last i with a full band
+      const size_t cnt = (size_t)(run_end - i + 1);
+      prng.fill_int_range((uint32_t)(2 * half), js.data() + i, cnt);
+      for (size_t k = 0; k < cnt; k++) js[i + k] += (uint32_t)(i + (int)k - half);
+      i += (int)cnt;
+    } else {
+      js[i] = (uint32_t)lo + prng.int_range((uint32_t)(hi - lo));
+      i++;
+    }
+  }
+  // ... then the swaps, with the random side prefetched
+  constexpr int AHEAD = 16;
+  for (i = 0; i <= last; i++) {
+    if (i + AHEAD <= last) __builtin_prefetch(a + js[i + AHEAD], 1);
+    std::swap(a[i], a[js[i]]);
+  }
+}
+
+static unsigned ray_index(int x, int y) {
+  return (unsigned)(std::atan2((double)(float)y, (double)(float)x) * 200 /
                         3.1415926535897932384626433832795028841971693993751 + 200);
 }
 
-int order_target_points(int mode, std::vector<Point> &pts, GRandMT &prng) {
+// Stable LSD radix sort of (key, payload) pairs by 32-bit key, ascending.
+static void radix_sort_pairs(std::vector<uint32_t> &keys, std::vector<uint32_t> &vals) {
+  const size_t n = keys.size();
+  std::vector<uint32_t> k2(n), v2(n);
+  for (int shift = 0; shift < 32; shift += 8) {
+    size_t hist[257] = {0};
+    for (size_t i = 0; i < n; i++) hist[((keys[i] >> shift) & 0xFFu) + 1]++;
+    if (hist[1] == n && shift) { continue; }  // all digits zero: pass is the identity
+    for (int d = 0; d < 256; d++) hist[d + 1] += hist[d];
+    for (size_t i = 0; i < n; i++) {
+      const size_t pos = hist[(keys[i] >> shift) & 0xFFu]++;
+      k2[pos] = keys[i];
+      v2[pos] = vals[i];
+    }
+    keys.swap(k2);
+    vals.swap(v2);
+  }
+}
+
+int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {
   const size_t n = pts.size();
   if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
   if (mode <= 1) {  // not Fisher-Yates: every i swaps with a draw over the whole vector
-    for (size_t i = 0; i < n; i++) std::swap(pts[i], pts[prng.int_range((uint32_t)n)]);
+    std::vector<uint32_t> js(n);
+    prng.fill_int_range((uint32_t)n, js.data(), n);
+    uint32_t *a = pts.data();
+    constexpr size_t AHEAD = 16;
+    for (size_t i = 0; i < n; i++) {
+      if (i + AHEAD < n) __builtin_prefetch(a + js[i + AHEAD], 1);
+      std::swap(a[i], a[js[i]]);
+    }
     return 0;
   }
   // centre of the bounding box; the upper bounds start at 0 as in the reference (engineTypes.h:192-226)
   int ulx = INT_MAX, uly = INT_MAX, lrx = 0, lry = 0;
-  for (const Point &p : pts) {
-    ulx = std::min(ulx, p.x); uly = std::min(uly, p.y);
-    lrx = std::max(lrx, p.x); lry = std::max(lry, p.y);
+  for (uint32_t p : pts) {
+    const int x = unpack_x(p), y = unpack_y(p);
+    ulx = std::min(ulx, x); uly = std::min(uly, y);
+    lrx = std::max(lrx, x); lry = std::max(lry, y);
   }
-  const Point c{(lrx - ulx) / 2 + ulx, (lry - uly) / 2 + uly};
-  struct Keyed { float fkey; int ikey; uint32_t orig; };
-  std::vector<Keyed> keys(n);
-  std::vector<Point> off(n);
-  for (size_t i = 0; i < n; i++) { off[i] = Point{pts[i].x - c.x, pts[i].y - c.y}; keys[i].orig = (uint32_t)i; keys[i].fkey = 0.f; keys[i].ikey = 0; }
+  const int cx = (lrx - ulx) / 2 + ulx, cy = (lry - uly) / 2 + uly;
+  // Sort keys as order-preserving 32-bit patterns (non-negative floats compare like their bit patterns).
+  std::vector<uint32_t> keys(n), idx(n);
   const bool brush = (mode == 2 || mode == 5 || mode == 8);  // 8 ("squeeze") nets out to mode 2's sort
   bool descending;
   if (brush) {
     unsigned maxray[401];
     std::memset(maxray, 0, sizeof maxray);
+    std::vector<uint16_t> ray(n);
     for (size_t i = 0; i < n; i++) {
-      const unsigned d = (unsigned)(off[i].x * off[i].x + off[i].y * off[i].y), g = ray_index(off[i]);
-      maxray[g] = std::max(maxray[g], d);
+      const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
+      const unsigned g = ray_index(ox, oy);
+      ray[i] = (uint16_t)g;
+      maxray[g] = std::max(maxray[g], (unsigned)(ox * ox + oy * oy));
     }
-    for (size_t i = 0; i < n; i++)
-      keys[i].fkey = (float)(off[i].y * off[i].y + off[i].x * off[i].x) / maxray[ray_index(off[i])];
+    for (size_t i = 0; i < n; i++) {
+      const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
+      const float k = (float)(oy * oy + ox * ox) / maxray[ray[i]];  // NaN only when n == 1
+      uint32_t bits;
+      std::memcpy(&bits, &k, 4);
+      keys[i] = bits;
+    }
     descending = (mode != 5);
   } else {
     const bool by_y = (mode == 4 || mode == 7);
-    for (size_t i = 0; i < n; i++) keys[i].ikey = by_y ? off[i].y * off[i].y : off[i].x * off[i].x;
+    for (size_t i = 0; i < n; i++) {
+      const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
+      keys[i] = (uint32_t)(by_y ? oy * oy : ox * ox);
+    }
     descending = (mode == 3 || mode == 4);
   }
   // glibc merge sort under comparators that never answer "equal" (engineTypes.h:51-56):
   // "less" kinds  -> ascending, equal keys in REVERSED input order; "more" kinds -> descending, input order kept.
   if (n > 1) {
     if (descending) {
-      if (brush) std::stable_sort(keys.begin(), keys.end(), [](const Keyed &a, const Keyed &b) { return a.fkey > b.fkey; });
-      else std::stable_sort(keys.begin(), keys.end(), [](const Keyed &a, const Keyed &b) { return a.ikey > b.ikey; });
+      for (size_t i = 0; i < n; i++) { keys[i] = ~keys[i]; idx[i] = (uint32_t)i; }
     } else {
       std::reverse(keys.begin(), keys.end());
-      if (brush) std::stable_sort(keys.begin(), keys.end(), [](const Keyed &a, const Keyed &b) { return a.fkey < b.fkey; });
-      else std::stable_sort(keys.begin(), keys.end(), [](const Keyed &a, const Keyed &b) { return a.ikey < b.ikey; });
+      for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)(n - 1 - i);
     }
+    radix_sort_pairs(keys, idx);
+    std::vector<uint32_t> sorted(n);
+    for (size_t i = 0; i < n; i++) sorted[i] = pts[idx[i]];
+    pts.swap(sorted);
   }
-  for (size_t i = 0; i < n; i++) pts[i] = Point{off[keys[i].orig].x + c.x, off[keys[i].orig].y + c.y};
   shuffle_bands(pts, prng);
   return 0;
 }

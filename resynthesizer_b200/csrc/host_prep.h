@@ -10,7 +10,10 @@
 
 namespace rs {
 
-struct Point { int x, y; };
+// Points are packed x | y << 16 (coordinates < 32768) all the way from the scan to the device.
+inline uint32_t pack_xy(int x, int y) { return (uint32_t)x | ((uint32_t)y << 16); }
+inline int unpack_x(uint32_t p) { return (int)(p & 0xFFFFu); }
+inline int unpack_y(uint32_t p) { return (int)(p >> 16); }
 
 // GLib GRand (MT19937) as the reference's product build draws it (lib/engine.c:643, lib/orderTarget.h:44,76).
 class GRandMT {
@@ -18,6 +21,7 @@ class GRandMT {
   explicit GRandMT(uint32_t seed);
   uint32_t next32();
   uint32_t int_range(uint32_t n);  // g_rand_int_range(0, n)
+  void fill_int_range(uint32_t n, uint32_t *out, size_t count);  // `count` successive int_range(n) draws
  private:
   uint32_t mt_[624];
   int mti_;
@@ -31,11 +35,11 @@ void build_metric_tables(double sensitivity, double map_weight, uint16_t color51
 void build_sorted_offsets(int target_w, int target_h, int corpus_w, int corpus_h, std::vector<uint32_t> &out);
 
 // lib/engine.c:338-431.  Points in row-major scan order.
-void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<Point> &out);
-void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<Point> &out);
+void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<uint32_t> &out);
+void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<uint32_t> &out);
 
 // lib/orderTarget.h:268-343 (+ brushfire.h, engineTypes.h).  Returns 0 or IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE.
-int order_target_points(int match_context_type, std::vector<Point> &pts, GRandMT &prng);
+int order_target_points(int match_context_type, std::vector<uint32_t> &pts, GRandMT &prng);
 
 // lib/passes.h:67-93.  Returns the estimated total visit count.
 uint32_t pass_schedule(uint32_t n_targets, uint32_t ends[6]);

@@ -10,8 +10,15 @@
 //            and hasValueMap: lib/engine.c:152-224)
 //   meta     per target-image pixel: visit-order index of a target pixel, RS_CTX_VALUED for a context pixel
 //            usable as neighbour, RS_NEVER otherwise
-//   prober   recentProberMap (lib/engine.c:314-327) as ((pass+1) << 29 | index), 0 = never probed; merged
-//            with atomicMax (within a pass the later visit has the larger index), double buffered per pass
+//   prober   recentProberMap (lib/engine.c:314-327), deterministic bounded-staleness version of the reference's
+//            live map.  A pass is cut into epochs of epoch_len visits; a visit of epoch e sees the stamps of
+//            earlier passes and of epochs <= e-2 of its own pass.  Three arrays (epoch mod 3), each one 64-bit
+//            word per corpus pixel holding two stamps ((pass+1) << 29 | index; 0 = never): hi = newest stamp
+//            written to this array, lo = newest stamp of an earlier epoch than hi's.  A visit of epoch e stamps
+//            only array e%3, by 64-bit CAS, and only once every visit of epochs <= e-2 has completed; so each
+//            array has one writing epoch at a time, and a reader of epoch e (which hides every stamp of its pass
+//            with index >= (e-1)*len: epochs e-1, e and the already-running e+1) finds the newest visible
+//            stamp of each array in hi or lo.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -25,11 +32,14 @@
 #define RS_MAX_NB 64
 #define RS_CHUNK 4          // neighbours gathered per lane between two early-out checks
 #define RS_LUT_WORDS (256 * 32)
+#define RS_MAX_EPOCHS 40     // epochs per pass: ceil(n / max(64, ceil(n/32))) <= 32
 
 struct RsCtrl {             // device-resident control block of one job (zeroed at upload)
   unsigned int next[6];     // next visit index to claim, per pass
   unsigned int betters[6];
   unsigned int done_ctas[6];
+  unsigned int epoch_done[6][40];  // per pass and epoch: visits completed (state word + stamps published)
+  unsigned int epoch_wm[6];        // per pass: number of leading epochs that are complete (what waiters poll)
   unsigned int stop;        // set by the last CTA of a pass when betters/n < fraction, or on cancel
   unsigned int passes_run;
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
@@ -46,8 +56,7 @@ struct RsDev {              // kernel argument (by value)
   const uint32_t *corpus_pts;
   const uint32_t *offsets;
   const uint32_t *lut_rep;  // [2][256][32] colour then map metric, replicated per lane (bank-conflict free)
-  const uint32_t *proberA;  // snapshot at pass start
-  uint32_t *proberB;        // being built by this pass
+  unsigned long long *prober[3];  // [cw*ch] each: stamps of epochs = 0, 1, 2 (mod 3), see above
   const uint2 *nb_lists;    // pass-0 patches gathered up front by k_gather_pass0: [nT][kmax-1]
   const uint8_t *nb_counts; // [nT] patch size of each pass-0 visit
   RsCtrl *ctrl;
@@ -57,6 +66,7 @@ struct RsDev {              // kernel argument (by value)
   uint32_t nT, nC, nOff;
   uint32_t kmax, probes, seed, penalty;
   uint32_t pass, pass_end;
+  uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
   uint32_t ends[6];
   int htile, vtile;
   double terminate_fraction;

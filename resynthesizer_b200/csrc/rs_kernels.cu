@@ -104,9 +104,10 @@ __global__ void k_copy_u32(const uint32_t *__restrict__ src, uint32_t *__restric
   for (; i < n; i += stride) dst[i] = src[i];
 }
 
-// Final colours and sources of the target points, from the newest published version of each.
-__global__ void k_extract(const unsigned long long *__restrict__ W, const uint32_t *__restrict__ targets, uint32_t n,
-                          int tw, uint32_t *__restrict__ colours, uint32_t *__restrict__ sources) {
+// Final colours of the target points, from the newest published version of each, written into the raw target
+// pixmap (colour bytes only: alpha and maps are never synthesised, lib/synthesize.h:403-419); sources optional.
+__global__ void k_writeback(const unsigned long long *__restrict__ W, const uint32_t *__restrict__ targets, uint32_t n,
+                            int tw, int bpp, int n_color, uint8_t *__restrict__ raw, uint32_t *__restrict__ sources) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t t = targets[i];
@@ -114,8 +115,9 @@ __global__ void k_extract(const unsigned long long *__restrict__ W, const uint32
   const unsigned long long a = W[2 * q], b = W[2 * q + 1];
   const unsigned va = (unsigned)(a >> 24) & 0xFFu, vb = (unsigned)(b >> 24) & 0xFFu;
   const unsigned long long w = (vb != 0xFFu && vb > va) ? b : a;
-  colours[i] = (uint32_t)(w & 0xFFFFFFull);
-  sources[i] = (uint32_t)(w >> 32);
+  uint8_t *p = raw + q * bpp;
+  for (int c = 0; c < n_color; c++) p[1 + c] = (uint8_t)(w >> (8 * c));
+  if (sources) sources[i] = (uint32_t)(w >> 32);
 }
 
 // ------------------------------------------------------------------------------ pass-0 patch precompute
@@ -176,6 +178,72 @@ __global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__re
   if (lane == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
 }
 
+// The first visits of pass 0 see almost no valued pixels and scan a long way down the offset table (all of it
+// when there is no context).  A whole CTA scans for one such visit: 1024 table entries per step, compacted in
+// table order through a shared-memory prefix over the 16 warps.
+#define RS_COOP_THREADS 512
+__global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsDev J, uint2 *__restrict__ lists,
+                                                                     uint8_t *__restrict__ counts, uint32_t v_end,
+                                                                     unsigned int *__restrict__ claim) {
+  __shared__ uint32_t s_cnt[2][RS_COOP_THREADS / 32];
+  __shared__ uint32_t s_v;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t stride = J.kmax - 1u;
+  unsigned long long scans = 0;
+  while (true) {
+    if (threadIdx.x == 0) s_v = atomicAdd(claim, 1u);
+    __syncthreads();
+    const uint32_t v = s_v;
+    if (v >= v_end) break;
+    const uint32_t tpos = __ldg(J.targets + v);
+    const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
+    uint2 *out = lists + (size_t)v * stride;
+    uint32_t count = 1;  // CTA-uniform
+    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 2 * RS_COOP_THREADS) {
+      uint32_t o[2], q[2], m[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const uint32_t j = base + warp * 64u + 32u * u + lane;
+        o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
+        if (j < J.nOff) {
+          o[u] = __ldg(J.offsets + j);
+          int x = px + rs_off_x(o[u]), y = py + rs_off_y(o[u]);
+          bool in = true;
+          if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+          else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+          if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+          else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+          if (in) {
+            q[u] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+            m[u] = __ldg(J.meta + q[u]);
+          }
+        }
+      }
+      const bool ok0 = (m[0] == RS_CTX_VALUED) || (m[0] < v), ok1 = (m[1] == RS_CTX_VALUED) || (m[1] < v);
+      const unsigned b0 = __ballot_sync(RS_FULL, ok0), b1 = __ballot_sync(RS_FULL, ok1);
+      const int buf = (int)((base / (2 * RS_COOP_THREADS)) & 1u);
+      if (lane == 0) s_cnt[buf][warp] = __popc(b0) + __popc(b1);
+      __syncthreads();
+      uint32_t before = 0, total = 0;
+#pragma unroll
+      for (int w2 = 0; w2 < RS_COOP_THREADS / 32; w2++) {
+        const uint32_t c = s_cnt[buf][w2];
+        before += (w2 < (int)warp) ? c : 0u;
+        total += c;
+      }
+      const uint32_t slot0 = count + before + __popc(b0 & lt), slot1 = count + before + __popc(b0) + __popc(b1 & lt);
+      if (ok0 && slot0 < J.kmax) out[slot0 - 1u] = make_uint2(o[0], q[0] | (m[0] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+      if (ok1 && slot1 < J.kmax) out[slot1 - 1u] = make_uint2(o[1], q[1] | (m[1] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+      count += total;
+      scans += (threadIdx.x == 0) ? 2ull * RS_COOP_THREADS : 0ull;
+    }
+    if (threadIdx.x == 0) counts[v] = (uint8_t)min(count, J.kmax);
+    __syncthreads();  // s_v is rewritten by the next claim
+  }
+  if (threadIdx.x == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
+}
+
 // --------------------------------------------------------------------------------------- the pass kernel
 #define RS_WARPS_PER_CTA 16
 #define RS_THREADS (RS_WARPS_PER_CTA * 32)
@@ -228,10 +296,9 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
       v = atomicAdd(&ctrl->next[pass], 1u);
       if (v < pass_end && (v & 4095u) == 0u) {  // progress tick + cancel poll (synthesize.h:493-497)
         J.host_ticks[pass] = v + 1u;
-        if (*J.host_cancel) {
+        if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
           atomicExch(&ctrl->stop, 1u);
           atomicAdd(&ctrl->next[pass], 0x40000000u);
-          v = 0xFFFFFFFFu;
         }
       }
     }
@@ -318,8 +385,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
     __syncwarp();
 
     // ---- heuristic 1 + 2 candidates (lib/synthesize.h:537-580): source of neighbour minus its offset,
-    //      dropped if outside/masked corpus, if this target index was the last prober of that corpus point
-    //      (snapshot at pass start), or if an earlier neighbour proposes the same point.
+    //      dropped if outside/masked corpus, if this target index was the last VISIBLE prober of that corpus
+    //      point (rs_device.cuh: epochs), or if an earlier neighbour proposes the same point.
     uint32_t mycand[2];
 #pragma unroll
     for (int rnd = 0; rnd < 2; rnd++) {
@@ -338,24 +405,54 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
         }
       }
       mycand[rnd] = c;
-      if (k < RS_MAX_NB) S.q[k] = c;
+      S.q[k] = c;
     }
     __syncwarp();
+    const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
+    const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
+    const uint32_t hide_base = tag | hide_from, my_base = tag | epoch0;
+    bool pskip[2] = {false, false};
+    for (int attempt = 0; attempt < 2; attempt++) {
+      bool any = false;
+#pragma unroll
+      for (int rnd = 0; rnd < 2; rnd++) {
+        const uint32_t c = mycand[rnd];
+        pskip[rnd] = false;
+        if (c != RS_NO_SRC) {
+          const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+          uint32_t newest = 0u;  // newest visible stamp over the three epoch arrays; 0 = never probed
+#pragma unroll
+          for (int t = 0; t < 3; t++) {
+            const unsigned long long e = rs_ld_state(J.prober[t] + a);
+            const uint32_t h = (uint32_t)(e >> 32);
+            newest = max(newest, (h >= hide_base) ? (uint32_t)e : h);
+          }
+          pskip[rnd] = newest != 0u && (newest & RS_IDX_MASK) == v;
+          any |= pskip[rnd];
+        }
+      }
+      // A "skip" verdict can still be overturned by a straggler of epochs <= e-2 (a "keep" verdict cannot):
+      // only then wait until every such visit has published its stamps, and look again.
+      if (attempt == 1 || hide_from == 0u || !__any_sync(RS_FULL, any)) break;
+      if (lane == 0) {
+        while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
+        __threadfence();
+      }
+      __syncwarp();
+    }
     uint32_t nHeur = 0;
 #pragma unroll
     for (int rnd = 0; rnd < 2; rnd++) {
       const uint32_t k = lane + 32u * rnd;
       const uint32_t c = mycand[rnd];
-      bool valid = (k < K) && (c != RS_NO_SRC);
+      bool valid = (c != RS_NO_SRC);
       if (valid) {
-        const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
-        const uint32_t pr = __ldg(J.proberA + a);  // 0 = never probed
-        bool skip = (pr >> 29) != 0u && (pr & RS_IDX_MASK) == v;
+        bool skip = pskip[rnd];
         for (uint32_t k2 = 0; k2 < k && !skip; k2++) skip = (S.q[k2] == c);
         if (skip) { valid = false; st_skips++; }
       }
       const unsigned b = __ballot_sync(RS_FULL, valid);
-      if (valid) S.aux[nHeur + __popc(b & lt)] = c;   // aux[] of lanes k>=32 is read above only in round 1 (own entry)
+      if (valid) S.aux[nHeur + __popc(b & lt)] = c;
       nHeur += __popc(b);
       __syncwarp();
     }
@@ -402,11 +499,44 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
     }
     // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
     const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
+    if (stampEnd > 0u && hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
+      if (lane == 0) {
+        while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);
+        __threadfence();
+      }
+      __syncwarp();
+    }
     for (uint32_t i = lane; i < stampEnd; i += 32) {
       const uint32_t c = candlist[i];
-      atomicMax(J.proberB + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu), tag | v);
+      unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+      const uint32_t st = tag | v;
+      unsigned long long old = rs_ld_state(pp);
+      while (true) {
+        const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
+        const unsigned long long nw = (hi >= my_base) ? (((unsigned long long)max(hi, st) << 32) | lo)
+                                                      : (((unsigned long long)st << 32) | hi);
+        if (nw == old) break;
+        const unsigned long long prev = atomicCAS(pp, old, nw);
+        if (prev == old) break;
+        old = prev;
+      }
     }
     __syncwarp();
+    if (lane == 0) {  // publish: this visit is complete (state word written, stamps merged)
+      __threadfence();
+      const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
+      if (atomicAdd(&ctrl->epoch_done[pass][epoch_idx], 1u) + 1u == esize) {
+        // last visit of its epoch: move the watermark over every leading epoch that is now complete
+        while (true) {
+          const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]);
+          const uint32_t first = wmk * J.epoch_len;
+          if (first >= pass_end) break;
+          if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk]) != min(J.epoch_len, pass_end - first)) break;
+          __threadfence();
+          atomicCAS(&ctrl->epoch_wm[pass], wmk, wmk + 1u);
+        }
+      }
+    }
   }
 
   // ---- flush per-warp statistics
@@ -501,7 +631,7 @@ struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evDone = nullptr;
-  DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, colours,
+  DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
@@ -538,7 +668,7 @@ static int ws_ensure_pinned(Workspace *w, size_t bytes) {
 static void ws_free(Workspace *w) {
   cudaSetDevice(w->device);
   DevBuf *all[] = {&w->raw_t, &w->raw_c, &w->corpus, &w->W, &w->meta, &w->tmaps, &w->targets, &w->cpts, &w->offsets,
-                   &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->colours, &w->sources, &w->ctrl,
+                   &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
                    &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
@@ -625,6 +755,8 @@ struct RsJob {
   Workspace *ws = nullptr;
   bool maps = false;
   uint32_t nT = 0, nC = 0, nOff = 0, penalty = 0;
+  uint32_t y_min = 0, y_max = 0;  // rows of the target image that hold target points
+  bool want_sources = false;
   float ms_passes = 0.f;
 };
 
@@ -691,6 +823,11 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
   const size_t tn = (size_t)d.tw * d.th, cn = (size_t)d.cw * d.ch;
   cudaStream_t s = w->stream;
   j->nT = n_targets; j->nC = n_corpus;
+  {
+    uint32_t lo = 0xFFFFu, hi = 0;
+    for (uint32_t i = 0; i < n_targets; i++) { const uint32_t y = targets[i] >> 16; lo = y < lo ? y : lo; hi = y > hi ? y : hi; }
+    j->y_min = lo; j->y_max = hi;
+  }
   j->penalty = 65535u * (uint32_t)d.n_color + map_lut_max * (uint32_t)d.n_map;
   int rc = 0;
   if ((rc = ws_ensure(w->raw_t, tn * d.bpp)) || (rc = ws_ensure(w->raw_c, cn * d.bpp)) ||
@@ -698,7 +835,7 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
       (rc = ws_ensure(w->meta, tn * 4)) || (rc = ws_ensure(w->tmaps, j->maps ? tn * 4 : 4)) ||
       (rc = ws_ensure(w->targets, (size_t)n_targets * 4)) || (rc = ws_ensure(w->cpts, (size_t)n_corpus * 4)) ||
       (rc = ws_ensure(w->lut256, 512 * 4)) || (rc = ws_ensure(w->lut_rep, 2 * RS_LUT_WORDS * 4)) ||
-      (rc = ws_ensure(w->prober0, cn * 4)) || (rc = ws_ensure(w->prober1, cn * 4)) ||
+      (rc = ws_ensure(w->prober0, cn * 8)) || (rc = ws_ensure(w->prober1, cn * 8)) || (rc = ws_ensure(w->prober2, cn * 8)) ||
       (rc = ws_ensure(w->colours, (size_t)n_targets * 4)) || (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) ||
       (rc = ws_ensure(w->ctrl, sizeof(RsCtrl) + 64)))
     return rc;
@@ -716,7 +853,8 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t o_t = 0, o_c = o_t + up(sz_t), o_tp = o_c + up(sz_c), o_cp = o_tp + up(sz_tp), o_off = o_cp + up(sz_cp),
                o_lut = o_off + up(sz_off), total = o_lut + up(sz_lut);
-  const size_t need_pin = total > (size_t)n_targets * 8 ? total : (size_t)n_targets * 8;
+  const size_t out_bytes = (size_t)(j->y_max - j->y_min + 1) * d.tw * d.bpp + (size_t)n_targets * 4 + 256;
+  const size_t need_pin = total > out_bytes ? total : out_bytes;
   if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
   uint8_t *pin = (uint8_t *)w->pin;
   memcpy(pin + o_t, target_raw, sz_t);
@@ -742,8 +880,9 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
     j->nOff = full_n;
   }
   RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl) + 64, s));
-  RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 4, s));
-  RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 4, s));
+  RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 8, s));
+  RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 8, s));
+  RS_CHECK(cudaMemsetAsync(w->prober2.p, 0, cn * 8, s));
   const int T = 256;
   k_canon_corpus<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
                                                           d.map_bip, j->maps ? nullptr : (uint32_t *)w->corpus.p,
@@ -772,8 +911,9 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.tmaps = j->maps ? (const uint32_t *)w->tmaps.p : nullptr;
   D.targets = (const uint32_t *)w->targets.p; D.corpus_pts = (const uint32_t *)w->cpts.p;
   D.offsets = (const uint32_t *)w->offsets.p; D.lut_rep = (const uint32_t *)w->lut_rep.p;
-  uint32_t *pr[2] = {(uint32_t *)w->prober0.p, (uint32_t *)w->prober1.p};
-  D.proberA = pr[pass & 1]; D.proberB = pr[(pass + 1) & 1];
+  D.prober[0] = (unsigned long long *)w->prober0.p; D.prober[1] = (unsigned long long *)w->prober1.p;
+  D.prober[2] = (unsigned long long *)w->prober2.p;
+  { const uint32_t e = (j->nT + 31u) / 32u; D.epoch_len = e < 64u ? 64u : e; }
   D.nb_lists = (const uint2 *)w->nb_lists.p; D.nb_counts = (const uint8_t *)w->nb_counts.p;
   D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
   D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch;
@@ -791,32 +931,36 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
-  const size_t cn = (size_t)j->d.cw * j->d.ch;
   const int grid = w->grid[j->maps ? 1 : 0];
   const size_t smem = pass_smem(j->maps);
-  uint32_t *pr[2] = {(uint32_t *)w->prober0.p, (uint32_t *)w->prober1.p};
   RS_CHECK(cudaEventRecord(w->ev0, s));
   {  // all pass-0 patches, dependency-free
     RsDev D0 = make_dev(j, 0);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
-    k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p,
-                                          (unsigned int *)((uint8_t *)w->ctrl.p + sizeof(RsCtrl)));
+    unsigned int *claims = (unsigned int *)((uint8_t *)w->ctrl.p + sizeof(RsCtrl));  // [0] coop, [1] warp kernel
+    const uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;  // the long scans: one CTA each
+    RS_CHECK(cudaMemcpyAsync(claims + 1, &v1, 4, cudaMemcpyHostToDevice, s));
+    k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, claims);
+    k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, claims + 1);
   }
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
-    if (p > 0)  // B := A before the pass stamps into B (pass-snapshot semantics of heuristic 2)
-      k_copy_u32<<<1184, 256, 0, s>>>(pr[p & 1], pr[(p + 1) & 1], cn, (const RsCtrl *)w->ctrl.p);
     RsDev D = make_dev(j, p);
     if (j->maps) k_synth_pass<true><<<grid, RS_THREADS, smem, s>>>(D);
     else k_synth_pass<false><<<grid, RS_THREADS, smem, s>>>(D);
   }
   RS_CHECK(cudaGetLastError());
   RS_CHECK(cudaEventRecord(w->ev1, s));
-  k_extract<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, (const uint32_t *)w->targets.p, j->nT,
-                                               j->d.tw, (uint32_t *)w->colours.p, (uint32_t *)w->sources.p);
-  // results land in pinned memory behind the same event
-  RS_CHECK(cudaMemcpyAsync(w->pin, w->colours.p, (size_t)j->nT * 4, cudaMemcpyDeviceToHost, s));
-  RS_CHECK(cudaMemcpyAsync((uint8_t *)w->pin + (size_t)j->nT * 4, w->sources.p, (size_t)j->nT * 4, cudaMemcpyDeviceToHost, s));
+  k_writeback<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, (const uint32_t *)w->targets.p, j->nT,
+                                                 j->d.tw, j->d.bpp, j->d.n_color, (uint8_t *)w->raw_t.p,
+                                                 j->want_sources ? (uint32_t *)w->sources.p : nullptr);
+  // the rows that contain target points land in pinned memory behind the same event
+  const size_t row_bytes = (size_t)j->d.tw * j->d.bpp, rows_bytes = (size_t)(j->y_max - j->y_min + 1) * row_bytes;
+  RS_CHECK(cudaMemcpyAsync(w->pin, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes, rows_bytes,
+                           cudaMemcpyDeviceToHost, s));
+  if (j->want_sources)
+    RS_CHECK(cudaMemcpyAsync((uint8_t *)w->pin + ((rows_bytes + 255) & ~(size_t)255), w->sources.p, (size_t)j->nT * 4,
+                             cudaMemcpyDeviceToHost, s));
   RS_CHECK(cudaMemcpyAsync(w->h_ctrl, w->ctrl.p, sizeof(RsCtrl), cudaMemcpyDeviceToHost, s));
   RS_CHECK(cudaEventRecord(w->evDone, s));
   // Host side of the progress/cancel contract: replay ticks in order while the device runs.
@@ -852,10 +996,16 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   return 0;
 }
 
-extern "C" int rs_job_download(RsJob *j, uint32_t *colours_out, uint32_t *sources_out) {
-  const Workspace *w = j->ws;  // rs_job_run left both arrays in pinned memory
-  memcpy(colours_out, w->pin, (size_t)j->nT * 4);
-  if (sources_out) memcpy(sources_out, (const uint8_t *)w->pin + (size_t)j->nT * 4, (size_t)j->nT * 4);
+extern "C" void rs_job_want_sources(RsJob *j, int yes) { j->want_sources = yes != 0; }
+
+extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sources_out) {
+  const Workspace *w = j->ws;  // rs_job_run left the rows (and sources) in pinned memory
+  const size_t row_bytes = (size_t)j->d.tw * j->d.bpp, rows_bytes = (size_t)(j->y_max - j->y_min + 1) * row_bytes;
+  memcpy(target_raw_out + (size_t)j->y_min * row_bytes, w->pin, rows_bytes);
+  if (sources_out) {
+    if (!j->want_sources) { g_err = "rs_job_download: sources were not requested before rs_job_run"; return 100; }
+    memcpy(sources_out, (const uint8_t *)w->pin + ((rows_bytes + 255) & ~(size_t)255), (size_t)j->nT * 4);
+  }
   return 0;
 }
 

@@ -1,0 +1,101 @@
+"""-m gpu: behaviour at the drop-in boundary through the CUDA engine: the reference's known answers
+(src/testSynth.c), progress-callback sequence, cancellation, row padding, imageSynth2, reentrancy."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import refdriver as R
+from resynthesizer_b200 import abi, api
+from resynthesizer_b200.synthetic import G, centered_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def test_testsynth_known_answers_on_gpu(built_lib):
+    p = abi.default_params()
+    img = np.zeros((3, 3, 4), np.uint8); img[0, 1, 3] = 1; img[1, 1] = [1, 1, 1, 1]; img[2, 2, 3] = 8
+    mask = np.zeros((3, 3), np.uint8); mask[1, 1] = 0xFF
+    err, percents = api.image_synth(img, mask, abi.T_RGBA, p, return_progress=True)
+    assert err == 0 and list(img[1, 1]) == [0, 0, 0, 1]          # testSynth.c:165-179
+    assert percents == [204750, 409500]                           # tick at index 0 of each of the two passes
+    img = np.array([[[128, 128, 128, 255], [1, 1, 1, 1], [0, 0, 0, 0]]], np.uint8)
+    m = np.array([[0, 255, 0]], np.uint8)
+    assert api.image_synth(img, m, abi.T_RGBA, p) == 0            # testSynth.c:183
+    assert img.reshape(-1).tolist() == [0x80, 0x80, 0x80, 0xFF, 0x80, 0x80, 0x80, 0x01, 0, 0, 0, 0]
+    img = np.array([[[128] * 3, [1] * 3, [2] * 3], [[64] * 3, [4] * 3, [3] * 3]], np.uint8)
+    m2 = np.array([[0, 0, 0], [0, 255, 0]], np.uint8)
+    assert api.image_synth(img, m2, abi.T_RGB, p) == 0            # testSynth.c:186
+    assert img.reshape(2, -1).tolist() == [[128] * 3 + [1] * 3 + [2] * 3, [64] * 3 + [1] * 3 + [3] * 3]
+    img = np.array([[[128, 255], [64, 1], [1, 0]]], np.uint8)
+    assert api.image_synth(img, m, abi.T_GrayA, p) == 0           # testSynth.c:189
+    assert img.reshape(-1).tolist() == [0x80, 0xFF, 0x80, 0x01, 0x01, 0x00]
+    img = np.array([[[128], [64], [1]]], np.uint8)
+    assert api.image_synth(img, m, abi.T_Gray, None) == 0         # NULL parameters -> defaults (testSynth.c:193)
+    assert img.reshape(-1).tolist()[0] == 0x80 and img.reshape(-1).tolist()[2] == 0x01
+    assert img.reshape(-1).tolist()[1] in (0x80, 0x01)            # the two corpus pixels tie; the PRNG picks
+
+
+def test_progress_sequence_equals_oracle(built_oracle, built_lib):
+    img = G(200, 160, 3, 3)
+    mask = centered_mask(200, 160, 120, 100)                      # 12000 targets: several ticks per pass
+    port = R.load_port(R.GPU_MODE)
+    pr = R.Progress()
+    assert R.image_synth(port, img, mask, abi.T_RGB, None, pr)[0] == 0
+    out = img.copy()
+    err, percents = api.image_synth(out, mask, abi.T_RGB, None, return_progress=True)
+    assert err == 0 and percents == pr.percents and len(percents) >= 10
+    assert percents == sorted(percents)
+
+
+def test_cancel_leaves_image_untouched(built_lib):
+    img = G(256, 256, 3, 4)
+    mask = centered_mask(256, 256, 128, 128)
+    out = img.copy()
+    err, percents = api.image_synth(out, mask, abi.T_RGB, None, cancel_after=2, return_progress=True)
+    assert err == 0                                               # success even when cancelled (engine.c:689)
+    assert (out == img).all()                                     # imageSynth skips the write-back (imageSynth.c:108)
+    assert 2 <= len(percents) < 20
+    # and the library is usable afterwards
+    out2 = img.copy()
+    assert api.image_synth(out2, mask, abi.T_RGB, None) == 0 and (out2 != img).any()
+
+
+def test_row_padding_and_imagesynth2(built_oracle, built_lib):
+    L = api.lib()
+    img = G(40, 30, 3, 8)
+    mask = centered_mask(40, 30, 12, 10)
+    mask2 = np.where(mask == 0, 255, 0).astype(np.uint8); mask2[:, :7] = 0
+    port = R.load_port(R.GPU_MODE)
+    err, want = R.image_synth(port, img, mask, abi.T_RGB, None, row_pad=5, mask2=mask2)
+    assert err == 0
+    rb = 40 * 3 + 5
+    buf = np.full((30, rb), 0xEE, np.uint8); buf[:, :120] = img.reshape(30, 120)
+    mbuf = np.zeros((30, 41), np.uint8); mbuf[:, :40] = mask
+    ib, _a = abi.image_buffer_padded(buf.reshape(-1), 40, 30, rb)
+    mb, _b = abi.image_buffer_padded(mbuf.reshape(-1), 40, 30, 41)
+    m2 = np.ascontiguousarray(mask2)
+    mb2, _c = abi.image_buffer_padded(m2.reshape(-1), 40, 30, 40)
+    cancel = C.c_int(0)
+    cb = abi.PROGRESS_CB(lambda p, c: None)
+    assert L.imageSynth2(C.byref(ib), C.byref(mb), C.byref(mb2), abi.T_RGB, None, cb, None, C.byref(cancel)) == 0
+    assert (buf[:, :120].reshape(30, 40, 3) == want).all() and (buf[:, 120:] == 0xEE).all()
+
+
+def test_reentrant_from_threads(built_oracle, built_lib):
+    """'The engine is reentrant, thread safe' (lib/imageSynth.c:13-15): concurrent jobs on separate images."""
+    img = [G(96, 80, 3, 50 + i) for i in range(4)]
+    mask = centered_mask(96, 80, 30, 24)
+    port = R.load_port(R.GPU_MODE)
+    want = [R.image_synth(port, im, mask, abi.T_RGB, None)[1] for im in img]
+    outs = [im.copy() for im in img]
+    errs = [None] * 4
+
+    def work(i):
+        errs[i] = api.image_synth(outs[i], mask, abi.T_RGB, None)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert errs == [0, 0, 0, 0]
+    for o, w in zip(outs, want):
+        assert (o == w).all()

@@ -120,3 +120,23 @@ def test_other_seed(built_oracle, built_lib):
     img = G(64, 64, 3, 77)
     mask = centered_mask(64, 64, 20, 20)
     _compare_simple(img, mask, abi.T_RGB, abi.make_params(0, 0, 2, 0.5, 0.117, 20, 80), seed=4242)
+
+
+def test_larger_job_is_deterministic_and_exact(built_oracle, built_lib):
+    """9216 targets, many epochs in flight: five runs must be identical to each other and to the oracle."""
+    img = G(256, 256, 3, 5150)
+    mask = centered_mask(256, 256, 96, 96)
+    st, ps = _compare_simple(img, mask, abi.T_RGB, None)
+    first = None
+    for _ in range(4):
+        out = img.copy()
+        assert api.image_synth(out, mask, abi.T_RGB, None) == 0
+        if first is None:
+            first = out
+        assert (out == first).all()
+        assert api.last_stats()["sum_best"] == st["sum_best"]
+
+
+def test_render_texture_bench_shape_small(built_oracle, built_lib):
+    """cfg2's shape at 1/8 scale: 128x128 target from a 64x64 corpus, ctx 0, 9/200 (dependency-heavy pass 0)."""
+    _engine_case(128, 128, 64, 64, 3, 0, False, abi.make_params(0, 0, 0, 0.5, 0.117, 9, 200), True)
