@@ -61,6 +61,14 @@ def workload(name, seed_shift=0, scale=1.0):
         return dict(name="cfg5 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=False,
                     tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+    if name.startswith("heal:"):   # heal:<image side>:<hole side>  (experiments)
+        _, side, hole = name.split(":")
+        side, hole = int(side), int(hole)
+        img = G(side, side, 3, 4321 + seed_shift)
+        m = centered_mask(side, side, hole, hole)
+        return dict(name="heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (side, side, hole, hole),
+                    params=abi.default_params(), n_color=3, n_map=0, alpha=False,
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
     raise SystemExit("unknown workload %s" % name)
 
 
@@ -145,7 +153,7 @@ def cpu_reference_run(wname, scale, steps, warmup, procs, libname="ref_rand_1t")
 
 
 def reference_sample_scale(wname):
-    return {"cfg2": 0.25, "cfg1": 1.0, "cfg5": 0.25}[wname]
+    return {"cfg2": 0.25, "cfg1": 1.0, "cfg5": 0.25}.get(wname, 1.0)
 
 
 def run_reference(a):
@@ -305,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg5"])
+    ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

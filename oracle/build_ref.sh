@@ -54,4 +54,13 @@ mk_tree "$TMP/t8" 1
   done
   gcc $CFLAGS -c "$HERE/grand_mt19937.c" -o grand_mt19937.o
   gcc -shared -o "$OUT/libref_mt_1t.so" *.o -lm )
+# The reference's own test harness (src/testSynth.c, minus its duplicate include at line 9), compiled unchanged
+# and linked against THIS repo's library instead of the reference objects: the drop-in check of INTEGRATION.md 3.1.
+PROD="$HERE/../resynthesizer_b200/lib"
+if [ -f "$PROD/libresynthesizer_b200.so" ]; then
+  sed '9d' "$REF/src/testSynth.c" > "$TMP/testSynth.c"
+  gcc -DSYNTH_LIB_ALONE -w -I "$TMP/t1" "$TMP/testSynth.c" -o "$OUT/testSynth_b200" \
+      -L "$PROD" -lresynthesizer_b200 -Wl,-rpath,'$ORIGIN/../../resynthesizer_b200/lib'
+  ( cd "$TMP/t1" && gcc $CFLAGS -I "$TMP/t1" -o "$OUT/testSynth_ref" "$TMP/testSynth.c" $SRCS -lm )
+fi
 echo "built: $(ls "$OUT")"

@@ -124,6 +124,59 @@ __device__ __forceinline__ void rs_tma_load_1d(void *smem_dst, const void *gmem_
                : "memory");
 }
 
+// ---- up to RS_CHUNK neighbour compares of one candidate: the body of computeBestFit's loop ----
+// (lib/synthesize.h:288-383).  All gathers are issued before the first table lookup.
+template <bool MAPS>
+__device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, const uint32_t *lutc, const uint32_t *lutm,
+                                                 const uint32_t *s_off, const uint32_t *s_pix, const uint32_t *s_map,
+                                                 uint32_t K, int cx, int cy, uint32_t k0, uint32_t &nCompares) {
+  const unsigned lane = threadIdx.x & 31u;
+  uint32_t cp[RS_CHUNK], cm[RS_CHUNK];
+#pragma unroll
+  for (int u = 0; u < RS_CHUNK; u++) {
+    const uint32_t kk = k0 + u;
+    cp[u] = 0u;  // mask byte 0: clipped or masked corpus point (lib/engine.c:505-517)
+    cm[u] = 0u;
+    if (kk < K) {
+      const uint32_t o = s_off[kk];
+      const int x = cx + rs_off_x(o), y = cy + rs_off_y(o);
+      if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
+        const size_t a = (size_t)y * (size_t)J.cw + (size_t)x;
+        if (MAPS) {
+          const uint2 t = __ldg(J.corpus8 + a);
+          cp[u] = t.x;
+          cm[u] = t.y;
+        } else {
+          cp[u] = __ldg(J.corpus4 + a);
+        }
+      }
+    }
+  }
+  uint32_t sum = 0;
+#pragma unroll
+  for (int u = 0; u < RS_CHUNK; u++) {
+    const uint32_t kk = k0 + u;
+    if (kk < K) {
+      nCompares++;
+      if ((cp[u] & 0xFFu) != 0xFFu) {
+        sum += J.penalty;  // MAX_WEIGHT*img_match_bpp + mapsMetric[0]*map_match_bpp (synthesize.h:306)
+      } else {
+        if (kk) {  // the target point itself carries no colour term (synthesize.h:328)
+          const uint32_t d = __vabsdiffu4(cp[u], s_pix[kk]);
+          sum += lutc[((d >> 8) & 0xFFu) * 32u + lane] + lutc[((d >> 16) & 0xFFu) * 32u + lane] +
+                 lutc[(d >> 24) * 32u + lane];
+        }
+        if (MAPS) {  // map terms also for the target point itself (synthesize.h:342-355)
+          const uint32_t d = __vabsdiffu4(cm[u], s_map[kk]);
+          sum += lutm[(d & 0xFFu) * 32u + lane] + lutm[((d >> 8) & 0xFFu) * 32u + lane] +
+                 lutm[((d >> 16) & 0xFFu) * 32u + lane];
+        }
+      }
+    }
+  }
+  return sum;
+}
+
 // ---- the patch distance with early-out, one candidate per lane, lanes refilled dynamically ----
 // Restates computeBestFit (lib/synthesize.h:266-400) for a whole candidate list at once.  Sequential
 // semantics = the FIRST candidate in list order with the minimum full sum wins (strict '<' to better,
@@ -162,48 +215,7 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, const uint32_t *lu
     if (!__any_sync(RS_FULL, active)) break;
     bool finished = false;
     if (active) {
-      uint32_t cp[RS_CHUNK], cm[RS_CHUNK];
-#pragma unroll
-      for (int u = 0; u < RS_CHUNK; u++) {
-        const uint32_t kk = k + u;
-        cp[u] = 0u;  // mask byte 0: clipped or masked corpus point (lib/engine.c:505-517)
-        cm[u] = 0u;
-        if (kk < K) {
-          const uint32_t o = s_off[kk];
-          const int x = cx + rs_off_x(o), y = cy + rs_off_y(o);
-          if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
-            const size_t a = (size_t)y * (size_t)J.cw + (size_t)x;
-            if (MAPS) {
-              const uint2 t = __ldg(J.corpus8 + a);
-              cp[u] = t.x;
-              cm[u] = t.y;
-            } else {
-              cp[u] = __ldg(J.corpus4 + a);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < RS_CHUNK; u++) {
-        const uint32_t kk = k + u;
-        if (kk < K) {
-          nCompares++;
-          if ((cp[u] & 0xFFu) != 0xFFu) {
-            partial += J.penalty;  // MAX_WEIGHT*img_match_bpp + mapsMetric[0]*map_match_bpp (synthesize.h:306)
-          } else {
-            if (kk) {  // the target point itself carries no colour term (synthesize.h:328)
-              const uint32_t d = __vabsdiffu4(cp[u], s_pix[kk]);
-              partial += lutc[((d >> 8) & 0xFFu) * 32u + lane] + lutc[((d >> 16) & 0xFFu) * 32u + lane] +
-                         lutc[(d >> 24) * 32u + lane];
-            }
-            if (MAPS) {  // map terms also for the target point itself (synthesize.h:342-355)
-              const uint32_t d = __vabsdiffu4(cm[u], s_map[kk]);
-              partial += lutm[(d & 0xFFu) * 32u + lane] + lutm[((d >> 8) & 0xFFu) * 32u + lane] +
-                         lutm[((d >> 16) & 0xFFu) * 32u + lane];
-            }
-          }
-        }
-      }
+      partial += rs_chunk_sum<MAPS>(J, lutc, lutm, s_off, s_pix, s_map, K, cx, cy, k, nCompares);
       k += RS_CHUNK;
       finished = (k >= K);
     }

@@ -256,19 +256,20 @@ struct WarpScratch {
   uint32_t aux[RS_MAX_NB];   // neighbour meta, later: neighbour source, later: compacted candidate list
 };
 
+struct VisitStats {  // per-warp counters, flushed once at kernel end
+  uint32_t visits = 0, compares = 0, issued = 0, scans = 0, heur = 0, skips = 0, perfect = 0, betters = 0;
+  unsigned long long evals = 0, sumbest = 0;
+};
+
+struct Visit {  // the visit a warp is working on (warp-uniform unless noted)
+  uint32_t v, K, nHeur, selfq, epoch_idx, hide_from, my_base;
+  unsigned long long selfw;  // lane 0 only: the visit's own state word of version `pass`
+};
+
+// Stage the replicated metric tables with one TMA bulk copy per table (whole CTA calls this).
 template <bool MAPS>
-__global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *lutm = lutc + RS_LUT_WORDS;  // only staged when MAPS
+__device__ __forceinline__ void rs_stage_tables(const RsDev &J, uint32_t *lutc, uint32_t *lutm, uint64_t *bar) {
   const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
-  WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + lut_bytes);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch) * RS_WARPS_PER_CTA);
-
-  RsCtrl *ctrl = J.ctrl;
-  if (rs_ld_u32_relaxed(&ctrl->stop)) return;
-
-  // Stage the replicated metric tables with one TMA bulk copy per table.
   if (threadIdx.x == 0) {
     rs_mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -278,285 +279,283 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
   }
   __syncthreads();
   rs_mbar_wait(bar, 0);
+}
 
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+// One warp: claim the next visit in order, gather its patch, wait for exactly the neighbour versions the
+// sequential loop would see, build the heuristic candidate list (S.aux[0..nHeur)).  False when the pass is exhausted.
+template <bool MAPS>
+__device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, WarpScratch &S, Visit &V, VisitStats &st) {
+  const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
-  WarpScratch &S = scratch[warp];
   const uint32_t pass = J.pass, pass_end = J.pass_end;
   const uint32_t tag = (pass + 1u) << 29;
+  // ---- claim the next visit, in order (lib/synthesize.h:480-482 with THREAD_LIMIT 1)
+  uint32_t v = 0;
+  if (lane == 0) {
+    v = atomicAdd(&ctrl->next[pass], 1u);
+    if (v < pass_end && (v & 4095u) == 0u) {  // progress tick + cancel poll (synthesize.h:493-497)
+      J.host_ticks[pass] = v + 1u;
+      if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
+        atomicExch(&ctrl->stop, 1u);
+        atomicAdd(&ctrl->next[pass], 0x40000000u);
+      }
+    }
+  }
+  v = __shfl_sync(RS_FULL, v, 0);
+  if (v >= pass_end) return false;
+  st.visits++;
 
-  uint32_t st_visits = 0, st_compares = 0, st_issued = 0, st_scans = 0, st_heur = 0, st_skips = 0, st_perfect = 0,
-           st_betters = 0;
-  unsigned long long st_evals = 0, st_sumbest = 0;
+  const uint32_t tpos = __ldg(J.targets + v);
+  const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
+  const uint32_t selfq = (uint32_t)py * (uint32_t)J.tw + (uint32_t)px;
 
-  while (true) {
-    // ---- claim the next visit, in order (lib/synthesize.h:480-482 with THREAD_LIMIT 1)
-    uint32_t v = 0;
-    if (lane == 0) {
-      v = atomicAdd(&ctrl->next[pass], 1u);
-      if (v < pass_end && (v & 4095u) == 0u) {  // progress tick + cancel poll (synthesize.h:493-497)
-        J.host_ticks[pass] = v + 1u;
-        if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
-          atomicExch(&ctrl->stop, 1u);
-          atomicAdd(&ctrl->next[pass], 0x40000000u);
+  // ---- gather the patch: self + nearest valued pixels (lib/synthesize.h:189-241)
+  if (lane == 0) {
+    S.off[0] = 0u;
+    S.q[0] = selfq;
+    S.aux[0] = v;
+  }
+  uint32_t count = 1;
+  if (pass == 0u && J.nb_lists != nullptr) {
+    // precomputed by k_gather_pass0; aux := 0 (< v+1) marks "target visited before me", else context
+    count = J.nb_counts[v];
+    const uint2 *lst = J.nb_lists + (size_t)v * (J.kmax - 1u);
+    for (uint32_t k = 1u + lane; k < count; k += 32) {
+      const uint2 e = __ldg(lst + (k - 1u));
+      S.off[k] = e.x;
+      S.q[k] = e.y & ~RS_TARGET_FLAG;
+      S.aux[k] = (e.y & RS_TARGET_FLAG) ? 0u : RS_CTX_VALUED;
+    }
+  } else {
+    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
+      const uint32_t j = base + lane;
+      bool ok = false;
+      uint32_t o = 0, q = 0, m = 0;
+      if (j < J.nOff) {
+        o = __ldg(J.offsets + j);
+        int x = px + rs_off_x(o), y = py + rs_off_y(o);
+        bool in = true;  // wrap when tiling, else clip (lib/synthesize.h:81-113); |offset| < image size
+        if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+        else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+        if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+        else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+        if (in) {
+          q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+          m = __ldg(J.meta + q);
+          // valued: usable context, or a target point already synthesised (in pass 0: visited before me)
+          ok = (pass == 0u) ? (m == RS_CTX_VALUED || m < v) : (m != RS_NEVER);
+        }
+      }
+      const unsigned b = __ballot_sync(RS_FULL, ok);
+      const uint32_t slot = count + __popc(b & lt);
+      if (ok && slot < J.kmax) {
+        S.off[slot] = o;
+        S.q[slot] = q;
+        S.aux[slot] = m;
+      }
+      count += __popc(b);
+      st.scans += (lane == 0) ? min(32u, J.nOff - base) : 0u;
+    }
+  }
+  const uint32_t K = min(count, J.kmax);
+  __syncwarp();
+
+  // ---- wait for exactly the versions the sequential order would see, then read them (one 64-bit load each)
+  unsigned long long selfw = 0;
+  for (uint32_t k = lane; k < K; k += 32) {
+    const uint32_t q = S.q[k], m = S.aux[k];
+    uint32_t r = 0;
+    if (k == 0) r = pass;
+    else if (m != RS_CTX_VALUED) {
+      if (m < v && m < pass_end) r = pass + 1u;
+      else for (uint32_t p2 = 0; p2 < pass; p2++) r += (m < J.ends[p2]) ? 1u : 0u;
+    }
+    const unsigned long long *wp = J.W + 2 * (size_t)q + (r & 1u);
+    unsigned long long w = rs_ld_state(wp);
+    while (((unsigned)(w >> 24) & 0xFFu) != r) {
+      __nanosleep(40);
+      w = rs_ld_state(wp);
+    }
+    if (k == 0) selfw = w;
+    S.pix[k] = ((uint32_t)w & 0xFFFFFFu) << 8;
+    if (MAPS) S.map[k] = __ldg(J.tmaps + q);
+    S.aux[k] = (uint32_t)(w >> 32);  // source of this neighbour, or RS_NO_SRC
+  }
+  __syncwarp();
+
+  // ---- heuristic 1 + 2 candidates (lib/synthesize.h:537-580): source of neighbour minus its offset,
+  //      dropped if outside/masked corpus, if this target index was the last VISIBLE prober of that corpus
+  //      point (rs_device.cuh: epochs), or if an earlier neighbour proposes the same point.
+  uint32_t mycand[2];
+#pragma unroll
+  for (int rnd = 0; rnd < 2; rnd++) {
+    const uint32_t k = lane + 32u * rnd;
+    uint32_t c = RS_NO_SRC;
+    if (k < K) {
+      const uint32_t src = S.aux[k];
+      if (src != RS_NO_SRC) {
+        const uint32_t o = S.off[k];
+        const int x = (int)(src & 0xFFFFu) - rs_off_x(o), y = (int)(src >> 16) - rs_off_y(o);
+        if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
+          const size_t a = (size_t)y * J.cw + x;
+          const uint32_t cm = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
+          if ((cm & 0xFFu) == 0xFFu) c = (uint32_t)x | ((uint32_t)y << 16);
         }
       }
     }
-    v = __shfl_sync(RS_FULL, v, 0);
-    if (v >= pass_end) break;
-    st_visits++;
-
-    const uint32_t tpos = __ldg(J.targets + v);
-    const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
-    const uint32_t selfq = (uint32_t)py * (uint32_t)J.tw + (uint32_t)px;
-
-    // ---- gather the patch: self + nearest valued pixels (lib/synthesize.h:189-241)
-    if (lane == 0) {
-      S.off[0] = 0u;
-      S.q[0] = selfq;
-      S.aux[0] = v;
-    }
-    uint32_t count = 1;
-    if (pass == 0u && J.nb_lists != nullptr) {
-      // precomputed by k_gather_pass0; aux := 0 (< v+1) marks "target visited before me", else context
-      count = J.nb_counts[v];
-      const uint2 *lst = J.nb_lists + (size_t)v * (J.kmax - 1u);
-      for (uint32_t k = 1u + lane; k < count; k += 32) {
-        const uint2 e = __ldg(lst + (k - 1u));
-        S.off[k] = e.x;
-        S.q[k] = e.y & ~RS_TARGET_FLAG;
-        S.aux[k] = (e.y & RS_TARGET_FLAG) ? 0u : RS_CTX_VALUED;
-      }
-    } else {
-      for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
-        const uint32_t j = base + lane;
-        bool ok = false;
-        uint32_t o = 0, q = 0, m = 0;
-        if (j < J.nOff) {
-          o = __ldg(J.offsets + j);
-          int x = px + rs_off_x(o), y = py + rs_off_y(o);
-          bool in = true;  // wrap when tiling, else clip (lib/synthesize.h:81-113); |offset| < image size
-          if (x < 0) { if (J.htile) x += J.tw; else in = false; }
-          else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
-          if (y < 0) { if (J.vtile) y += J.th; else in = false; }
-          else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
-          if (in) {
-            q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
-            m = __ldg(J.meta + q);
-            // valued: usable context, or a target point already synthesised (in pass 0: visited before me)
-            ok = (pass == 0u) ? (m == RS_CTX_VALUED || m < v) : (m != RS_NEVER);
-          }
-        }
-        const unsigned b = __ballot_sync(RS_FULL, ok);
-        const uint32_t slot = count + __popc(b & lt);
-        if (ok && slot < J.kmax) {
-          S.off[slot] = o;
-          S.q[slot] = q;
-          S.aux[slot] = m;
-        }
-        count += __popc(b);
-        st_scans += (lane == 0) ? min(32u, J.nOff - base) : 0u;
-      }
-    }
-    const uint32_t K = min(count, J.kmax);
-    __syncwarp();
-
-    // ---- wait for exactly the versions the sequential order would see, then read them (one 64-bit load each)
-    unsigned long long selfw = 0;
-    for (uint32_t k = lane; k < K; k += 32) {
-      const uint32_t q = S.q[k], m = S.aux[k];
-      uint32_t r = 0;
-      if (k == 0) r = pass;
-      else if (m != RS_CTX_VALUED) {
-        if (m < v && m < pass_end) r = pass + 1u;
-        else for (uint32_t p2 = 0; p2 < pass; p2++) r += (m < J.ends[p2]) ? 1u : 0u;
-      }
-      const unsigned long long *wp = J.W + 2 * (size_t)q + (r & 1u);
-      unsigned long long w = rs_ld_state(wp);
-      while (((unsigned)(w >> 24) & 0xFFu) != r) {
-        __nanosleep(40);
-        w = rs_ld_state(wp);
-      }
-      if (k == 0) selfw = w;
-      S.pix[k] = ((uint32_t)w & 0xFFFFFFu) << 8;
-      if (MAPS) S.map[k] = __ldg(J.tmaps + q);
-      S.aux[k] = (uint32_t)(w >> 32);  // source of this neighbour, or RS_NO_SRC
-    }
-    __syncwarp();
-
-    // ---- heuristic 1 + 2 candidates (lib/synthesize.h:537-580): source of neighbour minus its offset,
-    //      dropped if outside/masked corpus, if this target index was the last VISIBLE prober of that corpus
-    //      point (rs_device.cuh: epochs), or if an earlier neighbour proposes the same point.
-    uint32_t mycand[2];
+    mycand[rnd] = c;
+    S.q[k] = c;
+  }
+  __syncwarp();
+  const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
+  const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
+  const uint32_t hide_base = tag | hide_from;
+  bool pskip[2] = {false, false};
+  for (int attempt = 0; attempt < 2; attempt++) {
+    bool any = false;
 #pragma unroll
     for (int rnd = 0; rnd < 2; rnd++) {
-      const uint32_t k = lane + 32u * rnd;
-      uint32_t c = RS_NO_SRC;
-      if (k < K) {
-        const uint32_t src = S.aux[k];
-        if (src != RS_NO_SRC) {
-          const uint32_t o = S.off[k];
-          const int x = (int)(src & 0xFFFFu) - rs_off_x(o), y = (int)(src >> 16) - rs_off_y(o);
-          if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
-            const size_t a = (size_t)y * J.cw + x;
-            const uint32_t cm = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
-            if ((cm & 0xFFu) == 0xFFu) c = (uint32_t)x | ((uint32_t)y << 16);
-          }
-        }
-      }
-      mycand[rnd] = c;
-      S.q[k] = c;
-    }
-    __syncwarp();
-    const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
-    const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
-    const uint32_t hide_base = tag | hide_from, my_base = tag | epoch0;
-    bool pskip[2] = {false, false};
-    for (int attempt = 0; attempt < 2; attempt++) {
-      bool any = false;
-#pragma unroll
-      for (int rnd = 0; rnd < 2; rnd++) {
-        const uint32_t c = mycand[rnd];
-        pskip[rnd] = false;
-        if (c != RS_NO_SRC) {
-          const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
-          uint32_t newest = 0u;  // newest visible stamp over the three epoch arrays; 0 = never probed
-#pragma unroll
-          for (int t = 0; t < 3; t++) {
-            const unsigned long long e = rs_ld_state(J.prober[t] + a);
-            const uint32_t h = (uint32_t)(e >> 32);
-            newest = max(newest, (h >= hide_base) ? (uint32_t)e : h);
-          }
-          pskip[rnd] = newest != 0u && (newest & RS_IDX_MASK) == v;
-          any |= pskip[rnd];
-        }
-      }
-      // A "skip" verdict can still be overturned by a straggler of epochs <= e-2 (a "keep" verdict cannot):
-      // only then wait until every such visit has published its stamps, and look again.
-      if (attempt == 1 || hide_from == 0u || !__any_sync(RS_FULL, any)) break;
-      if (lane == 0) {
-        while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
-        __threadfence();
-      }
-      __syncwarp();
-    }
-    uint32_t nHeur = 0;
-#pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
-      const uint32_t k = lane + 32u * rnd;
       const uint32_t c = mycand[rnd];
-      bool valid = (c != RS_NO_SRC);
-      if (valid) {
-        bool skip = pskip[rnd];
-        for (uint32_t k2 = 0; k2 < k && !skip; k2++) skip = (S.q[k2] == c);
-        if (skip) { valid = false; st_skips++; }
-      }
-      const unsigned b = __ballot_sync(RS_FULL, valid);
-      if (valid) S.aux[nHeur + __popc(b & lt)] = c;
-      nHeur += __popc(b);
-      __syncwarp();
-    }
-    // NOTE: S.aux (sources) is overwritten by the compacted candidate list; sources are no longer needed,
-    // and round 1 lanes read their own S.aux[k] before any lane writes (mycand computed above).
-
-    // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
-    uint32_t bestSum = 0xFFFFFFFFu;
-    int bestIdx = 0x7FFFFFFF;
-    const uint32_t *candlist = S.aux;
-    rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, 0, (int)nHeur,
-                        [&](int i) { return candlist[i]; }, bestSum, bestIdx, st_compares, st_issued);
-    const uint32_t seed = J.seed, nC = J.nC;
-    const uint32_t *cpts = J.corpus_pts;
-    if (bestSum != 0u)
-      rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
-                          [&](int i) { return __ldg(cpts + rs_range(rs_probe_hash(seed, pass, v, (uint32_t)i - nHeur), nC)); },
-                          bestSum, bestIdx, st_compares, st_issued);
-
-    // ---- commit (lib/synthesize.h:620-639): new colour + source only if the source changed; always publish
-    const bool bettered = bestIdx != 0x7FFFFFFF;
-    const uint32_t total = nHeur + J.probes;
-    const uint32_t seq_evals = !bettered ? 0u : (bestSum == 0u ? (uint32_t)bestIdx + 1u : total);
-    if (lane == 0) {
-      uint32_t colour = (uint32_t)selfw & 0xFFFFFFu, src = (uint32_t)(selfw >> 32);
-      if (bettered) {
-        const uint32_t bp = ((uint32_t)bestIdx < nHeur)
-                                ? candlist[bestIdx]
-                                : __ldg(cpts + rs_range(rs_probe_hash(seed, pass, v, (uint32_t)bestIdx - nHeur), nC));
-        if (bp != src) {
-          const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
-          const uint32_t cpx = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
-          colour = cpx >> 8;
-          src = bp;
-          st_betters++;
+      pskip[rnd] = false;
+      if (c != RS_NO_SRC) {
+        const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+        uint32_t newest = 0u;  // newest visible stamp over the three epoch arrays; 0 = never probed
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const unsigned long long e = rs_ld_state(J.prober[t] + a);
+          const uint32_t h = (uint32_t)(e >> 32);
+          newest = max(newest, (h >= hide_base) ? (uint32_t)e : h);
         }
-        st_sumbest += bestSum;
+        pskip[rnd] = newest != 0u && (newest & RS_IDX_MASK) == v;
+        any |= pskip[rnd];
       }
-      rs_st_state(J.W + 2 * (size_t)selfq + ((pass + 1u) & 1u),
-                  ((unsigned long long)src << 32) | ((unsigned long long)(pass + 1u) << 24) | colour);
-      st_evals += seq_evals;
-      st_heur += min(nHeur, seq_evals);
-      st_perfect += (bettered && bestSum == 0u) ? 1u : 0u;
     }
-    // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
-    const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
-    if (stampEnd > 0u && hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
-      if (lane == 0) {
-        while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);
-        __threadfence();
-      }
-      __syncwarp();
-    }
-    for (uint32_t i = lane; i < stampEnd; i += 32) {
-      const uint32_t c = candlist[i];
-      unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
-      const uint32_t st = tag | v;
-      unsigned long long old = rs_ld_state(pp);
-      while (true) {
-        const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
-        const unsigned long long nw = (hi >= my_base) ? (((unsigned long long)max(hi, st) << 32) | lo)
-                                                      : (((unsigned long long)st << 32) | hi);
-        if (nw == old) break;
-        const unsigned long long prev = atomicCAS(pp, old, nw);
-        if (prev == old) break;
-        old = prev;
-      }
+    // A "skip" verdict can still be overturned by a straggler of epochs <= e-2 (a "keep" verdict cannot):
+    // only then wait until every such visit has published its stamps, and look again.
+    if (attempt == 1 || hide_from == 0u || !__any_sync(RS_FULL, any)) break;
+    if (lane == 0) {
+      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
+      __threadfence();
     }
     __syncwarp();
-    if (lane == 0) {  // publish: this visit is complete (state word written, stamps merged)
+  }
+  uint32_t nHeur = 0;
+#pragma unroll
+  for (int rnd = 0; rnd < 2; rnd++) {
+    const uint32_t k = lane + 32u * rnd;
+    const uint32_t c = mycand[rnd];
+    bool valid = (c != RS_NO_SRC);
+    if (valid) {
+      bool skip = pskip[rnd];
+      for (uint32_t k2 = 0; k2 < k && !skip; k2++) skip = (S.q[k2] == c);
+      if (skip) { valid = false; st.skips++; }
+    }
+    const unsigned b = __ballot_sync(RS_FULL, valid);
+    if (valid) S.aux[nHeur + __popc(b & lt)] = c;  // sources in S.aux are no longer needed (mycand holds mine)
+    nHeur += __popc(b);
+    __syncwarp();
+  }
+  V.v = v; V.K = K; V.nHeur = nHeur; V.selfq = selfq; V.epoch_idx = epoch_idx; V.hide_from = hide_from;
+  V.my_base = tag | epoch0; V.selfw = selfw;
+  return true;
+}
+
+// One warp: commit the winner (lib/synthesize.h:620-639), merge the heuristic-2 stamps, publish completion.
+template <bool MAPS>
+__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, const WarpScratch &S, const Visit &V,
+                                                uint32_t bestSum, int bestIdx, VisitStats &st) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t pass = J.pass, pass_end = J.pass_end, v = V.v, nHeur = V.nHeur;
+  const uint32_t tag = (pass + 1u) << 29;
+  const uint32_t *candlist = S.aux;
+  const bool bettered = bestIdx != 0x7FFFFFFF;
+  const uint32_t total = nHeur + J.probes;
+  const uint32_t seq_evals = !bettered ? 0u : (bestSum == 0u ? (uint32_t)bestIdx + 1u : total);
+  if (lane == 0) {  // new colour + source only if the source changed; the new version is always published
+    uint32_t colour = (uint32_t)V.selfw & 0xFFFFFFu, src = (uint32_t)(V.selfw >> 32);
+    if (bettered) {
+      const uint32_t bp = ((uint32_t)bestIdx < nHeur)
+                              ? candlist[bestIdx]
+                              : __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.nC));
+      if (bp != src) {
+        const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
+        const uint32_t cpx = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
+        colour = cpx >> 8;
+        src = bp;
+        st.betters++;
+      }
+      st.sumbest += bestSum;
+    }
+    rs_st_state(J.W + 2 * (size_t)V.selfq + ((pass + 1u) & 1u),
+                ((unsigned long long)src << 32) | ((unsigned long long)(pass + 1u) << 24) | colour);
+    st.evals += seq_evals;
+    st.heur += min(nHeur, seq_evals);
+    st.perfect += (bettered && bestSum == 0u) ? 1u : 0u;
+  }
+  // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
+  const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
+  if (stampEnd > 0u && V.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
+    if (lane == 0) {
+      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < V.epoch_idx) __nanosleep(100);
       __threadfence();
-      const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
-      if (atomicAdd(&ctrl->epoch_done[pass][epoch_idx], 1u) + 1u == esize) {
-        // last visit of its epoch: move the watermark over every leading epoch that is now complete
-        while (true) {
-          const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]);
-          const uint32_t first = wmk * J.epoch_len;
-          if (first >= pass_end) break;
-          if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk]) != min(J.epoch_len, pass_end - first)) break;
-          __threadfence();
-          atomicCAS(&ctrl->epoch_wm[pass], wmk, wmk + 1u);
-        }
+    }
+    __syncwarp();
+  }
+  for (uint32_t i = lane; i < stampEnd; i += 32) {
+    const uint32_t c = candlist[i];
+    unsigned long long *pp = J.prober[V.epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+    const uint32_t stp = tag | v;
+    unsigned long long old = rs_ld_state(pp);
+    while (true) {
+      const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
+      const unsigned long long nw = (hi >= V.my_base) ? (((unsigned long long)max(hi, stp) << 32) | lo)
+                                                      : (((unsigned long long)stp << 32) | hi);
+      if (nw == old) break;
+      const unsigned long long prev = atomicCAS(pp, old, nw);
+      if (prev == old) break;
+      old = prev;
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {  // publish: this visit is complete (state word written, stamps merged)
+    __threadfence();
+    const uint32_t epoch0 = V.epoch_idx * J.epoch_len;
+    const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
+    if (atomicAdd(&ctrl->epoch_done[pass][V.epoch_idx], 1u) + 1u == esize) {
+      // last visit of its epoch: move the watermark over every leading epoch that is now complete
+      while (true) {
+        const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]);
+        const uint32_t first = wmk * J.epoch_len;
+        if (first >= pass_end) break;
+        if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk]) != min(J.epoch_len, pass_end - first)) break;
+        __threadfence();
+        atomicCAS(&ctrl->epoch_wm[pass], wmk, wmk + 1u);
       }
     }
   }
+}
 
-  // ---- flush per-warp statistics
-  st_compares = __reduce_add_sync(RS_FULL, st_compares);
-  st_issued = __reduce_add_sync(RS_FULL, st_issued);
-  st_skips = __reduce_add_sync(RS_FULL, st_skips);
-  if (lane == 0 && st_visits) {
-    atomicAdd(&ctrl->visits, (unsigned long long)st_visits);
-    atomicAdd(&ctrl->pass_visits[pass], (unsigned long long)st_visits);
-    atomicAdd(&ctrl->evals, st_evals);
-    atomicAdd(&ctrl->evals_issued, (unsigned long long)st_issued);
-    atomicAdd(&ctrl->compares, (unsigned long long)st_compares);
-    atomicAdd(&ctrl->offset_scans, (unsigned long long)st_scans);
-    atomicAdd(&ctrl->heur_evals, (unsigned long long)st_heur);
-    atomicAdd(&ctrl->heur_skips, (unsigned long long)st_skips);
-    atomicAdd(&ctrl->perfect, (unsigned long long)st_perfect);
-    atomicAdd(&ctrl->sum_best[pass], st_sumbest);
-    atomicAdd(&ctrl->betters[pass], st_betters);
+// Whole CTA, at kernel end: flush the per-warp counters; the last CTA out decides whether later passes run
+// (lib/refiner.h:111): (float)betters/n < 0.1.
+__device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, VisitStats &st) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t pass = J.pass;
+  st.compares = __reduce_add_sync(RS_FULL, st.compares);
+  st.issued = __reduce_add_sync(RS_FULL, st.issued);
+  st.skips = __reduce_add_sync(RS_FULL, st.skips);
+  if (lane == 0 && (st.visits | st.compares | st.issued)) {
+    atomicAdd(&ctrl->visits, (unsigned long long)st.visits);
+    atomicAdd(&ctrl->pass_visits[pass], (unsigned long long)st.visits);
+    atomicAdd(&ctrl->evals, st.evals);
+    atomicAdd(&ctrl->evals_issued, (unsigned long long)st.issued);
+    atomicAdd(&ctrl->compares, (unsigned long long)st.compares);
+    atomicAdd(&ctrl->offset_scans, (unsigned long long)st.scans);
+    atomicAdd(&ctrl->heur_evals, (unsigned long long)st.heur);
+    atomicAdd(&ctrl->heur_skips, (unsigned long long)st.skips);
+    atomicAdd(&ctrl->perfect, (unsigned long long)st.perfect);
+    atomicAdd(&ctrl->sum_best[pass], st.sumbest);
+    atomicAdd(&ctrl->betters[pass], st.betters);
   }
-  // ---- last CTA out decides whether later passes run (lib/refiner.h:111): (float)betters/n < 0.1
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -568,6 +567,139 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
       if ((double)((float)b / (float)J.nT) < J.terminate_fraction) atomicExch(&ctrl->stop, 1u);
     }
   }
+}
+
+// ---- throughput mode: one warp per visit -------------------------------------------------------------------
+template <bool MAPS>
+__global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
+  uint32_t *lutm = lutc + RS_LUT_WORDS;  // only staged when MAPS
+  const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
+  WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + lut_bytes);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch) * RS_WARPS_PER_CTA);
+  RsCtrl *ctrl = J.ctrl;
+  if (rs_ld_u32_relaxed(&ctrl->stop)) return;
+  rs_stage_tables<MAPS>(J, lutc, lutm, bar);
+
+  WarpScratch &S = scratch[threadIdx.x >> 5];
+  VisitStats st;
+  Visit V;
+  while (rs_visit_prepare<MAPS>(J, ctrl, S, V, st)) {
+    // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
+    uint32_t bestSum = 0xFFFFFFFFu;
+    int bestIdx = 0x7FFFFFFF;
+    const uint32_t *candlist = S.aux;
+    const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = J.nC;
+    const uint32_t *cpts = J.corpus_pts;
+    rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, V.K, 0, (int)nHeur,
+                        [&](int i) { return candlist[i]; }, bestSum, bestIdx, st.compares, st.issued);
+    if (bestSum != 0u)
+      rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, V.K, (int)nHeur, (int)(nHeur + J.probes),
+                          [&](int i) { return __ldg(cpts + rs_range(rs_probe_hash(seed, pass, v, (uint32_t)i - nHeur), nC)); },
+                          bestSum, bestIdx, st.compares, st.issued);
+    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, st);
+  }
+  rs_pass_epilogue(J, ctrl, st);
+}
+
+// ---- latency mode: a team of W warps per visit ---------------------------------------------------------------
+// Dependency-bound phases (pass 0, small holes) are limited by depth x per-visit latency, not by throughput.
+// Warp 0 of a team prepares the visit as above; then all W*32 lanes evaluate: (A) every (heuristic candidate,
+// 4-neighbour chunk) pair in one gather round, sums merged by shared-memory atomics; (B) the random probes, one
+// per lane per round, early-out against a team-shared packed best (sum << 32 | index, atomicMin) -- the same
+// "first candidate with the minimum full sum" rule, hence the same bits as the warp kernel.
+struct TeamShared {
+  unsigned long long best;
+  uint32_t hsum[RS_MAX_NB];
+  uint32_t v, K, nHeur, alive;
+};
+
+__device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool MAPS>
+__global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J, const unsigned W) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
+  uint32_t *lutm = lutc + RS_LUT_WORDS;
+  const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
+  WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + lut_bytes);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch) * RS_WARPS_PER_CTA);
+  TeamShared *tshared = reinterpret_cast<TeamShared *>(bar + 2);
+  RsCtrl *ctrl = J.ctrl;
+  if (rs_ld_u32_relaxed(&ctrl->stop)) return;
+  rs_stage_tables<MAPS>(J, lutc, lutm, bar);
+
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned team = warp / W, wt = warp % W, T = W * 32u, tid = wt * 32u + lane;
+  const unsigned bar_id = 1u + team;
+  WarpScratch &S = scratch[team];
+  TeamShared &TS = tshared[team];
+  const uint32_t pass = J.pass, seed = J.seed, nC = J.nC;
+  VisitStats st;
+  Visit V;
+  while (true) {
+    if (wt == 0) {
+      const bool ok = rs_visit_prepare<MAPS>(J, ctrl, S, V, st);
+      if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = V.v; TS.K = V.K; TS.nHeur = V.nHeur; TS.best = ~0ull; }
+      for (uint32_t i = lane; i < RS_MAX_NB; i += 32) TS.hsum[i] = 0u;
+    }
+    rs_team_sync(bar_id, T);
+    if (!TS.alive) break;
+    const uint32_t v = TS.v, K = TS.K, nHeur = TS.nHeur;
+    // ---- (A) heuristic candidates: all (candidate, chunk) pairs at once
+    const uint32_t nch = (K + RS_CHUNK - 1u) / RS_CHUNK;
+    for (uint32_t t = tid; t < nHeur * nch; t += T) {
+      const uint32_t ci = t / nch, k0 = (t % nch) * RS_CHUNK;
+      const uint32_t c = S.aux[ci];
+      const uint32_t part = rs_chunk_sum<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, (int)(c & 0xFFFFu), (int)(c >> 16), k0, st.compares);
+      atomicAdd(&TS.hsum[ci], part);
+      st.issued += (k0 == 0u) ? 1u : 0u;
+    }
+    rs_team_sync(bar_id, T);
+    if (wt == 0) {  // first candidate with the minimum full sum
+      unsigned long long key = ~0ull;
+      for (uint32_t i = lane; i < nHeur; i += 32) {
+        const unsigned long long k2 = ((unsigned long long)TS.hsum[i] << 32) | i;
+        key = k2 < key ? k2 : key;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(RS_FULL, key, o);
+        key = other < key ? other : key;
+      }
+      if (lane == 0) TS.best = key;
+    }
+    rs_team_sync(bar_id, T);
+    // ---- (B) random probes: one candidate per lane per round, early-out against the shared best
+    volatile unsigned long long *vbest = &TS.best;
+    if ((uint32_t)(*vbest >> 32) != 0u) {
+      for (uint32_t j = tid; j < J.probes; j += T) {
+        if ((uint32_t)(*vbest >> 32) == 0u) break;  // perfect match: nothing later is evaluated (synthesize.h:599)
+        const uint32_t c = __ldg(J.corpus_pts + rs_range(rs_probe_hash(seed, pass, v, j), nC));
+        const int cx = (int)(c & 0xFFFFu), cy = (int)(c >> 16);
+        const unsigned long long idx = (unsigned long long)(nHeur + j);
+        uint32_t partial = 0;
+        bool alive = true;
+        st.issued++;
+        for (uint32_t k0 = 0; k0 < K; k0 += RS_CHUNK) {
+          partial += rs_chunk_sum<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, cx, cy, k0, st.compares);
+          if ((((unsigned long long)partial << 32) | idx) > *vbest) { alive = false; break; }
+        }
+        if (alive) atomicMin(&TS.best, ((unsigned long long)partial << 32) | idx);
+      }
+    }
+    rs_team_sync(bar_id, T);
+    if (wt == 0) {
+      const unsigned long long key = TS.best;
+      const uint32_t bestSum = (key == ~0ull) ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
+      const int bestIdx = (key == ~0ull) ? 0x7FFFFFFF : (int)(uint32_t)key;
+      rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, st);
+    }
+  }
+  rs_pass_epilogue(J, ctrl, st);
 }
 
 // ------------------------------------------------------------------------------ standalone best-fit kernel
@@ -683,12 +815,13 @@ static void ws_free(Workspace *w) {
 }
 
 static size_t pass_smem(bool maps) {
-  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + sizeof(WarpScratch) * RS_WARPS_PER_CTA + 16;
+  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + sizeof(WarpScratch) * RS_WARPS_PER_CTA + 16 + sizeof(TeamShared) * 8;
 }
 template <bool MAPS>
 static int configure_pass_kernel(Workspace *w) {
   const size_t smem = pass_smem(MAPS);
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0, sms = 0;
   RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS>, RS_THREADS, smem));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
@@ -927,6 +1060,21 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   return D;
 }
 
+// Warps per visit for pass p: 1 = throughput kernel, 2/4/8 = team kernel (latency mode).  A pass is bound either by
+// visit throughput (4736 resident warps / W visits in flight) or by the depth of its dependency chains times the
+// latency of one visit; small jobs and pass 0 (long chains through freshly valued pixels) are the latter.
+// Thresholds from sweeps on B200 (profiles/team_width_sweep_r01.txt); RS_TEAM_P0 / RS_TEAM_PN override.
+static unsigned team_width(const RsJob *j, uint32_t p) {
+  const char *e = getenv(p == 0 ? "RS_TEAM_P0" : "RS_TEAM_PN");
+  if (e) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return (unsigned)w; }
+  const uint32_t n = j->nT;
+  const bool heavy = j->d.patch_size >= 16;  // visits long enough to amortise the team barriers
+  if (n <= 32768u) return 8;
+  if (n <= 200000u) return p == 0 ? 8 : 4;
+  if (n <= 600000u) return p == 0 ? 4 : 2;
+  return (p == 0 && heavy) ? 4 : 1;
+}
+
 extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
@@ -946,8 +1094,14 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   }
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     RsDev D = make_dev(j, p);
-    if (j->maps) k_synth_pass<true><<<grid, RS_THREADS, smem, s>>>(D);
-    else k_synth_pass<false><<<grid, RS_THREADS, smem, s>>>(D);
+    const unsigned W = team_width(j, p);
+    if (W <= 1) {
+      if (j->maps) k_synth_pass<true><<<grid, RS_THREADS, smem, s>>>(D);
+      else k_synth_pass<false><<<grid, RS_THREADS, smem, s>>>(D);
+    } else {
+      if (j->maps) k_synth_pass_team<true><<<grid, RS_THREADS, smem, s>>>(D, W);
+      else k_synth_pass_team<false><<<grid, RS_THREADS, smem, s>>>(D, W);
+    }
   }
   RS_CHECK(cudaGetLastError());
   RS_CHECK(cudaEventRecord(w->ev1, s));

@@ -99,3 +99,29 @@ def test_reentrant_from_threads(built_oracle, built_lib):
     assert errs == [0, 0, 0, 0]
     for o, w in zip(outs, want):
         assert (o == w).all()
+
+
+def test_reference_testsynth_binary_runs_on_this_library(built_lib):
+    """src/testSynth.c of the reference, compiled unchanged (oracle/build_ref.sh) and linked against
+    libresynthesizer_b200.so: every 'Result:' it prints must equal its own 'Expect:' line, and the error cases must
+    return the reference's codes (6, 3, 2, 5)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "testSynth_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/testSynth_b200 not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    assert "After\n00 00 00 00  00 00 00 01  00 00 00 00" in out
+    assert "00 00 00 00  00 00 00 01  00 00 00 00  \n00 00 00 00  00 00 00 00  00 00 00 08" in out
+    blocks = out.split("\n\n")
+    errors = [int(l.split(":")[-1]) for l in out.splitlines() if "imageSynth returned error" in l]
+    assert errors == [6, 3, 2, 5]
+    norm = lambda s: " ".join(s.split())
+    checked = 0
+    for name in ("Test mix of full transparency and opaque", "Test RGB w/o alpha", "Test Gray w/ alpha"):
+        seg = out[out.index(name):]
+        expect = seg[seg.index("Expect:\n") + 8:seg.index("Result:\n")]
+        result = seg[seg.index("Result:\n") + 8:].split("\n\n")[0]
+        assert norm(expect) == norm(result), (name, expect, result)
+        checked += 1
+    assert checked == 3
