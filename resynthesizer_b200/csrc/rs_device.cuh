@@ -81,6 +81,11 @@ __host__ __device__ __forceinline__ uint32_t rs_probe_hash(uint32_t seed, uint32
   h = rs_mix32(h ^ (index * 0x85EBCA6Bu + 0x165667B1u));
   return rs_mix32(h + probe * 0xC2B2AE35u);
 }
+// rs_probe_hash(seed,pass,index,probe) == rs_mix32(rs_probe_hash_visit(seed,pass,index) + probe * 0xC2B2AE35u)
+__host__ __device__ __forceinline__ uint32_t rs_probe_hash_visit(uint32_t seed, uint32_t pass, uint32_t index) {
+  const uint32_t h = rs_mix32(seed + 0x9E3779B9u * (pass + 1u));
+  return rs_mix32(h ^ (index * 0x85EBCA6Bu + 0x165667B1u));
+}
 __device__ __forceinline__ uint32_t rs_range(uint32_t r, uint32_t n) { return __umulhi(r, n); }
 
 // ---- single-copy-atomic 64-bit state word access (coherent at L2, no fence needed) ----
@@ -125,54 +130,49 @@ __device__ __forceinline__ void rs_tma_load_1d(void *smem_dst, const void *gmem_
 }
 
 // ---- up to RS_CHUNK neighbour compares of one candidate: the body of computeBestFit's loop ----
-// (lib/synthesize.h:288-383).  All gathers are issued before the first table lookup.
+// (lib/synthesize.h:288-383).  Branch-free: every gather is issued (clamped to pixel 0 when the neighbour falls
+// outside the corpus or past the patch) before the first table lookup; validity is applied by selects.
+// lutc/lutm point at THIS LANE's column of the replicated tables (stride 32 words per table row).
 template <bool MAPS>
 __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, const uint32_t *lutc, const uint32_t *lutm,
                                                  const uint32_t *s_off, const uint32_t *s_pix, const uint32_t *s_map,
                                                  uint32_t K, int cx, int cy, uint32_t k0, uint32_t &nCompares) {
-  const unsigned lane = threadIdx.x & 31u;
   uint32_t cp[RS_CHUNK], cm[RS_CHUNK];
+  bool inb[RS_CHUNK];
 #pragma unroll
   for (int u = 0; u < RS_CHUNK; u++) {
     const uint32_t kk = k0 + u;
-    cp[u] = 0u;  // mask byte 0: clipped or masked corpus point (lib/engine.c:505-517)
-    cm[u] = 0u;
-    if (kk < K) {
-      const uint32_t o = s_off[kk];
-      const int x = cx + rs_off_x(o), y = cy + rs_off_y(o);
-      if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
-        const size_t a = (size_t)y * (size_t)J.cw + (size_t)x;
-        if (MAPS) {
-          const uint2 t = __ldg(J.corpus8 + a);
-          cp[u] = t.x;
-          cm[u] = t.y;
-        } else {
-          cp[u] = __ldg(J.corpus4 + a);
-        }
-      }
+    const bool valid = kk < K;
+    const uint32_t o = s_off[valid ? kk : 0u];
+    const int x = cx + rs_off_x(o), y = cy + rs_off_y(o);
+    inb[u] = valid && (unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch;
+    const uint32_t a = inb[u] ? (uint32_t)y * (uint32_t)J.cw + (uint32_t)x : 0u;
+    if (MAPS) {
+      const uint2 t = __ldg(J.corpus8 + a);
+      cp[u] = t.x;
+      cm[u] = t.y;
+    } else {
+      cp[u] = __ldg(J.corpus4 + a);
+      cm[u] = 0u;
     }
   }
   uint32_t sum = 0;
 #pragma unroll
   for (int u = 0; u < RS_CHUNK; u++) {
     const uint32_t kk = k0 + u;
-    if (kk < K) {
-      nCompares++;
-      if ((cp[u] & 0xFFu) != 0xFFu) {
-        sum += J.penalty;  // MAX_WEIGHT*img_match_bpp + mapsMetric[0]*map_match_bpp (synthesize.h:306)
-      } else {
-        if (kk) {  // the target point itself carries no colour term (synthesize.h:328)
-          const uint32_t d = __vabsdiffu4(cp[u], s_pix[kk]);
-          sum += lutc[((d >> 8) & 0xFFu) * 32u + lane] + lutc[((d >> 16) & 0xFFu) * 32u + lane] +
-                 lutc[(d >> 24) * 32u + lane];
-        }
-        if (MAPS) {  // map terms also for the target point itself (synthesize.h:342-355)
-          const uint32_t d = __vabsdiffu4(cm[u], s_map[kk]);
-          sum += lutm[(d & 0xFFu) * 32u + lane] + lutm[((d >> 8) & 0xFFu) * 32u + lane] +
-                 lutm[((d >> 16) & 0xFFu) * 32u + lane];
-        }
-      }
+    const bool valid = kk < K;
+    const uint32_t ks = valid ? kk : 0u;
+    // inside the corpus and selected (mask 0xFF)? else the maximum weighted difference (synthesize.h:291-307)
+    const bool usable = inb[u] && (cp[u] & 0xFFu) == 0xFFu;
+    const uint32_t d = __vabsdiffu4(cp[u], s_pix[ks]);
+    uint32_t t = lutc[((d >> 8) & 0xFFu) * 32u] + lutc[((d >> 16) & 0xFFu) * 32u] + lutc[(d >> 24) * 32u];
+    t = kk ? t : 0u;  // the target point itself carries no colour term (synthesize.h:328)
+    if (MAPS) {       // map terms also for the target point itself (synthesize.h:342-355)
+      const uint32_t dm = __vabsdiffu4(cm[u], s_map[ks]);
+      t += lutm[(dm & 0xFFu) * 32u] + lutm[((dm >> 8) & 0xFFu) * 32u] + lutm[((dm >> 16) & 0xFFu) * 32u];
     }
+    sum += valid ? (usable ? t : J.penalty) : 0u;
+    nCompares += valid ? 1u : 0u;
   }
   return sum;
 }
@@ -187,8 +187,7 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, const uint32_t *lu
                                               const uint32_t *s_off, const uint32_t *s_pix, const uint32_t *s_map,
                                               uint32_t K, int begin, int end, CandFn cand_of, uint32_t &bestSum,
                                               int &bestIdx, uint32_t &nCompares, uint32_t &nIssued) {
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt = (1u << lane) - 1u;
+  const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
   int next = begin;  // warp-uniform
   int myIdx = -1;
   int cx = 0, cy = 0;

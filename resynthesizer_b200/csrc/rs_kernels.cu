@@ -254,6 +254,7 @@ struct WarpScratch {
   uint32_t map[RS_MAX_NB];   // neighbour map bytes
   uint32_t q[RS_MAX_NB];     // neighbour pixel index, later: packed heuristic candidate or RS_NO_SRC
   uint32_t aux[RS_MAX_NB];   // neighbour meta, later: neighbour source, later: compacted candidate list
+  uint32_t hsum[RS_MAX_NB];  // full patch distance of each heuristic candidate
 };
 
 struct VisitStats {  // per-warp counters, flushed once at kernel end
@@ -433,10 +434,10 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
     // A "skip" verdict can still be overturned by a straggler of epochs <= e-2 (a "keep" verdict cannot):
     // only then wait until every such visit has published its stamps, and look again.
     if (attempt == 1 || hide_from == 0u || !__any_sync(RS_FULL, any)) break;
-    if (lane == 0) {
+    // (no fence: the stamps are 64-bit CAS results and the words read next are strong L2 loads issued after this
+    //  poll returns; a fence.gpu here would also invalidate the SM's L1 on every visit)
+    if (lane == 0)
       while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
-      __threadfence();
-    }
     __syncwarp();
   }
   uint32_t nHeur = 0;
@@ -495,10 +496,8 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
   // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
   const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
   if (stampEnd > 0u && V.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
-    if (lane == 0) {
+    if (lane == 0)
       while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < V.epoch_idx) __nanosleep(100);
-      __threadfence();
-    }
     __syncwarp();
   }
   for (uint32_t i = lane; i < stampEnd; i += 32) {
@@ -517,8 +516,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
     }
   }
   __syncwarp();
-  if (lane == 0) {  // publish: this visit is complete (state word written, stamps merged)
-    __threadfence();
+  if (lane == 0) {  // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
     const uint32_t epoch0 = V.epoch_idx * J.epoch_len;
     const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
     if (atomicAdd(&ctrl->epoch_done[pass][V.epoch_idx], 1u) + 1u == esize) {
@@ -528,7 +526,6 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
         const uint32_t first = wmk * J.epoch_len;
         if (first >= pass_end) break;
         if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk]) != min(J.epoch_len, pass_end - first)) break;
-        __threadfence();
         atomicCAS(&ctrl->epoch_wm[pass], wmk, wmk + 1u);
       }
     }
@@ -583,6 +580,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
   rs_stage_tables<MAPS>(J, lutc, lutm, bar);
 
   WarpScratch &S = scratch[threadIdx.x >> 5];
+  lutc += threadIdx.x & 31u;  // this lane's column of the replicated tables
+  lutm += threadIdx.x & 31u;
   VisitStats st;
   Visit V;
   while (rs_visit_prepare<MAPS>(J, ctrl, S, V, st)) {
@@ -592,11 +591,32 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
     const uint32_t *candlist = S.aux;
     const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = J.nC;
     const uint32_t *cpts = J.corpus_pts;
-    rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, V.K, 0, (int)nHeur,
-                        [&](int i) { return candlist[i]; }, bestSum, bestIdx, st.compares, st.issued);
+    const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
+    // Heuristic candidates (few, and the likely winners): every (candidate, 4-neighbour chunk) pair gets a lane, so
+    // all lanes work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
+    {
+      const unsigned lane = threadIdx.x & 31u;
+      const uint32_t K = V.K, nch = (K + RS_CHUNK - 1u) / RS_CHUNK, inv = (65536u + nch - 1u) / nch;
+      for (uint32_t i = lane; i < nHeur; i += 32) S.hsum[i] = 0u;
+      __syncwarp();
+      for (uint32_t t = lane; t < nHeur * nch; t += 32) {
+        const uint32_t ci = (t * inv) >> 16, k0 = (t - ci * nch) * RS_CHUNK;  // t / nch, exact for t < 1024, nch <= 16
+        const uint32_t c = candlist[ci];
+        atomicAdd(&S.hsum[ci], rs_chunk_sum<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, (int)(c & 0xFFFFu), (int)(c >> 16), k0, st.compares));
+        st.issued += (k0 == 0u) ? 1u : 0u;
+      }
+      __syncwarp();
+      uint32_t msum = 0xFFFFFFFFu;
+      for (uint32_t i = lane; i < nHeur; i += 32) msum = min(msum, S.hsum[i]);
+      msum = __reduce_min_sync(RS_FULL, msum);
+      int midx = 0x7FFFFFFF;
+      for (uint32_t i = lane; i < nHeur; i += 32) midx = (S.hsum[i] == msum) ? min(midx, (int)i) : midx;
+      midx = __reduce_min_sync(RS_FULL, midx);
+      if (nHeur) { bestSum = msum; bestIdx = midx; }
+    }
     if (bestSum != 0u)
       rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, V.K, (int)nHeur, (int)(nHeur + J.probes),
-                          [&](int i) { return __ldg(cpts + rs_range(rs_probe_hash(seed, pass, v, (uint32_t)i - nHeur), nC)); },
+                          [&](int i) { return __ldg(cpts + rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
                           bestSum, bestIdx, st.compares, st.issued);
     rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, st);
   }
@@ -638,6 +658,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J
   WarpScratch &S = scratch[team];
   TeamShared &TS = tshared[team];
   const uint32_t pass = J.pass, seed = J.seed, nC = J.nC;
+  lutc += lane;  // this lane's column of the replicated tables
+  lutm += lane;
   VisitStats st;
   Visit V;
   while (true) {
@@ -675,10 +697,11 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J
     rs_team_sync(bar_id, T);
     // ---- (B) random probes: one candidate per lane per round, early-out against the shared best
     volatile unsigned long long *vbest = &TS.best;
+    const uint32_t hv = rs_probe_hash_visit(seed, pass, v);
     if ((uint32_t)(*vbest >> 32) != 0u) {
       for (uint32_t j = tid; j < J.probes; j += T) {
         if ((uint32_t)(*vbest >> 32) == 0u) break;  // perfect match: nothing later is evaluated (synthesize.h:599)
-        const uint32_t c = __ldg(J.corpus_pts + rs_range(rs_probe_hash(seed, pass, v, j), nC));
+        const uint32_t c = __ldg(J.corpus_pts + rs_range(rs_mix32(hv + j * 0xC2B2AE35u), nC));
         const int cx = (int)(c & 0xFFFFu), cy = (int)(c >> 16);
         const unsigned long long idx = (unsigned long long)(nHeur + j);
         uint32_t partial = 0;
@@ -726,6 +749,8 @@ __global__ void __launch_bounds__(RS_THREADS, 2)
   rs_mbar_wait(bar, 0);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   WarpScratch &S = scratch[warp];
+  lutc += lane;
+  lutm += lane;
   for (uint32_t v = blockIdx.x * RS_WARPS_PER_CTA + warp; v < n_visits; v += gridDim.x * RS_WARPS_PER_CTA) {
     const uint32_t nb0 = nb_begin[v], K = min(nb_begin[v + 1] - nb0, (uint32_t)RS_MAX_NB);
     for (uint32_t k = lane; k < K; k += 32) {
