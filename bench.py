@@ -61,6 +61,22 @@ def workload(name, seed_shift=0, scale=1.0):
         return dict(name="cfg5 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=False,
                     tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+    if name == "cfg3":      # large-hole inpaint 4096^2 RGBA, 25% masked (centred 2048^2), transparent band, 30/200
+        s_ = int(4096 * scale)
+        img = G(s_, s_, 4, 3 + seed_shift)
+        img[:, :, 3] = 255
+        img[:, s_ // 8:s_ // 8 + s_ // 16, 3] = 0       # 256-px transparent band at x in [512,768)
+        m = centered_mask(s_, s_, s_ // 2, s_ // 2)
+        return dict(name="cfg3 inpaint %dx%d RGBA, %dx%d hole, ctx1, patch 30, probes 200" % (s_, s_, s_ // 2, s_ // 2),
+                    params=abi.default_params(), n_color=3, n_map=0, alpha=True,
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=5)
+    if name == "cfg4":      # map-style transfer 2048^2 / 2048^2, RGB maps = the images, mapWeight 0.5, tiling, 9/200
+        s_ = int(2048 * scale)
+        tgt = G(s_, s_, 3, 4 + seed_shift); cor = G(s_, s_, 3, 5 + seed_shift)
+        full = np.full((s_, s_), 255, np.uint8)
+        return dict(name="cfg4 map-style %dx%d target / corpus, RGB maps, mapWeight 0.5, tiled, ctx1, patch 9, probes 200" % (s_, s_),
+                    params=abi.make_params(1, 1, 1, 0.5, 0.117, 9, 200), n_color=3, n_map=3, alpha=False,
+                    tmask=full, tgt=tgt, cmask=full.copy(), cor=cor, bpp=7, tmaps=tgt.copy(), cmaps=cor.copy())
     if name.startswith("heal:"):   # heal:<image side>:<hole side>  (experiments)
         _, side, hole = name.split(":")
         side, hole = int(side), int(hole)
@@ -73,9 +89,11 @@ def workload(name, seed_shift=0, scale=1.0):
 
 
 def pixmaps(w):
-    tp = np.ascontiguousarray(np.concatenate([w["tmask"][:, :, None], w["tgt"]], axis=2))
-    cp = np.ascontiguousarray(np.concatenate([w["cmask"][:, :, None], w["cor"]], axis=2))
-    return tp, cp
+    tparts = [w["tmask"][:, :, None], w["tgt"]]
+    cparts = [w["cmask"][:, :, None], w["cor"]]
+    if "tmaps" in w:
+        tparts.append(w["tmaps"]); cparts.append(w["cmaps"])
+    return np.ascontiguousarray(np.concatenate(tparts, axis=2)), np.ascontiguousarray(np.concatenate(cparts, axis=2))
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -153,7 +171,7 @@ def cpu_reference_run(wname, scale, steps, warmup, procs, libname="ref_rand_1t")
 
 
 def reference_sample_scale(wname):
-    return {"cfg2": 0.25, "cfg1": 1.0, "cfg5": 0.25}.get(wname, 1.0)
+    return {"cfg2": 0.25, "cfg1": 1.0, "cfg5": 0.25, "cfg3": 0.0625, "cfg4": 0.125}.get(wname, 1.0)
 
 
 def run_reference(a):

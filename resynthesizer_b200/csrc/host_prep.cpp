@@ -14,20 +14,36 @@ GRandMT::GRandMT(uint32_t seed) {
   mti_ = 624;
 }
 
-uint32_t GRandMT::next32() {
-  if (mti_ >= 624) {
-    for (int k = 0; k < 624; k++) {
-      const uint32_t y = (mt_[k] & 0x80000000u) | (mt_[(k + 1) % 624] & 0x7fffffffu);
-      mt_[k] = mt_[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
-    mti_ = 0;
+// Regenerates the 624-word state.  Three dependency-free segments (each reads only words that are already final),
+// so the compiler can vectorise them; then the whole block is tempered in place into out_[].
+void GRandMT::refill() {
+  uint32_t *mt = mt_;
+  auto twist = [](uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+  };
+#pragma GCC ivdep
+  for (int k = 0; k < 227; k++) mt[k] = twist(mt[k], mt[k + 1], mt[k + 397]);
+#pragma GCC ivdep
+  for (int k = 227; k < 454; k++) mt[k] = twist(mt[k], mt[k + 1], mt[k - 227]);
+#pragma GCC ivdep
+  for (int k = 454; k < 623; k++) mt[k] = twist(mt[k], mt[k + 1], mt[k - 227]);
+  mt[623] = twist(mt[623], mt[0], mt[396]);
+#pragma GCC ivdep
+  for (int k = 0; k < 624; k++) {
+    uint32_t y = mt[k];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    out_[k] = y;
   }
-  uint32_t y = mt_[mti_++];
-  y ^= y >> 11;
-  y ^= (y << 7) & 0x9d2c5680u;
-  y ^= (y << 15) & 0xefc60000u;
-  y ^= y >> 18;
-  return y;
+  mti_ = 0;
+}
+
+uint32_t GRandMT::next32() {
+  if (mti_ >= 624) refill();
+  return out_[mti_++];
 }
 
 uint32_t GRandMT::int_range(uint32_t n) {
@@ -118,10 +134,19 @@ void GRandMT::fill_int_range(uint32_t n, uint32_t *out, size_t count) {
   if (leftover >= n) leftover -= n;
   const uint32_t maxvalue = (n <= 0x80000000u) ? 0xffffffffu - leftover : n - 1u;
   const FastMod fm(n);
-  for (size_t i = 0; i < count; i++) {
-    uint32_t v;
-    do v = next32(); while (v > maxvalue);
-    out[i] = fm.mod(v);
+  size_t i = 0;
+  while (i < count) {
+    if (mti_ >= 624) refill();
+    const int avail = 624 - mti_;
+    const size_t want = count - i;
+    const int take = (size_t)avail < want ? avail : (int)want;
+    const uint32_t *src = out_ + mti_;
+    int used = 0;
+    for (; used < take && i < count; used++) {  // rejection is rare (< 2^-12 per draw for n <= 2^20)
+      const uint32_t v = src[used];
+      if (v <= maxvalue) out[i++] = fm.mod(v);
+    }
+    mti_ += used;
   }
 }
 

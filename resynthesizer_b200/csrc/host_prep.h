@@ -23,7 +23,9 @@ class GRandMT {
   uint32_t int_range(uint32_t n);  // g_rand_int_range(0, n)
   void fill_int_range(uint32_t n, uint32_t *out, size_t count);  // `count` successive int_range(n) draws
  private:
+  void refill();
   uint32_t mt_[624];
+  uint32_t out_[624];  // tempered outputs of the current block
   int mti_;
 };
 

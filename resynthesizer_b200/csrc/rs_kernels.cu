@@ -133,16 +133,41 @@ __global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__re
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t stride = J.kmax - 1u;
   unsigned long long scans = 0;
-  while (true) {
-    uint32_t v = 0;
-    if (lane == 0) v = atomicAdd(claim, 1u);
-    v = __shfl_sync(RS_FULL, v, 0);
-    if (v >= J.nT) break;
+  // static striding: the long scans were taken by k_gather_pass0_coop, the rest are short and uniform
+  const uint32_t first = *claim;  // = number of visits the cooperative kernel handles
+  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t v = first + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < J.nT; v += nwarps) {
     const uint32_t tpos = __ldg(J.targets + v);
     const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
     uint2 *out = lists + (size_t)v * stride;
     uint32_t count = 1;
-    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 128) {
+    // Late visits find their patch within the first few dozen offsets: one 32-wide step first, then 128-wide steps.
+    uint32_t base = 1;
+    {
+      const uint32_t j = base + lane;
+      uint32_t o = 0, q = 0, m = RS_NEVER;
+      if (j < J.nOff) {
+        o = __ldg(J.offsets + j);
+        int x = px + rs_off_x(o), y = py + rs_off_y(o);
+        bool in = true;
+        if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+        else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+        if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+        else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+        if (in) {
+          q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+          m = __ldg(J.meta + q);
+        }
+      }
+      const bool ok = (m == RS_CTX_VALUED) || (m < v);
+      const unsigned b = __ballot_sync(RS_FULL, ok);
+      const uint32_t slot = count + __popc(b & lt);
+      if (ok && slot < J.kmax) out[slot - 1u] = make_uint2(o, q | (m == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+      count += __popc(b);
+      scans += 32;
+      base += 32;
+    }
+    for (; base < J.nOff && count < J.kmax; base += 128) {
       uint32_t o[4], q[4], m[4];
       bool ok[4];
 #pragma unroll
