@@ -226,16 +226,31 @@ def run_ours(a):
     n = int((w["tmask"] != 0).sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
+    B = max(1, a.batch)
+
     def one_step(seed):
-        tp, cp = pixmaps(w)
         api.set_seed(seed)
+        if B == 1:
+            tp, cp = pixmaps(w)
+            flush.fill_(seed & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            err = api.engine(w["params"], fi, tp, cp)
+            wall = time.perf_counter() - t0
+            assert err == 0
+            return wall, api.last_stats(), tp, cp
+        # a step = a batch of B independent jobs kept `slots` at a time on this GPU (rs_engine_batch)
+        jobs = [(w["params"], fi) + pixmaps(w) for _ in range(B)]
         flush.fill_(seed & 0xFF)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        err = api.engine(w["params"], fi, tp, cp)
+        errs = api.engine_batch(jobs, a.slots)
         wall = time.perf_counter() - t0
-        assert err == 0
-        return wall, api.last_stats(), tp, cp
+        assert not any(errs)
+        st = {k: 0 for k in ("evals", "evals_issued", "compares", "visits", "offset_scans")}
+        st.update(ms_kernels=wall * 1000.0, ms_prep=0.0, ms_h2d=0.0, ms_d2h=0.0, passes_run=0,
+                  n_corpus=int((w["cmask"] == 255).sum()))
+        return wall, st, jobs[0][2], jobs[0][3]
 
     for i in range(a.warmup):
         one_step(1000 + i)
@@ -261,7 +276,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.MAX)
     kern_s, e2e_s, t_total = [float(x) for x in agg.tolist()]
-    total_px = world * a.steps * n
+    total_px = world * a.steps * n * B
     evals = sum(s["evals"] for s in stats); issued = sum(s["evals_issued"] for s in stats)
     compares = sum(s["compares"] for s in stats); visits = sum(s["visits"] for s in stats)
     scans = sum(s["offset_scans"] for s in stats)
@@ -311,7 +326,8 @@ def run_ours(a):
     line = {"metric": METRIC, "value": total_px / kern_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000.0 * t_total / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
-            "config": {"workload": w["name"], "parallelism": "independent jobs, %d GPU(s)" % world,
+            "config": {"workload": w["name"] + (" x %d jobs per step, %d in flight" % (B, a.slots) if B > 1 else ""),
+                       "parallelism": "independent jobs, %d GPU(s)" % world,
                        "l2": "256 MiB flush between steps", "api": "engine() full API"},
             "evals_per_s": world * evals / kern_s, "evals_issued_per_s": world * issued / kern_s,
             "compares_per_s": world * compares / kern_s, "compares_per_eval_issued": compares / max(issued, 1),
@@ -333,6 +349,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=1, help="jobs per step (rs_engine_batch); value is then wall-clock based")
+    ap.add_argument("--slots", type=int, default=8, help="jobs in flight per GPU in batch mode")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -131,6 +131,13 @@ typedef struct {
   float ms_prep, ms_h2d, ms_kernels, ms_d2h, ms_total; /* host prep / copies / device passes (CUDA events) */
 } RsStats;
 void rs_get_stats(RsStats *out);
+/* Batch of independent jobs (the reference has no such call; its users loop over engine()).  Runs `n_jobs`
+ * engine() calls on `slots` host threads that share the current CUDA device; each job's kernels take 1/slots of
+ * the SMs.  Small jobs are latency-bound on their dependency chains, so running several side by side multiplies
+ * throughput.  errors_out[i] receives engine()'s return value for job i.  Progress/cancel are not forwarded.
+ * Returns 0 if every job returned 0, else the first non-zero code. */
+int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
+                    Map *const *targetMaps, Map *const *corpusMaps, int slots, int *errors_out);
 /* rs_keep_result(1): engine() calls on this thread also fetch what rs_get_last_result() returns (off by default). */
 void rs_keep_result(int yes);
 /* Visit order and final source (best corpus point) of each target point of the last engine() call on this

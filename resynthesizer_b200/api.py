@@ -199,3 +199,25 @@ def device_sorted_offsets(tw, th, cw, ch):
     x = (out & 0xFFFF).astype(np.int16).astype(np.int32)
     y = (out >> 16).astype(np.int16).astype(np.int32)
     return np.stack([x, y], axis=1)
+
+
+def engine_batch(jobs, slots=4):
+    """rs_engine_batch(): jobs = list of (params, fi, target_pixmap, corpus_pixmap); pixmaps change in place.
+    Returns the list of per-job error codes."""
+    L = lib()
+    n = len(jobs)
+    P = (abi.TImageSynthParameters * n)(*[j[0] for j in jobs])
+    keep = []
+    FI = (C.POINTER(abi.TFormatIndices) * n)()
+    TM = (C.POINTER(abi.Map) * n)()
+    CM = (C.POINTER(abi.Map) * n)()
+    for i, (_p, fi, tp, cp) in enumerate(jobs):
+        tm, k1 = abi.make_map(tp)
+        cm, k2 = abi.make_map(cp)
+        keep.append((fi, tm, cm, k1, k2))
+        FI[i] = C.pointer(fi); TM[i] = C.pointer(tm); CM[i] = C.pointer(cm)
+    errs = (C.c_int * n)()
+    L.rs_engine_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    rc = L.rs_engine_batch(n, P, FI, TM, CM, int(slots), errs)
+    _check(rc)
+    return list(errs)

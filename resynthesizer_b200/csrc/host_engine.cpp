@@ -4,7 +4,9 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/resynthesizer.h"
@@ -17,6 +19,7 @@ thread_local std::string t_err;
 thread_local RsStats t_stats;
 thread_local uint32_t t_seed = 1198472u;  // lib/engine.c:643
 thread_local bool t_device_chosen = false;
+thread_local int t_device = -1;  // ordinal chosen by rs_set_device / ensure_device on this thread
 thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-target sources (tests, quality metrics)
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
 
@@ -32,6 +35,7 @@ int ensure_device() {
   if (rs_cuda_device_count() <= 0) { t_err = "no CUDA device available (this library has no CPU path)"; return RS_ERROR_CUDA; }
   if (rs_cuda_set_device(ordinal)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
   t_device_chosen = true;
+  t_device = ordinal;
   return 0;
 }
 
@@ -63,6 +67,7 @@ extern "C" void rs_keep_result(int yes) { t_keep_result = yes != 0; }
 extern "C" int rs_set_device(int ordinal) {
   if (rs_cuda_set_device(ordinal)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
   t_device_chosen = true;
+  t_device = ordinal;
   return 0;
 }
 
@@ -213,6 +218,41 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
   (void)t2;
   return 0;  // success, also when cancelled (lib/engine.c:689)
+}
+
+// ------------------------------------------------------------------------------- batch of independent jobs
+extern "C" void rs_cuda_set_job_slots(int slots);
+extern "C" int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
+                               Map *const *targetMaps, Map *const *corpusMaps, int slots, int *errors_out) {
+  if (n_jobs <= 0) return 0;
+  if (slots < 1) slots = 1;
+  if (slots > n_jobs) slots = n_jobs;
+  if (int e = ensure_device()) return e;
+  int device = 0;
+  if (const char *e = std::getenv("RESYNTH_CUDA_DEVICE")) device = std::atoi(e);
+  device = t_device >= 0 ? t_device : device;
+  const uint32_t seed = t_seed;
+  std::vector<int> errs(n_jobs, 0);
+  std::atomic<int> next{0};
+  rs_cuda_set_job_slots(slots);
+  auto worker = [&]() {
+    rs_set_device(device);
+    rs_set_seed(seed);
+    int dummy_cancel = 0;
+    for (int i = next.fetch_add(1); i < n_jobs; i = next.fetch_add(1))
+      errs[i] = engine(params[i], indices[i], targetMaps[i], corpusMaps[i], [](int, void *) {}, nullptr, &dummy_cancel);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < slots; t++) pool.emplace_back(worker);
+  worker();
+  for (auto &t : pool) t.join();
+  rs_cuda_set_job_slots(1);
+  int first = 0;
+  for (int i = 0; i < n_jobs; i++) {
+    if (errors_out) errors_out[i] = errs[i];
+    if (!first && errs[i]) first = errs[i];
+  }
+  return first;
 }
 
 // ------------------------------------------------------------------------------- simple API (one image)

@@ -30,7 +30,9 @@
 #define RS_IDX_MASK 0x1FFFFFFFu
 #define RS_FULL 0xFFFFFFFFu
 #define RS_MAX_NB 64
-#define RS_CHUNK 4          // neighbours gathered per lane between two early-out checks
+#ifndef RS_CHUNK
+#define RS_CHUNK 3          // neighbours gathered per lane between two early-out checks (sweep: profiles/)
+#endif
 #define RS_LUT_WORDS (256 * 32)
 #define RS_MAX_EPOCHS 40     // epochs per pass: ceil(n / max(64, ceil(n/32))) <= 32
 

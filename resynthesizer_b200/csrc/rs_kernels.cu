@@ -7,7 +7,9 @@
 // hazards are removed by the two version slots of the state word (rs_device.cuh).
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -824,6 +826,8 @@ struct Workspace {
   uint32_t off_n = 0;
   int grid[2] = {0, 0};      // persistent grid of k_synth_pass<false/true>
 };
+static std::atomic<int> g_job_slots{1};
+extern "C" void rs_cuda_set_job_slots(int slots) { g_job_slots.store(slots < 1 ? 1 : slots); }
 static std::mutex g_pool_mutex;
 static std::vector<Workspace *> g_pool;
 
@@ -1129,7 +1133,12 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
-  const int grid = w->grid[j->maps ? 1 : 0];
+  int grid = w->grid[j->maps ? 1 : 0];
+  {  // several jobs sharing the device: each persistent grid takes its share of the SMs (rs_cuda_set_job_slots)
+    const int slots = g_job_slots.load();
+    if (slots > 1) { const int share = (grid + slots - 1) / slots; grid = share < 8 ? 8 : share; }
+    if (const char *e = getenv("RS_GRID_CAP")) { const int c = atoi(e); if (c > 0 && c < grid) grid = c; }
+  }
   const size_t smem = pass_smem(j->maps);
   RS_CHECK(cudaEventRecord(w->ev0, s));
   {  // all pass-0 patches, dependency-free
@@ -1170,6 +1179,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   // Host side of the progress/cancel contract: replay ticks in order while the device runs.
   uint32_t emitted[6] = {0, 0, 0, 0, 0, 0};  // ticks already forwarded per pass
   bool cancelled = false;
+  unsigned idle_spins = 0;
   auto emit_upto = [&](uint32_t p, uint32_t upto) {
     while (emitted[p] < upto) {
       const uint32_t idx = emitted[p] * 4096u;
@@ -1184,10 +1194,18 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     cudaError_t q = cudaEventQuery(w->evDone);
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) { g_err = std::string("rs_job_run: ") + cudaGetErrorString(q); return 100; }
+    bool progressed = false;
     for (uint32_t p = 0; p < j->d.n_passes; p++) {
       const unsigned int seen = ((volatile unsigned int *)w->h_ticks)[p];  // a started tick index + 1 (not monotone)
       if (seen == 0) break;
-      emit_upto(p, (seen - 1u) / 4096u + 1u);
+      const uint32_t upto = (seen - 1u) / 4096u + 1u;
+      progressed |= emitted[p] < upto;
+      emit_upto(p, upto);
+    }
+    if (!progressed) {  // nothing new: do not burn the core (many jobs may be waiting like this one)
+      if (++idle_spins > 200) { struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr); }
+    } else {
+      idle_spins = 0;
     }
   }
   RS_CHECK(cudaStreamSynchronize(s));
