@@ -29,7 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from resynthesizer_b200 import abi  # noqa: E402
+from resynthesizer_b200 import abi, sharding  # noqa: E402
 from resynthesizer_b200.synthetic import G, centered_mask  # noqa: E402
 
 METRIC = "synthesized target px/s"
@@ -272,10 +272,8 @@ def run_ours(a):
 
     kern_s = sum(s["ms_kernels"] for s in stats) / 1000.0
     e2e_s = sum(walls)
-    agg = torch.tensor([kern_s, e2e_s, t_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
-    kern_s, e2e_s, t_total = [float(x) for x in agg.tolist()]
+    # the only communication of the multi-GPU path: max over ranks of three timing scalars
+    kern_s, e2e_s, t_total = sharding.max_over_ranks([kern_s, e2e_s, t_total], device="cuda")
     total_px = world * a.steps * n * B
     evals = sum(s["evals"] for s in stats); issued = sum(s["evals_issued"] for s in stats)
     compares = sum(s["compares"] for s in stats); visits = sum(s["visits"] for s in stats)
