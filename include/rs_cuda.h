@@ -34,6 +34,7 @@ typedef struct {
   int32_t map_bip;               /* map_start_bip */
   int32_t alpha_bip;             /* byte index of alpha, or -1 */
   int32_t alpha_target;          /* isAlphaTarget */
+  int32_t alpha_source;          /* isAlphaSource */
   int32_t htile, vtile;          /* wrap neighbour coordinates in x / y */
   int32_t use_context;           /* matchContextType != 0 */
   uint32_t patch_size;           /* as passed by the caller (<= 64) */
@@ -48,6 +49,7 @@ typedef struct {
   uint64_t visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
   uint64_t betters[6], pass_visits[6], sum_best[6];
   uint32_t passes_run;
+  uint32_t n_corpus;             /* corpus points (counted on the device when not given by the caller) */
   float ms_passes;               /* CUDA-event time of all pass kernels of the last run */
 } RsJobCounters;
 
@@ -73,6 +75,15 @@ int rs_job_upload(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_r
                   const uint32_t *corpus_points, uint32_t n_corpus,
                   const uint32_t *offsets, uint32_t n_offsets,
                   const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max);
+/* The same upload in two asynchronous phases, so that the host can compute the visit order while the images are
+ * copied and prepared: (1) everything but the order -- y_min..y_max = rows of the target image that contain target
+ * points; corpus_points may be NULL: the device then builds the list (row-major, mask 0xFF and not transparent);
+ * (2) the visit order (n_targets points). */
+int rs_job_upload_images(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_raw, uint32_t n_targets,
+                         uint32_t y_min, uint32_t y_max, const uint32_t *corpus_points, uint32_t n_corpus,
+                         const uint32_t *offsets, uint32_t n_offsets,
+                         const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max);
+int rs_job_upload_order(RsJob *job, const uint32_t *targets);
 /* Runs all passes (early termination decided on the device), calling tick from the waiting host thread. */
 int rs_job_run(RsJob *job, RsTickFn tick, void *tick_ctx);
 /* target_raw_out: the caller's tw*th*bpp pixmap; the rows containing target points are overwritten with the

@@ -41,7 +41,7 @@ class RsStats(C.Structure):
 class RsJobDesc(C.Structure):
     _fields_ = [("tw", C.c_int32), ("th", C.c_int32), ("cw", C.c_int32), ("ch", C.c_int32), ("bpp", C.c_int32),
                 ("n_color", C.c_int32), ("n_map", C.c_int32), ("map_bip", C.c_int32), ("alpha_bip", C.c_int32),
-                ("alpha_target", C.c_int32), ("htile", C.c_int32), ("vtile", C.c_int32), ("use_context", C.c_int32),
+                ("alpha_target", C.c_int32), ("alpha_source", C.c_int32), ("htile", C.c_int32), ("vtile", C.c_int32), ("use_context", C.c_int32),
                 ("patch_size", C.c_uint32), ("max_probes", C.c_uint32), ("seed", C.c_uint32),
                 ("pass_end", C.c_uint32 * 6), ("n_passes", C.c_uint32), ("terminate_fraction", C.c_double)]
 

@@ -141,18 +141,12 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   uint8_t *tpix = reinterpret_cast<uint8_t *>(targetMap->data->data);
   const uint8_t *cpix = reinterpret_cast<const uint8_t *>(corpusMap->data->data);
 
-  static thread_local std::vector<uint32_t> targets, corpus;  // reused across calls: no page faults per job
+  static thread_local std::vector<uint32_t> targets;  // reused across calls: no page faults per job
   rs::collect_target_points(tpix, tw, th, bpp, targets);
   if (targets.empty()) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;  // lib/engine.c:605-610
-  rs::collect_corpus_points(cpix, cw, ch, bpp, *fi, corpus);
-  if (corpus.empty()) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;   // lib/engine.c:620-627
-
-  uint16_t c512[512];
-  uint32_t m512[512];
-  rs::build_metric_tables(prm.sensitivityToOutliers, prm.mapWeight, c512, m512);
-  rs::GRandMT prng(t_seed);
-  const int oerr = rs::order_target_points(prm.matchContextType, targets, prng);
-  if (oerr) return oerr;  // lib/engine.c:645-647
+  if (!rs::has_corpus_point(cpix, cw, ch, bpp, *fi)) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;   // lib/engine.c:620-627
+  if (prm.matchContextType < 0 || prm.matchContextType > 8)
+    return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;  // lib/engine.c:645-647 (orderTargetPoints' default case)
 
   if (tw > 32767 || th > 32767 || cw > 32767 || ch > 32767) {
     t_err = "image dimensions above 32767 are not supported by the packed device layout";
@@ -160,6 +154,9 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   }
   if (int e = ensure_device()) return e;
 
+  uint16_t c512[512];
+  uint32_t m512[512];
+  rs::build_metric_tables(prm.sensitivityToOutliers, prm.mapWeight, c512, m512);
   // metric by |difference| (both functions are even: matchWeighting.h:56-58,176)
   uint32_t c256[256], m256[256];
   for (int d = 0; d < 256; d++) { c256[d] = c512[256 + d]; m256[d] = m512[256 + d]; }
@@ -170,6 +167,7 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   desc.n_color = fi->img_match_bpp; desc.n_map = fi->map_match_bpp; desc.map_bip = fi->map_start_bip;
   desc.alpha_bip = (fi->isAlphaTarget || fi->isAlphaSource) ? fi->alpha_bip : -1;
   desc.alpha_target = fi->isAlphaTarget ? 1 : 0;
+  desc.alpha_source = fi->isAlphaSource ? 1 : 0;
   desc.htile = prm.isMakeSeamlesslyTileableHorizontally ? 1 : 0;
   desc.vtile = prm.isMakeSeamlesslyTileableVertically ? 1 : 0;
   desc.use_context = prm.matchContextType != 0;
@@ -178,15 +176,20 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   const uint32_t estimated = rs::pass_schedule(n, desc.pass_end);
   desc.n_passes = 6;
   desc.terminate_fraction = 0.1;  // IMAGE_SYNTH_TERMINATE_FRACTION, a double (lib/refiner.h:111)
-
-  const std::vector<uint32_t> &tpk = targets, &cpk = corpus;
+  const uint32_t y_min = (uint32_t)rs::unpack_y(targets.front()), y_max = (uint32_t)rs::unpack_y(targets.back());
   const double t1 = now_ms();
 
+  // Phase 1 (asynchronous): images, corpus points (compacted on the device), offsets table, tables, state init ...
   RsJob *job = nullptr;
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
-  int rc = rs_job_upload(job, tpix, cpix, tpk.data(), n, cpk.data(), (uint32_t)cpk.size(), nullptr, 0,
-                         c256, m256, m512[0]);  // offsets table: built and cached on the device
+  int rc = rs_job_upload_images(job, tpix, cpix, n, y_min, y_max, nullptr, 0, nullptr, 0, c256, m256, m512[0]);
   const double t2 = now_ms();
+  // ... while the host orders the target points with the reference's PRNG stream (lib/engine.c:643-645)
+  rs::GRandMT prng(t_seed);
+  rs::order_target_points(prm.matchContextType, targets, prng);
+  const double t2b = now_ms();
+  if (!rc) rc = rs_job_upload_order(job, targets.data());
+  const std::vector<uint32_t> &tpk = targets;
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
   if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, on_tick, &ts); }
   const double t3 = now_ms();
@@ -213,8 +216,8 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   t_stats.compares = jc.compares; t_stats.offset_scans = jc.offset_scans; t_stats.heur_evals = jc.heur_evals;
   t_stats.heur_skips = jc.heur_skips; t_stats.perfect = jc.perfect;
   for (int p = 0; p < 6; p++) { t_stats.betters[p] = jc.betters[p]; t_stats.pass_visits[p] = jc.pass_visits[p]; t_stats.sum_best[p] = jc.sum_best[p]; }
-  t_stats.passes_run = jc.passes_run; t_stats.n_targets = n; t_stats.n_corpus = (unsigned)cpk.size();
-  t_stats.ms_prep = (float)(t1 - t0); t_stats.ms_h2d = (float)(t2 - t1); t_stats.ms_kernels = jc.ms_passes;
+  t_stats.passes_run = jc.passes_run; t_stats.n_targets = n; t_stats.n_corpus = jc.n_corpus;
+  t_stats.ms_prep = (float)((t1 - t0) + (t2b - t2)); t_stats.ms_h2d = (float)(t2 - t1); t_stats.ms_kernels = jc.ms_passes;
   t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
   (void)t2;
   return 0;  // success, also when cancelled (lib/engine.c:689)

@@ -116,6 +116,17 @@ void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFor
   }
 }
 
+bool has_corpus_point(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi) {
+  const bool alpha = fi.isAlphaSource != 0;
+  const int ab = fi.alpha_bip;
+  const size_t n = (size_t)w * h;
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t *p = pix + i * bpp;
+    if (p[0] == 0xFF && (!alpha || p[ab] != 0)) return true;
+  }
+  return false;
+}
+
 // ---------------------------------------------------------------------------------------- ordering
 // v % n for a fixed n without a division per draw (Lemire, "Faster remainder by direct computation", 2019)
 struct FastMod {

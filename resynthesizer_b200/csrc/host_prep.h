@@ -40,6 +40,9 @@ void build_sorted_offsets(int target_w, int target_h, int corpus_w, int corpus_h
 void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<uint32_t> &out);
 void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<uint32_t> &out);
 
+// Is there any corpus point at all (mask 0xFF and not transparent)?  Stops at the first one (lib/engine.c:620-627).
+bool has_corpus_point(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi);
+
 // lib/orderTarget.h:268-343 (+ brushfire.h, engineTypes.h).  Returns 0 or IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE.
 int order_target_points(int match_context_type, std::vector<uint32_t> &pts, GRandMT &prng);
 

@@ -42,6 +42,7 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   unsigned int done_ctas[6];
   unsigned int epoch_done[6][40];  // per pass and epoch: visits completed (state word + stamps published)
   unsigned int epoch_wm[6];        // per pass: number of leading epochs that are complete (what waiters poll)
+  unsigned int n_corpus;    // number of corpus points (written at upload: host value or device compaction count)
   unsigned int stop;        // set by the last CTA of a pass when betters/n < fraction, or on cancel
   unsigned int passes_run;
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
@@ -65,7 +66,7 @@ struct RsDev {              // kernel argument (by value)
   volatile unsigned int *host_ticks;  // mapped pinned: [6] highest tick index started per pass (+1)
   const volatile int *host_cancel;    // mapped pinned
   int tw, th, cw, ch;
-  uint32_t nT, nC, nOff;
+  uint32_t nT, nOff;
   uint32_t kmax, probes, seed, penalty;
   uint32_t pass, pass_end;
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))

@@ -15,6 +15,8 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "../../include/rs_cuda.h"
 #include "rs_device.cuh"
@@ -273,6 +275,9 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
 
 // --------------------------------------------------------------------------------------- the pass kernel
 #define RS_WARPS_PER_CTA 16
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 2       // resident CTAs per SM the throughput kernel is compiled for (register cap 64)
+#endif
 #define RS_THREADS (RS_WARPS_PER_CTA * 32)
 
 struct WarpScratch {
@@ -504,7 +509,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
     if (bettered) {
       const uint32_t bp = ((uint32_t)bestIdx < nHeur)
                               ? candlist[bestIdx]
-                              : __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.nC));
+                              : __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
       if (bp != src) {
         const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
         const uint32_t cpx = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
@@ -595,7 +600,7 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, V
 
 // ---- throughput mode: one warp per visit -------------------------------------------------------------------
 template <bool MAPS>
-__global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_synth_pass(const RsDev J) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
   uint32_t *lutm = lutc + RS_LUT_WORDS;  // only staged when MAPS
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass(const RsDev J) {
     uint32_t bestSum = 0xFFFFFFFFu;
     int bestIdx = 0x7FFFFFFF;
     const uint32_t *candlist = S.aux;
-    const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = J.nC;
+    const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
     const uint32_t *cpts = J.corpus_pts;
     const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
     // Heuristic candidates (few, and the likely winners): every (candidate, 4-neighbour chunk) pair gets a lane, so
@@ -684,7 +689,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J
   const unsigned bar_id = 1u + team;
   WarpScratch &S = scratch[team];
   TeamShared &TS = tshared[team];
-  const uint32_t pass = J.pass, seed = J.seed, nC = J.nC;
+  const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
   lutc += lane;  // this lane's column of the replicated tables
   lutm += lane;
   VisitStats st;
@@ -943,6 +948,7 @@ struct RsJob {
   bool maps = false;
   uint32_t nT = 0, nC = 0, nOff = 0, penalty = 0;
   uint32_t y_min = 0, y_max = 0;  // rows of the target image that hold target points
+  size_t pin_targets_off = 0;     // where the visit order is staged in the pinned buffer
   bool want_sources = false;
   float ms_passes = 0.f;
 };
@@ -996,35 +1002,52 @@ static int build_offsets_on_device(Workspace *w, int ow, int oh, uint32_t n) {
   return 0;
 }
 
-extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *targets,
-                             uint32_t n_targets, const uint32_t *corpus_points, uint32_t n_corpus,
-                             const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
-                             const uint32_t *map_lut256, uint32_t map_lut_max) {
+// ---- corpus points on the device (replaces prepareCorpusPoints, lib/engine.c:400-431) ----
+// Row-major list of corpus pixels that are fully selected (mask 0xFF) and not totally transparent, as packed
+// x | y << 16: flag kernel + stable stream compaction + pack.  The count stays on the device (RsCtrl.n_corpus).
+__global__ void k_corpus_flags(const uint8_t *__restrict__ raw, uint32_t n_px, int bpp, int alpha_bip, int alpha_source,
+                               uint8_t *__restrict__ flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const uint8_t *p = raw + (size_t)i * bpp;
+  flags[i] = (p[0] == 0xFFu && (!alpha_source || p[alpha_bip] != 0)) ? 1 : 0;
+}
+__global__ void k_pack_points(uint32_t *__restrict__ pts, const unsigned int *__restrict__ n_ptr, int w) {
+  const uint32_t n = *n_ptr;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t idx = pts[i];
+    pts[i] = (idx % (uint32_t)w) | ((idx / (uint32_t)w) << 16);
+  }
+}
+
+// Phase 1 of the upload: everything that does not depend on the visit order.  Asynchronous on the job's stream,
+// so the host can compute the target order meanwhile (rs_job_upload_order).
+extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, uint32_t n_targets,
+                                    uint32_t y_min, uint32_t y_max, const uint32_t *corpus_points, uint32_t n_corpus,
+                                    const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
+                                    const uint32_t *map_lut256, uint32_t map_lut_max) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   const RsJobDesc &d = j->d;
-  if (n_targets == 0 || n_corpus == 0 || n_targets >= RS_IDX_MASK) {
-    g_err = "rs_job_upload: empty or oversized point list";
+  if (n_targets == 0 || (corpus_points && n_corpus == 0) || n_targets >= RS_IDX_MASK || y_max < y_min ||
+      y_max >= (uint32_t)d.th) {
+    g_err = "rs_job_upload_images: empty or oversized point list";
     return 100;
   }
   const size_t tn = (size_t)d.tw * d.th, cn = (size_t)d.cw * d.ch;
   cudaStream_t s = w->stream;
-  j->nT = n_targets; j->nC = n_corpus;
-  {
-    uint32_t lo = 0xFFFFu, hi = 0;
-    for (uint32_t i = 0; i < n_targets; i++) { const uint32_t y = targets[i] >> 16; lo = y < lo ? y : lo; hi = y > hi ? y : hi; }
-    j->y_min = lo; j->y_max = hi;
-  }
+  j->nT = n_targets; j->nC = corpus_points ? n_corpus : 0;
+  j->y_min = y_min; j->y_max = y_max;
   j->penalty = 65535u * (uint32_t)d.n_color + map_lut_max * (uint32_t)d.n_map;
+  const size_t cap_cpts = corpus_points ? (size_t)n_corpus : cn;
   int rc = 0;
   if ((rc = ws_ensure(w->raw_t, tn * d.bpp)) || (rc = ws_ensure(w->raw_c, cn * d.bpp)) ||
       (rc = ws_ensure(w->corpus, cn * (j->maps ? 8 : 4))) || (rc = ws_ensure(w->W, tn * 16)) ||
       (rc = ws_ensure(w->meta, tn * 4)) || (rc = ws_ensure(w->tmaps, j->maps ? tn * 4 : 4)) ||
-      (rc = ws_ensure(w->targets, (size_t)n_targets * 4)) || (rc = ws_ensure(w->cpts, (size_t)n_corpus * 4)) ||
+      (rc = ws_ensure(w->targets, (size_t)n_targets * 4)) || (rc = ws_ensure(w->cpts, cap_cpts * 4)) ||
       (rc = ws_ensure(w->lut256, 512 * 4)) || (rc = ws_ensure(w->lut_rep, 2 * RS_LUT_WORDS * 4)) ||
       (rc = ws_ensure(w->prober0, cn * 8)) || (rc = ws_ensure(w->prober1, cn * 8)) || (rc = ws_ensure(w->prober2, cn * 8)) ||
-      (rc = ws_ensure(w->colours, (size_t)n_targets * 4)) || (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) ||
-      (rc = ws_ensure(w->ctrl, sizeof(RsCtrl) + 64)))
+      (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) || (rc = ws_ensure(w->ctrl, sizeof(RsCtrl) + 64)))
     return rc;
   {
     uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
@@ -1035,29 +1058,47 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
   const int ow = d.tw < d.cw ? d.tw : d.cw, oh = d.th < d.ch ? d.th : d.ch;
   const uint32_t full_n = (uint32_t)(2 * ow - 1) * (uint32_t)(2 * oh - 1);
   // stage all host inputs through pinned memory so the copies are truly asynchronous
-  const size_t sz_t = tn * d.bpp, sz_c = cn * d.bpp, sz_tp = (size_t)n_targets * 4, sz_cp = (size_t)n_corpus * 4,
-               sz_off = offsets ? (size_t)n_offsets * 4 : 0, sz_lut = 512 * 4;
+  const size_t sz_t = tn * d.bpp, sz_c = cn * d.bpp, sz_tp = (size_t)n_targets * 4,
+               sz_cp = corpus_points ? (size_t)n_corpus * 4 : 0, sz_off = offsets ? (size_t)n_offsets * 4 : 0, sz_lut = 512 * 4;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t o_t = 0, o_c = o_t + up(sz_t), o_tp = o_c + up(sz_c), o_cp = o_tp + up(sz_tp), o_off = o_cp + up(sz_cp),
                o_lut = o_off + up(sz_off), total = o_lut + up(sz_lut);
   const size_t out_bytes = (size_t)(j->y_max - j->y_min + 1) * d.tw * d.bpp + (size_t)n_targets * 4 + 256;
   const size_t need_pin = total > out_bytes ? total : out_bytes;
   if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
+  j->pin_targets_off = o_tp;
   uint8_t *pin = (uint8_t *)w->pin;
-  memcpy(pin + o_t, target_raw, sz_t);
+  RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl) + 64, s));
   memcpy(pin + o_c, corpus_raw, sz_c);
-  memcpy(pin + o_tp, targets, sz_tp);
-  memcpy(pin + o_cp, corpus_points, sz_cp);
-  if (offsets) memcpy(pin + o_off, offsets, sz_off);
+  RS_CHECK(cudaMemcpyAsync(w->raw_c.p, pin + o_c, sz_c, cudaMemcpyHostToDevice, s));
+  memcpy(pin + o_t, target_raw, sz_t);
+  RS_CHECK(cudaMemcpyAsync(w->raw_t.p, pin + o_t, sz_t, cudaMemcpyHostToDevice, s));
   memcpy(pin + o_lut, color_lut256, 256 * 4);
   memcpy(pin + o_lut + 256 * 4, map_lut256, 256 * 4);
-  RS_CHECK(cudaMemcpyAsync(w->raw_t.p, pin + o_t, sz_t, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(w->raw_c.p, pin + o_c, sz_c, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(w->targets.p, pin + o_tp, sz_tp, cudaMemcpyHostToDevice, s));
-  RS_CHECK(cudaMemcpyAsync(w->cpts.p, pin + o_cp, sz_cp, cudaMemcpyHostToDevice, s));
   RS_CHECK(cudaMemcpyAsync(w->lut256.p, pin + o_lut, sz_lut, cudaMemcpyHostToDevice, s));
+  const int T = 256;
+  unsigned int *d_ncorpus = &((RsCtrl *)w->ctrl.p)->n_corpus;
+  if (corpus_points) {
+    memcpy(pin + o_cp, corpus_points, sz_cp);
+    RS_CHECK(cudaMemcpyAsync(w->cpts.p, pin + o_cp, sz_cp, cudaMemcpyHostToDevice, s));
+    *(uint32_t *)(pin + o_lut + 512 * 4 - 4) = 0;  // (unused slot) keep the staging area initialised
+    RS_CHECK(cudaMemcpyAsync(d_ncorpus, &j->nC, 4, cudaMemcpyHostToDevice, s));
+  } else {
+    if ((rc = ws_ensure(w->sort_keys_in, cn))) return rc;  // flags
+    k_corpus_flags<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (uint32_t)cn, d.bpp, d.alpha_bip,
+                                                            d.alpha_source, (uint8_t *)w->sort_keys_in.p);
+    thrust::counting_iterator<uint32_t> idx(0);
+    size_t tmp = 0;
+    RS_CHECK(cub::DeviceSelect::Flagged(nullptr, tmp, idx, (const uint8_t *)w->sort_keys_in.p, (uint32_t *)w->cpts.p,
+                                        d_ncorpus, (int)cn, s));
+    if ((rc = ws_ensure(w->sort_tmp, tmp))) return rc;
+    RS_CHECK(cub::DeviceSelect::Flagged(w->sort_tmp.p, tmp, idx, (const uint8_t *)w->sort_keys_in.p, (uint32_t *)w->cpts.p,
+                                        d_ncorpus, (int)cn, s));
+    k_pack_points<<<592, T, 0, s>>>((uint32_t *)w->cpts.p, d_ncorpus, d.cw);
+  }
   if (offsets) {
     if ((rc = ws_ensure(w->offsets, sz_off))) return rc;
+    memcpy(pin + o_off, offsets, sz_off);
     RS_CHECK(cudaMemcpyAsync(w->offsets.p, pin + o_off, sz_off, cudaMemcpyHostToDevice, s));
     w->off_w = w->off_h = 0; w->off_n = 0;  // not a cached full table
     j->nOff = n_offsets;
@@ -1066,11 +1107,9 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
       if ((rc = build_offsets_on_device(w, ow, oh, full_n))) return rc;
     j->nOff = full_n;
   }
-  RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl) + 64, s));
   RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 8, s));
   RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 8, s));
   RS_CHECK(cudaMemsetAsync(w->prober2.p, 0, cn * 8, s));
-  const int T = 256;
   k_canon_corpus<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
                                                           d.map_bip, j->maps ? nullptr : (uint32_t *)w->corpus.p,
                                                           j->maps ? (uint2 *)w->corpus.p : nullptr);
@@ -1078,13 +1117,38 @@ extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t 
                                                          d.map_bip, d.alpha_bip, d.alpha_target, d.use_context,
                                                          (unsigned long long *)w->W.p, (uint32_t *)w->meta.p,
                                                          j->maps ? (uint32_t *)w->tmaps.p : nullptr);
-  k_scatter_order<<<(n_targets + T - 1) / T, T, 0, s>>>((const uint32_t *)w->targets.p, n_targets, d.tw, (uint32_t *)w->meta.p);
   k_replicate_lut<<<(RS_LUT_WORDS + T - 1) / T, T, 0, s>>>((const uint32_t *)w->lut256.p, (const uint32_t *)w->lut256.p + 256,
                                                          (uint32_t *)w->lut_rep.p);
   RS_CHECK(cudaGetLastError());
   for (int p = 0; p < 6; p++) w->h_ticks[p] = 0;
   *w->h_cancel = 0;
   return 0;
+}
+
+// Phase 2 of the upload: the visit order (n_targets points as given to rs_job_upload_images).
+extern "C" int rs_job_upload_order(RsJob *j, const uint32_t *targets) {
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
+  uint8_t *pin = (uint8_t *)w->pin;
+  memcpy(pin + j->pin_targets_off, targets, (size_t)j->nT * 4);
+  RS_CHECK(cudaMemcpyAsync(w->targets.p, pin + j->pin_targets_off, (size_t)j->nT * 4, cudaMemcpyHostToDevice, w->stream));
+  k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>((const uint32_t *)w->targets.p, j->nT, j->d.tw,
+                                                             (uint32_t *)w->meta.p);
+  RS_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *targets,
+                             uint32_t n_targets, const uint32_t *corpus_points, uint32_t n_corpus,
+                             const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
+                             const uint32_t *map_lut256, uint32_t map_lut_max) {
+  if (n_targets == 0) { g_err = "rs_job_upload: no target points"; return 100; }
+  uint32_t lo = 0xFFFFu, hi = 0;
+  for (uint32_t i = 0; i < n_targets; i++) { const uint32_t y = targets[i] >> 16; lo = y < lo ? y : lo; hi = y > hi ? y : hi; }
+  if (int rc = rs_job_upload_images(j, target_raw, corpus_raw, n_targets, lo, hi, corpus_points, n_corpus, offsets,
+                                    n_offsets, color_lut256, map_lut256, map_lut_max))
+    return rc;
+  return rs_job_upload_order(j, targets);
 }
 
 static RsDev make_dev(const RsJob *j, uint32_t pass) {
@@ -1104,7 +1168,7 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.nb_lists = (const uint2 *)w->nb_lists.p; D.nb_counts = (const uint8_t *)w->nb_counts.p;
   D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
   D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch;
-  D.nT = j->nT; D.nC = j->nC; D.nOff = j->nOff;
+  D.nT = j->nT; D.nOff = j->nOff;
   uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;  // the size test follows the append (synthesize.h:222-224)
   D.kmax = kmax > RS_MAX_NB ? RS_MAX_NB : kmax;
   D.probes = d.max_probes; D.seed = d.seed; D.penalty = j->penalty;
@@ -1239,6 +1303,7 @@ extern "C" int rs_job_counters(RsJob *j, RsJobCounters *out) {
   out->perfect = c.perfect;
   for (int p = 0; p < 6; p++) { out->betters[p] = c.betters[p]; out->pass_visits[p] = c.pass_visits[p]; out->sum_best[p] = c.sum_best[p]; }
   out->passes_run = c.passes_run;
+  out->n_corpus = c.n_corpus;
   out->ms_passes = j->ms_passes;
   return 0;
 }
