@@ -51,6 +51,7 @@ typedef struct {
   uint32_t passes_run;
   uint32_t n_corpus;             /* corpus points (counted on the device when not given by the caller) */
   float ms_passes;               /* CUDA-event time of all pass kernels of the last run */
+  float ms_pass[6];              /* device-clock duration of each pass that ran (first claim to last CTA out) */
 } RsJobCounters;
 
 /* Called on the host, in order, for every (pass, index) with (index & 4095) == 0 that the device
@@ -94,6 +95,9 @@ int rs_job_download(RsJob *job, uint8_t *target_raw_out, uint32_t *sources_out);
 void rs_job_want_sources(RsJob *job, int yes);
 int rs_job_counters(RsJob *job, RsJobCounters *out);
 void rs_job_destroy(RsJob *job);
+/* Throughput profile of a pass of the last run: out_ns[i] = ns from the start of the pass to the claim of visit
+ * 4096 * i.  Returns the number of entries written (0 if the pass did not run). */
+uint32_t rs_job_timeline(RsJob *job, uint32_t pass, uint64_t *out_ns, uint32_t cap);
 /* Copies the job's neighbour-offset table back (parity tests of the device-side build). */
 int rs_job_read_offsets(RsJob *job, uint32_t *out, uint32_t cap);
 /* Frees the pooled workspaces (device buffers, pinned staging, streams) that jobs leave behind for reuse. */

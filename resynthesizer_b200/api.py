@@ -14,7 +14,8 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libresynthesizer_b200.so")
+# RS_LIB_VARIANT selects a differently compiled build of the same sources (kernel parameter sweeps, see build.py)
+LIB_PATH = os.path.join(_HERE, "lib", "libresynthesizer_b200%s.so" % os.environ.get("RS_LIB_VARIANT", ""))
 _lib = None
 
 
@@ -28,7 +29,7 @@ class RsStats(C.Structure):
                [("betters", C.c_ulonglong * 6), ("pass_visits", C.c_ulonglong * 6), ("sum_best", C.c_ulonglong * 6),
                 ("passes_run", C.c_uint), ("n_targets", C.c_uint), ("n_corpus", C.c_uint),
                 ("ms_prep", C.c_float), ("ms_h2d", C.c_float), ("ms_kernels", C.c_float),
-                ("ms_d2h", C.c_float), ("ms_total", C.c_float)]
+                ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("ms_pass", C.c_float * 6)]
 
     def as_dict(self):
         d = {}
@@ -89,6 +90,17 @@ def last_stats():
     s = RsStats()
     lib().rs_get_stats(C.byref(s))
     return s.as_dict()
+
+
+def last_timeline(pass_index):
+    """ns from the start of `pass_index` to the claim of its visit 4096*i, for the last engine() call made with
+    keep_result(True); empty if the pass did not run."""
+    out = np.zeros(512, np.uint64)
+    L = lib()
+    L.rs_get_timeline.argtypes = [C.c_uint, C.c_void_p, C.c_uint]
+    L.rs_get_timeline.restype = C.c_uint
+    n = L.rs_get_timeline(int(pass_index), out.ctypes.data, 512)
+    return out[:n].copy()
 
 
 class _Progress:

@@ -6,7 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libresynthesizer_b200.so")
+# RS_LIB_VARIANT=<suffix> with RS_NVCC_EXTRA=<-D...> builds a parameter-sweep variant beside the product library
+LIB = os.path.join(LIBDIR, "libresynthesizer_b200%s.so" % os.environ.get("RS_LIB_VARIANT", ""))
 SOURCES = ["rs_kernels.cu", "host_engine.cpp", "host_prep.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

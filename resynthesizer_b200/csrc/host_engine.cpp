@@ -22,6 +22,7 @@ thread_local bool t_device_chosen = false;
 thread_local int t_device = -1;  // ordinal chosen by rs_set_device / ensure_device on this thread
 thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-target sources (tests, quality metrics)
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
+thread_local std::vector<uint64_t> t_timeline[6];                   // of the last engine() call (rs_keep_result)
 
 double now_ms() {
   using namespace std::chrono;
@@ -210,6 +211,11 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   }
   RsJobCounters jc;
   rs_job_counters(job, &jc);
+  if (t_keep_result)
+    for (uint32_t p = 0; p < 6; p++) {
+      t_timeline[p].assign(512, 0);
+      t_timeline[p].resize(rs_job_timeline(job, p, t_timeline[p].data(), 512));
+    }
   rs_job_destroy(job);
   const double t4 = now_ms();
   t_stats.visits = jc.visits; t_stats.evals = jc.evals; t_stats.evals_issued = jc.evals_issued;
@@ -219,6 +225,7 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   t_stats.passes_run = jc.passes_run; t_stats.n_targets = n; t_stats.n_corpus = jc.n_corpus;
   t_stats.ms_prep = (float)((t1 - t0) + (t2b - t2)); t_stats.ms_h2d = (float)(t2 - t1); t_stats.ms_kernels = jc.ms_passes;
   t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
+  for (int p = 0; p < 6; p++) t_stats.ms_pass[p] = jc.ms_pass[p];
   (void)t2;
   return 0;  // success, also when cancelled (lib/engine.c:689)
 }
@@ -343,6 +350,13 @@ extern "C" uint32_t rs_get_last_result(uint32_t *targets_out, uint32_t *sources_
     if (targets_out) targets_out[i] = t_last_targets[i];
     if (sources_out) sources_out[i] = t_last_sources[i];
   }
+  return n;
+}
+
+extern "C" unsigned int rs_get_timeline(unsigned int pass, unsigned long long *out_ns, unsigned int cap) {
+  if (pass >= 6) return 0;
+  const unsigned int n = (unsigned int)t_timeline[pass].size() < cap ? (unsigned int)t_timeline[pass].size() : cap;
+  for (unsigned int i = 0; i < n; i++) out_ns[i] = t_timeline[pass][i];
   return n;
 }
 

@@ -1,9 +1,11 @@
 // Device-side building blocks of the synthesis pass (sm_100a).
 //
 // Data layout in HBM (one job; see DESIGN.md "Data layout"):
-//   corpus   canonical pixels, 4 B [mask,c0,c1,c2] (no map channels) or 8 B [mask,c0,c1,c2 | m0,m1,m2,0]
+//   corpus   canonical pixels, 4 B [c0,c1,c2,mask] (no map channels) or 8 B [c0,c1,c2,mask | m0,m1,m2,0]
 //            -> one aligned 32/64-bit gather per neighbour compare (lib/mapOps.h:147-152 interleaves the
-//            mask for the same reason)
+//            mask for the same reason); mask in the top byte makes "selected" one unsigned compare.
+//            One sentinel pixel (all zero: not selected) follows the image at index cw*ch; compares that fall
+//            outside the corpus read it instead of branching.
 //   W        dynamic state of every target-image pixel, 2 version slots x 64 bit:
 //            [c0,c1,c2 | ver | srcx16 | srcy16]; a visit of pass p publishes version p+1 into slot (p+1)&1
 //            with ONE 64-bit store, so readers need no fence (replaces targetMap colour bytes, sourceOfMap
@@ -20,6 +22,7 @@
 //            with index >= (e-1)*len: epochs e-1, e and the already-running e+1) finds the newest visible
 //            stamp of each array in hi or lo.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -31,23 +34,35 @@
 #define RS_FULL 0xFFFFFFFFu
 #define RS_MAX_NB 64
 #ifndef RS_CHUNK
-#define RS_CHUNK 3          // neighbours gathered per lane between two early-out checks (sweep: profiles/)
+#define RS_CHUNK 2          // neighbours gathered per lane between two early-out checks (sweep: profiles/)
 #endif
 #define RS_LUT_WORDS (256 * 32)
+#define RS_MAX_LAUNCHES 16   // pass-kernel launches per job: 6 passes, the first ones cut into up to 4 segments
+#define RS_TIMELINE 320      // progress ticks per pass whose start time is kept (4096 visits each)
 #define RS_MAX_EPOCHS 40     // epochs per pass: ceil(n / max(64, ceil(n/32))) <= 32
 
+struct __align__(128) RsLine {  // a counter alone on its 128-byte line: hot words must not share an L2 slice
+  unsigned int v;
+  unsigned int pad[31];
+};
 struct RsCtrl {             // device-resident control block of one job (zeroed at upload)
-  unsigned int next[6];     // next visit index to claim, per pass
+  // ---- results and statistics: the part copied back to the host after a run (up to RS_CTRL_COPY_BYTES)
   unsigned int betters[6];
-  unsigned int done_ctas[6];
-  unsigned int epoch_done[6][40];  // per pass and epoch: visits completed (state word + stamps published)
-  unsigned int epoch_wm[6];        // per pass: number of leading epochs that are complete (what waiters poll)
   unsigned int n_corpus;    // number of corpus points (written at upload: host value or device compaction count)
   unsigned int stop;        // set by the last CTA of a pass when betters/n < fraction, or on cancel
   unsigned int passes_run;
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
   unsigned long long pass_visits[6], sum_best[6];
+  unsigned long long pass_end_ns[6];          // globaltimer when the last CTA of a pass left
+  unsigned long long tick_ns[6][RS_TIMELINE];  // globaltimer when visit 4096 * i of a pass was claimed ([0] = pass start)
+  // ---- synchronisation words, one per line
+  RsLine next[RS_MAX_LAUNCHES];       // visits claimed so far, per pass-kernel launch (one atomicAdd per visit)
+  RsLine done_ctas[RS_MAX_LAUNCHES];  // CTAs that have left, per pass-kernel launch
+  RsLine epoch_wm[6];       // per pass: number of leading epochs that are complete (what waiters poll)
+  RsLine epoch_done[6][RS_MAX_EPOCHS];  // per pass and epoch: visits completed (state word + stamps published)
+  RsLine claims[2];         // work counters of the pass-0 gather kernels
 };
+#define RS_CTRL_COPY_BYTES offsetof(RsCtrl, next)
 
 struct RsDev {              // kernel argument (by value)
   const uint32_t *corpus4;
@@ -66,9 +81,12 @@ struct RsDev {              // kernel argument (by value)
   volatile unsigned int *host_ticks;  // mapped pinned: [6] highest tick index started per pass (+1)
   const volatile int *host_cancel;    // mapped pinned
   int tw, th, cw, ch;
+  uint32_t cn;              // cw * ch = index of the sentinel corpus pixel
   uint32_t nT, nOff;
   uint32_t kmax, probes, seed, penalty;
   uint32_t pass, pass_end;
+  uint32_t seg_begin, seg_end;  // this launch claims the visits [seg_begin, seg_end) of the pass, in order
+  uint32_t slot, last_seg;      // index of this launch's counters in RsCtrl; last launch of its pass?
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
   uint32_t ends[6];
   int htile, vtile;
@@ -106,6 +124,11 @@ __device__ __forceinline__ unsigned int rs_ld_u32_relaxed(const unsigned int *p)
   return v;
 }
 
+__device__ __forceinline__ unsigned long long rs_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ int rs_off_x(uint32_t o) { return (int)(short)(o & 0xFFFFu); }
 __device__ __forceinline__ int rs_off_y(uint32_t o) { return ((int)o) >> 16; }
 
@@ -132,24 +155,46 @@ __device__ __forceinline__ void rs_tma_load_1d(void *smem_dst, const void *gmem_
                : "memory");
 }
 
-// ---- up to RS_CHUNK neighbour compares of one candidate: the body of computeBestFit's loop ----
-// (lib/synthesize.h:288-383).  Branch-free: every gather is issued (clamped to pixel 0 when the neighbour falls
-// outside the corpus or past the patch) before the first table lookup; validity is applied by selects.
-// lutc/lutm point at THIS LANE's column of the replicated tables (stride 32 words per table row).
+// ---- one neighbour of the patch as the distance loop reads it (shared memory, one LDS.128, broadcast) ----
+// lin = dy * cw + dx and dx: the corpus pixel compared with this neighbour for candidate (cx, cy) is
+// clin + lin, inside the corpus iff (unsigned)(cx + dx) < cw and (unsigned)(clin + lin) < cw * ch.
+// pix = neighbour colours [c0,c1,c2,0]; pen = what an unusable corpus pixel costs (lib/synthesize.h:291-307).
+// Records past the patch (padding up to a whole chunk) have dx = RS_PAD_DX (never inside) and pen = 0.
+struct __align__(16) RsNb {
+  int32_t lin, dx;
+  uint32_t pix, pen;
+};
+#define RS_PAD_DX 0x40000000
+#define RS_NB_SLOTS (RS_MAX_NB + RS_CHUNK)
+
+__device__ __forceinline__ uint32_t rs_lds_u32(unsigned shared_addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+  return v;
+}
+// Sum of the three table entries selected by bytes 0..2 of d; `col` = shared-space address of THIS LANE's column of
+// a replicated table (row stride 128 B, so the 32 lanes of a warp never share a bank).
+__device__ __forceinline__ uint32_t rs_lut3(unsigned col, uint32_t d) {
+  return rs_lds_u32(col + __byte_perm(d, 0, 0x4440) * 128u) + rs_lds_u32(col + __byte_perm(d, 0, 0x4441) * 128u) +
+         rs_lds_u32(col + __byte_perm(d, 0, 0x4442) * 128u);
+}
+
+// ---- RS_CHUNK neighbour compares of one candidate: the body of computeBestFit's loop for neighbours k0.. ----
+// (lib/synthesize.h:288-383), k0 >= 1: the target point itself (k = 0) carries no colour term (synthesize.h:328) and
+// its corpus pixel is the candidate, always inside and selected; its map terms are added by the caller.
+// Branch-free: every gather is issued before the first table lookup; a pixel outside the corpus reads the sentinel
+// pixel cn (mask 0), so "usable" is one compare on the loaded word; padding records cost 0.
 template <bool MAPS>
-__device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, const uint32_t *lutc, const uint32_t *lutm,
-                                                 const uint32_t *s_off, const uint32_t *s_pix, const uint32_t *s_map,
-                                                 uint32_t K, int cx, int cy, uint32_t k0, uint32_t &nCompares) {
+__device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
+                                                 const uint32_t *nmap, int cx, uint32_t clin, uint32_t k0) {
+  RsNb r[RS_CHUNK];
   uint32_t cp[RS_CHUNK], cm[RS_CHUNK];
-  bool inb[RS_CHUNK];
 #pragma unroll
   for (int u = 0; u < RS_CHUNK; u++) {
-    const uint32_t kk = k0 + u;
-    const bool valid = kk < K;
-    const uint32_t o = s_off[valid ? kk : 0u];
-    const int x = cx + rs_off_x(o), y = cy + rs_off_y(o);
-    inb[u] = valid && (unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch;
-    const uint32_t a = inb[u] ? (uint32_t)y * (uint32_t)J.cw + (uint32_t)x : 0u;
+    r[u] = nb[k0 + u];
+    const uint32_t lin = clin + (uint32_t)r[u].lin;
+    const bool in = (unsigned)(cx + r[u].dx) < (unsigned)J.cw && lin < J.cn;
+    const uint32_t a = in ? lin : J.cn;
     if (MAPS) {
       const uint2 t = __ldg(J.corpus8 + a);
       cp[u] = t.x;
@@ -162,20 +207,9 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, const uint32_t 
   uint32_t sum = 0;
 #pragma unroll
   for (int u = 0; u < RS_CHUNK; u++) {
-    const uint32_t kk = k0 + u;
-    const bool valid = kk < K;
-    const uint32_t ks = valid ? kk : 0u;
-    // inside the corpus and selected (mask 0xFF)? else the maximum weighted difference (synthesize.h:291-307)
-    const bool usable = inb[u] && (cp[u] & 0xFFu) == 0xFFu;
-    const uint32_t d = __vabsdiffu4(cp[u], s_pix[ks]);
-    uint32_t t = lutc[((d >> 8) & 0xFFu) * 32u] + lutc[((d >> 16) & 0xFFu) * 32u] + lutc[(d >> 24) * 32u];
-    t = kk ? t : 0u;  // the target point itself carries no colour term (synthesize.h:328)
-    if (MAPS) {       // map terms also for the target point itself (synthesize.h:342-355)
-      const uint32_t dm = __vabsdiffu4(cm[u], s_map[ks]);
-      t += lutm[(dm & 0xFFu) * 32u] + lutm[((dm >> 8) & 0xFFu) * 32u] + lutm[((dm >> 16) & 0xFFu) * 32u];
-    }
-    sum += valid ? (usable ? t : J.penalty) : 0u;
-    nCompares += valid ? 1u : 0u;
+    uint32_t t = rs_lut3(lutc, __vabsdiffu4(cp[u], r[u].pix));
+    if (MAPS) t += rs_lut3(lutm, __vabsdiffu4(cm[u], nmap[k0 + u]));
+    sum += (cp[u] >= 0xFF000000u) ? t : r[u].pen;  // selected (mask 0xFF)? else the maximum weighted difference
   }
   return sum;
 }
@@ -185,39 +219,55 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, const uint32_t 
 // semantics = the FIRST candidate in list order with the minimum full sum wins (strict '<' to better,
 // synthesize.h:382); a lane therefore abandons only when (partial, index) > (best, bestIndex)
 // lexicographically.  Result is independent of scheduling, hence bit-exact.
+// Candidates are fetched a window of 32 ahead (one per lane, all lanes at once) and handed to the lanes that need
+// one by shuffle, so the dependent table load of cand_of() is off the critical path of a round.
+// K = patch size (>= 1); nb/nmap hold 1 + ceil((K-1)/RS_CHUNK)*RS_CHUNK records.
 template <bool MAPS, class CandFn>
-__device__ __forceinline__ void rs_eval_range(const RsDev &J, const uint32_t *lutc, const uint32_t *lutm,
-                                              const uint32_t *s_off, const uint32_t *s_pix, const uint32_t *s_map,
-                                              uint32_t K, int begin, int end, CandFn cand_of, uint32_t &bestSum,
-                                              int &bestIdx, uint32_t &nCompares, uint32_t &nIssued) {
-  const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
+__device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
+                                              const uint32_t *nmap, uint32_t K, int begin, int end, CandFn cand_of,
+                                              uint32_t &bestSum, int &bestIdx, uint32_t &nCompares, uint32_t &nIssued) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
   int next = begin;  // warp-uniform
+  int win0 = begin;  // candidate index held by lane 0 in wc; wn holds the 32 after
+  uint32_t wc = (win0 + (int)lane < end) ? cand_of(win0 + (int)lane) : 0u;
+  uint32_t wn = (win0 + 32 + (int)lane < end) ? cand_of(win0 + 32 + (int)lane) : 0u;
   int myIdx = -1;
-  int cx = 0, cy = 0;
-  uint32_t k = 0, partial = 0;
+  int cx = 0;
+  uint32_t clin = 0, k = 1, partial = 0, m0 = 0;
+  const uint32_t selfmap = MAPS ? nmap[0] : 0u;
   while (true) {
     if (bestSum == 0u && end > next) end = next;  // perfect match found: hand out nothing later (synthesize.h:565,599)
     const bool need = myIdx < 0;
-    const unsigned nb = __ballot_sync(RS_FULL, need);
-    if (nb && next < end) {
-      const int take = next + __popc(nb & lt);
+    const unsigned nbm = __ballot_sync(RS_FULL, need);
+    if (nbm && next < end) {
+      const int take = next + __popc(nbm & lt);
+      const int s = take - win0;  // 0..63
+      const uint32_t c0 = __shfl_sync(RS_FULL, wc, s & 31), c1 = __shfl_sync(RS_FULL, wn, s & 31);
       if (need && take < end) {
+        const uint32_t c = s < 32 ? c0 : c1;
         myIdx = take;
-        const uint32_t c = cand_of(take);
         cx = (int)(c & 0xFFFFu);
-        cy = (int)(c >> 16);
-        k = 0;
+        clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx;
+        if (MAPS) m0 = __ldg(&J.corpus8[clin].y);  // consumed after the first chunk's gathers are in flight
+        k = 1;
         partial = 0;
         nIssued++;
       }
-      next += __popc(nb);
+      next += __popc(nbm);
       if (next > end) next = end;
+      if (next - win0 >= 32) {
+        win0 += 32;
+        wc = wn;
+        wn = (win0 + 32 + (int)lane < end) ? cand_of(win0 + 32 + (int)lane) : 0u;
+      }
     }
     const bool active = myIdx >= 0;
     if (!__any_sync(RS_FULL, active)) break;
     bool finished = false;
     if (active) {
-      partial += rs_chunk_sum<MAPS>(J, lutc, lutm, s_off, s_pix, s_map, K, cx, cy, k, nCompares);
+      partial += rs_chunk_sum<MAPS>(J, lutc, lutm, nb, nmap, cx, clin, k);
+      if (MAPS && k == 1u) partial += rs_lut3(lutm, __vabsdiffu4(m0, selfmap));  // map terms of the target point itself (synthesize.h:342-355)
       k += RS_CHUNK;
       finished = (k >= K);
     }
@@ -231,6 +281,9 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, const uint32_t *lu
         bestIdx = mi;
       }
     }
-    if (active && (finished || worse)) myIdx = -1;
+    if (active && (finished || worse)) {
+      nCompares += min(k, K);
+      myIdx = -1;
+    }
   }
 }

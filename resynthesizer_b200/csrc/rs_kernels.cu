@@ -46,21 +46,22 @@ extern "C" int rs_cuda_device_count(void) {
 }
 
 // ------------------------------------------------------------------------------------------- init kernels
-// Raw internal pixel [mask][colours][alpha?][maps] -> canonical corpus pixel.
+// Raw internal pixel [mask][colours][alpha?][maps] -> canonical corpus pixel [c0,c1,c2,mask | maps]; thread n_px
+// writes the sentinel pixel (not selected) that out-of-corpus compares read.
 __global__ void k_canon_corpus(const uint8_t *__restrict__ raw, int n_px, int bpp, int n_color, int n_map, int map_bip,
                                uint32_t *__restrict__ out4, uint2 *__restrict__ out8) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_px) return;
-  const uint8_t *p = raw + (size_t)i * bpp;
-  uint32_t lo = p[0];
-  for (int c = 0; c < n_color; c++) lo |= (uint32_t)p[1 + c] << (8 * (c + 1));
-  if (out8) {
-    uint32_t hi = 0;
-    for (int c = 0; c < n_map; c++) hi |= (uint32_t)p[map_bip + c] << (8 * c);
-    out8[i] = make_uint2(lo, hi);
-  } else {
-    out4[i] = lo;
+  if (i > n_px) return;
+  uint32_t lo = 0, hi = 0;
+  if (i < n_px) {
+    const uint8_t *p = raw + (size_t)i * bpp;
+    lo = (uint32_t)p[0] << 24;
+    for (int c = 0; c < n_color; c++) lo |= (uint32_t)p[1 + c] << (8 * c);
+    if (out8)
+      for (int c = 0; c < n_map; c++) hi |= (uint32_t)p[map_bip + c] << (8 * c);
   }
+  if (out8) out8[i] = make_uint2(lo, hi);
+  else out4[i] = lo;
 }
 
 // Target image -> state words, meta, map bytes.  (lib/engine.c:338-391 hasValue rule, :207-224 sourceOf := none)
@@ -274,19 +275,28 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
 }
 
 // --------------------------------------------------------------------------------------- the pass kernel
-#define RS_WARPS_PER_CTA 16
-#ifndef RS_MIN_CTAS
-#define RS_MIN_CTAS 2       // resident CTAs per SM the throughput kernel is compiled for (register cap 64)
+// CTA shapes.  Throughput kernel: ONE 1024-thread CTA per SM (64 registers per thread), so the metric tables are
+// staged once per SM and the shared-memory carve-out leaves >= 124 KB of L1 for the offset/meta/point tables that
+// every visit re-reads (2 x 512 threads with map tables took the carve-out to 228 KB and cfg4 ran 1.8x slower).
+// Team kernel: 2 x 512 threads, at most 8 teams (W >= 2) per CTA, one named barrier per team.
+#ifndef RS_TP_WARPS
+#define RS_TP_WARPS 32
 #endif
-#define RS_THREADS (RS_WARPS_PER_CTA * 32)
+#ifndef RS_TP_MIN_CTAS
+#define RS_TP_MIN_CTAS 1
+#endif
+#define RS_TEAM_WARPS 16
+#define RS_TEAM_SLOTS 8
+#define RS_BF_WARPS 16
 
-struct WarpScratch {
-  uint32_t off[RS_MAX_NB];   // neighbour offsets (packed int16 pair), ascending distance; [0] = (0,0)
-  uint32_t pix[RS_MAX_NB];   // neighbour colours [0,c0,c1,c2]
-  uint32_t map[RS_MAX_NB];   // neighbour map bytes
+template <bool MAPS>
+struct __align__(16) WarpScratch {
+  RsNb nb[RS_NB_SLOTS];                   // the patch as the distance loop reads it (rs_device.cuh), padded to whole chunks
+  uint32_t map[MAPS ? RS_NB_SLOTS : 4];   // neighbour map bytes
+  uint32_t off[RS_MAX_NB];   // neighbour offsets (packed int16 pair), ascending distance; [0] = (0,0).  Dead once the
+                             // heuristic candidates exist: reused as the full patch distance of each of them (hsum)
   uint32_t q[RS_MAX_NB];     // neighbour pixel index, later: packed heuristic candidate or RS_NO_SRC
   uint32_t aux[RS_MAX_NB];   // neighbour meta, later: neighbour source, later: compacted candidate list
-  uint32_t hsum[RS_MAX_NB];  // full patch distance of each heuristic candidate
 };
 
 struct VisitStats {  // per-warp counters, flushed once at kernel end
@@ -317,7 +327,7 @@ __device__ __forceinline__ void rs_stage_tables(const RsDev &J, uint32_t *lutc, 
 // One warp: claim the next visit in order, gather its patch, wait for exactly the neighbour versions the
 // sequential loop would see, build the heuristic candidate list (S.aux[0..nHeur)).  False when the pass is exhausted.
 template <bool MAPS>
-__device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, WarpScratch &S, Visit &V, VisitStats &st) {
+__device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, Visit &V, VisitStats &st) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass, pass_end = J.pass_end;
@@ -325,17 +335,18 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
   // ---- claim the next visit, in order (lib/synthesize.h:480-482 with THREAD_LIMIT 1)
   uint32_t v = 0;
   if (lane == 0) {
-    v = atomicAdd(&ctrl->next[pass], 1u);
-    if (v < pass_end && (v & 4095u) == 0u) {  // progress tick + cancel poll (synthesize.h:493-497)
+    v = J.seg_begin + atomicAdd(&ctrl->next[J.slot].v, 1u);
+    if (v < J.seg_end && (v & 4095u) == 0u) {  // progress tick + cancel poll (synthesize.h:493-497)
       J.host_ticks[pass] = v + 1u;
+      if ((v >> 12) < RS_TIMELINE) ctrl->tick_ns[pass][v >> 12] = rs_globaltimer();
       if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
         atomicExch(&ctrl->stop, 1u);
-        atomicAdd(&ctrl->next[pass], 0x40000000u);
+        atomicAdd(&ctrl->next[J.slot].v, 0x40000000u);
       }
     }
   }
   v = __shfl_sync(RS_FULL, v, 0);
-  if (v >= pass_end) return false;
+  if (v >= J.seg_end) return false;
   st.visits++;
 
   const uint32_t tpos = __ldg(J.targets + v);
@@ -410,9 +421,26 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
       w = rs_ld_state(wp);
     }
     if (k == 0) selfw = w;
-    S.pix[k] = ((uint32_t)w & 0xFFFFFFu) << 8;
+    {
+      const uint32_t o = S.off[k];
+      RsNb r;
+      r.dx = rs_off_x(o);
+      r.lin = rs_off_y(o) * J.cw + r.dx;
+      r.pix = (uint32_t)w & 0xFFFFFFu;
+      r.pen = J.penalty;
+      S.nb[k] = r;
+    }
     if (MAPS) S.map[k] = __ldg(J.tmaps + q);
     S.aux[k] = (uint32_t)(w >> 32);  // source of this neighbour, or RS_NO_SRC
+  }
+  {  // pad the patch to whole chunks with records that cost nothing
+    const uint32_t nch = (K + RS_CHUNK - 2u) / RS_CHUNK, kpad = 1u + (nch ? nch : 1u) * RS_CHUNK;
+    for (uint32_t k = K + lane; k < kpad; k += 32) {
+      RsNb r;
+      r.lin = 0; r.dx = RS_PAD_DX; r.pix = 0u; r.pen = 0u;
+      S.nb[k] = r;
+      if (MAPS) S.map[k] = 0u;
+    }
   }
   __syncwarp();
 
@@ -432,7 +460,7 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
         if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
           const size_t a = (size_t)y * J.cw + x;
           const uint32_t cm = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
-          if ((cm & 0xFFu) == 0xFFu) c = (uint32_t)x | ((uint32_t)y << 16);
+          if (cm >= 0xFF000000u) c = (uint32_t)x | ((uint32_t)y << 16);
         }
       }
     }
@@ -469,7 +497,7 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
     // (no fence: the stamps are 64-bit CAS results and the words read next are strong L2 loads issued after this
     //  poll returns; a fence.gpu here would also invalidate the SM's L1 on every visit)
     if (lane == 0)
-      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
+      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
     __syncwarp();
   }
   uint32_t nHeur = 0;
@@ -495,7 +523,7 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
 
 // One warp: commit the winner (lib/synthesize.h:620-639), merge the heuristic-2 stamps, publish completion.
 template <bool MAPS>
-__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, const WarpScratch &S, const Visit &V,
+__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, const WarpScratch<MAPS> &S, const Visit &V,
                                                 uint32_t bestSum, int bestIdx, VisitStats &st) {
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t pass = J.pass, pass_end = J.pass_end, v = V.v, nHeur = V.nHeur;
@@ -513,7 +541,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
       if (bp != src) {
         const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
         const uint32_t cpx = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
-        colour = cpx >> 8;
+        colour = cpx & 0xFFFFFFu;
         src = bp;
         st.betters++;
       }
@@ -529,7 +557,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
   const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
   if (stampEnd > 0u && V.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
     if (lane == 0)
-      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]) + 1u < V.epoch_idx) __nanosleep(100);
+      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v) + 1u < V.epoch_idx) __nanosleep(100);
     __syncwarp();
   }
   for (uint32_t i = lane; i < stampEnd; i += 32) {
@@ -551,14 +579,14 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
   if (lane == 0) {  // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
     const uint32_t epoch0 = V.epoch_idx * J.epoch_len;
     const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
-    if (atomicAdd(&ctrl->epoch_done[pass][V.epoch_idx], 1u) + 1u == esize) {
+    if (atomicAdd(&ctrl->epoch_done[pass][V.epoch_idx].v, 1u) + 1u == esize) {
       // last visit of its epoch: move the watermark over every leading epoch that is now complete
       while (true) {
-        const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass]);
+        const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v);
         const uint32_t first = wmk * J.epoch_len;
         if (first >= pass_end) break;
-        if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk]) != min(J.epoch_len, pass_end - first)) break;
-        atomicCAS(&ctrl->epoch_wm[pass], wmk, wmk + 1u);
+        if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk].v) != min(J.epoch_len, pass_end - first)) break;
+        atomicCAS(&ctrl->epoch_wm[pass].v, wmk, wmk + 1u);
       }
     }
   }
@@ -588,32 +616,62 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, V
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned done = atomicAdd(&ctrl->done_ctas[pass], 1u) + 1u;
-    if (done == gridDim.x) {
+    const unsigned done = atomicAdd(&ctrl->done_ctas[J.slot].v, 1u) + 1u;
+    if (done == gridDim.x && J.last_seg) {
       __threadfence();
       const unsigned b = atomicAdd(&ctrl->betters[pass], 0u);
       ctrl->passes_run = pass + 1u;
+      ctrl->pass_end_ns[pass] = rs_globaltimer();
       if ((double)((float)b / (float)J.nT) < J.terminate_fraction) atomicExch(&ctrl->stop, 1u);
     }
   }
 }
 
-// ---- throughput mode: one warp per visit -------------------------------------------------------------------
+// One (heuristic candidate, chunk j) pair of the patch distance; chunk 0 also carries the target point's own terms.
 template <bool MAPS>
-__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_synth_pass(const RsDev J) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+__device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, unsigned lutm, const WarpScratch<MAPS> &S,
+                                                 uint32_t K, uint32_t c, uint32_t j, VisitStats &st) {
+  const int cx = (int)(c & 0xFFFFu);
+  const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx, k0 = 1u + j * RS_CHUNK;
+  uint32_t part = rs_chunk_sum<MAPS>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
+  if (j == 0u) {
+    if (MAPS) part += rs_lut3(lutm, __vabsdiffu4(__ldg(&J.corpus8[clin].y), S.map[0]));
+    st.issued++;
+    st.compares++;
+  }
+  st.compares += (k0 < K) ? min((uint32_t)RS_CHUNK, K - k0) : 0u;
+  return part;
+}
+
+struct PassSmem {  // carve-up of the dynamic shared memory of the pass kernels
+  unsigned lutc, lutm;  // shared-space addresses of this lane's table columns
+  void *scratch;
+  uint64_t *bar;
+};
+template <bool MAPS, int NSCRATCH>
+__device__ __forceinline__ PassSmem rs_pass_smem(const RsDev &J, unsigned char *smem_raw) {
   uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
   uint32_t *lutm = lutc + RS_LUT_WORDS;  // only staged when MAPS
   const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
-  WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + lut_bytes);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch) * RS_WARPS_PER_CTA);
+  PassSmem P;
+  P.scratch = smem_raw + lut_bytes;
+  P.bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch<MAPS>) * NSCRATCH);
+  rs_stage_tables<MAPS>(J, lutc, lutm, P.bar);
+  P.lutc = (unsigned)__cvta_generic_to_shared(lutc) + (threadIdx.x & 31u) * 4u;
+  P.lutm = (unsigned)__cvta_generic_to_shared(lutm) + (threadIdx.x & 31u) * 4u;
+  return P;
+}
+
+// ---- throughput mode: one warp per visit -------------------------------------------------------------------
+template <bool MAPS>
+__global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass(const RsDev J) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
   if (rs_ld_u32_relaxed(&ctrl->stop)) return;
-  rs_stage_tables<MAPS>(J, lutc, lutm, bar);
-
-  WarpScratch &S = scratch[threadIdx.x >> 5];
-  lutc += threadIdx.x & 31u;  // this lane's column of the replicated tables
-  lutm += threadIdx.x & 31u;
+  const PassSmem P = rs_pass_smem<MAPS, RS_TP_WARPS>(J, smem_raw);
+  const unsigned lutc = P.lutc, lutm = P.lutm;
+  WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[threadIdx.x >> 5];
+  const unsigned lane = threadIdx.x & 31u;
   VisitStats st;
   Visit V;
   while (rs_visit_prepare<MAPS>(J, ctrl, S, V, st)) {
@@ -621,33 +679,32 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_synth_pass(const Rs
     uint32_t bestSum = 0xFFFFFFFFu;
     int bestIdx = 0x7FFFFFFF;
     const uint32_t *candlist = S.aux;
-    const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
+    uint32_t *hsum = S.off;  // offsets are dead by now (WarpScratch)
+    const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus, K = V.K;
     const uint32_t *cpts = J.corpus_pts;
     const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
-    // Heuristic candidates (few, and the likely winners): every (candidate, 4-neighbour chunk) pair gets a lane, so
-    // all lanes work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
-    {
-      const unsigned lane = threadIdx.x & 31u;
-      const uint32_t K = V.K, nch = (K + RS_CHUNK - 1u) / RS_CHUNK, inv = (65536u + nch - 1u) / nch;
-      for (uint32_t i = lane; i < nHeur; i += 32) S.hsum[i] = 0u;
+    // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
+    // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
+    if (nHeur) {
+      const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, nch = nchr ? nchr : 1u, inv = 0xFFFFFFFFu / nch + 1u;
+      for (uint32_t i = lane; i < nHeur; i += 32) hsum[i] = 0u;
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
-        const uint32_t ci = (t * inv) >> 16, k0 = (t - ci * nch) * RS_CHUNK;  // t / nch, exact for t < 1024, nch <= 16
-        const uint32_t c = candlist[ci];
-        atomicAdd(&S.hsum[ci], rs_chunk_sum<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, (int)(c & 0xFFFFu), (int)(c >> 16), k0, st.compares));
-        st.issued += (k0 == 0u) ? 1u : 0u;
+        const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
+        atomicAdd(&hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, K, candlist[ci], j, st));
       }
       __syncwarp();
       uint32_t msum = 0xFFFFFFFFu;
-      for (uint32_t i = lane; i < nHeur; i += 32) msum = min(msum, S.hsum[i]);
+      for (uint32_t i = lane; i < nHeur; i += 32) msum = min(msum, hsum[i]);
       msum = __reduce_min_sync(RS_FULL, msum);
       int midx = 0x7FFFFFFF;
-      for (uint32_t i = lane; i < nHeur; i += 32) midx = (S.hsum[i] == msum) ? min(midx, (int)i) : midx;
+      for (uint32_t i = lane; i < nHeur; i += 32) midx = (hsum[i] == msum) ? min(midx, (int)i) : midx;
       midx = __reduce_min_sync(RS_FULL, midx);
-      if (nHeur) { bestSum = msum; bestIdx = midx; }
+      bestSum = msum;
+      bestIdx = midx;
     }
     if (bestSum != 0u)
-      rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, V.K, (int)nHeur, (int)(nHeur + J.probes),
+      rs_eval_range<MAPS>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
                           [&](int i) { return __ldg(cpts + rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
                           bestSum, bestIdx, st.compares, st.issued);
     rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, st);
@@ -658,7 +715,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS) k_synth_pass(const Rs
 // ---- latency mode: a team of W warps per visit ---------------------------------------------------------------
 // Dependency-bound phases (pass 0, small holes) are limited by depth x per-visit latency, not by throughput.
 // Warp 0 of a team prepares the visit as above; then all W*32 lanes evaluate: (A) every (heuristic candidate,
-// 4-neighbour chunk) pair in one gather round, sums merged by shared-memory atomics; (B) the random probes, one
+// chunk) pair in one gather round, sums merged by shared-memory atomics; (B) the random probes, one
 // per lane per round, early-out against a team-shared packed best (sum << 32 | index, atomicMin) -- the same
 // "first candidate with the minimum full sum" rule, hence the same bits as the warp kernel.
 struct TeamShared {
@@ -672,26 +729,20 @@ __device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
 }
 
 template <bool MAPS>
-__global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J, const unsigned W) {
+__global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const RsDev J, const unsigned W) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *lutm = lutc + RS_LUT_WORDS;
-  const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
-  WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + lut_bytes);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch) * RS_WARPS_PER_CTA);
-  TeamShared *tshared = reinterpret_cast<TeamShared *>(bar + 2);
   RsCtrl *ctrl = J.ctrl;
   if (rs_ld_u32_relaxed(&ctrl->stop)) return;
-  rs_stage_tables<MAPS>(J, lutc, lutm, bar);
+  const PassSmem P = rs_pass_smem<MAPS, RS_TEAM_SLOTS>(J, smem_raw);
+  const unsigned lutc = P.lutc, lutm = P.lutm;
+  TeamShared *tshared = reinterpret_cast<TeamShared *>(P.bar + 2);
 
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned team = warp / W, wt = warp % W, T = W * 32u, tid = wt * 32u + lane;
   const unsigned bar_id = 1u + team;
-  WarpScratch &S = scratch[team];
+  WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[team];
   TeamShared &TS = tshared[team];
   const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
-  lutc += lane;  // this lane's column of the replicated tables
-  lutm += lane;
   VisitStats st;
   Visit V;
   while (true) {
@@ -704,13 +755,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J
     if (!TS.alive) break;
     const uint32_t v = TS.v, K = TS.K, nHeur = TS.nHeur;
     // ---- (A) heuristic candidates: all (candidate, chunk) pairs at once
-    const uint32_t nch = (K + RS_CHUNK - 1u) / RS_CHUNK;
+    const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, nch = nchr ? nchr : 1u;
     for (uint32_t t = tid; t < nHeur * nch; t += T) {
-      const uint32_t ci = t / nch, k0 = (t % nch) * RS_CHUNK;
-      const uint32_t c = S.aux[ci];
-      const uint32_t part = rs_chunk_sum<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, (int)(c & 0xFFFFu), (int)(c >> 16), k0, st.compares);
-      atomicAdd(&TS.hsum[ci], part);
-      st.issued += (k0 == 0u) ? 1u : 0u;
+      const uint32_t ci = t / nch, j = t % nch;
+      atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, K, S.aux[ci], j, st));
     }
     rs_team_sync(bar_id, T);
     if (wt == 0) {  // first candidate with the minimum full sum
@@ -730,19 +778,24 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J
     // ---- (B) random probes: one candidate per lane per round, early-out against the shared best
     volatile unsigned long long *vbest = &TS.best;
     const uint32_t hv = rs_probe_hash_visit(seed, pass, v);
+    const uint32_t selfmap = MAPS ? S.map[0] : 0u;
     if ((uint32_t)(*vbest >> 32) != 0u) {
       for (uint32_t j = tid; j < J.probes; j += T) {
         if ((uint32_t)(*vbest >> 32) == 0u) break;  // perfect match: nothing later is evaluated (synthesize.h:599)
         const uint32_t c = __ldg(J.corpus_pts + rs_range(rs_mix32(hv + j * 0xC2B2AE35u), nC));
-        const int cx = (int)(c & 0xFFFFu), cy = (int)(c >> 16);
+        const int cx = (int)(c & 0xFFFFu);
+        const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx;
         const unsigned long long idx = (unsigned long long)(nHeur + j);
-        uint32_t partial = 0;
+        uint32_t partial = 0, k0 = 1;
+        if (MAPS) partial = rs_lut3(lutm, __vabsdiffu4(__ldg(&J.corpus8[clin].y), selfmap));
         bool alive = true;
         st.issued++;
-        for (uint32_t k0 = 0; k0 < K; k0 += RS_CHUNK) {
-          partial += rs_chunk_sum<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, cx, cy, k0, st.compares);
+        do {
+          partial += rs_chunk_sum<MAPS>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
+          k0 += RS_CHUNK;
           if ((((unsigned long long)partial << 32) | idx) > *vbest) { alive = false; break; }
-        }
+        } while (k0 < K);
+        st.compares += min(k0, K);
         if (alive) atomicMin(&TS.best, ((unsigned long long)partial << 32) | idx);
       }
     }
@@ -759,47 +812,42 @@ __global__ void __launch_bounds__(RS_THREADS, 2) k_synth_pass_team(const RsDev J
 
 // ------------------------------------------------------------------------------ standalone best-fit kernel
 template <bool MAPS>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_BF_WARPS * 32, 2)
     k_bestfit_batch(const RsDev J, uint32_t n_visits, const uint32_t *__restrict__ nb_begin,
                     const uint32_t *__restrict__ nb_offsets, const uint8_t *__restrict__ nb_pixels, int n_color,
                     int n_map, int map_bip, const uint32_t *__restrict__ cand_begin, const uint32_t *__restrict__ cands,
                     uint32_t *__restrict__ best_sum, int32_t *__restrict__ best_index) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
-  uint32_t *lutm = lutc + RS_LUT_WORDS;
-  const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
-  WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + lut_bytes);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch) * RS_WARPS_PER_CTA);
-  if (threadIdx.x == 0) {
-    rs_mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    rs_mbar_expect_tx(bar, lut_bytes);
-    rs_tma_load_1d(lutc, J.lut_rep, RS_LUT_WORDS * 4u, bar);
-    if (MAPS) rs_tma_load_1d(lutm, J.lut_rep + RS_LUT_WORDS, RS_LUT_WORDS * 4u, bar);
-  }
-  __syncthreads();
-  rs_mbar_wait(bar, 0);
+  const PassSmem P = rs_pass_smem<MAPS, RS_BF_WARPS>(J, smem_raw);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  WarpScratch &S = scratch[warp];
-  lutc += lane;
-  lutm += lane;
-  for (uint32_t v = blockIdx.x * RS_WARPS_PER_CTA + warp; v < n_visits; v += gridDim.x * RS_WARPS_PER_CTA) {
+  WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[warp];
+  for (uint32_t v = blockIdx.x * RS_BF_WARPS + warp; v < n_visits; v += gridDim.x * RS_BF_WARPS) {
     const uint32_t nb0 = nb_begin[v], K = min(nb_begin[v + 1] - nb0, (uint32_t)RS_MAX_NB);
-    for (uint32_t k = lane; k < K; k += 32) {
-      S.off[k] = nb_offsets[nb0 + k];
-      const uint8_t *p = nb_pixels + (size_t)(nb0 + k) * 8;
-      uint32_t col = 0, mp = 0;
-      for (int c = 0; c < n_color; c++) col |= (uint32_t)p[1 + c] << (8 * (c + 1));
-      for (int c = 0; c < n_map; c++) mp |= (uint32_t)p[map_bip + c] << (8 * c);
-      S.pix[k] = col;
-      S.map[k] = mp;
+    const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, kpad = 1u + (nchr ? nchr : 1u) * RS_CHUNK;
+    for (uint32_t k = lane; k < kpad; k += 32) {
+      RsNb r;
+      uint32_t mp = 0;
+      if (k < K) {
+        const uint32_t o = nb_offsets[nb0 + k];
+        const uint8_t *p = nb_pixels + (size_t)(nb0 + k) * 8;
+        uint32_t col = 0;
+        for (int c = 0; c < n_color; c++) col |= (uint32_t)p[1 + c] << (8 * c);
+        for (int c = 0; c < n_map; c++) mp |= (uint32_t)p[map_bip + c] << (8 * c);
+        r.dx = rs_off_x(o); r.lin = rs_off_y(o) * J.cw + r.dx; r.pix = col; r.pen = J.penalty;
+      } else {
+        r.lin = 0; r.dx = RS_PAD_DX; r.pix = 0u; r.pen = 0u;
+      }
+      S.nb[k] = r;
+      if (MAPS) S.map[k] = mp;
     }
     __syncwarp();
     const uint32_t c0 = cand_begin[v], nc = cand_begin[v + 1] - c0;
     uint32_t bestSum = 0xFFFFFFFFu, cmp = 0, iss = 0;
     int bestIdx = 0x7FFFFFFF;
-    rs_eval_range<MAPS>(J, lutc, lutm, S.off, S.pix, S.map, K, 0, (int)nc,
-                        [&](int i) { return __ldg(cands + c0 + i); }, bestSum, bestIdx, cmp, iss);
+    if (K)
+      rs_eval_range<MAPS>(J, P.lutc, P.lutm, S.nb, S.map, K, 0, (int)nc,
+                          [&](int i) { return __ldg(cands + c0 + i); }, bestSum, bestIdx, cmp, iss);
+    else if (nc) { bestSum = 0u; bestIdx = 0; }  // an empty patch matches anything perfectly
     if (lane == 0) {
       best_sum[v] = bestSum;
       best_index[v] = (bestIdx == 0x7FFFFFFF) ? -1 : bestIdx;
@@ -830,6 +878,7 @@ struct Workspace {
   int off_w = 0, off_h = 0;  // dimensions the resident offsets table was built for
   uint32_t off_n = 0;
   int grid[2] = {0, 0};      // persistent grid of k_synth_pass<false/true>
+  int grid_team[2] = {0, 0}; // persistent grid of k_synth_pass_team<false/true>
 };
 static std::atomic<int> g_job_slots{1};
 extern "C" void rs_cuda_set_job_slots(int slots) { g_job_slots.store(slots < 1 ? 1 : slots); }
@@ -873,19 +922,22 @@ static void ws_free(Workspace *w) {
   delete w;
 }
 
-static size_t pass_smem(bool maps) {
-  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + sizeof(WarpScratch) * RS_WARPS_PER_CTA + 16 + sizeof(TeamShared) * 8;
+static size_t pass_smem(bool maps, int scratch_slots) {
+  const size_t scratch = maps ? sizeof(WarpScratch<true>) : sizeof(WarpScratch<false>);
+  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + scratch * scratch_slots + 16 + sizeof(TeamShared) * RS_TEAM_SLOTS;
 }
 template <bool MAPS>
 static int configure_pass_kernel(Workspace *w) {
-  const size_t smem = pass_smem(MAPS);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 0, sms = 0;
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS>, RS_THREADS, smem));
+  const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS);
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
+  int per_sm = 0, per_sm_team = 0, sms = 0;
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS>, RS_TP_WARPS * 32, smem_tp));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS>, RS_TEAM_WARPS * 32, smem_team));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
-  if (per_sm < 1) { g_err = "k_synth_pass does not fit on an SM"; return 100; }
+  if (per_sm < 1 || per_sm_team < 1) { g_err = "the pass kernels do not fit on an SM"; return 100; }
   w->grid[MAPS ? 1 : 0] = per_sm * sms;
+  w->grid_team[MAPS ? 1 : 0] = per_sm_team * sms;
   return 0;
 }
 
@@ -913,7 +965,7 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming));
   WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
   WCHK(cudaHostAlloc(&w->h_cancel, sizeof(int), cudaHostAllocMapped));
-  WCHK(cudaHostAlloc(&w->h_ctrl, sizeof(RsCtrl), cudaHostAllocDefault));
+  WCHK(cudaHostAlloc(&w->h_ctrl, RS_CTRL_COPY_BYTES, cudaHostAllocDefault));
 #undef WCHK
   *out = w;
   return 0;
@@ -951,6 +1003,7 @@ struct RsJob {
   size_t pin_targets_off = 0;     // where the visit order is staged in the pinned buffer
   bool want_sources = false;
   float ms_passes = 0.f;
+  uint32_t launches = 0;          // pass-kernel launches of the last run
 };
 
 extern "C" void rs_job_destroy(RsJob *j) {
@@ -1042,12 +1095,12 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
   const size_t cap_cpts = corpus_points ? (size_t)n_corpus : cn;
   int rc = 0;
   if ((rc = ws_ensure(w->raw_t, tn * d.bpp)) || (rc = ws_ensure(w->raw_c, cn * d.bpp)) ||
-      (rc = ws_ensure(w->corpus, cn * (j->maps ? 8 : 4))) || (rc = ws_ensure(w->W, tn * 16)) ||
+      (rc = ws_ensure(w->corpus, (cn + 1) * (j->maps ? 8 : 4))) || (rc = ws_ensure(w->W, tn * 16)) ||
       (rc = ws_ensure(w->meta, tn * 4)) || (rc = ws_ensure(w->tmaps, j->maps ? tn * 4 : 4)) ||
       (rc = ws_ensure(w->targets, (size_t)n_targets * 4)) || (rc = ws_ensure(w->cpts, cap_cpts * 4)) ||
       (rc = ws_ensure(w->lut256, 512 * 4)) || (rc = ws_ensure(w->lut_rep, 2 * RS_LUT_WORDS * 4)) ||
       (rc = ws_ensure(w->prober0, cn * 8)) || (rc = ws_ensure(w->prober1, cn * 8)) || (rc = ws_ensure(w->prober2, cn * 8)) ||
-      (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) || (rc = ws_ensure(w->ctrl, sizeof(RsCtrl) + 64)))
+      (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) || (rc = ws_ensure(w->ctrl, sizeof(RsCtrl))))
     return rc;
   {
     uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
@@ -1068,7 +1121,7 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
   if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
   j->pin_targets_off = o_tp;
   uint8_t *pin = (uint8_t *)w->pin;
-  RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl) + 64, s));
+  RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl), s));
   memcpy(pin + o_c, corpus_raw, sz_c);
   RS_CHECK(cudaMemcpyAsync(w->raw_c.p, pin + o_c, sz_c, cudaMemcpyHostToDevice, s));
   memcpy(pin + o_t, target_raw, sz_t);
@@ -1110,7 +1163,7 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
   RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 8, s));
   RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 8, s));
   RS_CHECK(cudaMemsetAsync(w->prober2.p, 0, cn * 8, s));
-  k_canon_corpus<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
+  k_canon_corpus<<<(unsigned)((cn + T) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
                                                           d.map_bip, j->maps ? nullptr : (uint32_t *)w->corpus.p,
                                                           j->maps ? (uint2 *)w->corpus.p : nullptr);
   k_init_target<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_t.p, (int)tn, d.bpp, d.n_color, d.n_map,
@@ -1167,7 +1220,7 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   { const uint32_t e = (j->nT + 31u) / 32u; D.epoch_len = e < 64u ? 64u : e; }
   D.nb_lists = (const uint2 *)w->nb_lists.p; D.nb_counts = (const uint8_t *)w->nb_counts.p;
   D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
-  D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch;
+  D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch; D.cn = (uint32_t)d.cw * (uint32_t)d.ch;
   D.nT = j->nT; D.nOff = j->nOff;
   uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;  // the size test follows the append (synthesize.h:222-224)
   D.kmax = kmax > RS_MAX_NB ? RS_MAX_NB : kmax;
@@ -1178,54 +1231,100 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   return D;
 }
 
-// Warps per visit for pass p: 1 = throughput kernel, 2/4/8 = team kernel (latency mode).  A pass is bound either by
-// visit throughput (4736 resident warps / W visits in flight) or by the depth of its dependency chains times the
-// latency of one visit; small jobs and pass 0 (long chains through freshly valued pixels) are the latter.
-// Thresholds from sweeps on B200 (profiles/team_width_sweep_r01.txt); RS_TEAM_P0 / RS_TEAM_PN override.
-static unsigned team_width(const RsJob *j, uint32_t p) {
-  const char *e = getenv(p == 0 ? "RS_TEAM_P0" : "RS_TEAM_PN");
-  if (e) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) return (unsigned)w; }
+// Warps per visit: 1 = throughput kernel, 2/4/8 = team kernel (latency mode).  A stretch of a pass is bound either
+// by visit throughput (4736 resident warps / W visits in flight) or by the depth of its dependency chains times the
+// latency of one visit.  Small jobs are the latter throughout; so is the BEGINNING of pass 0 of any job: while few
+// target points have a value, the nearest valued pixels of a visit are the visits just before it, wherever they
+// are, and the pass runs almost serially (profiles/timeline_*.txt).  A pass is therefore cut into segments, one
+// launch each, whose width shrinks as the pass fills in.  Thresholds from sweeps on B200 (profiles/); RS_TEAM_P0 /
+// RS_TEAM_PN force one width for a whole pass, RS_SEG_P0="end:width,end:width,..." forces the pass-0 plan.
+struct Segment { uint32_t end; unsigned width; };
+static unsigned pass_width(const RsJob *j, uint32_t p) {
   const uint32_t n = j->nT;
-  const bool heavy = j->d.patch_size >= 16;  // visits long enough to amortise the team barriers
   if (n <= 32768u) return 8;
   if (n <= 200000u) return p == 0 ? 8 : 4;
   if (n <= 600000u) return p == 0 ? 4 : 2;
-  return (p == 0 && heavy) ? 4 : 1;
+  return 1;
+}
+static int plan_segments(const RsJob *j, uint32_t p, Segment *out /*[4]*/) {
+  const uint32_t end = j->d.pass_end[p];
+  const char *e = getenv(p == 0 ? "RS_TEAM_P0" : "RS_TEAM_PN");
+  if (e) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) { out[0] = {end, (unsigned)w}; return 1; } }
+  const unsigned base = pass_width(j, p);
+  if (p != 0) { out[0] = {end, base}; return 1; }
+  Segment plan[4] = {{16384u, 8u}, {65536u, 4u}, {262144u, 2u}, {0xFFFFFFFFu, 1u}};
+  if (const char *sp = getenv("RS_SEG_P0")) {  // "end:width,..." ; the last entry runs to the end of the pass
+    int k = 0;
+    while (*sp && k < 4) {
+      char *q = nullptr;
+      const unsigned long en = strtoul(sp, &q, 10);
+      if (q == sp || *q != ':') break;
+      const unsigned long wd = strtoul(q + 1, &q, 10);
+      plan[k++] = {(uint32_t)en, (unsigned)((wd == 2 || wd == 4 || wd == 8) ? wd : 1)};
+      sp = (*q == ',') ? q + 1 : q;
+    }
+    if (k) { plan[k - 1].end = 0xFFFFFFFFu; for (; k < 4; k++) plan[k] = {0xFFFFFFFFu, 1u}; }
+  }
+  int n = 0;
+  uint32_t begin = 0;
+  for (int k = 0; k < 4 && begin < end; k++) {
+    const unsigned w = plan[k].width > base ? plan[k].width : base;
+    const uint32_t se = plan[k].end < end ? plan[k].end : end;
+    if (se <= begin) continue;
+    if (n && out[n - 1].width == w) out[n - 1].end = se;  // same width as the previous segment: one launch
+    else out[n++] = {se, w};
+    begin = se;
+  }
+  if (n == 0) out[n++] = {end, base};
+  out[n - 1].end = end;
+  return n;
 }
 
 extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
-  int grid = w->grid[j->maps ? 1 : 0];
+  int grid = w->grid[j->maps ? 1 : 0], grid_team = w->grid_team[j->maps ? 1 : 0];
   {  // several jobs sharing the device: each persistent grid takes its share of the SMs (rs_cuda_set_job_slots)
     const int slots = g_job_slots.load();
-    if (slots > 1) { const int share = (grid + slots - 1) / slots; grid = share < 8 ? 8 : share; }
-    if (const char *e = getenv("RS_GRID_CAP")) { const int c = atoi(e); if (c > 0 && c < grid) grid = c; }
+    if (slots > 1) {
+      grid = (grid + slots - 1) / slots; if (grid < 4) grid = 4;
+      grid_team = (grid_team + slots - 1) / slots; if (grid_team < 8) grid_team = 8;
+    }
+    if (const char *e = getenv("RS_GRID_CAP")) { const int c = atoi(e); if (c > 0 && c < grid) grid = c; if (c > 0 && c < grid_team) grid_team = c; }
   }
-  const size_t smem = pass_smem(j->maps);
+  const size_t smem_tp = pass_smem(j->maps, RS_TP_WARPS), smem_team = pass_smem(j->maps, RS_TEAM_SLOTS);
   RS_CHECK(cudaEventRecord(w->ev0, s));
   {  // all pass-0 patches, dependency-free
     RsDev D0 = make_dev(j, 0);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
-    unsigned int *claims = (unsigned int *)((uint8_t *)w->ctrl.p + sizeof(RsCtrl));  // [0] coop, [1] warp kernel
+    RsLine *claims = ((RsCtrl *)w->ctrl.p)->claims;  // [0] coop, [1] warp kernel
     const uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;  // the long scans: one CTA each
-    RS_CHECK(cudaMemcpyAsync(claims + 1, &v1, 4, cudaMemcpyHostToDevice, s));
-    k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, claims);
-    k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, claims + 1);
+    RS_CHECK(cudaMemcpyAsync(&claims[1].v, &v1, 4, cudaMemcpyHostToDevice, s));
+    k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[0].v);
+    k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, &claims[1].v);
   }
+  uint32_t slot = 0;
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     RsDev D = make_dev(j, p);
-    const unsigned W = team_width(j, p);
-    if (W <= 1) {
-      if (j->maps) k_synth_pass<true><<<grid, RS_THREADS, smem, s>>>(D);
-      else k_synth_pass<false><<<grid, RS_THREADS, smem, s>>>(D);
-    } else {
-      if (j->maps) k_synth_pass_team<true><<<grid, RS_THREADS, smem, s>>>(D, W);
-      else k_synth_pass_team<false><<<grid, RS_THREADS, smem, s>>>(D, W);
+    Segment seg[4];
+    const int nseg = plan_segments(j, p, seg);
+    uint32_t begin = 0;
+    for (int k = 0; k < nseg; k++) {
+      D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
+      const unsigned W = seg[k].width;
+      if (W <= 1) {
+        if (j->maps) k_synth_pass<true><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+        else k_synth_pass<false><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+      } else {
+        if (j->maps) k_synth_pass_team<true><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+        else k_synth_pass_team<false><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+      }
+      begin = seg[k].end;
     }
   }
+  j->launches = slot;
   RS_CHECK(cudaGetLastError());
   RS_CHECK(cudaEventRecord(w->ev1, s));
   k_writeback<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, (const uint32_t *)w->targets.p, j->nT,
@@ -1238,7 +1337,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   if (j->want_sources)
     RS_CHECK(cudaMemcpyAsync((uint8_t *)w->pin + ((rows_bytes + 255) & ~(size_t)255), w->sources.p, (size_t)j->nT * 4,
                              cudaMemcpyDeviceToHost, s));
-  RS_CHECK(cudaMemcpyAsync(w->h_ctrl, w->ctrl.p, sizeof(RsCtrl), cudaMemcpyDeviceToHost, s));
+  RS_CHECK(cudaMemcpyAsync(w->h_ctrl, w->ctrl.p, RS_CTRL_COPY_BYTES, cudaMemcpyDeviceToHost, s));
   RS_CHECK(cudaEventRecord(w->evDone, s));
   // Host side of the progress/cancel contract: replay ticks in order while the device runs.
   uint32_t emitted[6] = {0, 0, 0, 0, 0, 0};  // ticks already forwarded per pass
@@ -1305,7 +1404,22 @@ extern "C" int rs_job_counters(RsJob *j, RsJobCounters *out) {
   out->passes_run = c.passes_run;
   out->n_corpus = c.n_corpus;
   out->ms_passes = j->ms_passes;
+  for (uint32_t p = 0; p < c.passes_run && p < 6; p++)
+    out->ms_pass[p] = c.pass_end_ns[p] > c.tick_ns[p][0] ? (float)((c.pass_end_ns[p] - c.tick_ns[p][0]) * 1e-6) : 0.f;
   return 0;
+}
+
+// Start time (ns since the pass began) of every 4096th visit of a pass of the last run: the throughput profile of
+// the pass.  Returns the number of entries written.
+extern "C" uint32_t rs_job_timeline(RsJob *j, uint32_t pass, uint64_t *out_ns, uint32_t cap) {
+  const RsCtrl &c = *j->ws->h_ctrl;
+  if (pass >= 6 || pass >= c.passes_run) return 0;
+  const unsigned long long started = c.pass_visits[pass];
+  uint32_t n = started ? (uint32_t)((started - 1ull) / 4096ull + 1ull) : 0u;
+  if (n > RS_TIMELINE) n = RS_TIMELINE;
+  if (n > cap) n = cap;
+  for (uint32_t i = 0; i < n; i++) out_ns[i] = c.tick_ns[pass][i] - c.tick_ns[pass][0];
+  return n;
 }
 
 // Device-built offsets table of a job, for parity tests against the host/oracle table.
@@ -1336,7 +1450,7 @@ extern "C" int rs_bestfit_batch(const RsJobDesc *desc, const uint8_t *corpus_raw
   int rc = 0;
 #define BCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = 100; goto done; } } while (0)
   BCHK(cudaMalloc(&d_raw, cn * desc->bpp));
-  if (maps) BCHK(cudaMalloc(&d_c8, cn * 8)); else BCHK(cudaMalloc(&d_c4, cn * 4));
+  if (maps) BCHK(cudaMalloc(&d_c8, (cn + 1) * 8)); else BCHK(cudaMalloc(&d_c4, (cn + 1) * 4));
   BCHK(cudaMalloc(&d_lut, 512 * 4)); BCHK(cudaMalloc(&d_rep, 2 * RS_LUT_WORDS * 4));
   BCHK(cudaMalloc(&d_nbb, (size_t)(n_visits + 1) * 4)); BCHK(cudaMalloc(&d_cb, (size_t)(n_visits + 1) * 4));
   BCHK(cudaMalloc(&d_nbo, (size_t)(n_nb + 1) * 4)); BCHK(cudaMalloc(&d_nbpix, (size_t)(n_nb + 1) * 8));
@@ -1351,22 +1465,22 @@ extern "C" int rs_bestfit_batch(const RsJobDesc *desc, const uint8_t *corpus_raw
   BCHK(cudaMemcpy(d_nbpix, nb_pixels, (size_t)n_nb * 8, cudaMemcpyHostToDevice));
   BCHK(cudaMemcpy(d_c, cands, (size_t)n_cand * 4, cudaMemcpyHostToDevice));
   {
-    k_canon_corpus<<<(unsigned)((cn + 255) / 256), 256>>>(d_raw, (int)cn, desc->bpp, desc->n_color, desc->n_map,
+    k_canon_corpus<<<(unsigned)((cn + 256) / 256), 256>>>(d_raw, (int)cn, desc->bpp, desc->n_color, desc->n_map,
                                                         desc->map_bip, d_c4, d_c8);
     k_replicate_lut<<<(RS_LUT_WORDS + 255) / 256, 256>>>(d_lut, d_lut + 256, d_rep);
     RsDev D;
     memset(&D, 0, sizeof D);
-    D.corpus4 = d_c4; D.corpus8 = d_c8; D.lut_rep = d_rep; D.cw = desc->cw; D.ch = desc->ch;
+    D.corpus4 = d_c4; D.corpus8 = d_c8; D.lut_rep = d_rep; D.cw = desc->cw; D.ch = desc->ch; D.cn = (uint32_t)cn;
     D.penalty = 65535u * (uint32_t)desc->n_color + map_lut_max * (uint32_t)desc->n_map;
-    const size_t smem = pass_smem(maps);
-    const unsigned grid = (n_visits + RS_WARPS_PER_CTA - 1) / RS_WARPS_PER_CTA;
+    const size_t smem = pass_smem(maps, RS_BF_WARPS);
+    const unsigned grid = (n_visits + RS_BF_WARPS - 1) / RS_BF_WARPS;
     if (maps) {
       BCHK(cudaFuncSetAttribute(k_bestfit_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_bestfit_batch<true><<<grid > 1184 ? 1184 : grid, RS_THREADS, smem>>>(D, n_visits, d_nbb, d_nbo, d_nbpix, desc->n_color, desc->n_map,
+      k_bestfit_batch<true><<<grid > 1184 ? 1184 : grid, RS_BF_WARPS * 32, smem>>>(D, n_visits, d_nbb, d_nbo, d_nbpix, desc->n_color, desc->n_map,
                                                        desc->map_bip, d_cb, d_c, d_bs, d_bi);
     } else {
       BCHK(cudaFuncSetAttribute(k_bestfit_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k_bestfit_batch<false><<<grid > 1184 ? 1184 : grid, RS_THREADS, smem>>>(D, n_visits, d_nbb, d_nbo, d_nbpix, desc->n_color, desc->n_map,
+      k_bestfit_batch<false><<<grid > 1184 ? 1184 : grid, RS_BF_WARPS * 32, smem>>>(D, n_visits, d_nbb, d_nbo, d_nbpix, desc->n_color, desc->n_map,
                                                         desc->map_bip, d_cb, d_c, d_bs, d_bi);
     }
     BCHK(cudaGetLastError());
