@@ -130,11 +130,15 @@ typedef struct {
   unsigned int passes_run, n_targets, n_corpus;
   float ms_prep, ms_h2d, ms_kernels, ms_d2h, ms_total; /* host prep / copies / device passes (CUDA events) */
   float ms_pass[6];                                    /* device-clock duration of each pass that ran */
+  float ms_synth;                                      /* CUDA-event time of the pass kernels alone */
+  unsigned int kernel_launches, synth_launches_run;    /* kernels launched by the job; pass launches that did work */
 } RsStats;
 /* Throughput profile of the last engine() call on this thread (needs rs_keep_result(1)): ns from the start of
  * `pass` to the claim of its visit 4096 * i.  Returns the number of entries written. */
 unsigned int rs_get_timeline(unsigned int pass, unsigned long long *out_ns, unsigned int cap);
 void rs_get_stats(RsStats *out);
+/* CUDA kernels launched by all engine() calls of this process so far (any thread). */
+unsigned long long rs_total_kernel_launches(void);
 /* Batch of independent jobs (the reference has no such call; its users loop over engine()).  Runs `n_jobs`
  * engine() calls on `slots` host threads that share the current CUDA device; each job's kernels take 1/slots of
  * the SMs.  Small jobs are latency-bound on their dependency chains, so running several side by side multiplies

@@ -52,6 +52,9 @@ typedef struct {
   uint32_t n_corpus;             /* corpus points (counted on the device when not given by the caller) */
   float ms_passes;               /* CUDA-event time of all pass kernels of the last run */
   float ms_pass[6];              /* device-clock duration of each pass that ran (first claim to last CTA out) */
+  float ms_synth;                /* CUDA-event time of the pass kernels alone (ms_passes minus the pass-0 patch gather) */
+  uint32_t kernel_launches;      /* kernels this job launched: upload/init, pass-0 gather, passes, write-back */
+  uint32_t synth_launches_run;   /* pass-kernel launches that did work (launches of passes after the stop rule exit at once) */
 } RsJobCounters;
 
 /* Called on the host, in order, for every (pass, index) with (index & 4095) == 0 that the device
@@ -108,6 +111,11 @@ void rs_cuda_release_cached(void);
  * nb_offsets (packed int16 pairs) / nb_pixels (8 raw pixel bytes each); candidates
  * [cand_begin[v], cand_begin[v+1]) of cands (packed x|y<<16).  Outputs per visit: best sum (0xFFFFFFFF if no
  * candidate), index of the winning candidate within the visit's list (-1 if none). */
+/* Micro-benchmark: sustained rate of independent, uniformly random aligned loads of elem_bytes (4 or 8) from a
+ * device buffer of buffer_bytes, in loads per second (best of `repeats`, CUDA events).  The distance loop does one
+ * such load per neighbour compare, so this is its practical ceiling on this GPU. */
+int rs_cuda_gather_rate(size_t buffer_bytes, int elem_bytes, int repeats, double *loads_per_s);
+
 int rs_bestfit_batch(const RsJobDesc *desc, const uint8_t *corpus_raw,
                      const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max,
                      uint32_t n_visits, const uint32_t *nb_begin, const uint32_t *nb_offsets,

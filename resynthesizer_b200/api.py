@@ -29,7 +29,8 @@ class RsStats(C.Structure):
                [("betters", C.c_ulonglong * 6), ("pass_visits", C.c_ulonglong * 6), ("sum_best", C.c_ulonglong * 6),
                 ("passes_run", C.c_uint), ("n_targets", C.c_uint), ("n_corpus", C.c_uint),
                 ("ms_prep", C.c_float), ("ms_h2d", C.c_float), ("ms_kernels", C.c_float),
-                ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("ms_pass", C.c_float * 6)]
+                ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("ms_pass", C.c_float * 6), ("ms_synth", C.c_float),
+                ("kernel_launches", C.c_uint), ("synth_launches_run", C.c_uint)]
 
     def as_dict(self):
         d = {}
@@ -90,6 +91,23 @@ def last_stats():
     s = RsStats()
     lib().rs_get_stats(C.byref(s))
     return s.as_dict()
+
+
+def total_kernel_launches():
+    L = lib()
+    L.rs_total_kernel_launches.restype = C.c_ulonglong
+    return int(L.rs_total_kernel_launches())
+
+
+def gather_rate(buffer_bytes, elem_bytes=4, repeats=3):
+    """Sustained random-gather rate of this GPU for corpus-pixel-sized loads, loads/s (rs_cuda_gather_rate)."""
+    L = lib()
+    L.rs_cuda_gather_rate.argtypes = [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.rs_cuda_gather_rate.restype = C.c_int
+    out = C.c_double(0.0)
+    if L.rs_cuda_gather_rate(int(buffer_bytes), int(elem_bytes), int(repeats), C.byref(out)):
+        raise ResynthError("rs_cuda_gather_rate failed")
+    return out.value
 
 
 def last_timeline(pass_index):

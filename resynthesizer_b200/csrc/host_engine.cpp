@@ -24,6 +24,8 @@ thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-ta
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
 thread_local std::vector<uint64_t> t_timeline[6];                   // of the last engine() call (rs_keep_result)
 
+std::atomic<unsigned long long> g_kernel_launches{0};  // every kernel any engine() call of this process launched
+
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
@@ -64,6 +66,7 @@ int on_tick(void *p, uint32_t /*pass*/, uint32_t /*index*/) {
 extern "C" const char *rs_last_error(void) { return t_err.c_str(); }
 extern "C" void rs_get_stats(RsStats *out) { *out = t_stats; }
 extern "C" void rs_set_seed(unsigned int seed) { t_seed = seed; }
+extern "C" unsigned long long rs_total_kernel_launches(void) { return g_kernel_launches.load(); }
 extern "C" void rs_keep_result(int yes) { t_keep_result = yes != 0; }
 extern "C" int rs_set_device(int ordinal) {
   if (rs_cuda_set_device(ordinal)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
@@ -226,6 +229,8 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   t_stats.ms_prep = (float)((t1 - t0) + (t2b - t2)); t_stats.ms_h2d = (float)(t2 - t1); t_stats.ms_kernels = jc.ms_passes;
   t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
   for (int p = 0; p < 6; p++) t_stats.ms_pass[p] = jc.ms_pass[p];
+  g_kernel_launches.fetch_add(jc.kernel_launches);
+  t_stats.ms_synth = jc.ms_synth; t_stats.kernel_launches = jc.kernel_launches; t_stats.synth_launches_run = jc.synth_launches_run;
   (void)t2;
   return 0;  // success, also when cancelled (lib/engine.c:689)
 }

@@ -867,7 +867,7 @@ struct DevBuf {
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evDone = nullptr;
+  cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
@@ -916,6 +916,7 @@ static void ws_free(Workspace *w) {
   if (w->h_cancel) cudaFreeHost(w->h_cancel);
   if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
   if (w->ev0) cudaEventDestroy(w->ev0);
+  if (w->evG) cudaEventDestroy(w->evG);
   if (w->ev1) cudaEventDestroy(w->ev1);
   if (w->evDone) cudaEventDestroy(w->evDone);
   if (w->stream) cudaStreamDestroy(w->stream);
@@ -961,6 +962,7 @@ static int ws_acquire(Workspace **out) {
 #define WCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ws_free(w); return 100; } } while (0)
   WCHK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
   WCHK(cudaEventCreate(&w->ev0));
+  WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
   WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming));
   WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
@@ -1004,6 +1006,9 @@ struct RsJob {
   bool want_sources = false;
   float ms_passes = 0.f;
   uint32_t launches = 0;          // pass-kernel launches of the last run
+  uint32_t pass_launches[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
+  float ms_synth = 0.f;           // CUDA-event time of the pass kernels alone (after the pass-0 patch gather)
 };
 
 extern "C" void rs_job_destroy(RsJob *j) {
@@ -1130,6 +1135,8 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
   memcpy(pin + o_lut + 256 * 4, map_lut256, 256 * 4);
   RS_CHECK(cudaMemcpyAsync(w->lut256.p, pin + o_lut, sz_lut, cudaMemcpyHostToDevice, s));
   const int T = 256;
+  bool built_offsets = false;
+  int offset_sort_bits = 1;
   unsigned int *d_ncorpus = &((RsCtrl *)w->ctrl.p)->n_corpus;
   if (corpus_points) {
     memcpy(pin + o_cp, corpus_points, sz_cp);
@@ -1156,8 +1163,12 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
     w->off_w = w->off_h = 0; w->off_n = 0;  // not a cached full table
     j->nOff = n_offsets;
   } else {
-    if (!(w->off_w == ow && w->off_h == oh && w->off_n == full_n))
+    if (!(w->off_w == ow && w->off_h == oh && w->off_n == full_n)) {
       if ((rc = build_offsets_on_device(w, ow, oh, full_n))) return rc;
+      built_offsets = true;
+      const uint32_t maxd = (uint32_t)((ow - 1) * (ow - 1) + (oh - 1) * (oh - 1));
+      while (offset_sort_bits < 32 && (maxd >> offset_sort_bits)) offset_sort_bits++;
+    }
     j->nOff = full_n;
   }
   RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 8, s));
@@ -1173,6 +1184,7 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
   k_replicate_lut<<<(RS_LUT_WORDS + T - 1) / T, T, 0, s>>>((const uint32_t *)w->lut256.p, (const uint32_t *)w->lut256.p + 256,
                                                          (uint32_t *)w->lut_rep.p);
   RS_CHECK(cudaGetLastError());
+  j->upload_launches = 3u + (corpus_points ? 0u : 4u) + (built_offsets ? 1u + (uint32_t)((offset_sort_bits + 7) / 8) + 2u : 0u);
   for (int p = 0; p < 6; p++) w->h_ticks[p] = 0;
   *w->h_cancel = 0;
   return 0;
@@ -1185,6 +1197,7 @@ extern "C" int rs_job_upload_order(RsJob *j, const uint32_t *targets) {
   uint8_t *pin = (uint8_t *)w->pin;
   memcpy(pin + j->pin_targets_off, targets, (size_t)j->nT * 4);
   RS_CHECK(cudaMemcpyAsync(w->targets.p, pin + j->pin_targets_off, (size_t)j->nT * 4, cudaMemcpyHostToDevice, w->stream));
+  j->upload_launches += 1u;
   k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>((const uint32_t *)w->targets.p, j->nT, j->d.tw,
                                                              (uint32_t *)w->meta.p);
   RS_CHECK(cudaGetLastError());
@@ -1305,12 +1318,14 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[0].v);
     k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, &claims[1].v);
   }
+  RS_CHECK(cudaEventRecord(w->evG, s));
   uint32_t slot = 0;
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     RsDev D = make_dev(j, p);
     Segment seg[4];
     const int nseg = plan_segments(j, p, seg);
     uint32_t begin = 0;
+    j->pass_launches[p] = (uint32_t)nseg;
     for (int k = 0; k < nseg; k++) {
       D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
       const unsigned W = seg[k].width;
@@ -1378,6 +1393,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     if (started) emit_upto(p, (uint32_t)((started - 1ull) / 4096ull + 1ull));
   }
   RS_CHECK(cudaEventElapsedTime(&j->ms_passes, w->ev0, w->ev1));
+  RS_CHECK(cudaEventElapsedTime(&j->ms_synth, w->evG, w->ev1));
   return 0;
 }
 
@@ -1404,6 +1420,9 @@ extern "C" int rs_job_counters(RsJob *j, RsJobCounters *out) {
   out->passes_run = c.passes_run;
   out->n_corpus = c.n_corpus;
   out->ms_passes = j->ms_passes;
+  out->ms_synth = j->ms_synth;
+  out->kernel_launches = j->upload_launches + 2u + j->launches + 1u;  // + pass-0 gather x2, passes, write-back
+  for (uint32_t p = 0; p < c.passes_run && p < 6; p++) out->synth_launches_run += j->pass_launches[p];
   for (uint32_t p = 0; p < c.passes_run && p < 6; p++)
     out->ms_pass[p] = c.pass_end_ns[p] > c.tick_ns[p][0] ? (float)((c.pass_end_ns[p] - c.tick_ns[p][0]) * 1e-6) : 0.f;
   return 0;
@@ -1430,6 +1449,64 @@ extern "C" int rs_job_read_offsets(RsJob *j, uint32_t *out, uint32_t cap) {
   RS_CHECK(cudaStreamSynchronize(w->stream));
   RS_CHECK(cudaMemcpy(out, w->offsets.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// ------------------------------------------------------------------------------- gather-rate micro-benchmark
+// What the distance loop is made of: independent, uniformly random aligned loads of one corpus pixel (4 or 8 bytes)
+// from a buffer the size of a corpus.  Gives the rate this GPU sustains for that access pattern (L1/L2 sector
+// gathers), the practical ceiling of neighbour compares per second.
+template <typename T>
+__global__ void __launch_bounds__(1024, 1) k_gather_rate(const T *__restrict__ buf, uint32_t n_elems, uint32_t iters,
+                                                         unsigned long long *__restrict__ sink) {
+  uint32_t h = rs_mix32(blockIdx.x * 1024u + threadIdx.x + 0x9E3779B9u);
+  unsigned long long acc = 0;
+  for (uint32_t i = 0; i < iters; i++) {
+    uint32_t idx[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) { h = h * 1664525u + 1013904223u; idx[u] = __umulhi(rs_mix32(h), n_elems); }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const T v = __ldg(buf + idx[u]);
+      acc += (sizeof(T) == 8) ? (unsigned long long)((const uint32_t *)&v)[0] + ((const uint32_t *)&v)[sizeof(T) / 4 - 1]
+                              : (unsigned long long)((const uint32_t *)&v)[0];
+    }
+  }
+  if (acc == 0x123456789ull) *sink = acc;  // keep the loads alive
+}
+extern "C" int rs_cuda_gather_rate(size_t buffer_bytes, int elem_bytes, int repeats, double *loads_per_s) {
+  if (elem_bytes != 4 && elem_bytes != 8) { g_err = "rs_cuda_gather_rate: element size must be 4 or 8"; return 100; }
+  const uint32_t n = (uint32_t)(buffer_bytes / (size_t)elem_bytes);
+  void *buf = nullptr;
+  unsigned long long *sink = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  int sms = 148, dev = 0, rc = 0;
+  float best = 1e30f;
+  const uint32_t iters = 256;
+#define GCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = 100; goto out; } } while (0)
+  GCHK(cudaGetDevice(&dev));
+  GCHK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  GCHK(cudaMalloc(&buf, (size_t)n * elem_bytes));
+  GCHK(cudaMalloc(&sink, 8));
+  GCHK(cudaMemset(buf, 1, (size_t)n * elem_bytes));
+  GCHK(cudaEventCreate(&e0));
+  GCHK(cudaEventCreate(&e1));
+  for (int r = 0; r < repeats + 1; r++) {
+    GCHK(cudaEventRecord(e0));
+    if (elem_bytes == 4) k_gather_rate<uint32_t><<<sms, 1024>>>((const uint32_t *)buf, n, iters, sink);
+    else k_gather_rate<uint2><<<sms, 1024>>>((const uint2 *)buf, n, iters, sink);
+    GCHK(cudaEventRecord(e1));
+    GCHK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    GCHK(cudaEventElapsedTime(&ms, e0, e1));
+    if (r > 0 && ms < best) best = ms;
+  }
+  *loads_per_s = (double)sms * 1024.0 * iters * 8.0 / (best * 1e-3);
+out:
+#undef GCHK
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(buf); cudaFree(sink);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------- rs_bestfit_batch
