@@ -36,6 +36,12 @@
 #ifndef RS_CHUNK
 #define RS_CHUNK 2          // neighbours gathered per lane between two early-out checks (sweep: profiles/)
 #endif
+#ifndef RS_X_TRACK
+#define RS_X_TRACK 1
+#endif
+#ifndef RS_X_RED
+#define RS_X_RED 1
+#endif
 #define RS_LUT_WORDS (256 * 32)
 #define RS_MAX_LAUNCHES 16   // pass-kernel launches per job: 6 passes, the first ones cut into up to 4 segments
 #define RS_TIMELINE 320      // progress ticks per pass whose start time is kept (4096 visits each)
@@ -219,13 +225,15 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, 
 // semantics = the FIRST candidate in list order with the minimum full sum wins (strict '<' to better,
 // synthesize.h:382); a lane therefore abandons only when (partial, index) > (best, bestIndex)
 // lexicographically.  Result is independent of scheduling, hence bit-exact.
+// bestLin/bestCx return the winner's corpus pixel (linear index, x) when a candidate of this range wins.
 // Candidates are fetched a window of 32 ahead (one per lane, all lanes at once) and handed to the lanes that need
 // one by shuffle, so the dependent table load of cand_of() is off the critical path of a round.
 // K = patch size (>= 1); nb/nmap hold 1 + ceil((K-1)/RS_CHUNK)*RS_CHUNK records.
 template <bool MAPS, class CandFn>
 __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
                                               const uint32_t *nmap, uint32_t K, int begin, int end, CandFn cand_of,
-                                              uint32_t &bestSum, int &bestIdx, uint32_t &nCompares, uint32_t &nIssued) {
+                                              uint32_t &bestSum, int &bestIdx, uint32_t &bestLin, int &bestCx,
+                                              uint32_t &nCompares, uint32_t &nIssued) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   int next = begin;  // warp-uniform
@@ -252,7 +260,6 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
         if (MAPS) m0 = __ldg(&J.corpus8[clin].y);  // consumed after the first chunk's gathers are in flight
         k = 1;
         partial = 0;
-        nIssued++;
       }
       next += __popc(nbm);
       if (next > end) next = end;
@@ -263,7 +270,10 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
       }
     }
     const bool active = myIdx >= 0;
-    if (!__any_sync(RS_FULL, active)) break;
+    if (!__any_sync(RS_FULL, active)) {
+      nIssued += (lane == 0u) ? (uint32_t)(next - begin) : 0u;  // every candidate handed out, counted once
+      break;
+    }
     bool finished = false;
     if (active) {
       partial += rs_chunk_sum<MAPS>(J, lutc, lutm, nb, nmap, cx, clin, k);
@@ -279,6 +289,12 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
       if (m < bestSum || (m == bestSum && mi < bestIdx)) {
         bestSum = m;
         bestIdx = mi;
+        // the winner's corpus pixel travels with it, so the commit needs no point lookup
+#if RS_X_TRACK
+        const int src = __ffs(__ballot_sync(RS_FULL, propose && myIdx == mi)) - 1;
+        bestLin = __shfl_sync(RS_FULL, clin, src);
+        bestCx = __shfl_sync(RS_FULL, cx, src);
+#endif
       }
     }
     if (active && (finished || worse)) {

@@ -285,9 +285,33 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
 #ifndef RS_TP_MIN_CTAS
 #define RS_TP_MIN_CTAS 1
 #endif
+#ifndef RS_X_OWNCOL
+#define RS_X_OWNCOL 1
+#endif
+#ifndef RS_CLAIM_AHEAD
+#define RS_CLAIM_AHEAD 0    // 1: throughput kernel claims the next visit before the distance phase of the current one (no gain measured)
+#endif
 #define RS_TEAM_WARPS 16
 #define RS_TEAM_SLOTS 8
 #define RS_BF_WARPS 16
+
+// Registers are the scarce resource of the pass kernels (64 per thread), and what the distance loop does with a spare
+// one is keep another gather in flight.  So everything a visit needs only before or after that loop lives in the
+// warp's shared-memory scratch (WarpScratch::vis, ::st), written and read by lane 0.
+struct VisitShared {   // handed from rs_visit_prepare to rs_visit_finish
+  unsigned long long selfw;  // the visit's own state word of version `pass`
+  uint32_t selfq, epoch_idx, hide_from, my_base;
+};
+struct WarpStats {     // per-warp counters, flushed once at kernel end
+  unsigned long long evals, sumbest;
+  uint32_t visits, scans, heur, skips, perfect, betters;
+};
+struct LaneStats {     // per-lane counters of the distance loop (registers), reduced at kernel end
+  uint32_t compares = 0, issued = 0;
+};
+struct Visit {         // the visit a warp is working on (warp-uniform registers)
+  uint32_t v, K, nHeur;
+};
 
 template <bool MAPS>
 struct __align__(16) WarpScratch {
@@ -297,16 +321,8 @@ struct __align__(16) WarpScratch {
                              // heuristic candidates exist: reused as the full patch distance of each of them (hsum)
   uint32_t q[RS_MAX_NB];     // neighbour pixel index, later: packed heuristic candidate or RS_NO_SRC
   uint32_t aux[RS_MAX_NB];   // neighbour meta, later: neighbour source, later: compacted candidate list
-};
-
-struct VisitStats {  // per-warp counters, flushed once at kernel end
-  uint32_t visits = 0, compares = 0, issued = 0, scans = 0, heur = 0, skips = 0, perfect = 0, betters = 0;
-  unsigned long long evals = 0, sumbest = 0;
-};
-
-struct Visit {  // the visit a warp is working on (warp-uniform unless noted)
-  uint32_t v, K, nHeur, selfq, epoch_idx, hide_from, my_base;
-  unsigned long long selfw;  // lane 0 only: the visit's own state word of version `pass`
+  VisitShared vis;
+  WarpStats st;
 };
 
 // Stage the replicated metric tables with one TMA bulk copy per table (whole CTA calls this).
@@ -324,32 +340,53 @@ __device__ __forceinline__ void rs_stage_tables(const RsDev &J, uint32_t *lutc, 
   rs_mbar_wait(bar, 0);
 }
 
-// One warp: claim the next visit in order, gather its patch, wait for exactly the neighbour versions the
-// sequential loop would see, build the heuristic candidate list (S.aux[0..nHeur)).  False when the pass is exhausted.
+// Claim the next visit of this launch, in order (lib/synthesize.h:480-482 with THREAD_LIMIT 1).  Split in two so that
+// the round trip of the atomic can overlap other work: rs_claim_issue returns lane 0's raw ticket,
+// rs_claim_resolve turns it into the warp-uniform visit index (>= J.seg_end: nothing left) and does the
+// progress tick + cancel poll of the reference (synthesize.h:493-497).
+__device__ __forceinline__ uint32_t rs_claim_issue(const RsDev &J, RsCtrl *ctrl) {
+  uint32_t raw = 0;
+  if ((threadIdx.x & 31u) == 0u) raw = atomicAdd(&ctrl->next[J.slot].v, 1u);
+  return raw;
+}
+__device__ __forceinline__ uint32_t rs_claim_resolve(const RsDev &J, RsCtrl *ctrl, uint32_t raw) {
+  uint32_t v = J.seg_begin + raw;
+  if ((threadIdx.x & 31u) == 0u && v < J.seg_end && (v & 4095u) == 0u) {
+    const uint32_t pass = J.pass;
+    J.host_ticks[pass] = v + 1u;
+    if ((v >> 12) < RS_TIMELINE) ctrl->tick_ns[pass][v >> 12] = rs_globaltimer();
+    if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
+      atomicExch(&ctrl->stop, 1u);
+      atomicAdd(&ctrl->next[J.slot].v, 0x40000000u);
+    }
+  }
+  return __shfl_sync(RS_FULL, v, 0);
+}
+
+// Lane 0: until every visit of the epochs <= epoch_idx - 2 of this pass has completed.  Finishing visits only count
+// themselves (a fire-and-forget reduction); whoever waits moves the watermark over the leading complete epochs.
+__device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uint32_t epoch_idx) {
+  const uint32_t pass = J.pass;
+  while (true) {
+    const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v);
+    if (wmk + 1u >= epoch_idx) break;
+    const uint32_t first = wmk * J.epoch_len;
+    if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk].v) == min(J.epoch_len, J.pass_end - first))
+      atomicCAS(&ctrl->epoch_wm[pass].v, wmk, wmk + 1u);
+    else
+      __nanosleep(100);
+  }
+}
+
+// One warp: gather the patch of visit v (target point tpos), wait for exactly the neighbour versions the
+// sequential loop would see, build the heuristic candidate list (S.aux[0..nHeur)).
 template <bool MAPS>
-__device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, Visit &V, VisitStats &st) {
+__device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, Visit &V,
+                                                 const uint32_t v, const uint32_t tpos) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass, pass_end = J.pass_end;
   const uint32_t tag = (pass + 1u) << 29;
-  // ---- claim the next visit, in order (lib/synthesize.h:480-482 with THREAD_LIMIT 1)
-  uint32_t v = 0;
-  if (lane == 0) {
-    v = J.seg_begin + atomicAdd(&ctrl->next[J.slot].v, 1u);
-    if (v < J.seg_end && (v & 4095u) == 0u) {  // progress tick + cancel poll (synthesize.h:493-497)
-      J.host_ticks[pass] = v + 1u;
-      if ((v >> 12) < RS_TIMELINE) ctrl->tick_ns[pass][v >> 12] = rs_globaltimer();
-      if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
-        atomicExch(&ctrl->stop, 1u);
-        atomicAdd(&ctrl->next[J.slot].v, 0x40000000u);
-      }
-    }
-  }
-  v = __shfl_sync(RS_FULL, v, 0);
-  if (v >= J.seg_end) return false;
-  st.visits++;
-
-  const uint32_t tpos = __ldg(J.targets + v);
   const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
   const uint32_t selfq = (uint32_t)py * (uint32_t)J.tw + (uint32_t)px;
 
@@ -398,7 +435,7 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
         S.aux[slot] = m;
       }
       count += __popc(b);
-      st.scans += (lane == 0) ? min(32u, J.nOff - base) : 0u;
+      if (lane == 0) S.st.scans += min(32u, J.nOff - base);
     }
   }
   const uint32_t K = min(count, J.kmax);
@@ -447,6 +484,10 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
   // ---- heuristic 1 + 2 candidates (lib/synthesize.h:537-580): source of neighbour minus its offset,
   //      dropped if outside/masked corpus, if this target index was the last VISIBLE prober of that corpus
   //      point (rs_device.cuh: epochs), or if an earlier neighbour proposes the same point.
+  //      The corpus pixel and the three stamp words of a candidate are fetched in one round trip.
+  const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
+  const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
+  const uint32_t hide_base = tag | hide_from;
   uint32_t mycand[2];
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
@@ -468,9 +509,6 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
     S.q[k] = c;
   }
   __syncwarp();
-  const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
-  const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
-  const uint32_t hide_base = tag | hide_from;
   bool pskip[2] = {false, false};
   for (int attempt = 0; attempt < 2; attempt++) {
     bool any = false;
@@ -480,7 +518,7 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
       pskip[rnd] = false;
       if (c != RS_NO_SRC) {
         const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
-        uint32_t newest = 0u;  // newest visible stamp over the three epoch arrays; 0 = never probed
+        uint32_t newest = 0u;
 #pragma unroll
         for (int t = 0; t < 3; t++) {
           const unsigned long long e = rs_ld_state(J.prober[t] + a);
@@ -491,16 +529,11 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
         any |= pskip[rnd];
       }
     }
-    // A "skip" verdict can still be overturned by a straggler of epochs <= e-2 (a "keep" verdict cannot):
-    // only then wait until every such visit has published its stamps, and look again.
     if (attempt == 1 || hide_from == 0u || !__any_sync(RS_FULL, any)) break;
-    // (no fence: the stamps are 64-bit CAS results and the words read next are strong L2 loads issued after this
-    //  poll returns; a fence.gpu here would also invalidate the SM's L1 on every visit)
-    if (lane == 0)
-      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v) + 1u < epoch_idx) __nanosleep(100);  // epochs <= e-2 complete
+    if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
     __syncwarp();
   }
-  uint32_t nHeur = 0;
+  uint32_t nHeur = 0, nSkips = 0;
 #pragma unroll
   for (int rnd = 0; rnd < 2; rnd++) {
     const uint32_t k = lane + 32u * rnd;
@@ -509,65 +542,85 @@ __device__ __forceinline__ bool rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
     if (valid) {
       bool skip = pskip[rnd];
       for (uint32_t k2 = 0; k2 < k && !skip; k2++) skip = (S.q[k2] == c);
-      if (skip) { valid = false; st.skips++; }
+      if (skip) valid = false;
     }
     const unsigned b = __ballot_sync(RS_FULL, valid);
+    nSkips += __popc(__ballot_sync(RS_FULL, c != RS_NO_SRC)) - __popc(b);
     if (valid) S.aux[nHeur + __popc(b & lt)] = c;  // sources in S.aux are no longer needed (mycand holds mine)
     nHeur += __popc(b);
     __syncwarp();
   }
-  V.v = v; V.K = K; V.nHeur = nHeur; V.selfq = selfq; V.epoch_idx = epoch_idx; V.hide_from = hide_from;
-  V.my_base = tag | epoch0; V.selfw = selfw;
-  return true;
+  V.v = v; V.K = K; V.nHeur = nHeur;
+  if (lane == 0) {
+    S.vis.selfw = selfw; S.vis.selfq = selfq; S.vis.epoch_idx = epoch_idx; S.vis.hide_from = hide_from;
+    S.vis.my_base = tag | epoch0;
+    S.st.visits++;
+    S.st.skips += nSkips;
+  }
+  __syncwarp();
 }
 
 // One warp: commit the winner (lib/synthesize.h:620-639), merge the heuristic-2 stamps, publish completion.
+// hcol[i] = colour of heuristic candidate i (fetched with its first chunk); best_lin/best_cx = the winning probe's
+// corpus pixel as the distance loop tracked it, or best_lin = RS_NO_SRC: look the point up from its index.
 template <bool MAPS>
-__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, const WarpScratch<MAPS> &S, const Visit &V,
-                                                uint32_t bestSum, int bestIdx, VisitStats &st) {
+__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, const Visit &V,
+                                                uint32_t bestSum, int bestIdx, uint32_t best_lin, int best_cx) {
   const unsigned lane = threadIdx.x & 31u;
-  const uint32_t pass = J.pass, pass_end = J.pass_end, v = V.v, nHeur = V.nHeur;
+  const uint32_t pass = J.pass, v = V.v, nHeur = V.nHeur;
   const uint32_t tag = (pass + 1u) << 29;
-  const uint32_t *candlist = S.aux;
+  const uint32_t *candlist = S.aux, *hcol = S.q;
+  const uint32_t epoch_idx = S.vis.epoch_idx, my_base = S.vis.my_base;
   const bool bettered = bestIdx != 0x7FFFFFFF;
   const uint32_t total = nHeur + J.probes;
   const uint32_t seq_evals = !bettered ? 0u : (bestSum == 0u ? (uint32_t)bestIdx + 1u : total);
   if (lane == 0) {  // new colour + source only if the source changed; the new version is always published
-    uint32_t colour = (uint32_t)V.selfw & 0xFFFFFFu, src = (uint32_t)(V.selfw >> 32);
+    const unsigned long long selfw = S.vis.selfw;
+    uint32_t colour = (uint32_t)selfw & 0xFFFFFFu, src = (uint32_t)(selfw >> 32);
     if (bettered) {
-      const uint32_t bp = ((uint32_t)bestIdx < nHeur)
-                              ? candlist[bestIdx]
-                              : __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
-      if (bp != src) {
-        const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
-        const uint32_t cpx = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
-        colour = cpx & 0xFFFFFFu;
-        src = bp;
-        st.betters++;
+      uint32_t bp, bcol = 0;
+      const bool heur = (uint32_t)bestIdx < nHeur;
+      if (heur) {
+        bp = candlist[bestIdx];
+#if RS_X_OWNCOL
+        bcol = hcol[bestIdx];
+#endif
+      } else if (best_lin != RS_NO_SRC) {
+        bp = (uint32_t)best_cx | (((best_lin - (uint32_t)best_cx) / (uint32_t)J.cw) << 16);
+      } else {
+        bp = __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
       }
-      st.sumbest += bestSum;
+      if (bp != src) {
+        if (!heur || !RS_X_OWNCOL) {
+          const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
+          bcol = (MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a)) & 0xFFFFFFu;
+        }
+        colour = bcol;
+        src = bp;
+        S.st.betters++;
+      }
+      S.st.sumbest += bestSum;
     }
-    rs_st_state(J.W + 2 * (size_t)V.selfq + ((pass + 1u) & 1u),
+    rs_st_state(J.W + 2 * (size_t)S.vis.selfq + ((pass + 1u) & 1u),
                 ((unsigned long long)src << 32) | ((unsigned long long)(pass + 1u) << 24) | colour);
-    st.evals += seq_evals;
-    st.heur += min(nHeur, seq_evals);
-    st.perfect += (bettered && bestSum == 0u) ? 1u : 0u;
+    S.st.evals += seq_evals;
+    S.st.heur += min(nHeur, seq_evals);
+    S.st.perfect += (bettered && bestSum == 0u) ? 1u : 0u;
   }
   // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
   const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
-  if (stampEnd > 0u && V.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
-    if (lane == 0)
-      while (rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v) + 1u < V.epoch_idx) __nanosleep(100);
+  if (stampEnd > 0u && S.vis.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
+    if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
     __syncwarp();
   }
   for (uint32_t i = lane; i < stampEnd; i += 32) {
     const uint32_t c = candlist[i];
-    unsigned long long *pp = J.prober[V.epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+    unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
     const uint32_t stp = tag | v;
     unsigned long long old = rs_ld_state(pp);
     while (true) {
       const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
-      const unsigned long long nw = (hi >= V.my_base) ? (((unsigned long long)max(hi, stp) << 32) | lo)
+      const unsigned long long nw = (hi >= my_base) ? (((unsigned long long)max(hi, stp) << 32) | lo)
                                                       : (((unsigned long long)stp << 32) | hi);
       if (nw == old) break;
       const unsigned long long prev = atomicCAS(pp, old, nw);
@@ -576,11 +629,16 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
     }
   }
   __syncwarp();
-  if (lane == 0) {  // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
-    const uint32_t epoch0 = V.epoch_idx * J.epoch_len;
+  // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
+#if RS_X_RED
+  if (lane == 0)
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->epoch_done[pass][epoch_idx].v) : "memory");
+#else
+  if (lane == 0) {
+    const uint32_t pass_end = J.pass_end;
+    const uint32_t epoch0 = epoch_idx * J.epoch_len;
     const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
-    if (atomicAdd(&ctrl->epoch_done[pass][V.epoch_idx].v, 1u) + 1u == esize) {
-      // last visit of its epoch: move the watermark over every leading epoch that is now complete
+    if (atomicAdd(&ctrl->epoch_done[pass][epoch_idx].v, 1u) + 1u == esize) {
       while (true) {
         const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v);
         const uint32_t first = wmk * J.epoch_len;
@@ -590,28 +648,30 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, co
       }
     }
   }
+#endif
 }
 
 // Whole CTA, at kernel end: flush the per-warp counters; the last CTA out decides whether later passes run
 // (lib/refiner.h:111): (float)betters/n < 0.1.
-__device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, VisitStats &st) {
+__device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, LaneStats &ls, const WarpStats *ws) {
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t pass = J.pass;
-  st.compares = __reduce_add_sync(RS_FULL, st.compares);
-  st.issued = __reduce_add_sync(RS_FULL, st.issued);
-  st.skips = __reduce_add_sync(RS_FULL, st.skips);
-  if (lane == 0 && (st.visits | st.compares | st.issued)) {
-    atomicAdd(&ctrl->visits, (unsigned long long)st.visits);
-    atomicAdd(&ctrl->pass_visits[pass], (unsigned long long)st.visits);
-    atomicAdd(&ctrl->evals, st.evals);
-    atomicAdd(&ctrl->evals_issued, (unsigned long long)st.issued);
-    atomicAdd(&ctrl->compares, (unsigned long long)st.compares);
-    atomicAdd(&ctrl->offset_scans, (unsigned long long)st.scans);
-    atomicAdd(&ctrl->heur_evals, (unsigned long long)st.heur);
-    atomicAdd(&ctrl->heur_skips, (unsigned long long)st.skips);
-    atomicAdd(&ctrl->perfect, (unsigned long long)st.perfect);
-    atomicAdd(&ctrl->sum_best[pass], st.sumbest);
-    atomicAdd(&ctrl->betters[pass], st.betters);
+  ls.compares = __reduce_add_sync(RS_FULL, ls.compares);
+  ls.issued = __reduce_add_sync(RS_FULL, ls.issued);
+  if (lane == 0 && (ls.compares | ls.issued)) {
+    atomicAdd(&ctrl->evals_issued, (unsigned long long)ls.issued);
+    atomicAdd(&ctrl->compares, (unsigned long long)ls.compares);
+  }
+  if (lane == 0 && ws != nullptr && ws->visits) {  // ws: the counters of the warp that prepared and committed visits
+    atomicAdd(&ctrl->visits, (unsigned long long)ws->visits);
+    atomicAdd(&ctrl->pass_visits[pass], (unsigned long long)ws->visits);
+    atomicAdd(&ctrl->evals, ws->evals);
+    atomicAdd(&ctrl->offset_scans, (unsigned long long)ws->scans);
+    atomicAdd(&ctrl->heur_evals, (unsigned long long)ws->heur);
+    atomicAdd(&ctrl->heur_skips, (unsigned long long)ws->skips);
+    atomicAdd(&ctrl->perfect, (unsigned long long)ws->perfect);
+    atomicAdd(&ctrl->sum_best[pass], ws->sumbest);
+    atomicAdd(&ctrl->betters[pass], ws->betters);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -630,12 +690,25 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, V
 // One (heuristic candidate, chunk j) pair of the patch distance; chunk 0 also carries the target point's own terms.
 template <bool MAPS>
 __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, unsigned lutm, const WarpScratch<MAPS> &S,
-                                                 uint32_t K, uint32_t c, uint32_t j, VisitStats &st) {
+                                                 uint32_t *hcol, uint32_t K, uint32_t ci, uint32_t j, LaneStats &st) {
+  const uint32_t c = S.aux[ci];
   const int cx = (int)(c & 0xFFFFu);
   const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx, k0 = 1u + j * RS_CHUNK;
+  uint32_t own_x = 0, own_y = 0;  // the candidate's own pixel: its colour is what a win commits (synthesize.h:403-419)
+#if RS_X_OWNCOL
+  if (j == 0u) {
+    if (MAPS) { const uint2 t = __ldg(J.corpus8 + clin); own_x = t.x; own_y = t.y; }
+    else own_x = __ldg(J.corpus4 + clin);
+  }
+#else
+  if (MAPS && j == 0u) own_y = __ldg(&J.corpus8[clin].y);
+#endif
   uint32_t part = rs_chunk_sum<MAPS>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
   if (j == 0u) {
-    if (MAPS) part += rs_lut3(lutm, __vabsdiffu4(__ldg(&J.corpus8[clin].y), S.map[0]));
+    if (MAPS) part += rs_lut3(lutm, __vabsdiffu4(own_y, S.map[0]));
+#if RS_X_OWNCOL
+    hcol[ci] = own_x & 0xFFFFFFu;
+#endif
     st.issued++;
     st.compares++;
   }
@@ -672,15 +745,26 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   const unsigned lutc = P.lutc, lutm = P.lutm;
   WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
-  VisitStats st;
+  LaneStats st;
   Visit V;
-  while (rs_visit_prepare<MAPS>(J, ctrl, S, V, st)) {
+  if (lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
+  // The claim of the NEXT visit is issued before the distance phase and resolved after it, and the next target point
+  // is fetched while this visit commits: two dependent round trips off the critical path of every visit.  A visit
+  // claimed ahead waits for its warp's current visit; that one has a smaller index and cannot depend on it, so the
+  // lowest unfinished visit can always proceed (no deadlock).
+  uint32_t v = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
+  uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
+  while (v < J.seg_end) {
+    rs_visit_prepare<MAPS>(J, ctrl, S, V, v, tpos);
+#if RS_CLAIM_AHEAD
+    const uint32_t ticket = rs_claim_issue(J, ctrl);
+#endif
     // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
-    uint32_t bestSum = 0xFFFFFFFFu;
-    int bestIdx = 0x7FFFFFFF;
-    const uint32_t *candlist = S.aux;
+    uint32_t bestSum = 0xFFFFFFFFu, bestLin = RS_NO_SRC;
+    int bestIdx = 0x7FFFFFFF, bestCx = 0;
     uint32_t *hsum = S.off;  // offsets are dead by now (WarpScratch)
-    const uint32_t nHeur = V.nHeur, v = V.v, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus, K = V.K;
+    uint32_t *hcol = S.q;    // so are the per-neighbour candidates: colour of each heuristic candidate
+    const uint32_t nHeur = V.nHeur, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus, K = V.K;
     const uint32_t *cpts = J.corpus_pts;
     const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
     // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
@@ -691,7 +775,7 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
         const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
-        atomicAdd(&hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, K, candlist[ci], j, st));
+        atomicAdd(&hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, hcol, K, ci, j, st));
       }
       __syncwarp();
       uint32_t msum = 0xFFFFFFFFu;
@@ -706,10 +790,21 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     if (bestSum != 0u)
       rs_eval_range<MAPS>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
                           [&](int i) { return __ldg(cpts + rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
-                          bestSum, bestIdx, st.compares, st.issued);
-    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, st);
+                          bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued);
+#if RS_CLAIM_AHEAD
+    const uint32_t v_next = rs_claim_resolve(J, ctrl, ticket);
+    const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
+    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, bestLin, bestCx);
+#else
+    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, bestLin, bestCx);
+    const uint32_t v_next = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
+    const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
+#endif
+    v = v_next;
+    tpos = tpos_next;
   }
-  rs_pass_epilogue(J, ctrl, st);
+  __syncwarp();
+  rs_pass_epilogue(J, ctrl, st, &S.st);
 }
 
 // ---- latency mode: a team of W warps per visit ---------------------------------------------------------------
@@ -743,11 +838,14 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
   WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[team];
   TeamShared &TS = tshared[team];
   const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
-  VisitStats st;
+  LaneStats st;
   Visit V;
+  if (wt == 0 && lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
   while (true) {
     if (wt == 0) {
-      const bool ok = rs_visit_prepare<MAPS>(J, ctrl, S, V, st);
+      const uint32_t vc = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
+      const bool ok = vc < J.seg_end;
+      if (ok) rs_visit_prepare<MAPS>(J, ctrl, S, V, vc, __ldg(J.targets + vc));
       if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = V.v; TS.K = V.K; TS.nHeur = V.nHeur; TS.best = ~0ull; }
       for (uint32_t i = lane; i < RS_MAX_NB; i += 32) TS.hsum[i] = 0u;
     }
@@ -758,7 +856,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, nch = nchr ? nchr : 1u;
     for (uint32_t t = tid; t < nHeur * nch; t += T) {
       const uint32_t ci = t / nch, j = t % nch;
-      atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, K, S.aux[ci], j, st));
+      atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, S.q, K, ci, j, st));
     }
     rs_team_sync(bar_id, T);
     if (wt == 0) {  // first candidate with the minimum full sum
@@ -804,10 +902,11 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       const unsigned long long key = TS.best;
       const uint32_t bestSum = (key == ~0ull) ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
       const int bestIdx = (key == ~0ull) ? 0x7FFFFFFF : (int)(uint32_t)key;
-      rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, st);
+      rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, RS_NO_SRC, 0);
     }
   }
-  rs_pass_epilogue(J, ctrl, st);
+  __syncwarp();
+  rs_pass_epilogue(J, ctrl, st, wt == 0 ? &S.st : nullptr);
 }
 
 // ------------------------------------------------------------------------------ standalone best-fit kernel
@@ -842,11 +941,11 @@ __global__ void __launch_bounds__(RS_BF_WARPS * 32, 2)
     }
     __syncwarp();
     const uint32_t c0 = cand_begin[v], nc = cand_begin[v + 1] - c0;
-    uint32_t bestSum = 0xFFFFFFFFu, cmp = 0, iss = 0;
-    int bestIdx = 0x7FFFFFFF;
+    uint32_t bestSum = 0xFFFFFFFFu, cmp = 0, iss = 0, blin = 0;
+    int bestIdx = 0x7FFFFFFF, bcx = 0;
     if (K)
       rs_eval_range<MAPS>(J, P.lutc, P.lutm, S.nb, S.map, K, 0, (int)nc,
-                          [&](int i) { return __ldg(cands + c0 + i); }, bestSum, bestIdx, cmp, iss);
+                          [&](int i) { return __ldg(cands + c0 + i); }, bestSum, bestIdx, blin, bcx, cmp, iss);
     else if (nc) { bestSum = 0u; bestIdx = 0; }  // an empty patch matches anything perfectly
     if (lane == 0) {
       best_sum[v] = bestSum;
