@@ -33,8 +33,14 @@
 #define RS_IDX_MASK 0x1FFFFFFFu
 #define RS_FULL 0xFFFFFFFFu
 #define RS_MAX_NB 64
-#ifndef RS_CHUNK
-#define RS_CHUNK 2          // neighbours gathered per lane between two early-out checks (sweep: profiles/)
+// Neighbours gathered per lane between two early-out checks (template parameter CH of the distance code).  More per
+// check = more gathers in flight and fewer rounds for long patches, but more wasted compares for short ones; B200
+// sweeps (profiles/): 2 for patches below RS_CHUNK_SWITCH_K neighbours, 3 from there on.
+#define RS_CHUNK_SMALL 2
+#define RS_CHUNK_LARGE 3
+#define RS_CHUNK_MAX 4
+#ifndef RS_CHUNK_SWITCH_K
+#define RS_CHUNK_SWITCH_K 16
 #endif
 #ifndef RS_X_TRACK
 #define RS_X_TRACK 1
@@ -93,6 +99,7 @@ struct RsDev {              // kernel argument (by value)
   uint32_t pass, pass_end;
   uint32_t seg_begin, seg_end;  // this launch claims the visits [seg_begin, seg_end) of the pass, in order
   uint32_t slot, last_seg;      // index of this launch's counters in RsCtrl; last launch of its pass?
+  uint32_t chunk;               // CH the launched kernel was instantiated with (patch padding follows it)
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
   uint32_t ends[6];
   int htile, vtile;
@@ -171,7 +178,7 @@ struct __align__(16) RsNb {
   uint32_t pix, pen;
 };
 #define RS_PAD_DX 0x40000000
-#define RS_NB_SLOTS (RS_MAX_NB + RS_CHUNK)
+#define RS_NB_SLOTS (RS_MAX_NB + RS_CHUNK_MAX)
 
 __device__ __forceinline__ uint32_t rs_lds_u32(unsigned shared_addr) {
   uint32_t v;
@@ -185,18 +192,18 @@ __device__ __forceinline__ uint32_t rs_lut3(unsigned col, uint32_t d) {
          rs_lds_u32(col + __byte_perm(d, 0, 0x4442) * 128u);
 }
 
-// ---- RS_CHUNK neighbour compares of one candidate: the body of computeBestFit's loop for neighbours k0.. ----
+// ---- CH neighbour compares of one candidate: the body of computeBestFit's loop for neighbours k0.. ----
 // (lib/synthesize.h:288-383), k0 >= 1: the target point itself (k = 0) carries no colour term (synthesize.h:328) and
 // its corpus pixel is the candidate, always inside and selected; its map terms are added by the caller.
 // Branch-free: every gather is issued before the first table lookup; a pixel outside the corpus reads the sentinel
 // pixel cn (mask 0), so "usable" is one compare on the loaded word; padding records cost 0.
-template <bool MAPS>
+template <bool MAPS, int CH>
 __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
                                                  const uint32_t *nmap, int cx, uint32_t clin, uint32_t k0) {
-  RsNb r[RS_CHUNK];
-  uint32_t cp[RS_CHUNK], cm[RS_CHUNK];
+  RsNb r[CH];
+  uint32_t cp[CH], cm[CH];
 #pragma unroll
-  for (int u = 0; u < RS_CHUNK; u++) {
+  for (int u = 0; u < CH; u++) {
     r[u] = nb[k0 + u];
     const uint32_t lin = clin + (uint32_t)r[u].lin;
     const bool in = (unsigned)(cx + r[u].dx) < (unsigned)J.cw && lin < J.cn;
@@ -212,7 +219,7 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, 
   }
   uint32_t sum = 0;
 #pragma unroll
-  for (int u = 0; u < RS_CHUNK; u++) {
+  for (int u = 0; u < CH; u++) {
     uint32_t t = rs_lut3(lutc, __vabsdiffu4(cp[u], r[u].pix));
     if (MAPS) t += rs_lut3(lutm, __vabsdiffu4(cm[u], nmap[k0 + u]));
     sum += (cp[u] >= 0xFF000000u) ? t : r[u].pen;  // selected (mask 0xFF)? else the maximum weighted difference
@@ -228,8 +235,8 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, 
 // bestLin/bestCx return the winner's corpus pixel (linear index, x) when a candidate of this range wins.
 // Candidates are fetched a window of 32 ahead (one per lane, all lanes at once) and handed to the lanes that need
 // one by shuffle, so the dependent table load of cand_of() is off the critical path of a round.
-// K = patch size (>= 1); nb/nmap hold 1 + ceil((K-1)/RS_CHUNK)*RS_CHUNK records.
-template <bool MAPS, class CandFn>
+// K = patch size (>= 1); nb/nmap hold 1 + ceil((K-1)/CH)*CH records.
+template <bool MAPS, int CH, class CandFn>
 __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
                                               const uint32_t *nmap, uint32_t K, int begin, int end, CandFn cand_of,
                                               uint32_t &bestSum, int &bestIdx, uint32_t &bestLin, int &bestCx,
@@ -276,9 +283,9 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
     }
     bool finished = false;
     if (active) {
-      partial += rs_chunk_sum<MAPS>(J, lutc, lutm, nb, nmap, cx, clin, k);
+      partial += rs_chunk_sum<MAPS, CH>(J, lutc, lutm, nb, nmap, cx, clin, k);
       if (MAPS && k == 1u) partial += rs_lut3(lutm, __vabsdiffu4(m0, selfmap));  // map terms of the target point itself (synthesize.h:342-355)
-      k += RS_CHUNK;
+      k += CH;
       finished = (k >= K);
     }
     const bool worse = active && (partial > bestSum || (partial == bestSum && myIdx > bestIdx));

@@ -471,7 +471,7 @@ __device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
     S.aux[k] = (uint32_t)(w >> 32);  // source of this neighbour, or RS_NO_SRC
   }
   {  // pad the patch to whole chunks with records that cost nothing
-    const uint32_t nch = (K + RS_CHUNK - 2u) / RS_CHUNK, kpad = 1u + (nch ? nch : 1u) * RS_CHUNK;
+    const uint32_t nch = (K + J.chunk - 2u) / J.chunk, kpad = 1u + (nch ? nch : 1u) * J.chunk;
     for (uint32_t k = K + lane; k < kpad; k += 32) {
       RsNb r;
       r.lin = 0; r.dx = RS_PAD_DX; r.pix = 0u; r.pen = 0u;
@@ -688,12 +688,12 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, L
 }
 
 // One (heuristic candidate, chunk j) pair of the patch distance; chunk 0 also carries the target point's own terms.
-template <bool MAPS>
+template <bool MAPS, int CH>
 __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, unsigned lutm, const WarpScratch<MAPS> &S,
                                                  uint32_t *hcol, uint32_t K, uint32_t ci, uint32_t j, LaneStats &st) {
   const uint32_t c = S.aux[ci];
   const int cx = (int)(c & 0xFFFFu);
-  const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx, k0 = 1u + j * RS_CHUNK;
+  const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx, k0 = 1u + j * CH;
   uint32_t own_x = 0, own_y = 0;  // the candidate's own pixel: its colour is what a win commits (synthesize.h:403-419)
 #if RS_X_OWNCOL
   if (j == 0u) {
@@ -703,7 +703,7 @@ __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, 
 #else
   if (MAPS && j == 0u) own_y = __ldg(&J.corpus8[clin].y);
 #endif
-  uint32_t part = rs_chunk_sum<MAPS>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
+  uint32_t part = rs_chunk_sum<MAPS, CH>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
   if (j == 0u) {
     if (MAPS) part += rs_lut3(lutm, __vabsdiffu4(own_y, S.map[0]));
 #if RS_X_OWNCOL
@@ -712,7 +712,7 @@ __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, 
     st.issued++;
     st.compares++;
   }
-  st.compares += (k0 < K) ? min((uint32_t)RS_CHUNK, K - k0) : 0u;
+  st.compares += (k0 < K) ? min((uint32_t)CH, K - k0) : 0u;
   return part;
 }
 
@@ -736,7 +736,7 @@ __device__ __forceinline__ PassSmem rs_pass_smem(const RsDev &J, unsigned char *
 }
 
 // ---- throughput mode: one warp per visit -------------------------------------------------------------------
-template <bool MAPS>
+template <bool MAPS, int CH>
 __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass(const RsDev J) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
@@ -770,12 +770,12 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
     // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
     if (nHeur) {
-      const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, nch = nchr ? nchr : 1u, inv = 0xFFFFFFFFu / nch + 1u;
+      const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = 0xFFFFFFFFu / nch + 1u;
       for (uint32_t i = lane; i < nHeur; i += 32) hsum[i] = 0u;
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
         const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
-        atomicAdd(&hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, hcol, K, ci, j, st));
+        atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, hcol, K, ci, j, st));
       }
       __syncwarp();
       uint32_t msum = 0xFFFFFFFFu;
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
       bestIdx = midx;
     }
     if (bestSum != 0u)
-      rs_eval_range<MAPS>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
+      rs_eval_range<MAPS, CH>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
                           [&](int i) { return __ldg(cpts + rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
                           bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued);
 #if RS_CLAIM_AHEAD
@@ -823,7 +823,7 @@ __device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool MAPS>
+template <bool MAPS, int CH>
 __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const RsDev J, const unsigned W) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
@@ -853,10 +853,10 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     if (!TS.alive) break;
     const uint32_t v = TS.v, K = TS.K, nHeur = TS.nHeur;
     // ---- (A) heuristic candidates: all (candidate, chunk) pairs at once
-    const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, nch = nchr ? nchr : 1u;
+    const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u;
     for (uint32_t t = tid; t < nHeur * nch; t += T) {
       const uint32_t ci = t / nch, j = t % nch;
-      atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS>(J, lutc, lutm, S, S.q, K, ci, j, st));
+      atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, S.q, K, ci, j, st));
     }
     rs_team_sync(bar_id, T);
     if (wt == 0) {  // first candidate with the minimum full sum
@@ -889,8 +889,8 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
         bool alive = true;
         st.issued++;
         do {
-          partial += rs_chunk_sum<MAPS>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
-          k0 += RS_CHUNK;
+          partial += rs_chunk_sum<MAPS, CH>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
+          k0 += CH;
           if ((((unsigned long long)partial << 32) | idx) > *vbest) { alive = false; break; }
         } while (k0 < K);
         st.compares += min(k0, K);
@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(RS_BF_WARPS * 32, 2)
   WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[warp];
   for (uint32_t v = blockIdx.x * RS_BF_WARPS + warp; v < n_visits; v += gridDim.x * RS_BF_WARPS) {
     const uint32_t nb0 = nb_begin[v], K = min(nb_begin[v + 1] - nb0, (uint32_t)RS_MAX_NB);
-    const uint32_t nchr = (K + RS_CHUNK - 2u) / RS_CHUNK, kpad = 1u + (nchr ? nchr : 1u) * RS_CHUNK;
+    const uint32_t nchr = (K + RS_CHUNK_SMALL - 2u) / RS_CHUNK_SMALL, kpad = 1u + (nchr ? nchr : 1u) * RS_CHUNK_SMALL;
     for (uint32_t k = lane; k < kpad; k += 32) {
       RsNb r;
       uint32_t mp = 0;
@@ -944,7 +944,7 @@ __global__ void __launch_bounds__(RS_BF_WARPS * 32, 2)
     uint32_t bestSum = 0xFFFFFFFFu, cmp = 0, iss = 0, blin = 0;
     int bestIdx = 0x7FFFFFFF, bcx = 0;
     if (K)
-      rs_eval_range<MAPS>(J, P.lutc, P.lutm, S.nb, S.map, K, 0, (int)nc,
+      rs_eval_range<MAPS, RS_CHUNK_SMALL>(J, P.lutc, P.lutm, S.nb, S.map, K, 0, (int)nc,
                           [&](int i) { return __ldg(cands + c0 + i); }, bestSum, bestIdx, blin, bcx, cmp, iss);
     else if (nc) { bestSum = 0u; bestIdx = 0; }  // an empty patch matches anything perfectly
     if (lane == 0) {
@@ -976,8 +976,8 @@ struct Workspace {
   RsCtrl *h_ctrl = nullptr;
   int off_w = 0, off_h = 0;  // dimensions the resident offsets table was built for
   uint32_t off_n = 0;
-  int grid[2] = {0, 0};      // persistent grid of k_synth_pass<false/true>
-  int grid_team[2] = {0, 0}; // persistent grid of k_synth_pass_team<false/true>
+  int grid[4] = {0, 0, 0, 0};       // persistent grid of k_synth_pass<maps, chunk>: index 2 * maps + (chunk == large)
+  int grid_team[4] = {0, 0, 0, 0};  // persistent grid of k_synth_pass_team, likewise
 };
 static std::atomic<int> g_job_slots{1};
 extern "C" void rs_cuda_set_job_slots(int slots) { g_job_slots.store(slots < 1 ? 1 : slots); }
@@ -1026,18 +1026,19 @@ static size_t pass_smem(bool maps, int scratch_slots) {
   const size_t scratch = maps ? sizeof(WarpScratch<true>) : sizeof(WarpScratch<false>);
   return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + scratch * scratch_slots + 16 + sizeof(TeamShared) * RS_TEAM_SLOTS;
 }
-template <bool MAPS>
+template <bool MAPS, int CH>
 static int configure_pass_kernel(Workspace *w) {
   const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
   int per_sm = 0, per_sm_team = 0, sms = 0;
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS>, RS_TP_WARPS * 32, smem_tp));
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS>, RS_TEAM_WARPS * 32, smem_team));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH>, RS_TP_WARPS * 32, smem_tp));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS, CH>, RS_TEAM_WARPS * 32, smem_team));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
   if (per_sm < 1 || per_sm_team < 1) { g_err = "the pass kernels do not fit on an SM"; return 100; }
-  w->grid[MAPS ? 1 : 0] = per_sm * sms;
-  w->grid_team[MAPS ? 1 : 0] = per_sm_team * sms;
+  const int slot = (MAPS ? 2 : 0) + (CH == RS_CHUNK_LARGE ? 1 : 0);
+  w->grid[slot] = per_sm * sms;
+  w->grid_team[slot] = per_sm_team * sms;
   return 0;
 }
 
@@ -1055,8 +1056,10 @@ static int ws_acquire(Workspace **out) {
   }
   Workspace *w = new Workspace();
   w->device = dev;
-  int rc = configure_pass_kernel<false>(w);
-  if (!rc) rc = configure_pass_kernel<true>(w);
+  int rc = configure_pass_kernel<false, RS_CHUNK_SMALL>(w);
+  if (!rc) rc = configure_pass_kernel<false, RS_CHUNK_LARGE>(w);
+  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_SMALL>(w);
+  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_LARGE>(w);
   if (rc) { delete w; return rc; }
 #define WCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ws_free(w); return 100; } } while (0)
   WCHK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
@@ -1396,7 +1399,11 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   cudaStream_t s = w->stream;
-  int grid = w->grid[j->maps ? 1 : 0], grid_team = w->grid_team[j->maps ? 1 : 0];
+  uint32_t kmax_run = j->d.patch_size < 2 ? 2 : j->d.patch_size;
+  bool large = kmax_run >= RS_CHUNK_SWITCH_K;
+  if (const char *e = getenv("RS_CHUNK")) large = atoi(e) >= RS_CHUNK_LARGE;
+  const int gslot = (j->maps ? 2 : 0) + (large ? 1 : 0);
+  int grid = w->grid[gslot], grid_team = w->grid_team[gslot];
   {  // several jobs sharing the device: each persistent grid takes its share of the SMs (rs_cuda_set_job_slots)
     const int slots = g_job_slots.load();
     if (slots > 1) {
@@ -1428,12 +1435,17 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     for (int k = 0; k < nseg; k++) {
       D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
       const unsigned W = seg[k].width;
+      D.chunk = large ? RS_CHUNK_LARGE : RS_CHUNK_SMALL;
       if (W <= 1) {
-        if (j->maps) k_synth_pass<true><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
-        else k_synth_pass<false><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+        if (j->maps) { if (large) k_synth_pass<true, RS_CHUNK_LARGE><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+                       else k_synth_pass<true, RS_CHUNK_SMALL><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D); }
+        else { if (large) k_synth_pass<false, RS_CHUNK_LARGE><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+               else k_synth_pass<false, RS_CHUNK_SMALL><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D); }
       } else {
-        if (j->maps) k_synth_pass_team<true><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
-        else k_synth_pass_team<false><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+        if (j->maps) { if (large) k_synth_pass_team<true, RS_CHUNK_LARGE><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+                       else k_synth_pass_team<true, RS_CHUNK_SMALL><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W); }
+        else { if (large) k_synth_pass_team<false, RS_CHUNK_LARGE><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+               else k_synth_pass_team<false, RS_CHUNK_SMALL><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W); }
       }
       begin = seg[k].end;
     }
@@ -1648,6 +1660,7 @@ extern "C" int rs_bestfit_batch(const RsJobDesc *desc, const uint8_t *corpus_raw
     memset(&D, 0, sizeof D);
     D.corpus4 = d_c4; D.corpus8 = d_c8; D.lut_rep = d_rep; D.cw = desc->cw; D.ch = desc->ch; D.cn = (uint32_t)cn;
     D.penalty = 65535u * (uint32_t)desc->n_color + map_lut_max * (uint32_t)desc->n_map;
+    D.chunk = RS_CHUNK_SMALL;
     const size_t smem = pass_smem(maps, RS_BF_WARPS);
     const unsigned grid = (n_visits + RS_BF_WARPS - 1) / RS_BF_WARPS;
     if (maps) {
