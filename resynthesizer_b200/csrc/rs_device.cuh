@@ -197,6 +197,41 @@ __device__ __forceinline__ uint32_t rs_lut3(unsigned col, uint32_t d) {
 // its corpus pixel is the candidate, always inside and selected; its map terms are added by the caller.
 // Branch-free: every gather is issued before the first table lookup; a pixel outside the corpus reads the sentinel
 // pixel cn (mask 0), so "usable" is one compare on the loaded word; padding records cost 0.
+// The two halves of a chunk, usable apart: the gathers need only the patch GEOMETRY (lin, dx of the records), the
+// table lookups need the neighbour colours.  The team kernel issues the gathers of a visit's probes while the visit
+// is still waiting for its neighbours to be synthesised.
+template <bool MAPS, int CH>
+__device__ __forceinline__ void rs_chunk_gather(const RsDev &J, const RsNb *nb, int cx, uint32_t clin, uint32_t k0,
+                                                uint32_t (&cp)[CH], uint32_t (&cm)[CH]) {
+#pragma unroll
+  for (int u = 0; u < CH; u++) {
+    const int2 g = *reinterpret_cast<const int2 *>(&nb[k0 + u]);  // lin, dx
+    const uint32_t lin = clin + (uint32_t)g.x;
+    const bool in = (unsigned)(cx + g.y) < (unsigned)J.cw && lin < J.cn;
+    const uint32_t a = in ? lin : J.cn;
+    if (MAPS) {
+      const uint2 t = __ldg(J.corpus8 + a);
+      cp[u] = t.x;
+      cm[u] = t.y;
+    } else {
+      cp[u] = __ldg(J.corpus4 + a);
+      cm[u] = 0u;
+    }
+  }
+}
+template <bool MAPS, int CH>
+__device__ __forceinline__ uint32_t rs_chunk_reduce(unsigned lutc, unsigned lutm, const RsNb *nb, const uint32_t *nmap,
+                                                    uint32_t k0, const uint32_t (&cp)[CH], const uint32_t (&cm)[CH]) {
+  uint32_t sum = 0;
+#pragma unroll
+  for (int u = 0; u < CH; u++) {
+    const uint2 pv = *reinterpret_cast<const uint2 *>(&nb[k0 + u].pix);  // pix, pen
+    uint32_t t = rs_lut3(lutc, __vabsdiffu4(cp[u], pv.x));
+    if (MAPS) t += rs_lut3(lutm, __vabsdiffu4(cm[u], nmap[k0 + u]));
+    sum += (cp[u] >= 0xFF000000u) ? t : pv.y;
+  }
+  return sum;
+}
 template <bool MAPS, int CH>
 __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
                                                  const uint32_t *nmap, int cx, uint32_t clin, uint32_t k0) {

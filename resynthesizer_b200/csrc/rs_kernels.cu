@@ -380,13 +380,19 @@ __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uin
 
 // One warp: gather the patch of visit v (target point tpos), wait for exactly the neighbour versions the
 // sequential loop would see, build the heuristic candidate list (S.aux[0..nHeur)).
+// A visit is prepared in three steps.  (1) GEOMETRY: which pixels form the patch -- depends on nothing another visit
+// of this pass computes.  (2) VALUES: wait for exactly the neighbour versions the sequential loop would see and read
+// colours + sources.  (3) CANDIDATES: heuristic candidates from the neighbours' sources.  The throughput kernel runs
+// them back to back; the team kernel lets the other warps of the team fetch the probes' corpus pixels between (1)
+// and (2)/(3), because those gathers need the geometry only.
+//
+// (1) One warp: gather the patch of visit v (target point tpos): S.off / S.q / S.aux(meta) and the geometry half of
+// the distance records S.nb[k].{lin,dx,pen}, padded to whole chunks.  Returns K.
 template <bool MAPS>
-__device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, Visit &V,
-                                                 const uint32_t v, const uint32_t tpos) {
+__device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS> &S, const uint32_t v, const uint32_t tpos) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
-  const uint32_t pass = J.pass, pass_end = J.pass_end;
-  const uint32_t tag = (pass + 1u) << 29;
+  const uint32_t pass = J.pass;
   const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
   const uint32_t selfq = (uint32_t)py * (uint32_t)J.tw + (uint32_t)px;
 
@@ -394,6 +400,7 @@ __device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
   if (lane == 0) {
     S.off[0] = 0u;
     S.q[0] = selfq;
+    S.vis.selfq = selfq;
     S.aux[0] = v;
   }
   uint32_t count = 1;
@@ -440,9 +447,33 @@ __device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
   }
   const uint32_t K = min(count, J.kmax);
   __syncwarp();
+  {  // geometry half of the distance records, padded to whole chunks with records that cost nothing
+    const uint32_t nch = (K + J.chunk - 2u) / J.chunk, kpad = 1u + (nch ? nch : 1u) * J.chunk;
+    for (uint32_t k = lane; k < kpad; k += 32) {
+      RsNb r;
+      if (k < K) {
+        const uint32_t o = S.off[k];
+        r.dx = rs_off_x(o);
+        r.lin = rs_off_y(o) * J.cw + r.dx;
+        r.pix = 0u;
+        r.pen = J.penalty;
+      } else {
+        r.lin = 0; r.dx = RS_PAD_DX; r.pix = 0u; r.pen = 0u;
+        if (MAPS) S.map[k] = 0u;
+      }
+      S.nb[k] = r;
+    }
+  }
+  __syncwarp();
+  return K;
+}
 
-  // ---- wait for exactly the versions the sequential order would see, then read them (one 64-bit load each)
-  unsigned long long selfw = 0;
+// (2) One warp: wait for exactly the versions the sequential order would see, then read them (one 64-bit load each):
+// colours into S.nb[k].pix (+ S.map), sources into S.aux.
+template <bool MAPS>
+__device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS> &S, const uint32_t v, const uint32_t K) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t pass = J.pass, pass_end = J.pass_end;
   for (uint32_t k = lane; k < K; k += 32) {
     const uint32_t q = S.q[k], m = S.aux[k];
     uint32_t r = 0;
@@ -457,29 +488,22 @@ __device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
       __nanosleep(40);
       w = rs_ld_state(wp);
     }
-    if (k == 0) selfw = w;
-    {
-      const uint32_t o = S.off[k];
-      RsNb r;
-      r.dx = rs_off_x(o);
-      r.lin = rs_off_y(o) * J.cw + r.dx;
-      r.pix = (uint32_t)w & 0xFFFFFFu;
-      r.pen = J.penalty;
-      S.nb[k] = r;
-    }
+    if (k == 0) S.vis.selfw = w;
+    S.nb[k].pix = (uint32_t)w & 0xFFFFFFu;
     if (MAPS) S.map[k] = __ldg(J.tmaps + q);
     S.aux[k] = (uint32_t)(w >> 32);  // source of this neighbour, or RS_NO_SRC
   }
-  {  // pad the patch to whole chunks with records that cost nothing
-    const uint32_t nch = (K + J.chunk - 2u) / J.chunk, kpad = 1u + (nch ? nch : 1u) * J.chunk;
-    for (uint32_t k = K + lane; k < kpad; k += 32) {
-      RsNb r;
-      r.lin = 0; r.dx = RS_PAD_DX; r.pix = 0u; r.pen = 0u;
-      S.nb[k] = r;
-      if (MAPS) S.map[k] = 0u;
-    }
-  }
   __syncwarp();
+}
+
+// (3) One warp: the heuristic candidate list S.aux[0..nHeur) of visit v, and what rs_visit_finish needs (S.vis).
+template <bool MAPS>
+__device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, Visit &V,
+                                                    const uint32_t v, const uint32_t K) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t pass = J.pass;
+  const uint32_t tag = (pass + 1u) << 29;
 
   // ---- heuristic 1 + 2 candidates (lib/synthesize.h:537-580): source of neighbour minus its offset,
   //      dropped if outside/masked corpus, if this target index was the last VISIBLE prober of that corpus
@@ -552,7 +576,7 @@ __device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
   }
   V.v = v; V.K = K; V.nHeur = nHeur;
   if (lane == 0) {
-    S.vis.selfw = selfw; S.vis.selfq = selfq; S.vis.epoch_idx = epoch_idx; S.vis.hide_from = hide_from;
+    S.vis.epoch_idx = epoch_idx; S.vis.hide_from = hide_from;
     S.vis.my_base = tag | epoch0;
     S.st.visits++;
     S.st.skips += nSkips;
@@ -561,11 +585,13 @@ __device__ __forceinline__ void rs_visit_prepare(const RsDev &J, RsCtrl *ctrl, W
 }
 
 // One warp: commit the winner (lib/synthesize.h:620-639), merge the heuristic-2 stamps, publish completion.
-// hcol[i] = colour of heuristic candidate i (fetched with its first chunk); best_lin/best_cx = the winning probe's
-// corpus pixel as the distance loop tracked it, or best_lin = RS_NO_SRC: look the point up from its index.
+// hcol[i] = colour of heuristic candidate i (fetched with its first chunk).  For a winning probe: win_pt = its corpus
+// point if the distance phase tracked it (else RS_NO_SRC: looked up from the probe's index), win_col = its colour if
+// have_col (else fetched here).
 template <bool MAPS>
 __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, const Visit &V,
-                                                uint32_t bestSum, int bestIdx, uint32_t best_lin, int best_cx) {
+                                                uint32_t bestSum, int bestIdx, uint32_t win_pt, uint32_t win_col,
+                                                bool have_col) {
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t pass = J.pass, v = V.v, nHeur = V.nHeur;
   const uint32_t tag = (pass + 1u) << 29;
@@ -585,13 +611,14 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
 #if RS_X_OWNCOL
         bcol = hcol[bestIdx];
 #endif
-      } else if (best_lin != RS_NO_SRC) {
-        bp = (uint32_t)best_cx | (((best_lin - (uint32_t)best_cx) / (uint32_t)J.cw) << 16);
+      } else if (win_pt != RS_NO_SRC) {
+        bp = win_pt;
+        bcol = win_col;
       } else {
         bp = __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
       }
       if (bp != src) {
-        if (!heur || !RS_X_OWNCOL) {
+        if ((!heur && !(have_col && win_pt != RS_NO_SRC)) || !RS_X_OWNCOL) {
           const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
           bcol = (MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a)) & 0xFFFFFFu;
         }
@@ -755,7 +782,11 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   uint32_t v = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
   uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
   while (v < J.seg_end) {
-    rs_visit_prepare<MAPS>(J, ctrl, S, V, v, tpos);
+    {
+      const uint32_t Kv = rs_visit_geometry<MAPS>(J, S, v, tpos);
+      rs_visit_values<MAPS>(J, S, v, Kv);
+      rs_visit_candidates<MAPS>(J, ctrl, S, V, v, Kv);
+    }
 #if RS_CLAIM_AHEAD
     const uint32_t ticket = rs_claim_issue(J, ctrl);
 #endif
@@ -794,9 +825,13 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
 #if RS_CLAIM_AHEAD
     const uint32_t v_next = rs_claim_resolve(J, ctrl, ticket);
     const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
-    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, bestLin, bestCx);
+    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx,
+                          bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
+                          0u, false);
 #else
-    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, bestLin, bestCx);
+    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx,
+                          bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
+                          0u, false);
     const uint32_t v_next = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
     const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
 #endif
@@ -817,12 +852,27 @@ struct TeamShared {
   unsigned long long best;
   uint32_t hsum[RS_MAX_NB];
   uint32_t v, K, nHeur, alive;
+  uint32_t win_pt, win_col;  // corpus point and colour of the winning probe, written by the lane that evaluated it
 };
 
 __device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One visit of a team, in the order things become possible (the critical path is what latency mode is about):
+//   warp 0                                      the other warps (one probe per lane)
+//   claim, target point, patch GEOMETRY
+//   ---------------------------------------------------------------- barrier A
+//   wait for the neighbours, read VALUES        probe's corpus point, gathers of its first chunk + its own pixel
+//   ---------------------------------------------------------------- barrier B
+//   heuristic CANDIDATES                        table lookups of the first chunk -> partial sum
+//   ---------------------------------------------------------------- barrier C
+//   all warps: (heuristic candidate, chunk) pairs                     -> barrier D -> warp 0: best heuristic -> E
+//   all warps: probes continue from their second chunk, early-out against the shared best; rest of the probes
+//   ---------------------------------------------------------------- barrier F
+//   the lane that owns the winning probe publishes its point + colour -> barrier G -> warp 0 commits
+// So the gathers of every probe's first chunk, and the colour a winning probe commits, are fetched while the visit
+// is still waiting for its dependencies; none of them is on the critical path.
 template <bool MAPS, int CH>
 __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const RsDev J, const unsigned W) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -838,6 +888,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
   WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[team];
   TeamShared &TS = tshared[team];
   const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
+  const uint32_t nPre = min(J.probes, T - 32u);  // probes fetched ahead, one per lane of warps 1..W-1
   LaneStats st;
   Visit V;
   if (wt == 0 && lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -845,47 +896,92 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     if (wt == 0) {
       const uint32_t vc = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
       const bool ok = vc < J.seg_end;
-      if (ok) rs_visit_prepare<MAPS>(J, ctrl, S, V, vc, __ldg(J.targets + vc));
-      if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = V.v; TS.K = V.K; TS.nHeur = V.nHeur; TS.best = ~0ull; }
+      uint32_t Kc = 0;
+      if (ok) Kc = rs_visit_geometry<MAPS>(J, S, vc, __ldg(J.targets + vc));
+      if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = vc; TS.K = Kc; TS.nHeur = 0u; TS.best = ~0ull; TS.win_pt = RS_NO_SRC; }
       for (uint32_t i = lane; i < RS_MAX_NB; i += 32) TS.hsum[i] = 0u;
     }
-    rs_team_sync(bar_id, T);
+    rs_team_sync(bar_id, T);  // A
     if (!TS.alive) break;
-    const uint32_t v = TS.v, K = TS.K, nHeur = TS.nHeur;
-    // ---- (A) heuristic candidates: all (candidate, chunk) pairs at once
-    const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u;
-    for (uint32_t t = tid; t < nHeur * nch; t += T) {
-      const uint32_t ci = t / nch, j = t % nch;
-      atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, S.q, K, ci, j, st));
-    }
-    rs_team_sync(bar_id, T);
-    if (wt == 0) {  // first candidate with the minimum full sum
-      unsigned long long key = ~0ull;
-      for (uint32_t i = lane; i < nHeur; i += 32) {
-        const unsigned long long k2 = ((unsigned long long)TS.hsum[i] << 32) | i;
-        key = k2 < key ? k2 : key;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(RS_FULL, key, o);
-        key = other < key ? other : key;
-      }
-      if (lane == 0) TS.best = key;
-    }
-    rs_team_sync(bar_id, T);
-    // ---- (B) random probes: one candidate per lane per round, early-out against the shared best
-    volatile unsigned long long *vbest = &TS.best;
+    const uint32_t v = TS.v, K = TS.K;
     const uint32_t hv = rs_probe_hash_visit(seed, pass, v);
+    // ---- my probe (warps 1..W-1): point, first-chunk gathers, own pixel -- all independent of other visits
+    const bool pre = wt != 0 && (tid - 32u) < nPre;
+    uint32_t pc = 0, pclin = 0, pown_x = 0, pown_y = 0, ppartial = 0, cp[CH], cm[CH];
+    int pcx = 0;
+    if (wt == 0) {
+      rs_visit_values<MAPS>(J, S, v, K);
+    } else if (pre) {
+      pc = __ldg(J.corpus_pts + rs_range(rs_mix32(hv + (tid - 32u) * 0xC2B2AE35u), nC));
+      pcx = (int)(pc & 0xFFFFu);
+      pclin = (pc >> 16) * (uint32_t)J.cw + (uint32_t)pcx;
+      if (MAPS) { const uint2 t = __ldg(J.corpus8 + pclin); pown_x = t.x; pown_y = t.y; }
+      else pown_x = __ldg(J.corpus4 + pclin);
+      rs_chunk_gather<MAPS, CH>(J, S.nb, pcx, pclin, 1u, cp, cm);
+    }
+    rs_team_sync(bar_id, T);  // B
+    if (wt == 0) {
+      rs_visit_candidates<MAPS>(J, ctrl, S, V, v, K);
+      if (lane == 0) TS.nHeur = V.nHeur;
+    } else if (pre) {
+      ppartial = rs_chunk_reduce<MAPS, CH>(lutc, lutm, S.nb, S.map, 1u, cp, cm);
+      if (MAPS) ppartial += rs_lut3(lutm, __vabsdiffu4(pown_y, S.map[0]));
+    }
+    rs_team_sync(bar_id, T);  // C
+    const uint32_t nHeur = TS.nHeur;
+    // ---- heuristic candidates: all (candidate, chunk) pairs at once
+    const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u;
+    if (nHeur) {
+      for (uint32_t t = tid; t < nHeur * nch; t += T) {
+        const uint32_t ci = t / nch, j = t % nch;
+        atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, S.q, K, ci, j, st));
+      }
+      rs_team_sync(bar_id, T);  // D
+      if (wt == 0) {  // first candidate with the minimum full sum
+        unsigned long long key = ~0ull;
+        for (uint32_t i = lane; i < nHeur; i += 32) {
+          const unsigned long long k2 = ((unsigned long long)TS.hsum[i] << 32) | i;
+          key = k2 < key ? k2 : key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(RS_FULL, key, o);
+          key = other < key ? other : key;
+        }
+        if (lane == 0) TS.best = key;
+      }
+      rs_team_sync(bar_id, T);  // E
+    }
+    // ---- random probes, early-out against the shared best (sum << 32 | index, atomicMin): the fetched-ahead ones
+    //      resume after their first chunk, the rest (probes >= nPre) run from the start
+    volatile unsigned long long *vbest = &TS.best;
     const uint32_t selfmap = MAPS ? S.map[0] : 0u;
+    unsigned long long mykey = ~0ull;  // key of a probe this lane took to the end
+    uint32_t mypt = 0, mycol = 0;
     if ((uint32_t)(*vbest >> 32) != 0u) {
-      for (uint32_t j = tid; j < J.probes; j += T) {
+      if (pre) {
+        const unsigned long long idx = (unsigned long long)(nHeur + (tid - 32u));
+        uint32_t partial = ppartial, k0 = 1u + CH;
+        bool alive = (((unsigned long long)partial << 32) | idx) < *vbest;
+        st.issued++;
+        while (alive && k0 < K) {
+          partial += rs_chunk_sum<MAPS, CH>(J, lutc, lutm, S.nb, S.map, pcx, pclin, k0);
+          k0 += CH;
+          alive = !((((unsigned long long)partial << 32) | idx) > *vbest);
+        }
+        st.compares += min(k0, K);
+        if (alive) { mykey = ((unsigned long long)partial << 32) | idx; mypt = pc; mycol = pown_x & 0xFFFFFFu; atomicMin(&TS.best, mykey); }
+      }
+      for (uint32_t j = nPre + tid; j < J.probes; j += T) {
         if ((uint32_t)(*vbest >> 32) == 0u) break;  // perfect match: nothing later is evaluated (synthesize.h:599)
         const uint32_t c = __ldg(J.corpus_pts + rs_range(rs_mix32(hv + j * 0xC2B2AE35u), nC));
         const int cx = (int)(c & 0xFFFFu);
         const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx;
         const unsigned long long idx = (unsigned long long)(nHeur + j);
-        uint32_t partial = 0, k0 = 1;
-        if (MAPS) partial = rs_lut3(lutm, __vabsdiffu4(__ldg(&J.corpus8[clin].y), selfmap));
+        uint32_t partial = 0, k0 = 1, own_x, own_y = 0;
+        if (MAPS) { const uint2 t = __ldg(J.corpus8 + clin); own_x = t.x; own_y = t.y; }
+        else own_x = __ldg(J.corpus4 + clin);
+        if (MAPS) partial = rs_lut3(lutm, __vabsdiffu4(own_y, selfmap));
         bool alive = true;
         st.issued++;
         do {
@@ -894,15 +990,21 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
           if ((((unsigned long long)partial << 32) | idx) > *vbest) { alive = false; break; }
         } while (k0 < K);
         st.compares += min(k0, K);
-        if (alive) atomicMin(&TS.best, ((unsigned long long)partial << 32) | idx);
+        if (alive) {
+          const unsigned long long key = ((unsigned long long)partial << 32) | idx;
+          if (key < mykey) { mykey = key; mypt = c; mycol = own_x & 0xFFFFFFu; }
+          atomicMin(&TS.best, key);
+        }
       }
     }
-    rs_team_sync(bar_id, T);
+    rs_team_sync(bar_id, T);  // F
+    if (mykey == TS.best && mykey != ~0ull) { TS.win_pt = mypt; TS.win_col = mycol; }
+    rs_team_sync(bar_id, T);  // G
     if (wt == 0) {
       const unsigned long long key = TS.best;
       const uint32_t bestSum = (key == ~0ull) ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
       const int bestIdx = (key == ~0ull) ? 0x7FFFFFFF : (int)(uint32_t)key;
-      rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, RS_NO_SRC, 0);
+      rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, TS.win_pt, TS.win_col, true);
     }
   }
   __syncwarp();
