@@ -132,7 +132,12 @@ typedef struct {
   float ms_pass[6];                                    /* device-clock duration of each pass that ran */
   float ms_synth;                                      /* CUDA-event time of the pass kernels alone */
   unsigned int kernel_launches, synth_launches_run;    /* kernels launched by the job; pass launches that did work */
+  unsigned int order_cache_hit;                        /* 1: the visit order came from the device-side cache */
 } RsStats;
+/* The visit order of the target points is a pure function of (selection, image size, matchContextType, seed) and is
+ * kept on the device for later jobs with the same key (16 entries / 1 GiB, least recently used out first).
+ * rs_order_cache(0) drops the entries and disables the cache, rs_order_cache(1) enables it (default). */
+void rs_order_cache(int enabled);
 /* Throughput profile of the last engine() call on this thread (needs rs_keep_result(1)): ns from the start of
  * `pass` to the claim of its visit 4096 * i.  Returns the number of entries written. */
 unsigned int rs_get_timeline(unsigned int pass, unsigned long long *out_ns, unsigned int cap);

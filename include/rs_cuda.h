@@ -57,6 +57,20 @@ typedef struct {
   uint32_t synth_launches_run;   /* pass-kernel launches that did work (launches of passes after the stop rule exit at once) */
 } RsJobCounters;
 
+/* The target selection (mask byte != 0) as the device sees it: count, first/last row, 128-bit digest. */
+typedef struct {
+  uint64_t h1, h2;
+  uint32_t n, ymin, ymax, pad;
+} RsTargetDigest;
+/* What a visit order is a function of (lib/orderTarget.h): the selection, the image size, matchContextType and the
+ * seed of the ordering PRNG stream. */
+typedef struct {
+  uint64_t h1, h2;
+  uint32_t n;
+  int32_t tw, th, mode;
+  uint32_t seed;
+} RsOrderKey;
+
 /* Called on the host, in order, for every (pass, index) with (index & 4095) == 0 that the device
  * has started (lib/synthesize.h:493-497).  Return non-zero to cancel the job. */
 typedef int (*RsTickFn)(void *ctx, uint32_t pass, uint32_t index);
@@ -89,6 +103,23 @@ int rs_job_upload_images(RsJob *job, const uint8_t *target_raw, const uint8_t *c
                          const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max);
 int rs_job_upload_order(RsJob *job, const uint32_t *targets);
 /* Runs all passes (early termination decided on the device), calling tick from the waiting host thread. */
+/* The same upload with the target points found on the device (no per-pixel work on the host):
+ *   rs_job_stage       host -> device, state init, corpus points, offsets table, selection digest; asynchronous
+ *   rs_job_digest      waits for the digest only (the first thing the stream computes)
+ *   rs_job_bind_order  1: a visit order for this key is cached on the device and now bound to the job; 0: miss
+ *   rs_job_set_order   miss path: the points as ordered by the host (with a key they stay on the device for later
+ *                      jobs; NULL: not cached)
+ * rs_cuda_order_cache(0) drops the cached orders and disables the cache. */
+int rs_job_stage(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *color_lut256,
+                 const uint32_t *map_lut256, uint32_t map_lut_max);
+int rs_job_digest(RsJob *job, RsTargetDigest *out);
+int rs_job_bind_order(RsJob *job, const RsTargetDigest *digest, const RsOrderKey *key);
+int rs_job_set_order(RsJob *job, const uint32_t *ordered_points, const RsOrderKey *key);
+void rs_cuda_order_cache(int enabled);
+/* Pass schedule (prefix length of each pass), when it was not known at rs_job_create (target points counted on the
+ * device). */
+void rs_job_set_passes(RsJob *job, const uint32_t *pass_end, uint32_t n_passes);
+
 int rs_job_run(RsJob *job, RsTickFn tick, void *tick_ctx);
 /* target_raw_out: the caller's tw*th*bpp pixmap; the rows containing target points are overwritten with the
  * device's copy, which differs from the uploaded one only in the colour bytes of target points.

@@ -30,7 +30,7 @@ class RsStats(C.Structure):
                 ("passes_run", C.c_uint), ("n_targets", C.c_uint), ("n_corpus", C.c_uint),
                 ("ms_prep", C.c_float), ("ms_h2d", C.c_float), ("ms_kernels", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float), ("ms_pass", C.c_float * 6), ("ms_synth", C.c_float),
-                ("kernel_launches", C.c_uint), ("synth_launches_run", C.c_uint)]
+                ("kernel_launches", C.c_uint), ("synth_launches_run", C.c_uint), ("order_cache_hit", C.c_uint)]
 
     def as_dict(self):
         d = {}
@@ -91,6 +91,11 @@ def last_stats():
     s = RsStats()
     lib().rs_get_stats(C.byref(s))
     return s.as_dict()
+
+
+def order_cache(enabled=True):
+    """Enable (default) or drop + disable the device-side cache of visit orders (rs_order_cache)."""
+    lib().rs_order_cache(1 if enabled else 0)
 
 
 def total_kernel_launches():

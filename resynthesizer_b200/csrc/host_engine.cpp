@@ -66,6 +66,7 @@ int on_tick(void *p, uint32_t /*pass*/, uint32_t /*index*/) {
 extern "C" const char *rs_last_error(void) { return t_err.c_str(); }
 extern "C" void rs_get_stats(RsStats *out) { *out = t_stats; }
 extern "C" void rs_set_seed(unsigned int seed) { t_seed = seed; }
+extern "C" void rs_order_cache(int enabled) { rs_cuda_order_cache(enabled); }
 extern "C" unsigned long long rs_total_kernel_launches(void) { return g_kernel_launches.load(); }
 extern "C" void rs_keep_result(int yes) { t_keep_result = yes != 0; }
 extern "C" int rs_set_device(int ordinal) {
@@ -145,12 +146,12 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   uint8_t *tpix = reinterpret_cast<uint8_t *>(targetMap->data->data);
   const uint8_t *cpix = reinterpret_cast<const uint8_t *>(corpusMap->data->data);
 
-  static thread_local std::vector<uint32_t> targets;  // reused across calls: no page faults per job
-  rs::collect_target_points(tpix, tw, th, bpp, targets);
-  if (targets.empty()) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;  // lib/engine.c:605-610
-  if (!rs::has_corpus_point(cpix, cw, ch, bpp, *fi)) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;   // lib/engine.c:620-627
+  // Empty target / corpus and the context-type range are detected on the host, before CUDA is touched
+  // (lib/engine.c:605-610, 620-627, 645-647); everything else about the points happens on the device.
+  if (!rs::has_target_point(tpix, tw, th, bpp)) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;
+  if (!rs::has_corpus_point(cpix, cw, ch, bpp, *fi)) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;
   if (prm.matchContextType < 0 || prm.matchContextType > 8)
-    return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;  // lib/engine.c:645-647 (orderTargetPoints' default case)
+    return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;  // orderTargetPoints' default case
 
   if (tw > 32767 || th > 32767 || cw > 32767 || ch > 32767) {
     t_err = "image dimensions above 32767 are not supported by the packed device layout";
@@ -176,23 +177,44 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   desc.vtile = prm.isMakeSeamlesslyTileableVertically ? 1 : 0;
   desc.use_context = prm.matchContextType != 0;
   desc.patch_size = prm.patchSize; desc.max_probes = prm.maxProbeCount; desc.seed = t_seed;
-  const uint32_t n = (uint32_t)targets.size();
-  const uint32_t estimated = rs::pass_schedule(n, desc.pass_end);
   desc.n_passes = 6;
   desc.terminate_fraction = 0.1;  // IMAGE_SYNTH_TERMINATE_FRACTION, a double (lib/refiner.h:111)
-  const uint32_t y_min = (uint32_t)rs::unpack_y(targets.front()), y_max = (uint32_t)rs::unpack_y(targets.back());
   const double t1 = now_ms();
 
-  // Phase 1 (asynchronous): images, corpus points (compacted on the device), offsets table, tables, state init ...
+  // Stage the images (asynchronous: host -> device, state init, corpus points, offsets table) and get the digest of
+  // the target selection back: number of target points, their rows, and the key of the visit-order cache.
   RsJob *job = nullptr;
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
-  int rc = rs_job_upload_images(job, tpix, cpix, n, y_min, y_max, nullptr, 0, nullptr, 0, c256, m256, m512[0]);
+  RsTargetDigest dg;
+  int rc = rs_job_stage(job, tpix, cpix, c256, m256, m512[0]);
+  if (!rc) rc = rs_job_digest(job, &dg);
+  if (rc) { t_err = rs_cuda_last_error(); rs_job_destroy(job); return RS_ERROR_CUDA; }
+  const uint32_t n = dg.n;
+  uint32_t pass_end[6];
+  const uint32_t estimated = rs::pass_schedule(n, pass_end);
+  rs_job_set_passes(job, pass_end, 6);
   const double t2 = now_ms();
-  // ... while the host orders the target points with the reference's PRNG stream (lib/engine.c:643-645)
-  rs::GRandMT prng(t_seed);
-  rs::order_target_points(prm.matchContextType, targets, prng);
+  // The visit order (lib/engine.c:643-645) is a pure function of the selection, the image size, the context type and
+  // the seed: jobs that share them (a batch, the frames of a clip) order their points once; the list stays on the device.
+  RsOrderKey key;
+  std::memset(&key, 0, sizeof key);
+  key.h1 = dg.h1; key.h2 = dg.h2; key.n = n; key.tw = tw; key.th = th; key.mode = prm.matchContextType; key.seed = t_seed;
+  static thread_local std::vector<uint32_t> targets;  // reused across calls: no page faults per job
+  int hit = t_keep_result ? 0 : rs_job_bind_order(job, &dg, &key);
+  if (hit == 0) {
+    if (t_keep_result) hit = rs_job_bind_order(job, &dg, nullptr) == 100 ? 100 : 0;  // sizes only; the order is wanted on the host
+    if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
+      rs::collect_target_points(tpix, tw, th, bpp, targets);
+      if (targets.size() != n) { t_err = "target point count differs between host and device"; rc = 100; }
+      if (!rc) {
+        rs::GRandMT prng(t_seed);
+        rs::order_target_points(prm.matchContextType, targets, prng);
+        rc = rs_job_set_order(job, targets.data(), t_keep_result ? nullptr : &key);
+      }
+    }
+  }
+  if (hit == 100) rc = 100;
   const double t2b = now_ms();
-  if (!rc) rc = rs_job_upload_order(job, targets.data());
   const std::vector<uint32_t> &tpk = targets;
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
   if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, on_tick, &ts); }
@@ -227,6 +249,7 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   for (int p = 0; p < 6; p++) { t_stats.betters[p] = jc.betters[p]; t_stats.pass_visits[p] = jc.pass_visits[p]; t_stats.sum_best[p] = jc.sum_best[p]; }
   t_stats.passes_run = jc.passes_run; t_stats.n_targets = n; t_stats.n_corpus = jc.n_corpus;
   t_stats.ms_prep = (float)((t1 - t0) + (t2b - t2)); t_stats.ms_h2d = (float)(t2 - t1); t_stats.ms_kernels = jc.ms_passes;
+  t_stats.order_cache_hit = hit == 1 ? 1u : 0u;
   t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
   for (int p = 0; p < 6; p++) t_stats.ms_pass[p] = jc.ms_pass[p];
   g_kernel_launches.fetch_add(jc.kernel_launches);

@@ -1,6 +1,8 @@
 #include "host_prep.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -116,6 +118,14 @@ void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFor
   }
 }
 
+// Is any pixel selected?  Sparse samples first (a selection is rarely a single pixel), then every pixel.
+bool has_target_point(const uint8_t *pix, int w, int h, int bpp) {
+  const size_t n = (size_t)w * h;
+  for (size_t i = 0; i < n; i += 61) if (pix[i * bpp] != 0) return true;
+  for (size_t i = 0; i < n; i++) if (pix[i * bpp] != 0) return true;
+  return false;
+}
+
 bool has_corpus_point(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi) {
   const bool alpha = fi.isAlphaSource != 0;
   const int ab = fi.alpha_bip;
@@ -217,14 +227,38 @@ int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {
   const size_t n = pts.size();
   if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
   if (mode <= 1) {  // not Fisher-Yates: every i swaps with a draw over the whole vector
-    std::vector<uint32_t> js(n);
-    prng.fill_int_range((uint32_t)n, js.data(), n);
+    static thread_local std::vector<uint32_t> js;  // reused: no page faults per job
+    js.resize(n);
     uint32_t *a = pts.data();
-    constexpr size_t AHEAD = 16;
-    for (size_t i = 0; i < n; i++) {
-      if (i + AHEAD < n) __builtin_prefetch(a + js[i + AHEAD], 1);
-      std::swap(a[i], a[js[i]]);
+    constexpr size_t AHEAD = 16, BLOCK = 1u << 16;
+    if (n < 4 * BLOCK) {
+      prng.fill_int_range((uint32_t)n, js.data(), n);
+      for (size_t i = 0; i < n; i++) {
+        if (i + AHEAD < n) __builtin_prefetch(a + js[i + AHEAD], 1);
+        std::swap(a[i], a[js[i]]);
+      }
+      return 0;
     }
+    // Large vectors: the draws (MT19937 blocks + range reduction) and the swaps (random access) cost about the same and
+    // the draws do not depend on the swaps, so a second thread produces them a block ahead of the swap loop.
+    std::atomic<size_t> ready{0};
+    uint32_t *jp = js.data();
+    std::thread producer([&]() {
+      for (size_t off = 0; off < n; off += BLOCK) {
+        const size_t len = n - off < BLOCK ? n - off : BLOCK;
+        prng.fill_int_range((uint32_t)n, jp + off, len);
+        ready.store(off + len, std::memory_order_release);
+      }
+    });
+    for (size_t off = 0; off < n; off += BLOCK) {
+      const size_t end = n - off < BLOCK ? n : off + BLOCK;
+      while (ready.load(std::memory_order_acquire) < end) { /* spin: the producer is at most a block away */ }
+      for (size_t i = off; i < end; i++) {
+        if (i + AHEAD < end) __builtin_prefetch(a + jp[i + AHEAD], 1);
+        std::swap(a[i], a[jp[i]]);
+      }
+    }
+    producer.join();
     return 0;
   }
   // centre of the bounding box; the upper bounds start at 0 as in the reference (engineTypes.h:192-226)

@@ -41,6 +41,7 @@ void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vecto
 void collect_corpus_points(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi, std::vector<uint32_t> &out);
 
 // Is there any corpus point at all (mask 0xFF and not transparent)?  Stops at the first one (lib/engine.c:620-627).
+bool has_target_point(const uint8_t *pix, int w, int h, int bpp);
 bool has_corpus_point(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi);
 
 // lib/orderTarget.h:268-343 (+ brushfire.h, engineTypes.h).  Returns 0 or IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE.

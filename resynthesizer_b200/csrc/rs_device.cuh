@@ -63,6 +63,9 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   unsigned int n_corpus;    // number of corpus points (written at upload: host value or device compaction count)
   unsigned int stop;        // set by the last CTA of a pass when betters/n < fraction, or on cancel
   unsigned int passes_run;
+  unsigned int dg_align;
+  unsigned long long dg_h1, dg_h2;        // digest of the target selection (k_target_digest), layout = RsTargetDigest
+  unsigned int dg_n, dg_ymin, dg_ymax, dg_pad;
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
   unsigned long long pass_visits[6], sum_best[6];
   unsigned long long pass_end_ns[6];          // globaltimer when the last CTA of a pass left

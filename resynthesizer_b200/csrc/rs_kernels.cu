@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1073,6 +1074,10 @@ struct Workspace {
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
+  void *pin_order = nullptr;  // pinned staging of a visit order
+  size_t pin_order_cap = 0;
+  RsTargetDigest *h_digest = nullptr;  // pinned
+  cudaEvent_t evDigest = nullptr;
   unsigned int *h_ticks = nullptr;
   int *h_cancel = nullptr;
   RsCtrl *h_ctrl = nullptr;
@@ -1113,6 +1118,9 @@ static void ws_free(Workspace *w) {
                    &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
+  if (w->pin_order) cudaFreeHost(w->pin_order);
+  if (w->h_digest) cudaFreeHost(w->h_digest);
+  if (w->evDigest) cudaEventDestroy(w->evDigest);
   if (w->h_ticks) cudaFreeHost(w->h_ticks);
   if (w->h_cancel) cudaFreeHost(w->h_cancel);
   if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
@@ -1169,6 +1177,8 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
   WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evDigest, cudaEventDisableTiming));
+  WCHK(cudaHostAlloc(&w->h_digest, sizeof(RsTargetDigest), cudaHostAllocDefault));
   WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
   WCHK(cudaHostAlloc(&w->h_cancel, sizeof(int), cudaHostAllocMapped));
   WCHK(cudaHostAlloc(&w->h_ctrl, RS_CTRL_COPY_BYTES, cudaHostAllocDefault));
@@ -1200,13 +1210,25 @@ __global__ void k_gen_offsets(int w, int h, uint32_t n, uint32_t *__restrict__ k
 }
 
 // ------------------------------------------------------------------------------------------------ the job
+// Visit orders kept on the device, keyed by what they are a function of.  A batch of jobs with the same selection
+// (frames of a video, a set of equally sized images with the same hole) orders its target points once.
+struct OrderEntry {
+  RsOrderKey key;
+  int device = 0;
+  uint32_t *dev = nullptr;
+  uint32_t n = 0;
+  unsigned long long stamp = 0;
+  ~OrderEntry() { if (dev) { cudaSetDevice(device); cudaFree(dev); } }
+};
 struct RsJob {
   RsJobDesc d;
   Workspace *ws = nullptr;
   bool maps = false;
   uint32_t nT = 0, nC = 0, nOff = 0, penalty = 0;
   uint32_t y_min = 0, y_max = 0;  // rows of the target image that hold target points
-  size_t pin_targets_off = 0;     // where the visit order is staged in the pinned buffer
+  size_t out_bytes = 0;           // pinned bytes the results need (rows with target points + sources)
+  std::shared_ptr<OrderEntry> order;     // cached visit order this job reads, if any
+  const uint32_t *targets_dev = nullptr;  // the visit order on the device (cache entry or the workspace's buffer)
   bool want_sources = false;
   float ms_passes = 0.f;
   uint32_t launches = 0;          // pass-kernel launches of the last run
@@ -1282,70 +1304,112 @@ __global__ void k_pack_points(uint32_t *__restrict__ pts, const unsigned int *__
   }
 }
 
-// Phase 1 of the upload: everything that does not depend on the visit order.  Asynchronous on the job's stream,
-// so the host can compute the target order meanwhile (rs_job_upload_order).
-extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, uint32_t n_targets,
-                                    uint32_t y_min, uint32_t y_max, const uint32_t *corpus_points, uint32_t n_corpus,
-                                    const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
-                                    const uint32_t *map_lut256, uint32_t map_lut_max) {
+// ---- target points and their digest on the device ----
+// The selection (mask byte != 0) of the target image, 32 pixels per word: count, row range and a 128-bit digest
+// (sum over words of two different mixes of (word index, word), so the order of accumulation does not matter).
+// The digest keys the visit-order cache: the order is a pure function of (selection, image size, mode, seed).
+__device__ __forceinline__ unsigned long long rs_mix64(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31; return x;
+}
+__global__ void __launch_bounds__(256) k_target_digest(const uint8_t *__restrict__ raw, uint32_t n_px, int bpp, int tw,
+                                                       RsCtrl *__restrict__ ctrl) {
+  unsigned long long h1 = 0, h2 = 0;
+  uint32_t cnt = 0, ymin = 0xFFFFFFFFu, ymax = 0;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_round = (n_px + 31u) & ~31u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+    const bool sel = i < n_px && raw[(size_t)i * bpp] != 0;
+    const uint32_t w = __ballot_sync(RS_FULL, sel);
+    if (lane == 0 && w) {
+      const uint32_t wi = i >> 5;
+      h1 += rs_mix64(((unsigned long long)wi << 32) | w);
+      h2 += rs_mix64((((unsigned long long)w << 32) | wi) ^ 0x9E3779B97F4A7C15ull);
+      cnt += __popc(w);
+      const uint32_t first = i + (__ffs(w) - 1), last = i + (31 - __clz(w));
+      ymin = min(ymin, first / (uint32_t)tw);
+      ymax = max(ymax, last / (uint32_t)tw);
+    }
+  }
+  if (lane == 0 && cnt) {
+    atomicAdd(&ctrl->dg_h1, h1);
+    atomicAdd(&ctrl->dg_h2, h2);
+    atomicAdd(&ctrl->dg_n, cnt);
+    atomicMin(&ctrl->dg_ymin, ymin);
+    atomicMax(&ctrl->dg_ymax, ymax);
+  }
+}
+static std::mutex g_order_mutex;
+static std::vector<std::shared_ptr<OrderEntry>> g_orders;
+static unsigned long long g_order_clock = 0;
+static std::atomic<int> g_order_cache_on{1};
+extern "C" void rs_cuda_order_cache(int enabled) {
+  g_order_cache_on.store(enabled ? 1 : 0);
+  if (!enabled) { std::lock_guard<std::mutex> lk(g_order_mutex); g_orders.clear(); }
+}
+static bool key_equal(const RsOrderKey &a, const RsOrderKey &b) {
+  return a.h1 == b.h1 && a.h2 == b.h2 && a.n == b.n && a.tw == b.tw && a.th == b.th && a.mode == b.mode && a.seed == b.seed;
+}
+
+// Stage 1 of an upload: everything that does not depend on the target points.  Asynchronous on the job's stream.
+static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *corpus_points,
+                        uint32_t n_corpus, const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
+                        const uint32_t *map_lut256, uint32_t map_lut_max, bool digest) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   const RsJobDesc &d = j->d;
-  if (n_targets == 0 || (corpus_points && n_corpus == 0) || n_targets >= RS_IDX_MASK || y_max < y_min ||
-      y_max >= (uint32_t)d.th) {
-    g_err = "rs_job_upload_images: empty or oversized point list";
-    return 100;
-  }
+  if (corpus_points && n_corpus == 0) { g_err = "rs_job upload: empty corpus point list"; return 100; }
   const size_t tn = (size_t)d.tw * d.th, cn = (size_t)d.cw * d.ch;
   cudaStream_t s = w->stream;
-  j->nT = n_targets; j->nC = corpus_points ? n_corpus : 0;
-  j->y_min = y_min; j->y_max = y_max;
+  j->nC = corpus_points ? n_corpus : 0;
   j->penalty = 65535u * (uint32_t)d.n_color + map_lut_max * (uint32_t)d.n_map;
   const size_t cap_cpts = corpus_points ? (size_t)n_corpus : cn;
   int rc = 0;
   if ((rc = ws_ensure(w->raw_t, tn * d.bpp)) || (rc = ws_ensure(w->raw_c, cn * d.bpp)) ||
       (rc = ws_ensure(w->corpus, (cn + 1) * (j->maps ? 8 : 4))) || (rc = ws_ensure(w->W, tn * 16)) ||
       (rc = ws_ensure(w->meta, tn * 4)) || (rc = ws_ensure(w->tmaps, j->maps ? tn * 4 : 4)) ||
-      (rc = ws_ensure(w->targets, (size_t)n_targets * 4)) || (rc = ws_ensure(w->cpts, cap_cpts * 4)) ||
+      (rc = ws_ensure(w->cpts, cap_cpts * 4)) ||
       (rc = ws_ensure(w->lut256, 512 * 4)) || (rc = ws_ensure(w->lut_rep, 2 * RS_LUT_WORDS * 4)) ||
       (rc = ws_ensure(w->prober0, cn * 8)) || (rc = ws_ensure(w->prober1, cn * 8)) || (rc = ws_ensure(w->prober2, cn * 8)) ||
-      (rc = ws_ensure(w->sources, (size_t)n_targets * 4)) || (rc = ws_ensure(w->ctrl, sizeof(RsCtrl))))
+      (rc = ws_ensure(w->ctrl, sizeof(RsCtrl))))
     return rc;
-  {
-    uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
-    if (kmax > RS_MAX_NB) kmax = RS_MAX_NB;
-    if ((rc = ws_ensure(w->nb_lists, (size_t)n_targets * (kmax - 1) * sizeof(uint2))) || (rc = ws_ensure(w->nb_counts, n_targets))) return rc;
-  }
   // neighbour offsets: caller-provided table, or built (and kept) on the device
   const int ow = d.tw < d.cw ? d.tw : d.cw, oh = d.th < d.ch ? d.th : d.ch;
   const uint32_t full_n = (uint32_t)(2 * ow - 1) * (uint32_t)(2 * oh - 1);
   // stage all host inputs through pinned memory so the copies are truly asynchronous
-  const size_t sz_t = tn * d.bpp, sz_c = cn * d.bpp, sz_tp = (size_t)n_targets * 4,
-               sz_cp = corpus_points ? (size_t)n_corpus * 4 : 0, sz_off = offsets ? (size_t)n_offsets * 4 : 0, sz_lut = 512 * 4;
+  const size_t sz_t = tn * d.bpp, sz_c = cn * d.bpp, sz_cp = corpus_points ? (size_t)n_corpus * 4 : 0,
+               sz_off = offsets ? (size_t)n_offsets * 4 : 0, sz_lut = 512 * 4;
   auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t o_t = 0, o_c = o_t + up(sz_t), o_tp = o_c + up(sz_c), o_cp = o_tp + up(sz_tp), o_off = o_cp + up(sz_cp),
+  const size_t o_t = 0, o_c = o_t + up(sz_t), o_cp = o_c + up(sz_c), o_off = o_cp + up(sz_cp),
                o_lut = o_off + up(sz_off), total = o_lut + up(sz_lut);
-  const size_t out_bytes = (size_t)(j->y_max - j->y_min + 1) * d.tw * d.bpp + (size_t)n_targets * 4 + 256;
-  const size_t need_pin = total > out_bytes ? total : out_bytes;
+  const size_t need_pin = total > j->out_bytes ? total : j->out_bytes;
   if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
-  j->pin_targets_off = o_tp;
   uint8_t *pin = (uint8_t *)w->pin;
   RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl), s));
-  memcpy(pin + o_c, corpus_raw, sz_c);
-  RS_CHECK(cudaMemcpyAsync(w->raw_c.p, pin + o_c, sz_c, cudaMemcpyHostToDevice, s));
   memcpy(pin + o_t, target_raw, sz_t);
   RS_CHECK(cudaMemcpyAsync(w->raw_t.p, pin + o_t, sz_t, cudaMemcpyHostToDevice, s));
+  const int T = 256;
+  j->upload_launches = 0;
+  if (digest) {  // first, so that its result can come back while the rest of the staging runs
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+    const uint32_t ymin_init = 0xFFFFFFFFu;
+    RS_CHECK(cudaMemcpyAsync(&((RsCtrl *)w->ctrl.p)->dg_ymin, &ymin_init, 4, cudaMemcpyHostToDevice, s));
+    k_target_digest<<<sms * 8, 256, 0, s>>>((const uint8_t *)w->raw_t.p, (uint32_t)tn, d.bpp, d.tw, (RsCtrl *)w->ctrl.p);
+    RS_CHECK(cudaMemcpyAsync(w->h_digest, &((RsCtrl *)w->ctrl.p)->dg_h1, sizeof(RsTargetDigest), cudaMemcpyDeviceToHost, s));
+    RS_CHECK(cudaEventRecord(w->evDigest, s));
+    j->upload_launches += 1u;
+  }
+  memcpy(pin + o_c, corpus_raw, sz_c);
+  RS_CHECK(cudaMemcpyAsync(w->raw_c.p, pin + o_c, sz_c, cudaMemcpyHostToDevice, s));
   memcpy(pin + o_lut, color_lut256, 256 * 4);
   memcpy(pin + o_lut + 256 * 4, map_lut256, 256 * 4);
   RS_CHECK(cudaMemcpyAsync(w->lut256.p, pin + o_lut, sz_lut, cudaMemcpyHostToDevice, s));
-  const int T = 256;
   bool built_offsets = false;
   int offset_sort_bits = 1;
   unsigned int *d_ncorpus = &((RsCtrl *)w->ctrl.p)->n_corpus;
   if (corpus_points) {
     memcpy(pin + o_cp, corpus_points, sz_cp);
     RS_CHECK(cudaMemcpyAsync(w->cpts.p, pin + o_cp, sz_cp, cudaMemcpyHostToDevice, s));
-    *(uint32_t *)(pin + o_lut + 512 * 4 - 4) = 0;  // (unused slot) keep the staging area initialised
     RS_CHECK(cudaMemcpyAsync(d_ncorpus, &j->nC, 4, cudaMemcpyHostToDevice, s));
   } else {
     if ((rc = ws_ensure(w->sort_keys_in, cn))) return rc;  // flags
@@ -1388,24 +1452,134 @@ extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const u
   k_replicate_lut<<<(RS_LUT_WORDS + T - 1) / T, T, 0, s>>>((const uint32_t *)w->lut256.p, (const uint32_t *)w->lut256.p + 256,
                                                          (uint32_t *)w->lut_rep.p);
   RS_CHECK(cudaGetLastError());
-  j->upload_launches = 3u + (corpus_points ? 0u : 4u) + (built_offsets ? 1u + (uint32_t)((offset_sort_bits + 7) / 8) + 2u : 0u);
+  j->upload_launches += 3u + (corpus_points ? 0u : 4u) + (built_offsets ? 1u + (uint32_t)((offset_sort_bits + 7) / 8) + 2u : 0u);
   for (int p = 0; p < 6; p++) w->h_ticks[p] = 0;
   *w->h_cancel = 0;
   return 0;
 }
 
+// Everything whose size follows the number of target points.  `idle`: nothing of this job is in flight on the stream
+// (pinned staging may be reallocated).
+static int set_targets(RsJob *j, uint32_t n_targets, uint32_t y_min, uint32_t y_max, bool idle) {
+  Workspace *w = j->ws;
+  const RsJobDesc &d = j->d;
+  if (n_targets == 0 || n_targets >= RS_IDX_MASK || y_max < y_min || y_max >= (uint32_t)d.th) {
+    g_err = "rs_job upload: empty or oversized target point list";
+    return 100;
+  }
+  j->nT = n_targets; j->y_min = y_min; j->y_max = y_max;
+  uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
+  if (kmax > RS_MAX_NB) kmax = RS_MAX_NB;
+  int rc = 0;
+  if ((rc = ws_ensure(w->nb_lists, (size_t)n_targets * (kmax - 1) * sizeof(uint2))) || (rc = ws_ensure(w->nb_counts, n_targets)) ||
+      (rc = ws_ensure(w->sources, (size_t)n_targets * 4)))
+    return rc;
+  j->out_bytes = (size_t)(y_max - y_min + 1) * d.tw * d.bpp + (size_t)n_targets * 4 + 512;
+  if (idle && (rc = ws_ensure_pinned(w, j->out_bytes))) return rc;
+  return 0;
+}
+
+// Phase 1 of the upload with the target points known to the caller (count and row range): everything that does not
+// depend on the visit ORDER.  Asynchronous on the job's stream, so the host can order the points meanwhile.
+extern "C" int rs_job_upload_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, uint32_t n_targets,
+                                    uint32_t y_min, uint32_t y_max, const uint32_t *corpus_points, uint32_t n_corpus,
+                                    const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
+                                    const uint32_t *map_lut256, uint32_t map_lut_max) {
+  if (int rc = set_targets(j, n_targets, y_min, y_max, true)) return rc;
+  return stage_images(j, target_raw, corpus_raw, corpus_points, n_corpus, offsets, n_offsets, color_lut256, map_lut256,
+                      map_lut_max, false);
+}
+
 // Phase 2 of the upload: the visit order (n_targets points as given to rs_job_upload_images).
-extern "C" int rs_job_upload_order(RsJob *j, const uint32_t *targets) {
+static int upload_order_impl(RsJob *j, const uint32_t *targets, const RsOrderKey *key) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
-  uint8_t *pin = (uint8_t *)w->pin;
-  memcpy(pin + j->pin_targets_off, targets, (size_t)j->nT * 4);
-  RS_CHECK(cudaMemcpyAsync(w->targets.p, pin + j->pin_targets_off, (size_t)j->nT * 4, cudaMemcpyHostToDevice, w->stream));
+  const size_t bytes = (size_t)j->nT * 4;
+  if (bytes > w->pin_order_cap) {
+    if (w->pin_order) cudaFreeHost(w->pin_order);
+    w->pin_order = nullptr; w->pin_order_cap = 0;
+    RS_CHECK(cudaHostAlloc(&w->pin_order, bytes + bytes / 8 + 4096, cudaHostAllocDefault));
+    w->pin_order_cap = bytes + bytes / 8 + 4096;
+  }
+  uint32_t *dst = nullptr;
+  j->order.reset();
+  if (key && g_order_cache_on.load()) {  // the uploaded order becomes a cache entry
+    auto e = std::make_shared<OrderEntry>();
+    e->key = *key; e->device = w->device; e->n = j->nT;
+    RS_CHECK(cudaMalloc(&e->dev, bytes));
+    dst = e->dev;
+    j->order = e;
+    std::lock_guard<std::mutex> lk(g_order_mutex);
+    e->stamp = ++g_order_clock;
+    g_orders.push_back(e);
+    size_t total = 0;
+    for (auto &o : g_orders) total += (size_t)o->n * 4;
+    while (g_orders.size() > 16 || (total > ((size_t)1 << 30) && g_orders.size() > 1)) {  // evict the least recently used
+      size_t lru = 0;
+      for (size_t i = 1; i < g_orders.size(); i++) if (g_orders[i]->stamp < g_orders[lru]->stamp) lru = i;
+      total -= (size_t)g_orders[lru]->n * 4;
+      g_orders.erase(g_orders.begin() + lru);
+    }
+  } else {
+    if (int rc = ws_ensure(w->targets, bytes)) return rc;
+    dst = (uint32_t *)w->targets.p;
+  }
+  j->targets_dev = dst;
+  memcpy(w->pin_order, targets, bytes);
+  RS_CHECK(cudaMemcpyAsync(dst, w->pin_order, bytes, cudaMemcpyHostToDevice, w->stream));
   j->upload_launches += 1u;
-  k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>((const uint32_t *)w->targets.p, j->nT, j->d.tw,
-                                                             (uint32_t *)w->meta.p);
+  k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>(dst, j->nT, j->d.tw, (uint32_t *)w->meta.p);
   RS_CHECK(cudaGetLastError());
   return 0;
+}
+extern "C" int rs_job_upload_order(RsJob *j, const uint32_t *targets) { return upload_order_impl(j, targets, nullptr); }
+
+// ---- the same upload with the target points found on the device ----
+extern "C" int rs_job_stage(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *color_lut256,
+                            const uint32_t *map_lut256, uint32_t map_lut_max) {
+  j->out_bytes = 0;
+  return stage_images(j, target_raw, corpus_raw, nullptr, 0, nullptr, 0, color_lut256, map_lut256, map_lut_max, true);
+}
+extern "C" int rs_job_digest(RsJob *j, RsTargetDigest *out) {
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
+  RS_CHECK(cudaEventSynchronize(w->evDigest));
+  *out = *w->h_digest;
+  return 0;
+}
+// Binds the cached visit order for `key` to the job.  Returns 1 on a hit, 0 on a miss (the caller orders the points
+// and calls rs_job_set_order), 100 on error.  `dg` = what rs_job_digest returned.
+extern "C" int rs_job_bind_order(RsJob *j, const RsTargetDigest *dg, const RsOrderKey *key) {
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
+  // the staging copies are not all done yet: the pinned buffer must not move now (idle = false); it already holds the
+  // whole input, which is at least as large as the rows that come back
+  if (int rc = set_targets(j, dg->n, dg->ymin, dg->ymax, false)) return rc;
+  if (j->out_bytes > w->pin_cap) {  // (cannot happen for same-sized in/out images; be safe)
+    RS_CHECK(cudaStreamSynchronize(w->stream));
+    if (int rc = ws_ensure_pinned(w, j->out_bytes)) return rc;
+  }
+  if (!key || !g_order_cache_on.load()) return 0;
+  std::shared_ptr<OrderEntry> hit;
+  {
+    std::lock_guard<std::mutex> lk(g_order_mutex);
+    for (auto &e : g_orders)
+      if (e->device == w->device && key_equal(e->key, *key)) { e->stamp = ++g_order_clock; hit = e; break; }
+  }
+  if (!hit) return 0;
+  j->order = hit;
+  j->targets_dev = hit->dev;
+  j->upload_launches += 1u;
+  k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>(hit->dev, j->nT, j->d.tw, (uint32_t *)w->meta.p);
+  RS_CHECK(cudaGetLastError());
+  return 1;
+}
+extern "C" void rs_job_set_passes(RsJob *j, const uint32_t *pass_end, uint32_t n_passes) {
+  for (uint32_t p = 0; p < 6; p++) j->d.pass_end[p] = p < n_passes ? pass_end[p] : 0u;
+  j->d.n_passes = n_passes > 6 ? 6 : n_passes;
+}
+extern "C" int rs_job_set_order(RsJob *j, const uint32_t *targets, const RsOrderKey *key) {
+  return upload_order_impl(j, targets, key);
 }
 
 extern "C" int rs_job_upload(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *targets,
@@ -1430,7 +1604,7 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.corpus8 = j->maps ? (const uint2 *)w->corpus.p : nullptr;
   D.W = (unsigned long long *)w->W.p; D.meta = (const uint32_t *)w->meta.p;
   D.tmaps = j->maps ? (const uint32_t *)w->tmaps.p : nullptr;
-  D.targets = (const uint32_t *)w->targets.p; D.corpus_pts = (const uint32_t *)w->cpts.p;
+  D.targets = j->targets_dev; D.corpus_pts = (const uint32_t *)w->cpts.p;
   D.offsets = (const uint32_t *)w->offsets.p; D.lut_rep = (const uint32_t *)w->lut_rep.p;
   D.prober[0] = (unsigned long long *)w->prober0.p; D.prober[1] = (unsigned long long *)w->prober1.p;
   D.prober[2] = (unsigned long long *)w->prober2.p;
@@ -1555,7 +1729,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   j->launches = slot;
   RS_CHECK(cudaGetLastError());
   RS_CHECK(cudaEventRecord(w->ev1, s));
-  k_writeback<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, (const uint32_t *)w->targets.p, j->nT,
+  k_writeback<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, j->targets_dev, j->nT,
                                                  j->d.tw, j->d.bpp, j->d.n_color, (uint8_t *)w->raw_t.p,
                                                  j->want_sources ? (uint32_t *)w->sources.p : nullptr);
   // the rows that contain target points land in pinned memory behind the same event

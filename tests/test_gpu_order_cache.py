@@ -1,0 +1,69 @@
+"""Device-side cache of visit orders: same key -> hit and identical output; different selection, seed or mode -> miss."""
+import numpy as np
+import pytest
+
+from resynthesizer_b200 import abi, api
+from resynthesizer_b200.synthetic import G, centered_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def _job(seed_img, hole, mode=1):
+    img = G(96, 80, 3, seed_img)
+    m = centered_mask(96, 80, hole, hole)
+    p = abi.make_params(0, 0, mode, 0.5, 0.117, 16, 60)
+    tp = np.ascontiguousarray(np.concatenate([m[:, :, None], img], axis=2))
+    cp = np.ascontiguousarray(np.concatenate([(255 - m)[:, :, None], img], axis=2))
+    return p, tp, cp
+
+
+def _run(p, tp, cp):
+    fi = api.format_indices(3, 0, False, False, False)
+    t = tp.copy()
+    assert api.engine(p, fi, t, cp) == 0
+    return t, api.last_stats()
+
+
+def test_hit_is_identical_and_misses_are_misses():
+    api.order_cache(False)          # drop whatever earlier tests left
+    api.order_cache(True)
+    try:
+        api.set_seed(1198472)
+        p, tp, cp = _job(7, 24)
+        a, sa = _run(p, tp, cp)
+        b, sb = _run(p, tp, cp)
+        assert sa["order_cache_hit"] == 0 and sb["order_cache_hit"] == 1
+        assert (a == b).all()
+        # another image with the SAME selection: the order is shared, the result is that image's own
+        p2, tp2, cp2 = _job(8, 24)
+        c, sc = _run(p2, tp2, cp2)
+        assert sc["order_cache_hit"] == 1
+        api.order_cache(False)
+        c_ref, s_ref = _run(p2, tp2, cp2)
+        assert s_ref["order_cache_hit"] == 0 and (c == c_ref).all()
+        api.order_cache(True)
+        # different selection / context type / seed: all misses
+        _run(p, tp, cp)
+        assert _run(*_job(7, 26))[1]["order_cache_hit"] == 0
+        assert _run(*_job(7, 24, mode=2))[1]["order_cache_hit"] == 0
+        api.set_seed(5)
+        assert _run(p, tp, cp)[1]["order_cache_hit"] == 0
+        assert _run(p, tp, cp)[1]["order_cache_hit"] == 1
+    finally:
+        api.set_seed(1198472)
+        api.order_cache(True)
+
+
+def test_gather_rate_and_timeline():
+    assert api.gather_rate(1 << 18, 4, 1) > 1e9
+    api.keep_result(True)
+    try:
+        p, tp, cp = _job(9, 32)
+        _run(p, tp, cp)
+        st = api.last_stats()
+        t = api.last_timeline(0)
+        assert len(t) >= 1 and t[0] == 0
+        assert st["passes_run"] >= 1 and st["ms_pass"][0] > 0 and st["kernel_launches"] > 0
+        assert st["synth_launches_run"] >= st["passes_run"]
+    finally:
+        api.keep_result(False)
