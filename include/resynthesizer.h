@@ -147,7 +147,8 @@ unsigned long long rs_total_kernel_launches(void);
 /* Batch of independent jobs (the reference has no such call; its users loop over engine()).  Runs `n_jobs`
  * engine() calls on `slots` host threads that share the current CUDA device; each job's kernels take 1/slots of
  * the SMs.  Small jobs are latency-bound on their dependency chains, so running several side by side multiplies
- * throughput.  errors_out[i] receives engine()'s return value for job i.  Progress/cancel are not forwarded.
+ * throughput; `slots` is an upper bound: jobs of 16 k+ target points run at most 4 at a time, 200 k+ at most 2 (they
+ * fill the GPU on their own; the rest only overlaps host work and copies with kernels).  errors_out[i] receives engine()'s return value for job i.  Progress/cancel are not forwarded.
  * Returns 0 if every job returned 0, else the first non-zero code. */
 int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
                     Map *const *targetMaps, Map *const *corpusMaps, int slots, int *errors_out);

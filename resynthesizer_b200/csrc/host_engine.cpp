@@ -265,6 +265,18 @@ extern "C" int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, 
   if (n_jobs <= 0) return 0;
   if (slots < 1) slots = 1;
   if (slots > n_jobs) slots = n_jobs;
+  {  // Side-by-side jobs pay off while a job is latency-bound (few thousand target points: B200 sweeps in profiles/);
+     // from ~16 k points on a job fills the GPU by itself and more than a few in flight only overlap host work and
+     // copies with kernels.  Estimate the size of the first job from a sparse sample of its mask.
+    const Map *m = targetMaps[0];
+    const uint8_t *pix = reinterpret_cast<const uint8_t *>(m->data->data);
+    const size_t npx = (size_t)m->width * m->height, step = 61;
+    size_t hits = 0;
+    for (size_t i = 0; i < npx; i += step) hits += pix[i * m->depth] != 0;
+    const size_t n_est = hits * step;
+    const int cap = n_est >= 200000 ? 2 : (n_est >= 16384 ? 4 : 8);
+    if (slots > cap) slots = cap;
+  }
   if (int e = ensure_device()) return e;
   int device = 0;
   if (const char *e = std::getenv("RESYNTH_CUDA_DEVICE")) device = std::atoi(e);

@@ -97,11 +97,41 @@ void build_sorted_offsets(int tw, int th, int cw, int ch, std::vector<uint32_t> 
 
 // ------------------------------------------------------------------------------------------ points
 void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<uint32_t> &out) {
-  out.clear();
-  for (int y = 0; y < h; y++) {
-    const uint8_t *row = pix + (size_t)y * w * bpp;
-    for (int x = 0; x < w; x++)
-      if (row[(size_t)x * bpp] != 0) out.push_back(pack_xy(x, y));
+  const size_t npx = (size_t)w * h;
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nt = npx < ((size_t)1 << 21) ? 1 : (int)std::min<unsigned>(8u, hw ? hw : 1u);
+  if (nt <= 1) {
+    out.clear();
+    for (int y = 0; y < h; y++) {
+      const uint8_t *row = pix + (size_t)y * w * bpp;
+      for (int x = 0; x < w; x++)
+        if (row[(size_t)x * bpp] != 0) out.push_back(pack_xy(x, y));
+    }
+    return;
+  }
+  // large images: row bands on several cores (count, then fill at the band's offset: row-major order is kept)
+  std::vector<size_t> cnt((size_t)nt + 1, 0);
+  const int per = (h + nt - 1) / nt;
+  auto band = [&](int t, bool fill) {
+    const int y0 = std::min(h, t * per), y1 = std::min(h, (t + 1) * per);
+    size_t c = 0;
+    uint32_t *dst = fill ? out.data() + cnt[t] : nullptr;
+    for (int y = y0; y < y1; y++) {
+      const uint8_t *row = pix + (size_t)y * w * bpp;
+      for (int x = 0; x < w; x++)
+        if (row[(size_t)x * bpp] != 0) { if (fill) dst[c] = pack_xy(x, y); c++; }
+    }
+    if (!fill) cnt[t + 1] = c;
+  };
+  for (int phase = 0; phase < 2; phase++) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; t++) th.emplace_back(band, t, phase == 1);
+    band(0, phase == 1);
+    for (auto &x : th) x.join();
+    if (phase == 0) {
+      for (int t = 0; t < nt; t++) cnt[t + 1] += cnt[t];
+      out.resize(cnt[nt]);
+    }
   }
 }
 
@@ -171,32 +201,64 @@ void GRandMT::fill_int_range(uint32_t n, uint32_t *out, size_t count) {
   }
 }
 
+// for i in [0, n): swap(a[i], a[j_i]) where the draws j_i come from `fill(offset, count, out)` in order.  The draws
+// (MT19937 blocks + range reduction) and the swaps (random access) cost about the same and the draws do not depend on
+// the swaps, so for large vectors a second thread produces them a block ahead of the swap loop.
+template <class Fill>
+static void swaps_from_draws(uint32_t *a, size_t n, Fill fill) {
+  static thread_local std::vector<uint32_t> js;  // reused: no page faults per job
+  js.resize(n);
+  uint32_t *jp = js.data();
+  constexpr size_t AHEAD = 16, BLOCK = 1u << 16;
+  if (n < 4 * BLOCK) {
+    fill((size_t)0, n, jp);
+    for (size_t i = 0; i < n; i++) {
+      if (i + AHEAD < n) __builtin_prefetch(a + jp[i + AHEAD], 1);
+      std::swap(a[i], a[jp[i]]);
+    }
+    return;
+  }
+  std::atomic<size_t> ready{0};
+  std::thread producer([&]() {
+    for (size_t off = 0; off < n; off += BLOCK) {
+      const size_t len = n - off < BLOCK ? n - off : BLOCK;
+      fill(off, len, jp + off);
+      ready.store(off + len, std::memory_order_release);
+    }
+  });
+  for (size_t off = 0; off < n; off += BLOCK) {
+    const size_t end = n - off < BLOCK ? n : off + BLOCK;
+    while (ready.load(std::memory_order_acquire) < end) { /* spin: the producer is at most a block away */ }
+    for (size_t i = off; i < end; i++) {
+      if (i + AHEAD < end) __builtin_prefetch(a + jp[i + AHEAD], 1);
+      std::swap(a[i], a[jp[i]]);
+    }
+  }
+  producer.join();
+}
+
+// lib/orderTarget.h:57-80: every i swaps with a draw from the band [i - half, i + half) clipped to the vector.
 static void shuffle_bands(std::vector<uint32_t> &p, GRandMT &prng) {
   const int last = (int)p.size() - 1;
   const int half = (int)(p.size() * 0.1);  // IMAGE_SYNTH_BAND_FRACTION
-  uint32_t *a = p.data();
-  // draws first (the band is 2*half wide except within `half` of either end: that run is drawn in bulk) ...
-  std::vector<uint32_t> js((size_t)last + 1);
-  int i = 0;
-  while (i <= last) {
-    const int lo = std::max(i - half, 0), hi = std::min(i + half, last);
-    if (i >= half && i + half <= last && hi - lo == 2 * half) {
-      const int run_end = last - half;  // inclusive: last i with a full band
-      const size_t cnt = (size_t)(run_end - i + 1);
-      prng.fill_int_range((uint32_t)(2 * half), js.data() + i, cnt);
-      for (size_t k = 0; k < cnt; k++) js[i + k] += (uint32_t)(i + (int)k - half);
-      i += (int)cnt;
-    } else {
-      js[i] = (uint32_t)lo + prng.int_range((uint32_t)(hi - lo));
-      i++;
+  // the band is 2*half wide except within `half` of either end: the full-band run is drawn in bulk
+  swaps_from_draws(p.data(), p.size(), [&](size_t off, size_t count, uint32_t *out) {
+    size_t k = 0;
+    while (k < count) {
+      const int i = (int)(off + k);
+      const int lo = std::max(i - half, 0), hi = std::min(i + half, last);
+      if (i >= half && i + half <= last && hi - lo == 2 * half) {
+        const int run_end = std::min(last - half, (int)(off + count) - 1);  // inclusive: last i of this call with a full band
+        const size_t cnt = (size_t)(run_end - i + 1);
+        prng.fill_int_range((uint32_t)(2 * half), out + k, cnt);
+        for (size_t t = 0; t < cnt; t++) out[k + t] += (uint32_t)(i + (int)t - half);
+        k += cnt;
+      } else {
+        out[k] = (uint32_t)lo + prng.int_range((uint32_t)(hi - lo));
+        k++;
+      }
     }
-  }
-  // ... then the swaps, with the random side prefetched
-  constexpr int AHEAD = 16;
-  for (i = 0; i <= last; i++) {
-    if (i + AHEAD <= last) __builtin_prefetch(a + js[i + AHEAD], 1);
-    std::swap(a[i], a[js[i]]);
-  }
+  });
 }
 
 static unsigned ray_index(int x, int y) {
@@ -204,61 +266,57 @@ static unsigned ray_index(int x, int y) {
                         3.1415926535897932384626433832795028841971693993751 + 200);
 }
 
-// Stable LSD radix sort of (key, payload) pairs by 32-bit key, ascending.
+// Stable LSD radix sort of (key, payload) pairs by 32-bit key, ascending: 11-bit digits (3 passes), passes whose digit
+// is the same for every key skipped, buffers reused across calls.
 static void radix_sort_pairs(std::vector<uint32_t> &keys, std::vector<uint32_t> &vals) {
   const size_t n = keys.size();
-  std::vector<uint32_t> k2(n), v2(n);
-  for (int shift = 0; shift < 32; shift += 8) {
-    size_t hist[257] = {0};
-    for (size_t i = 0; i < n; i++) hist[((keys[i] >> shift) & 0xFFu) + 1]++;
-    if (hist[1] == n && shift) { continue; }  // all digits zero: pass is the identity
-    for (int d = 0; d < 256; d++) hist[d + 1] += hist[d];
+  static thread_local std::vector<uint32_t> k2, v2;
+  k2.resize(n); v2.resize(n);
+  constexpr int BITS = 11, BUCKETS = 1 << BITS;
+  std::vector<size_t> hist((size_t)3 * BUCKETS, 0);
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t k = keys[i];
+    hist[k & (BUCKETS - 1)]++;
+    hist[BUCKETS + ((k >> BITS) & (BUCKETS - 1))]++;
+    hist[2 * BUCKETS + (k >> (2 * BITS))]++;
+  }
+  for (int pass = 0; pass < 3; pass++) {
+    size_t *h = hist.data() + (size_t)pass * BUCKETS;
+    const int shift = pass * BITS;
+    bool trivial = false;
+    size_t sum = 0;
+    for (int d = 0; d < BUCKETS; d++) { if (h[d] == n) trivial = true; const size_t c = h[d]; h[d] = sum; sum += c; }
+    if (trivial) continue;  // every key has the same digit: the pass is the identity
+    const uint32_t *ks = keys.data(), *vs = vals.data();
+    uint32_t *kd = k2.data(), *vd = v2.data();
     for (size_t i = 0; i < n; i++) {
-      const size_t pos = hist[(keys[i] >> shift) & 0xFFu]++;
-      k2[pos] = keys[i];
-      v2[pos] = vals[i];
+      const size_t pos = h[(ks[i] >> shift) & (BUCKETS - 1)]++;
+      kd[pos] = ks[i];
+      vd[pos] = vs[i];
     }
     keys.swap(k2);
     vals.swap(v2);
   }
 }
 
+// Runs body(begin, end) over [0, n) on up to 8 threads (one for small n).
+template <class Body>
+static void parallel_ranges(size_t n, Body body) {
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = n < ((size_t)1 << 17) ? 1 : std::min<size_t>(8, hw ? hw : 1);
+  if (nt <= 1) { body((size_t)0, n, (size_t)0); return; }
+  std::vector<std::thread> th;
+  const size_t per = (n + nt - 1) / nt;
+  for (size_t t = 1; t < nt; t++) th.emplace_back([=, &body]() { body(std::min(n, t * per), std::min(n, (t + 1) * per), t); });
+  body((size_t)0, std::min(n, per), (size_t)0);
+  for (auto &x : th) x.join();
+}
+
 int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {
   const size_t n = pts.size();
   if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
   if (mode <= 1) {  // not Fisher-Yates: every i swaps with a draw over the whole vector
-    static thread_local std::vector<uint32_t> js;  // reused: no page faults per job
-    js.resize(n);
-    uint32_t *a = pts.data();
-    constexpr size_t AHEAD = 16, BLOCK = 1u << 16;
-    if (n < 4 * BLOCK) {
-      prng.fill_int_range((uint32_t)n, js.data(), n);
-      for (size_t i = 0; i < n; i++) {
-        if (i + AHEAD < n) __builtin_prefetch(a + js[i + AHEAD], 1);
-        std::swap(a[i], a[js[i]]);
-      }
-      return 0;
-    }
-    // Large vectors: the draws (MT19937 blocks + range reduction) and the swaps (random access) cost about the same and
-    // the draws do not depend on the swaps, so a second thread produces them a block ahead of the swap loop.
-    std::atomic<size_t> ready{0};
-    uint32_t *jp = js.data();
-    std::thread producer([&]() {
-      for (size_t off = 0; off < n; off += BLOCK) {
-        const size_t len = n - off < BLOCK ? n - off : BLOCK;
-        prng.fill_int_range((uint32_t)n, jp + off, len);
-        ready.store(off + len, std::memory_order_release);
-      }
-    });
-    for (size_t off = 0; off < n; off += BLOCK) {
-      const size_t end = n - off < BLOCK ? n : off + BLOCK;
-      while (ready.load(std::memory_order_acquire) < end) { /* spin: the producer is at most a block away */ }
-      for (size_t i = off; i < end; i++) {
-        if (i + AHEAD < end) __builtin_prefetch(a + jp[i + AHEAD], 1);
-        std::swap(a[i], a[jp[i]]);
-      }
-    }
-    producer.join();
+    swaps_from_draws(pts.data(), n, [&](size_t, size_t count, uint32_t *out) { prng.fill_int_range((uint32_t)n, out, count); });
     return 0;
   }
   // centre of the bounding box; the upper bounds start at 0 as in the reference (engineTypes.h:192-226)
@@ -274,22 +332,30 @@ int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {
   const bool brush = (mode == 2 || mode == 5 || mode == 8);  // 8 ("squeeze") nets out to mode 2's sort
   bool descending;
   if (brush) {
-    unsigned maxray[401];
-    std::memset(maxray, 0, sizeof maxray);
+    // the ray index needs libm's atan2 bit for bit (brushfire.h); it is the bulk of the work, so it runs on several cores
+    unsigned maxray_t[8][401];
+    std::memset(maxray_t, 0, sizeof maxray_t);
     std::vector<uint16_t> ray(n);
-    for (size_t i = 0; i < n; i++) {
-      const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
-      const unsigned g = ray_index(ox, oy);
-      ray[i] = (uint16_t)g;
-      maxray[g] = std::max(maxray[g], (unsigned)(ox * ox + oy * oy));
-    }
-    for (size_t i = 0; i < n; i++) {
-      const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
-      const float k = (float)(oy * oy + ox * ox) / maxray[ray[i]];  // NaN only when n == 1
-      uint32_t bits;
-      std::memcpy(&bits, &k, 4);
-      keys[i] = bits;
-    }
+    parallel_ranges(n, [&](size_t b, size_t e, size_t t) {
+      unsigned *mr = maxray_t[t];
+      for (size_t i = b; i < e; i++) {
+        const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
+        const unsigned g = ray_index(ox, oy);
+        ray[i] = (uint16_t)g;
+        mr[g] = std::max(mr[g], (unsigned)(ox * ox + oy * oy));
+      }
+    });
+    unsigned maxray[401];
+    for (int g = 0; g < 401; g++) { unsigned m = 0; for (int t = 0; t < 8; t++) m = std::max(m, maxray_t[t][g]); maxray[g] = m; }
+    parallel_ranges(n, [&](size_t b, size_t e, size_t) {
+      for (size_t i = b; i < e; i++) {
+        const int ox = unpack_x(pts[i]) - cx, oy = unpack_y(pts[i]) - cy;
+        const float k = (float)(oy * oy + ox * ox) / maxray[ray[i]];  // NaN only when n == 1
+        uint32_t bits;
+        std::memcpy(&bits, &k, 4);
+        keys[i] = bits;
+      }
+    });
     descending = (mode != 5);
   } else {
     const bool by_y = (mode == 4 || mode == 7);

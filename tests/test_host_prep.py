@@ -60,6 +60,18 @@ def test_target_order(built_oracle, built_lib, mode, shape):
     assert sorted(map(tuple, a)) == sorted(map(tuple, pts))
 
 
+@pytest.mark.parametrize("mode", [0, 2, 3, 5])
+def test_target_order_large(built_oracle, built_lib, mode):
+    """Above 2^18 points the draws come from a producer thread and the brushfire keys from several: same order."""
+    L = api.lib(); port = R.load_port()
+    pts = _points(760, 620, "ring")
+    assert len(pts) > (1 << 18)
+    a, b = pts.copy(), pts.copy()
+    assert L.rs_host_order_targets(mode, a.ctypes.data, len(a), 1198472) == 0
+    assert port.port_order(mode, b.ctypes.data, len(b), 1198472) == 0
+    assert (a == b).all()
+
+
 def test_target_order_bad_mode(built_lib):
     L = api.lib()
     a = _points(4, 4)
