@@ -1070,7 +1070,8 @@ struct DevBuf {
 };
 struct Workspace {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: work that may run beside the main stream's
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts;
@@ -1130,6 +1131,9 @@ static void ws_free(Workspace *w) {
   if (w->evG) cudaEventDestroy(w->evG);
   if (w->ev1) cudaEventDestroy(w->ev1);
   if (w->evDone) cudaEventDestroy(w->evDone);
+  if (w->evFork) cudaEventDestroy(w->evFork);
+  if (w->evJoin) cudaEventDestroy(w->evJoin);
+  if (w->stream2) cudaStreamDestroy(w->stream2);
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;
 }
@@ -1175,6 +1179,9 @@ static int ws_acquire(Workspace **out) {
   if (rc) { delete w; return rc; }
 #define WCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ws_free(w); return 100; } } while (0)
   WCHK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  WCHK(cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking));
+  WCHK(cudaEventCreateWithFlags(&w->evFork, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evJoin, cudaEventDisableTiming));
   WCHK(cudaEventCreate(&w->ev0));
   WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
@@ -1727,8 +1734,14 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     RsLine *claims = ((RsCtrl *)w->ctrl.p)->claims;  // [0] coop, [1] warp kernel
     const uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;  // the long scans: one CTA each
     RS_CHECK(cudaMemcpyAsync(&claims[1].v, &v1, 4, cudaMemcpyHostToDevice, s));
+    // The two gather kernels write disjoint visits; the cooperative one is a single wave of long scans that leaves
+    // half of every SM idle, so the warp kernel runs beside it on a second stream.
+    RS_CHECK(cudaEventRecord(w->evFork, s));
+    RS_CHECK(cudaStreamWaitEvent(w->stream2, w->evFork, 0));
+    k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, &claims[1].v);
+    RS_CHECK(cudaEventRecord(w->evJoin, w->stream2));
     k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[0].v);
-    k_gather_pass0<<<sms * 8, 256, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, &claims[1].v);
+    RS_CHECK(cudaStreamWaitEvent(s, w->evJoin, 0));
   }
   RS_CHECK(cudaEventRecord(w->evG, s));
   uint32_t slot = 0;
