@@ -63,7 +63,7 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   unsigned int n_corpus;    // number of corpus points (written at upload: host value or device compaction count)
   unsigned int stop;        // set by the last CTA of a pass when betters/n < fraction, or on cancel
   unsigned int passes_run;
-  unsigned int dg_align;
+  unsigned int fault;       // set by a warp whose wait for another visit outlived RS_SPIN_LIMIT_NS: the job is invalid
   unsigned long long dg_h1, dg_h2;        // digest of the target selection (k_target_digest), layout = RsTargetDigest
   unsigned int dg_n, dg_ymin, dg_ymax, dg_pad;
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
@@ -145,6 +145,23 @@ __device__ __forceinline__ unsigned long long rs_globaltimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// A wait on another visit normally lasts microseconds.  If the inputs are inconsistent (a corrupted order, a bug) it
+// would last forever and take the GPU with it; instead the waiter gives up after RS_SPIN_LIMIT_NS, flags the job as
+// faulted (rs_job_run then returns an error) and every other waiter follows within a few thousand polls.
+#define RS_SPIN_LIMIT_NS 10000000000ull
+struct RsSpinGuard {
+  unsigned long long t0 = 0;
+  unsigned int polls = 0;
+  __device__ __forceinline__ bool expired(RsCtrl *ctrl) {
+    if ((++polls & 4095u) != 0u) return false;
+    const unsigned long long now = rs_globaltimer();
+    if (t0 == 0) t0 = now;
+    if (*(volatile unsigned int *)&ctrl->fault) return true;
+    if (now - t0 > RS_SPIN_LIMIT_NS) { atomicExch(&ctrl->fault, 1u); return true; }
+    return false;
+  }
+};
+
 __device__ __forceinline__ int rs_off_x(uint32_t o) { return (int)(short)(o & 0xFFFFu); }
 __device__ __forceinline__ int rs_off_y(uint32_t o) { return ((int)o) >> 16; }
 

@@ -370,9 +370,10 @@ __device__ __forceinline__ uint32_t rs_claim_resolve(const RsDev &J, RsCtrl *ctr
 // themselves (a fire-and-forget reduction); whoever waits moves the watermark over the leading complete epochs.
 __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uint32_t epoch_idx) {
   const uint32_t pass = J.pass;
+  RsSpinGuard guard;
   while (true) {
     const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v);
-    if (wmk + 1u >= epoch_idx) break;
+    if (wmk + 1u >= epoch_idx || guard.expired(ctrl)) break;
     const uint32_t first = wmk * J.epoch_len;
     if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk].v) == min(J.epoch_len, J.pass_end - first))
       atomicCAS(&ctrl->epoch_wm[pass].v, wmk, wmk + 1u);
@@ -487,9 +488,11 @@ __device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS
     }
     const unsigned long long *wp = J.W + 2 * (size_t)q + (r & 1u);
     unsigned long long w = rs_ld_state(wp);
+    RsSpinGuard guard;
     while (((unsigned)(w >> 24) & 0xFFu) != r) {
       __nanosleep(40);
       w = rs_ld_state(wp);
+      if (guard.expired(J.ctrl)) break;
     }
     if (k == 0) S.vis.selfw = w;
     S.nb[k].pix = (uint32_t)w & 0xFFFFFFu;
@@ -1227,7 +1230,12 @@ struct OrderEntry {
   uint32_t *dev = nullptr;
   uint32_t n = 0;
   unsigned long long stamp = 0;
-  ~OrderEntry() { if (dev) { cudaSetDevice(device); cudaFree(dev); } }
+  cudaEvent_t ready = nullptr;  // recorded behind the upload on the creating job's stream: other streams wait on it
+  ~OrderEntry() {
+    cudaSetDevice(device);
+    if (ready) cudaEventDestroy(ready);
+    if (dev) cudaFree(dev);
+  }
 };
 struct RsJob {
   RsJobDesc d;
@@ -1540,15 +1548,28 @@ static int upload_order_impl(RsJob *j, const uint32_t *targets, const RsOrderKey
   }
   uint32_t *dst = nullptr;
   j->order.reset();
+  std::shared_ptr<OrderEntry> entry;
   if (key && g_order_cache_on.load()) {  // the uploaded order becomes a cache entry
-    auto e = std::make_shared<OrderEntry>();
-    e->key = *key; e->device = w->device; e->n = j->nT;
-    RS_CHECK(cudaMalloc(&e->dev, bytes));
-    dst = e->dev;
-    j->order = e;
+    entry = std::make_shared<OrderEntry>();
+    entry->key = *key; entry->device = w->device; entry->n = j->nT;
+    RS_CHECK(cudaMalloc(&entry->dev, bytes));
+    RS_CHECK(cudaEventCreateWithFlags(&entry->ready, cudaEventDisableTiming));
+    dst = entry->dev;
+    j->order = entry;
+  } else {
+    if (int rc = ws_ensure(w->targets, bytes)) return rc;
+    dst = (uint32_t *)w->targets.p;
+  }
+  j->targets_dev = dst;
+  memcpy(w->pin_order, targets, bytes);
+  RS_CHECK(cudaMemcpyAsync(dst, w->pin_order, bytes, cudaMemcpyHostToDevice, w->stream));
+  if (entry) {
+    // visible to other jobs only once the event that follows its upload exists: a job on another stream that hits this
+    // entry makes its stream wait for that event before reading the order
+    RS_CHECK(cudaEventRecord(entry->ready, w->stream));
     std::lock_guard<std::mutex> lk(g_order_mutex);
-    e->stamp = ++g_order_clock;
-    g_orders.push_back(e);
+    entry->stamp = ++g_order_clock;
+    g_orders.push_back(entry);
     size_t total = 0;
     for (auto &o : g_orders) total += (size_t)o->n * 4;
     while (g_orders.size() > 16 || (total > ((size_t)1 << 30) && g_orders.size() > 1)) {  // evict the least recently used
@@ -1557,13 +1578,7 @@ static int upload_order_impl(RsJob *j, const uint32_t *targets, const RsOrderKey
       total -= (size_t)g_orders[lru]->n * 4;
       g_orders.erase(g_orders.begin() + lru);
     }
-  } else {
-    if (int rc = ws_ensure(w->targets, bytes)) return rc;
-    dst = (uint32_t *)w->targets.p;
   }
-  j->targets_dev = dst;
-  memcpy(w->pin_order, targets, bytes);
-  RS_CHECK(cudaMemcpyAsync(dst, w->pin_order, bytes, cudaMemcpyHostToDevice, w->stream));
   j->upload_launches += 1u;
   k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>(dst, j->nT, j->d.tw, (uint32_t *)w->meta.p);
   RS_CHECK(cudaGetLastError());
@@ -1606,6 +1621,7 @@ extern "C" int rs_job_bind_order(RsJob *j, const RsTargetDigest *dg, const RsOrd
   if (!hit) return 0;
   j->order = hit;
   j->targets_dev = hit->dev;
+  RS_CHECK(cudaStreamWaitEvent(w->stream, hit->ready, 0));  // the entry may still be on its way up on another stream
   j->upload_launches += 1u;
   k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>(hit->dev, j->nT, j->d.tw, (uint32_t *)w->meta.p);
   RS_CHECK(cudaGetLastError());
@@ -1821,6 +1837,10 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     const unsigned long long started = w->h_ctrl->pass_visits[p];
     if (started) emit_upto(p, (uint32_t)((started - 1ull) / 4096ull + 1ull));
+  }
+  if (w->h_ctrl->fault) {
+    g_err = "rs_job_run: a visit waited more than 10 s for another one (inconsistent inputs); the result is invalid";
+    return 100;
   }
   RS_CHECK(cudaEventElapsedTime(&j->ms_passes, w->ev0, w->ev1));
   RS_CHECK(cudaEventElapsedTime(&j->ms_synth, w->evG, w->ev1));

@@ -67,3 +67,31 @@ def test_gather_rate_and_timeline():
         assert st["synth_launches_run"] >= st["passes_run"]
     finally:
         api.keep_result(False)
+
+
+def test_concurrent_jobs_share_a_fresh_entry():
+    """A batch whose jobs all have the same selection: the first job to order its points publishes the entry while the
+    others are already looking for it (the entry's upload is on another stream).  Every result must equal the
+    single-job result."""
+    api.order_cache(False)
+    api.order_cache(True)
+    try:
+        api.set_seed(1198472)
+        fi = api.format_indices(3, 0, False, False, False)
+        singles = []
+        for k in range(4):
+            p, tp, cp = _job(20 + k, 28)
+            api.order_cache(False)
+            singles.append(_run(p, tp, cp)[0])
+        for rep in range(3):
+            api.order_cache(False)      # drop the entries: every repetition starts cold
+            api.order_cache(True)
+            jobs = []
+            for i in range(24):
+                p, tp, cp = _job(20 + i % 4, 28)
+                jobs.append((p, fi, tp.copy(), cp))
+            assert not any(api.engine_batch(jobs, 8))
+            for i, jb in enumerate(jobs):
+                assert (jb[2] == singles[i % 4]).all(), "job %d of repetition %d differs" % (i, rep)
+    finally:
+        api.order_cache(True)
