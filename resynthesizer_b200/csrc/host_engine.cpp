@@ -204,13 +204,11 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   if (hit == 0) {
     if (t_keep_result) hit = rs_job_bind_order(job, &dg, nullptr) == 100 ? 100 : 0;  // sizes only; the order is wanted on the host
     if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
-      rs::collect_target_points(tpix, tw, th, bpp, targets);
-      if (targets.size() != n) { t_err = "target point count differs between host and device"; rc = 100; }
-      if (!rc) {
-        rs::GRandMT prng(t_seed);
-        rs::order_target_points(prm.matchContextType, targets, prng);
-        rc = rs_job_set_order(job, targets.data(), t_keep_result ? nullptr : &key);
+      if (rs::collect_and_order(prm.matchContextType, tpix, tw, th, bpp, n, t_seed, targets) != 0 || targets.size() != n) {
+        t_err = "target point count differs between host and device";
+        rc = 100;
       }
+      if (!rc) rc = rs_job_set_order(job, targets.data(), t_keep_result ? nullptr : &key);
     }
   }
   if (hit == 100) rc = 100;

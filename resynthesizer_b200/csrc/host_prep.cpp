@@ -99,7 +99,7 @@ void build_sorted_offsets(int tw, int th, int cw, int ch, std::vector<uint32_t> 
 void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<uint32_t> &out) {
   const size_t npx = (size_t)w * h;
   unsigned hw = std::thread::hardware_concurrency();
-  const int nt = npx < ((size_t)1 << 21) ? 1 : (int)std::min<unsigned>(8u, hw ? hw : 1u);
+  const int nt = npx < ((size_t)1 << 19) ? 1 : (int)std::min<unsigned>(npx < ((size_t)1 << 21) ? 4u : 8u, hw ? hw : 1u);
   if (nt <= 1) {
     out.clear();
     for (int y = 0; y < h; y++) {
@@ -209,7 +209,7 @@ static void swaps_from_draws(uint32_t *a, size_t n, Fill fill) {
   static thread_local std::vector<uint32_t> js;  // reused: no page faults per job
   js.resize(n);
   uint32_t *jp = js.data();
-  constexpr size_t AHEAD = 16, BLOCK = 1u << 16;
+  constexpr size_t AHEAD = 64, BLOCK = 1u << 16;
   if (n < 4 * BLOCK) {
     fill((size_t)0, n, jp);
     for (size_t i = 0; i < n; i++) {
@@ -310,6 +310,47 @@ static void parallel_ranges(size_t n, Body body) {
   for (size_t t = 1; t < nt; t++) th.emplace_back([=, &body]() { body(std::min(n, t * per), std::min(n, (t + 1) * per), t); });
   body((size_t)0, std::min(n, per), (size_t)0);
   for (auto &x : th) x.join();
+}
+
+// collect_target_points + order_target_points for a pixmap whose number of selected pixels is already known (the device
+// counted them).  For the shuffling modes the draws depend on that number and the seed only, so their producer thread
+// starts before the points are collected and the two overlap.
+int collect_and_order(int mode, const uint8_t *pix, int w, int h, int bpp, size_t n_known, uint32_t seed,
+                      std::vector<uint32_t> &pts) {
+  if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
+  constexpr size_t BLOCK = 1u << 16;
+  if (mode > 1 || n_known < 4 * BLOCK) {
+    collect_target_points(pix, w, h, bpp, pts);
+    GRandMT prng(seed);
+    return order_target_points(mode, pts, prng);
+  }
+  static thread_local std::vector<uint32_t> js;
+  js.resize(n_known);
+  uint32_t *jp = js.data();
+  const size_t n = n_known;
+  std::atomic<size_t> ready{0};
+  std::thread producer([&]() {
+    GRandMT prng(seed);
+    for (size_t off = 0; off < n; off += BLOCK) {
+      const size_t len = n - off < BLOCK ? n - off : BLOCK;
+      prng.fill_int_range((uint32_t)n, jp + off, len);
+      ready.store(off + len, std::memory_order_release);
+    }
+  });
+  collect_target_points(pix, w, h, bpp, pts);
+  if (pts.size() != n) { producer.join(); return -1; }  // the caller's count was wrong: nothing was swapped yet
+  uint32_t *a = pts.data();
+  constexpr size_t AHEAD = 64;
+  for (size_t off = 0; off < n; off += BLOCK) {
+    const size_t end = n - off < BLOCK ? n : off + BLOCK;
+    while (ready.load(std::memory_order_acquire) < end) { /* spin: the producer is ahead after the collect */ }
+    for (size_t i = off; i < end; i++) {
+      if (i + AHEAD < end) __builtin_prefetch(a + jp[i + AHEAD], 1);
+      std::swap(a[i], a[jp[i]]);
+    }
+  }
+  producer.join();
+  return 0;
 }
 
 int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {

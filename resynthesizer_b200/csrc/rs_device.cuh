@@ -42,12 +42,6 @@
 #ifndef RS_CHUNK_SWITCH_K
 #define RS_CHUNK_SWITCH_K 16
 #endif
-#ifndef RS_X_TRACK
-#define RS_X_TRACK 1
-#endif
-#ifndef RS_X_RED
-#define RS_X_RED 1
-#endif
 #define RS_LUT_WORDS (256 * 32)
 #define RS_MAX_LAUNCHES 16   // pass-kernel launches per job: 6 passes, the first ones cut into up to 4 segments
 #define RS_TIMELINE 320      // progress ticks per pass whose start time is kept (4096 visits each)
@@ -352,11 +346,9 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
         bestSum = m;
         bestIdx = mi;
         // the winner's corpus pixel travels with it, so the commit needs no point lookup
-#if RS_X_TRACK
         const int src = __ffs(__ballot_sync(RS_FULL, propose && myIdx == mi)) - 1;
         bestLin = __shfl_sync(RS_FULL, clin, src);
         bestCx = __shfl_sync(RS_FULL, cx, src);
-#endif
       }
     }
     if (active && (finished || worse)) {

@@ -105,13 +105,6 @@ __global__ void k_replicate_lut(const uint32_t *__restrict__ c256, const uint32_
   }
 }
 
-__global__ void k_copy_u32(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, size_t n, const RsCtrl *ctrl) {
-  if (ctrl && ctrl->stop) return;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) dst[i] = src[i];
-}
-
 // Final colours of the target points, from the newest published version of each, written into the raw target
 // pixmap (colour bytes only: alpha and maps are never synthesised, lib/synthesize.h:403-419); sources optional.
 __global__ void k_writeback(const unsigned long long *__restrict__ W, const uint32_t *__restrict__ targets, uint32_t n,
@@ -287,12 +280,6 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
 #endif
 #ifndef RS_TP_MIN_CTAS
 #define RS_TP_MIN_CTAS 1
-#endif
-#ifndef RS_X_OWNCOL
-#define RS_X_OWNCOL 1
-#endif
-#ifndef RS_CLAIM_AHEAD
-#define RS_CLAIM_AHEAD 0    // 1: throughput kernel claims the next visit before the distance phase of the current one (no gain measured)
 #endif
 #define RS_TEAM_WARPS 16
 #define RS_TEAM_SLOTS 8
@@ -614,9 +601,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
       const bool heur = (uint32_t)bestIdx < nHeur;
       if (heur) {
         bp = candlist[bestIdx];
-#if RS_X_OWNCOL
         bcol = hcol[bestIdx];
-#endif
       } else if (win_pt != RS_NO_SRC) {
         bp = win_pt;
         bcol = win_col;
@@ -624,7 +609,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
         bp = __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
       }
       if (bp != src) {
-        if ((!heur && !(have_col && win_pt != RS_NO_SRC)) || !RS_X_OWNCOL) {
+        if (!heur && !(have_col && win_pt != RS_NO_SRC)) {
           const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
           bcol = (MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a)) & 0xFFFFFFu;
         }
@@ -663,25 +648,8 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
   }
   __syncwarp();
   // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
-#if RS_X_RED
   if (lane == 0)
     asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->epoch_done[pass][epoch_idx].v) : "memory");
-#else
-  if (lane == 0) {
-    const uint32_t pass_end = J.pass_end;
-    const uint32_t epoch0 = epoch_idx * J.epoch_len;
-    const uint32_t esize = min(J.epoch_len, pass_end - epoch0);
-    if (atomicAdd(&ctrl->epoch_done[pass][epoch_idx].v, 1u) + 1u == esize) {
-      while (true) {
-        const uint32_t wmk = rs_ld_u32_relaxed(&ctrl->epoch_wm[pass].v);
-        const uint32_t first = wmk * J.epoch_len;
-        if (first >= pass_end) break;
-        if (rs_ld_u32_relaxed(&ctrl->epoch_done[pass][wmk].v) != min(J.epoch_len, pass_end - first)) break;
-        atomicCAS(&ctrl->epoch_wm[pass].v, wmk, wmk + 1u);
-      }
-    }
-  }
-#endif
 }
 
 // Whole CTA, at kernel end: flush the per-warp counters; the last CTA out decides whether later passes run
@@ -728,20 +696,14 @@ __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, 
   const int cx = (int)(c & 0xFFFFu);
   const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx, k0 = 1u + j * CH;
   uint32_t own_x = 0, own_y = 0;  // the candidate's own pixel: its colour is what a win commits (synthesize.h:403-419)
-#if RS_X_OWNCOL
   if (j == 0u) {
     if (MAPS) { const uint2 t = __ldg(J.corpus8 + clin); own_x = t.x; own_y = t.y; }
     else own_x = __ldg(J.corpus4 + clin);
   }
-#else
-  if (MAPS && j == 0u) own_y = __ldg(&J.corpus8[clin].y);
-#endif
   uint32_t part = rs_chunk_sum<MAPS, CH>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
   if (j == 0u) {
     if (MAPS) part += rs_lut3(lutm, __vabsdiffu4(own_y, S.map[0]));
-#if RS_X_OWNCOL
     hcol[ci] = own_x & 0xFFFFFFu;
-#endif
     st.issued++;
     st.compares++;
   }
@@ -781,10 +743,6 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   LaneStats st;
   Visit V;
   if (lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
-  // The claim of the NEXT visit is issued before the distance phase and resolved after it, and the next target point
-  // is fetched while this visit commits: two dependent round trips off the critical path of every visit.  A visit
-  // claimed ahead waits for its warp's current visit; that one has a smaller index and cannot depend on it, so the
-  // lowest unfinished visit can always proceed (no deadlock).
   uint32_t v = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
   uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
   while (v < J.seg_end) {
@@ -793,9 +751,6 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
       rs_visit_values<MAPS>(J, S, v, Kv);
       rs_visit_candidates<MAPS>(J, ctrl, S, V, v, Kv);
     }
-#if RS_CLAIM_AHEAD
-    const uint32_t ticket = rs_claim_issue(J, ctrl);
-#endif
     // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
     uint32_t bestSum = 0xFFFFFFFFu, bestLin = RS_NO_SRC;
     int bestIdx = 0x7FFFFFFF, bestCx = 0;
@@ -828,19 +783,11 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
       rs_eval_range<MAPS, CH>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
                           [&](int i) { return __ldg(cpts + rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
                           bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued);
-#if RS_CLAIM_AHEAD
-    const uint32_t v_next = rs_claim_resolve(J, ctrl, ticket);
-    const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
-    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx,
-                          bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
-                          0u, false);
-#else
     rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx,
                           bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
                           0u, false);
     const uint32_t v_next = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
     const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
-#endif
     v = v_next;
     tpos = tpos_next;
   }
