@@ -113,6 +113,14 @@ int rs_job_upload_order(RsJob *job, const uint32_t *targets);
 int rs_job_stage(RsJob *job, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *color_lut256,
                  const uint32_t *map_lut256, uint32_t map_lut_max);
 int rs_job_digest(RsJob *job, RsTargetDigest *out);
+/* rs_job_stage for the simple API (lib/imageSynth.h:31-52): ONE image of tw x th pixels, bpp - 1 channels, rows
+ * img_row_bytes apart, its selection mask and optionally an explicit corpus mask (imageSynth2; NULL: the corpus is what
+ * is not selected).  The internal [mask][channels] pixmaps are built on the device.  rs_job_download_simple copies
+ * the rows that hold target points back into the caller's image. */
+int rs_job_stage_simple(RsJob *job, const uint8_t *img, size_t img_row_bytes, const uint8_t *mask, size_t mask_row_bytes,
+                        const uint8_t *mask2, size_t mask2_row_bytes, const uint32_t *color_lut256,
+                        const uint32_t *map_lut256, uint32_t map_lut_max);
+int rs_job_download_simple(RsJob *job, uint8_t *img, size_t img_row_bytes);
 int rs_job_bind_order(RsJob *job, const RsTargetDigest *digest, const RsOrderKey *key);
 int rs_job_set_order(RsJob *job, const uint32_t *ordered_points, const RsOrderKey *key);
 void rs_cuda_order_cache(int enabled);

@@ -132,24 +132,57 @@ extern "C" void prepareDefaultFormatIndices(TFormatIndices *o) {
   prepareImageFormatIndices(o, 3, 0, 1, 1, 0);
 }
 
-// ------------------------------------------------------------------------------------------ engine()
-extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *targetMap, Map *corpusMap,
-                      void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag) {
+// ------------------------------------------------------------------------------------------ the job, host side
+namespace {
+
+// Where the pixels of a job are.  Full API: two caller-owned internal pixmaps [mask][colours][alpha?][maps].
+// Simple API: ONE image + selection mask (+ explicit corpus mask); nothing is repacked on the host -- the planes go to
+// the device as they are and the pixmaps are built there (lib/imageSynth.c:61-137 does it with per-pixel loops).
+struct PixelSource {
+  int tw = 0, th = 0, cw = 0, ch = 0, bpp = 0;
+  uint8_t *tpix = nullptr;         // full API
+  const uint8_t *cpix = nullptr;
+  ImageBuffer *img = nullptr, *mask = nullptr, *mask2 = nullptr;  // simple API
+  bool simple() const { return img != nullptr; }
+};
+
+bool any_target(const PixelSource &s) {
+  if (!s.simple()) return rs::has_target_point(s.tpix, s.tw, s.th, s.bpp);
+  for (int y = 0; y < s.th; y++) {
+    const uint8_t *row = s.mask->data + (size_t)y * s.mask->rowBytes;
+    for (int x = 0; x < s.tw; x++) if (row[x]) return true;
+  }
+  return false;
+}
+bool any_corpus(const PixelSource &s, const TFormatIndices &fi) {
+  if (!s.simple()) return rs::has_corpus_point(s.cpix, s.cw, s.ch, s.bpp, fi);
+  const int nc = s.bpp - 1;
+  const bool alpha = fi.isAlphaSource != 0;
+  for (int y = 0; y < s.th; y++) {
+    const uint8_t *mrow = s.mask2 ? s.mask2->data + (size_t)y * s.mask2->rowBytes : s.mask->data + (size_t)y * s.mask->rowBytes;
+    const uint8_t *irow = s.img->data + (size_t)y * s.img->rowBytes;
+    for (int x = 0; x < s.tw; x++) {
+      const bool selected = s.mask2 ? mrow[x] == 0xFF : mrow[x] == 0;  // inverted selection mask, or the explicit one
+      if (selected && (!alpha || irow[(size_t)x * nc + (fi.alpha_bip - 1)] != 0)) return true;
+    }
+  }
+  return false;
+}
+
+// Everything engine() and imageSynth() share.  write_back: results go to the caller's buffers (imageSynth skips that
+// when cancelled, lib/imageSynth.c:108).
+int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource &src,
+               void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag, bool skip_write_back_if_cancelled) {
   const double t0 = now_ms();
   std::memset(&t_stats, 0, sizeof t_stats);
   t_err.clear();
   if (prm.patchSize > 64) return IMAGE_SYNTH_ERROR_PATCH_SIZE_EXCEEDED;  // lib/engine.c:591
-
-  const int tw = (int)targetMap->width, th = (int)targetMap->height;
-  const int cw = (int)corpusMap->width, ch = (int)corpusMap->height;
-  const int bpp = fi->total_bpp;
-  uint8_t *tpix = reinterpret_cast<uint8_t *>(targetMap->data->data);
-  const uint8_t *cpix = reinterpret_cast<const uint8_t *>(corpusMap->data->data);
+  const int tw = src.tw, th = src.th, cw = src.cw, ch = src.ch, bpp = src.bpp;
 
   // Empty target / corpus and the context-type range are detected on the host, before CUDA is touched
   // (lib/engine.c:605-610, 620-627, 645-647); everything else about the points happens on the device.
-  if (!rs::has_target_point(tpix, tw, th, bpp)) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;
-  if (!rs::has_corpus_point(cpix, cw, ch, bpp, *fi)) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;
+  if (!any_target(src)) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;
+  if (!any_corpus(src, *fi)) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;
   if (prm.matchContextType < 0 || prm.matchContextType > 8)
     return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;  // orderTargetPoints' default case
 
@@ -186,7 +219,10 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   RsJob *job = nullptr;
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
   RsTargetDigest dg;
-  int rc = rs_job_stage(job, tpix, cpix, c256, m256, m512[0]);
+  int rc = src.simple()
+               ? rs_job_stage_simple(job, src.img->data, src.img->rowBytes, src.mask->data, src.mask->rowBytes,
+                                     src.mask2 ? src.mask2->data : nullptr, src.mask2 ? src.mask2->rowBytes : 0, c256, m256, m512[0])
+               : rs_job_stage(job, src.tpix, src.cpix, c256, m256, m512[0]);
   if (!rc) rc = rs_job_digest(job, &dg);
   if (rc) { t_err = rs_cuda_last_error(); rs_job_destroy(job); return RS_ERROR_CUDA; }
   const uint32_t n = dg.n;
@@ -204,7 +240,9 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   if (hit == 0) {
     if (t_keep_result) hit = rs_job_bind_order(job, &dg, nullptr) == 100 ? 100 : 0;  // sizes only; the order is wanted on the host
     if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
-      if (rs::collect_and_order(prm.matchContextType, tpix, tw, th, bpp, n, t_seed, targets) != 0 || targets.size() != n) {
+      const uint8_t *mask0 = src.simple() ? src.mask->data : src.tpix;
+      const size_t pstride = src.simple() ? 1 : (size_t)bpp, rstride = src.simple() ? src.mask->rowBytes : (size_t)tw * bpp;
+      if (rs::collect_and_order(prm.matchContextType, mask0, tw, th, pstride, rstride, n, t_seed, targets) != 0 || targets.size() != n) {
         t_err = "target point count differs between host and device";
         rc = 100;
       }
@@ -213,19 +251,20 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   }
   if (hit == 100) rc = 100;
   const double t2b = now_ms();
-  const std::vector<uint32_t> &tpk = targets;
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
   if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, on_tick, &ts); }
   const double t3 = now_ms();
   if (!rc) {
     // engine() mutates the colour bytes of targetMap in place (lib/synthesize.h:403-419); alpha and maps untouched
+    const bool write_back = !(skip_write_back_if_cancelled && *cancelFlag);
     if (t_keep_result) {
       t_last_sources.assign(n, 0xFFFFFFFFu);
-      t_last_targets = tpk;
-      rc = rs_job_download(job, tpix, t_last_sources.data());
-    } else {
-      rc = rs_job_download(job, tpix, nullptr);
+      t_last_targets = targets;
+      rc = rs_job_download(job, src.simple() || !write_back ? nullptr : src.tpix, t_last_sources.data());
+    } else if (!src.simple() && write_back) {
+      rc = rs_job_download(job, src.tpix, nullptr);
     }
+    if (!rc && src.simple() && write_back) rc = rs_job_download_simple(job, src.img->data, src.img->rowBytes);
   }
   if (rc) {
     t_err = rs_cuda_last_error();
@@ -252,8 +291,21 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
   for (int p = 0; p < 6; p++) t_stats.ms_pass[p] = jc.ms_pass[p];
   g_kernel_launches.fetch_add(jc.kernel_launches);
   t_stats.ms_synth = jc.ms_synth; t_stats.kernel_launches = jc.kernel_launches; t_stats.synth_launches_run = jc.synth_launches_run;
-  (void)t2;
   return 0;  // success, also when cancelled (lib/engine.c:689)
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ engine()
+extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *targetMap, Map *corpusMap,
+                      void (*progressCallback)(int, void *), void *contextInfo, int *cancelFlag) {
+  PixelSource src;
+  src.tw = (int)targetMap->width; src.th = (int)targetMap->height;
+  src.cw = (int)corpusMap->width; src.ch = (int)corpusMap->height;
+  src.bpp = fi->total_bpp;
+  src.tpix = reinterpret_cast<uint8_t *>(targetMap->data->data);
+  src.cpix = reinterpret_cast<const uint8_t *>(corpusMap->data->data);
+  return synth_core(prm, fi, src, progressCallback, contextInfo, cancelFlag, false);
 }
 
 // ------------------------------------------------------------------------------- batch of independent jobs
@@ -305,7 +357,10 @@ extern "C" int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, 
 
 // ------------------------------------------------------------------------------- simple API (one image)
 namespace {
-// lib/adaptSimple.h:47-96,260-358: unpadded internal pixmaps [mask][channels], corpus mask inverted or explicit
+// lib/imageSynth.c:61-216 + lib/adaptSimple.h: one image, its selection mask, optionally an explicit corpus mask.  The
+// reference repacks them into two internal pixmaps on the host and copies every pixel back; here the caller's planes
+// are staged as they are, the pixmaps are built on the device and only the rows with target points come back
+// (the other pixels are unchanged by definition).
 int simple_api(ImageBuffer *img, ImageBuffer *mask, ImageBuffer *mask2, TImageFormat fmt, TImageSynthParameters *prm,
                void (*cb)(int, void *), void *ctx, int *cancel) {
   if (img->width != mask->width || img->height != mask->height) return IMAGE_SYNTH_ERROR_IMAGE_MASK_MISMATCH;
@@ -313,29 +368,11 @@ int simple_api(ImageBuffer *img, ImageBuffer *mask, ImageBuffer *mask2, TImageFo
   if (!prm) { setDefaultParams(&defaults); prm = &defaults; }
   TFormatIndices fi;
   if (int e = prepareImageFormatIndicesFromFormatType(&fi, fmt)) return e;
-  const unsigned nc = countPixelelsPerPixelForFormat(fmt), depth = nc + 1, w = img->width, h = img->height;
-  std::vector<uint8_t> t((size_t)w * h * depth), c((size_t)w * h * depth);
-  for (unsigned y = 0; y < h; y++) {
-    const uint8_t *srow = img->data + (size_t)y * img->rowBytes, *mrow = mask->data + (size_t)y * mask->rowBytes;
-    const uint8_t *m2row = mask2 ? mask2->data + (size_t)y * mask2->rowBytes : nullptr;
-    for (unsigned x = 0; x < w; x++) {
-      const size_t o = ((size_t)y * w + x) * depth;
-      t[o] = mrow[x];
-      c[o] = m2row ? m2row[x] : (uint8_t)~mrow[x];
-      for (unsigned k = 0; k < nc; k++) t[o + 1 + k] = c[o + 1 + k] = srow[(size_t)x * nc + k];
-    }
-  }
-  GArray ta{reinterpret_cast<char *>(t.data()), w * h}, ca{reinterpret_cast<char *>(c.data()), w * h};
-  Map tm{w, h, depth, &ta}, cm{w, h, depth, &ca};
-  const int err = engine(*prm, &fi, &tm, &cm, cb, ctx, cancel);
-  if (!err && !*cancel) {  // lib/imageSynth.c:108-124: all channels (alpha unchanged) of all pixels go back
-    for (unsigned y = 0; y < h; y++) {
-      uint8_t *drow = img->data + (size_t)y * img->rowBytes;
-      for (unsigned x = 0; x < w; x++)
-        for (unsigned k = 0; k < nc; k++) drow[(size_t)x * nc + k] = t[((size_t)y * w + x) * depth + 1 + k];
-    }
-  }
-  return err;
+  PixelSource src;
+  src.tw = src.cw = (int)img->width; src.th = src.ch = (int)img->height;
+  src.bpp = (int)countPixelelsPerPixelForFormat(fmt) + 1;
+  src.img = img; src.mask = mask; src.mask2 = mask2;
+  return synth_core(*prm, &fi, src, cb, ctx, cancel, true);
 }
 }  // namespace
 

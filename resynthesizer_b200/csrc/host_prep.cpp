@@ -97,15 +97,21 @@ void build_sorted_offsets(int tw, int th, int cw, int ch, std::vector<uint32_t> 
 
 // ------------------------------------------------------------------------------------------ points
 void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vector<uint32_t> &out) {
+  collect_target_points_strided(pix, w, h, (size_t)bpp, (size_t)w * bpp, out);
+}
+
+// mask0 = the mask byte of pixel (0,0); pixel (x,y) has its mask byte at mask0 + y * row_stride + x * pixel_stride.
+void collect_target_points_strided(const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride,
+                                   std::vector<uint32_t> &out) {
   const size_t npx = (size_t)w * h;
   unsigned hw = std::thread::hardware_concurrency();
   const int nt = npx < ((size_t)1 << 19) ? 1 : (int)std::min<unsigned>(npx < ((size_t)1 << 21) ? 4u : 8u, hw ? hw : 1u);
   if (nt <= 1) {
     out.clear();
     for (int y = 0; y < h; y++) {
-      const uint8_t *row = pix + (size_t)y * w * bpp;
+      const uint8_t *row = mask0 + (size_t)y * row_stride;
       for (int x = 0; x < w; x++)
-        if (row[(size_t)x * bpp] != 0) out.push_back(pack_xy(x, y));
+        if (row[(size_t)x * pixel_stride] != 0) out.push_back(pack_xy(x, y));
     }
     return;
   }
@@ -117,9 +123,9 @@ void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vecto
     size_t c = 0;
     uint32_t *dst = fill ? out.data() + cnt[t] : nullptr;
     for (int y = y0; y < y1; y++) {
-      const uint8_t *row = pix + (size_t)y * w * bpp;
+      const uint8_t *row = mask0 + (size_t)y * row_stride;
       for (int x = 0; x < w; x++)
-        if (row[(size_t)x * bpp] != 0) { if (fill) dst[c] = pack_xy(x, y); c++; }
+        if (row[(size_t)x * pixel_stride] != 0) { if (fill) dst[c] = pack_xy(x, y); c++; }
     }
     if (!fill) cnt[t + 1] = c;
   };
@@ -315,12 +321,12 @@ static void parallel_ranges(size_t n, Body body) {
 // collect_target_points + order_target_points for a pixmap whose number of selected pixels is already known (the device
 // counted them).  For the shuffling modes the draws depend on that number and the seed only, so their producer thread
 // starts before the points are collected and the two overlap.
-int collect_and_order(int mode, const uint8_t *pix, int w, int h, int bpp, size_t n_known, uint32_t seed,
-                      std::vector<uint32_t> &pts) {
+int collect_and_order(int mode, const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride, size_t n_known,
+                      uint32_t seed, std::vector<uint32_t> &pts) {
   if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
   constexpr size_t BLOCK = 1u << 16;
   if (mode > 1 || n_known < 4 * BLOCK) {
-    collect_target_points(pix, w, h, bpp, pts);
+    collect_target_points_strided(mask0, w, h, pixel_stride, row_stride, pts);
     GRandMT prng(seed);
     return order_target_points(mode, pts, prng);
   }
@@ -337,7 +343,7 @@ int collect_and_order(int mode, const uint8_t *pix, int w, int h, int bpp, size_
       ready.store(off + len, std::memory_order_release);
     }
   });
-  collect_target_points(pix, w, h, bpp, pts);
+  collect_target_points_strided(mask0, w, h, pixel_stride, row_stride, pts);
   if (pts.size() != n) { producer.join(); return -1; }  // the caller's count was wrong: nothing was swapped yet
   uint32_t *a = pts.data();
   constexpr size_t AHEAD = 64;

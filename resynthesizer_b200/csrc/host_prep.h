@@ -47,8 +47,10 @@ bool has_corpus_point(const uint8_t *pix, int w, int h, int bpp, const TFormatIn
 // lib/orderTarget.h:268-343 (+ brushfire.h, engineTypes.h).  Returns 0 or IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE.
 int order_target_points(int match_context_type, std::vector<uint32_t> &pts, GRandMT &prng);
 // Both steps for a pixmap with n_known selected pixels, overlapped where the mode allows; -1 if the count was wrong.
-int collect_and_order(int match_context_type, const uint8_t *pix, int w, int h, int bpp, size_t n_known, uint32_t seed,
-                      std::vector<uint32_t> &pts);
+int collect_and_order(int match_context_type, const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride,
+                      size_t n_known, uint32_t seed, std::vector<uint32_t> &pts);
+void collect_target_points_strided(const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride,
+                                   std::vector<uint32_t> &out);
 
 // lib/passes.h:67-93.  Returns the estimated total visit count.
 uint32_t pass_schedule(uint32_t n_targets, uint32_t ends[6]);

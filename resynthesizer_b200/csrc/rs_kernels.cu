@@ -1024,7 +1024,7 @@ struct Workspace {
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
-      sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts;
+      sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, simg, smask, smask2;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
   void *pin_order = nullptr;  // pinned staging of a visit order
@@ -1068,7 +1068,8 @@ static void ws_free(Workspace *w) {
   cudaSetDevice(w->device);
   DevBuf *all[] = {&w->raw_t, &w->raw_c, &w->corpus, &w->W, &w->meta, &w->tmaps, &w->targets, &w->cpts, &w->offsets,
                    &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
-                   &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts};
+                   &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts,
+                   &w->simg, &w->smask, &w->smask2};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
   if (w->pin_order) cudaFreeHost(w->pin_order);
@@ -1195,6 +1196,7 @@ struct RsJob {
   const uint32_t *targets_dev = nullptr;  // the visit order on the device (cache entry or the workspace's buffer)
   bool want_sources = false;
   float ms_passes = 0.f;
+  bool simple = false;            // staged by rs_job_stage_simple: results go back in the caller's image layout
   uint32_t launches = 0;          // pass-kernel launches of the last run
   uint32_t pass_launches[6] = {0, 0, 0, 0, 0, 0};
   uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
@@ -1314,6 +1316,29 @@ static bool key_equal(const RsOrderKey &a, const RsOrderKey &b) {
   return a.h1 == b.h1 && a.h2 == b.h2 && a.n == b.n && a.tw == b.tw && a.th == b.th && a.mode == b.mode && a.seed == b.seed;
 }
 
+// ---- simple API (imageSynth): the caller's image + mask planes go up as they are; the internal pixmaps
+// [mask][channels] of target and corpus (lib/imageSynth.c:61-137, lib/adaptSimple.h) are built here, and only the
+// image rows that hold target points come back, in the caller's layout.
+__global__ void k_build_simple(const uint8_t *__restrict__ img, const uint8_t *__restrict__ mask,
+                               const uint8_t *__restrict__ mask2, uint32_t n_px, int nc, uint8_t *__restrict__ raw_t,
+                               uint8_t *__restrict__ raw_c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const int bpp = nc + 1;
+  const uint8_t m = mask[i];
+  uint8_t *t = raw_t + (size_t)i * bpp, *c = raw_c + (size_t)i * bpp;
+  t[0] = m;
+  c[0] = mask2 ? mask2[i] : (uint8_t)~m;  // the corpus is what is NOT selected, or an explicit second mask (imageSynth2)
+  for (int k = 0; k < nc; k++) { const uint8_t v = img[(size_t)i * nc + k]; t[1 + k] = v; c[1 + k] = v; }
+}
+__global__ void k_extract_simple(const uint8_t *__restrict__ raw_t, uint32_t first_px, uint32_t n_px, int nc,
+                                 uint8_t *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_px) return;
+  const uint8_t *t = raw_t + (size_t)(first_px + i) * (nc + 1);
+  for (int k = 0; k < nc; k++) out[(size_t)i * nc + k] = t[1 + k];
+}
+
 // Host copy into pinned staging followed by the H2D copy, in pieces: a piece goes to the device while the next one is
 // being copied, and large images are copied by several cores (a single core moves ~9 GB/s, PCIe 5 takes 25+).
 static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t bytes, cudaStream_t s) {
@@ -1344,13 +1369,38 @@ static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t b
   return 0;
 }
 
+// The same for `rows` rows of row_len bytes that sit src_stride apart in the caller's buffer (ImageBuffer.rowBytes).
+static int stage_rows_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t rows, size_t row_len, size_t src_stride,
+                                cudaStream_t s) {
+  if (src_stride == row_len) return stage_to_device(dev, pin, src, rows * row_len, s);
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+  auto band = [=](size_t t) {
+    const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
+    for (size_t y = b; y < e; y++) memcpy(pin + y * row_len, src + y * src_stride, row_len);
+  };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nt; t++) th.emplace_back(band, t);
+  band(0);
+  for (auto &x : th) x.join();
+  RS_CHECK(cudaMemcpyAsync(dev, pin, rows * row_len, cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+struct SimpleSource {  // imageSynth's inputs, as the caller holds them
+  const uint8_t *img, *mask, *mask2;
+  size_t img_rb, mask_rb, mask2_rb;
+  int nc;
+};
+
 // Stage 1 of an upload: everything that does not depend on the target points.  Asynchronous on the job's stream.
 static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corpus_raw, const uint32_t *corpus_points,
                         uint32_t n_corpus, const uint32_t *offsets, uint32_t n_offsets, const uint32_t *color_lut256,
-                        const uint32_t *map_lut256, uint32_t map_lut_max, bool digest) {
+                        const uint32_t *map_lut256, uint32_t map_lut_max, bool digest, const SimpleSource *simple = nullptr) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   const RsJobDesc &d = j->d;
+  j->simple = simple != nullptr;
   if (corpus_points && n_corpus == 0) { g_err = "rs_job upload: empty corpus point list"; return 100; }
   const size_t tn = (size_t)d.tw * d.th, cn = (size_t)d.cw * d.ch;
   cudaStream_t s = w->stream;
@@ -1379,9 +1429,22 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
   if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
   uint8_t *pin = (uint8_t *)w->pin;
   RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl), s));
-  if ((rc = stage_to_device(w->raw_t.p, pin + o_t, target_raw, sz_t, s))) return rc;
   const int T = 256;
   j->upload_launches = 0;
+  if (simple) {  // image + mask planes up (they fit the staging regions of the two pixmaps), pixmaps built on the device
+    const size_t sz_img = tn * simple->nc;
+    if ((rc = ws_ensure(w->simg, sz_img)) || (rc = ws_ensure(w->smask, tn)) || (rc = ws_ensure(w->smask2, simple->mask2 ? tn : 4)))
+      return rc;
+    if ((rc = stage_rows_to_device(w->smask.p, pin + o_t + sz_img, simple->mask, d.th, d.tw, simple->mask_rb, s))) return rc;
+    if ((rc = stage_rows_to_device(w->simg.p, pin + o_t, simple->img, d.th, (size_t)d.tw * simple->nc, simple->img_rb, s))) return rc;
+    if (simple->mask2 && (rc = stage_rows_to_device(w->smask2.p, pin + o_c, simple->mask2, d.th, d.tw, simple->mask2_rb, s))) return rc;
+    k_build_simple<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->simg.p, (const uint8_t *)w->smask.p,
+                                                            simple->mask2 ? (const uint8_t *)w->smask2.p : nullptr, (uint32_t)tn,
+                                                            simple->nc, (uint8_t *)w->raw_t.p, (uint8_t *)w->raw_c.p);
+    j->upload_launches += 1u;
+  } else if ((rc = stage_to_device(w->raw_t.p, pin + o_t, target_raw, sz_t, s))) {
+    return rc;
+  }
   if (digest) {  // first, so that its result can come back while the rest of the staging runs
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
@@ -1392,7 +1455,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     RS_CHECK(cudaEventRecord(w->evDigest, s));
     j->upload_launches += 1u;
   }
-  if ((rc = stage_to_device(w->raw_c.p, pin + o_c, corpus_raw, sz_c, s))) return rc;
+  if (!simple && (rc = stage_to_device(w->raw_c.p, pin + o_c, corpus_raw, sz_c, s))) return rc;
   memcpy(pin + o_lut, color_lut256, 256 * 4);
   memcpy(pin + o_lut + 256 * 4, map_lut256, 256 * 4);
   RS_CHECK(cudaMemcpyAsync(w->lut256.p, pin + o_lut, sz_lut, cudaMemcpyHostToDevice, s));
@@ -1538,6 +1601,27 @@ extern "C" int rs_job_stage(RsJob *j, const uint8_t *target_raw, const uint8_t *
                             const uint32_t *map_lut256, uint32_t map_lut_max) {
   j->out_bytes = 0;
   return stage_images(j, target_raw, corpus_raw, nullptr, 0, nullptr, 0, color_lut256, map_lut256, map_lut_max, true);
+}
+extern "C" int rs_job_stage_simple(RsJob *j, const uint8_t *img, size_t img_row_bytes, const uint8_t *mask,
+                                   size_t mask_row_bytes, const uint8_t *mask2, size_t mask2_row_bytes,
+                                   const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max) {
+  const RsJobDesc &d = j->d;
+  if (d.tw != d.cw || d.th != d.ch || d.n_map != 0 || d.bpp < 2 || d.bpp > 5) {
+    g_err = "rs_job_stage_simple: the simple API has one image (target = corpus), 1-4 channels and no maps";
+    return 100;
+  }
+  const SimpleSource src{img, mask, mask2, img_row_bytes, mask_row_bytes, mask2_row_bytes, d.bpp - 1};
+  j->out_bytes = 0;
+  return stage_images(j, nullptr, nullptr, nullptr, 0, nullptr, 0, color_lut256, map_lut256, map_lut_max, true, &src);
+}
+// The rows of the image that hold target points, back into the caller's buffer (all channels: alpha is unchanged).
+extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_bytes) {
+  const Workspace *w = j->ws;
+  if (!j->simple) { g_err = "rs_job_download_simple: the job was not staged by rs_job_stage_simple"; return 100; }
+  const size_t row_len = (size_t)j->d.tw * (j->d.bpp - 1);
+  for (uint32_t y = j->y_min; y <= j->y_max; y++)
+    memcpy(img + (size_t)y * img_row_bytes, (const uint8_t *)w->pin + (size_t)(y - j->y_min) * row_len, row_len);
+  return 0;
 }
 extern "C" int rs_job_digest(RsJob *j, RsTargetDigest *out) {
   Workspace *w = j->ws;
@@ -1740,8 +1824,16 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
                                                  j->want_sources ? (uint32_t *)w->sources.p : nullptr);
   // the rows that contain target points land in pinned memory behind the same event
   const size_t row_bytes = (size_t)j->d.tw * j->d.bpp, rows_bytes = (size_t)(j->y_max - j->y_min + 1) * row_bytes;
-  RS_CHECK(cudaMemcpyAsync(w->pin, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes, rows_bytes,
-                           cudaMemcpyDeviceToHost, s));
+  if (j->simple) {  // the caller's layout: channels only, no mask byte
+    const int nc = j->d.bpp - 1;
+    const uint32_t npx = (j->y_max - j->y_min + 1) * (uint32_t)j->d.tw;
+    k_extract_simple<<<(npx + 255) / 256, 256, 0, s>>>((const uint8_t *)w->raw_t.p, j->y_min * (uint32_t)j->d.tw, npx, nc,
+                                                       (uint8_t *)w->simg.p);
+    RS_CHECK(cudaMemcpyAsync(w->pin, w->simg.p, (size_t)npx * nc, cudaMemcpyDeviceToHost, s));
+  } else {
+    RS_CHECK(cudaMemcpyAsync(w->pin, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes, rows_bytes,
+                             cudaMemcpyDeviceToHost, s));
+  }
   if (j->want_sources)
     RS_CHECK(cudaMemcpyAsync((uint8_t *)w->pin + ((rows_bytes + 255) & ~(size_t)255), w->sources.p, (size_t)j->nT * 4,
                              cudaMemcpyDeviceToHost, s));
@@ -1799,7 +1891,10 @@ extern "C" void rs_job_want_sources(RsJob *j, int yes) { j->want_sources = yes !
 extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sources_out) {
   const Workspace *w = j->ws;  // rs_job_run left the rows (and sources) in pinned memory
   const size_t row_bytes = (size_t)j->d.tw * j->d.bpp, rows_bytes = (size_t)(j->y_max - j->y_min + 1) * row_bytes;
-  memcpy(target_raw_out + (size_t)j->y_min * row_bytes, w->pin, rows_bytes);
+  if (target_raw_out) {
+    if (j->simple) { g_err = "rs_job_download: a job staged by rs_job_stage_simple returns its rows through rs_job_download_simple"; return 100; }
+    memcpy(target_raw_out + (size_t)j->y_min * row_bytes, w->pin, rows_bytes);
+  }
   if (sources_out) {
     if (!j->want_sources) { g_err = "rs_job_download: sources were not requested before rs_job_run"; return 100; }
     memcpy(sources_out, (const uint8_t *)w->pin + ((rows_bytes + 255) & ~(size_t)255), (size_t)j->nT * 4);
