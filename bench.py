@@ -53,14 +53,14 @@ def workload(name, seed_shift=0, scale=1.0):
         m = centered_mask(s, s, s // 8, s // 8)
         return dict(name="cfg1 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=False,
-                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4, simple=abi.T_RGB)
     if name == "cfg5":      # one heal job of the batch config: 2048^2, 256^2 hole, 30/200
         s = int(2048 * scale)
         img = G(s, s, 3, 100 + seed_shift)
         m = centered_mask(s, s, s // 8, s // 8)
         return dict(name="cfg5 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=False,
-                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4, simple=abi.T_RGB)
     if name == "cfg3":      # large-hole inpaint 4096^2 RGBA, 25% masked (centred 2048^2), transparent band, 30/200
         s_ = int(4096 * scale)
         img = G(s_, s_, 4, 3 + seed_shift)
@@ -69,7 +69,7 @@ def workload(name, seed_shift=0, scale=1.0):
         m = centered_mask(s_, s_, s_ // 2, s_ // 2)
         return dict(name="cfg3 inpaint %dx%d RGBA, %dx%d hole, ctx1, patch 30, probes 200" % (s_, s_, s_ // 2, s_ // 2),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=True,
-                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=5)
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=5, simple=abi.T_RGBA)
     if name == "cfg4":      # map-style transfer 2048^2 / 2048^2, RGB maps = the images, mapWeight 0.5, tiling, 9/200
         s_ = int(2048 * scale)
         tgt = G(s_, s_, 3, 4 + seed_shift); cor = G(s_, s_, 3, 5 + seed_shift)
@@ -84,7 +84,7 @@ def workload(name, seed_shift=0, scale=1.0):
         m = centered_mask(side, side, hole, hole)
         return dict(name="heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (side, side, hole, hole),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=False,
-                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4)
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4, simple=abi.T_RGB)
     raise SystemExit("unknown workload %s" % name)
 
 
@@ -228,6 +228,16 @@ def run_ours(a):
 
     def one_step(seed):
         api.set_seed(seed)
+        if B == 1 and "simple" in w:
+            # the heal configurations are imageSynth() jobs (BASELINE.json configs 1, 3, 5): one image + mask, host buffers
+            img = w["tgt"].copy()
+            flush.fill_(seed & 0xFF)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            err = api.image_synth(img, w["tmask"], w["simple"], w["params"])
+            wall = time.perf_counter() - t0
+            assert err == 0
+            return wall, api.last_stats(), img, w["tmask"]
         if B == 1:
             tp, cp = pixmaps(w)
             flush.fill_(seed & 0xFF)
@@ -269,8 +279,9 @@ def run_ours(a):
     for i in range(a.steps):
         wall, st, tp, cp = one_step(SEED)
         walls.append(wall); stats.append(st)
-        h2d = tp.nbytes + cp.nbytes + 4 * n + 4 * st["n_corpus"]  # + offsets table, counted below
-        d2h = 4 * n
+        h2d = tp.nbytes + cp.nbytes + 4 * n      # both pixmaps (or image + mask) and the visit order
+        d2h = int((np.flatnonzero(w["tmask"].any(axis=1))[[0, -1]] * [-1, 1]).sum() + 1) * w["tmask"].shape[1] * (
+            (w["bpp"] - 1) if "simple" in w and B == 1 else w["bpp"])   # the rows that hold target points
     barrier()
     t_total = time.perf_counter() - t_begin
     n_launches = api.total_kernel_launches() - launches0
@@ -352,7 +363,8 @@ def run_ours(a):
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
             "config": {"workload": w["name"] + (" x %d jobs per step, %d in flight, visit-order cache on" % (B, a.slots) if B > 1 else ""),
                        "parallelism": "independent jobs, %d GPU(s)" % world,
-                       "l2": "256 MiB flush between steps", "api": "engine() full API"},
+                       "l2": "256 MiB flush between steps",
+                       "api": "imageSynth() simple API" if ("simple" in w and B == 1) else "engine() full API"},
             "evals_per_s": world * evals / kern_s, "evals_issued_per_s": world * issued / kern_s,
             "compares_per_s": world * compares / kern_s, "compares_per_eval_issued": compares / max(issued, 1),
             "passes_run": stats[-1]["passes_run"], "visits_per_step": visits / a.steps,
