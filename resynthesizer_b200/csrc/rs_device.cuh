@@ -38,7 +38,12 @@
 // sweeps (profiles/): 2 for patches below RS_CHUNK_SWITCH_K neighbours, 3 from there on.
 #define RS_CHUNK_SMALL 2
 #define RS_CHUNK_LARGE 3
-#define RS_CHUNK_MAX 4
+#define RS_CHUNK_MAX 8
+// Latency mode (team kernel): after a probe's first chunk the rest of its patch is walked RS_CHUNK_CONT neighbours at a
+// time -- lanes are plentiful there and what counts is the number of dependent gather rounds, not wasted compares.
+#ifndef RS_CHUNK_CONT
+#define RS_CHUNK_CONT 6
+#endif
 #ifndef RS_CHUNK_SWITCH_K
 #define RS_CHUNK_SWITCH_K 16
 #endif

@@ -439,7 +439,9 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
   const uint32_t K = min(count, J.kmax);
   __syncwarp();
   {  // geometry half of the distance records, padded to whole chunks with records that cost nothing
-    const uint32_t nch = (K + J.chunk - 2u) / J.chunk, kpad = 1u + (nch ? nch : 1u) * J.chunk;
+    // (whole chunks of the launched kernel's size, and a continuation chunk of the team kernel may start at any k < K)
+    const uint32_t nch = (K + J.chunk - 2u) / J.chunk;
+    const uint32_t kpad = min((uint32_t)RS_NB_SLOTS, max(1u + (nch ? nch : 1u) * J.chunk, K + (uint32_t)RS_CHUNK_MAX));
     for (uint32_t k = lane; k < kpad; k += 32) {
       RsNb r;
       if (k < K) {
@@ -918,8 +920,8 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
         bool alive = (((unsigned long long)partial << 32) | idx) < *vbest;
         st.issued++;
         while (alive && k0 < K) {
-          partial += rs_chunk_sum<MAPS, CH>(J, lutc, lutm, S.nb, S.map, pcx, pclin, k0);
-          k0 += CH;
+          partial += rs_chunk_sum<MAPS, RS_CHUNK_CONT>(J, lutc, lutm, S.nb, S.map, pcx, pclin, k0);
+          k0 += RS_CHUNK_CONT;
           alive = !((((unsigned long long)partial << 32) | idx) > *vbest);
         }
         st.compares += min(k0, K);
