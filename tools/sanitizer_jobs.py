@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0,'/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from resynthesizer_b200 import api, abi
 from resynthesizer_b200.synthetic import G, centered_mask
