@@ -77,13 +77,14 @@ def workload(name, seed_shift=0, scale=1.0):
         return dict(name="cfg4 map-style %dx%d target / corpus, RGB maps, mapWeight 0.5, tiled, ctx1, patch 9, probes 200" % (s_, s_),
                     params=abi.make_params(1, 1, 1, 0.5, 0.117, 9, 200), n_color=3, n_map=3, alpha=False,
                     tmask=full, tgt=tgt, cmask=full.copy(), cor=cor, bpp=7, tmaps=tgt.copy(), cmaps=cor.copy())
-    if name.startswith("heal:"):   # heal:<image side>:<hole side>  (experiments)
-        _, side, hole = name.split(":")
-        side, hole = int(side), int(hole)
+    if name.startswith("heal:"):   # heal:<image side>:<hole side>[:<matchContextType>]  (experiments)
+        parts = name.split(":")
+        side, hole = int(parts[1]), int(parts[2])
+        mode = int(parts[3]) if len(parts) > 3 else 1
         img = G(side, side, 3, 4321 + seed_shift)
         m = centered_mask(side, side, hole, hole)
-        return dict(name="heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (side, side, hole, hole),
-                    params=abi.default_params(), n_color=3, n_map=0, alpha=False,
+        return dict(name="heal %dx%d, %dx%d hole, ctx%d, patch 30, probes 200" % (side, side, hole, hole, mode),
+                    params=abi.make_params(0, 0, mode, 0.5, 0.117, 30, 200), n_color=3, n_map=0, alpha=False,
                     tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4, simple=abi.T_RGB)
     raise SystemExit("unknown workload %s" % name)
 

@@ -138,6 +138,10 @@ typedef struct {
  * kept on the device for later jobs with the same key (16 entries / 1 GiB, least recently used out first).
  * rs_order_cache(0) drops the entries and disables the cache, rs_order_cache(1) enables it (default). */
 void rs_order_cache(int enabled);
+/* Orderings 2-8 (matchContextType) sort the target points by a geometric key: the keys are computed on the host (the
+ * brushfire ray index needs libm's atan2 bit for bit), the pairs are sorted on the device when there are at least
+ * n_points of them (default 65536; below, the host's radix sort is quicker than the copies).  Same result either way. */
+void rs_set_device_sort_min(unsigned int n_points);
 /* Throughput profile of the last engine() call on this thread (needs rs_keep_result(1)): ns from the start of
  * `pass` to the claim of its visit 4096 * i.  Returns the number of entries written. */
 unsigned int rs_get_timeline(unsigned int pass, unsigned long long *out_ns, unsigned int cap);

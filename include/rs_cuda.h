@@ -43,6 +43,9 @@ typedef struct {
   uint32_t pass_end[6];          /* prefix length of each pass (lib/passes.h:67-93) */
   uint32_t n_passes;             /* <= 6 */
   double terminate_fraction;     /* stop after a pass when (float)betters/n, widened to double, is below this (0.1) */
+  int32_t ordered_visits;        /* hint: the visit order is spatially sorted (matchContextType 2..8), not a shuffle:
+                                    pass 0 is then a narrow dependency front and runs in latency mode throughout */
+  int32_t reserved;
 } RsJobDesc;
 
 typedef struct {
@@ -124,6 +127,9 @@ int rs_job_download_simple(RsJob *job, uint8_t *img, size_t img_row_bytes);
 int rs_job_bind_order(RsJob *job, const RsTargetDigest *digest, const RsOrderKey *key);
 int rs_job_set_order(RsJob *job, const uint32_t *ordered_points, const RsOrderKey *key);
 void rs_cuda_order_cache(int enabled);
+/* Stable ascending radix sort of n (key, value) pairs on the low key_bits bits of the keys, host buffers in place, on a
+ * side stream of the job (it runs beside the staging).  The sort step of the target orderings 2-8. */
+int rs_job_sort_pairs(RsJob *job, uint32_t *keys, uint32_t *vals, uint32_t n, int key_bits);
 /* Pass schedule (prefix length of each pass), when it was not known at rs_job_create (target points counted on the
  * device). */
 void rs_job_set_passes(RsJob *job, const uint32_t *pass_end, uint32_t n_passes);

@@ -45,7 +45,8 @@ class RsJobDesc(C.Structure):
                 ("n_color", C.c_int32), ("n_map", C.c_int32), ("map_bip", C.c_int32), ("alpha_bip", C.c_int32),
                 ("alpha_target", C.c_int32), ("alpha_source", C.c_int32), ("htile", C.c_int32), ("vtile", C.c_int32), ("use_context", C.c_int32),
                 ("patch_size", C.c_uint32), ("max_probes", C.c_uint32), ("seed", C.c_uint32),
-                ("pass_end", C.c_uint32 * 6), ("n_passes", C.c_uint32), ("terminate_fraction", C.c_double)]
+                ("pass_end", C.c_uint32 * 6), ("n_passes", C.c_uint32), ("terminate_fraction", C.c_double),
+                ("ordered_visits", C.c_int32), ("reserved", C.c_int32)]
 
 
 def lib():
@@ -96,6 +97,11 @@ def last_stats():
 def order_cache(enabled=True):
     """Enable (default) or drop + disable the device-side cache of visit orders (rs_order_cache)."""
     lib().rs_order_cache(1 if enabled else 0)
+
+
+def set_device_sort_min(n_points):
+    """Point lists of at least n_points are sorted on the device for orderings 2-8 (rs_set_device_sort_min)."""
+    lib().rs_set_device_sort_min(int(n_points))
 
 
 def total_kernel_launches():

@@ -2,6 +2,7 @@
 // error codes, progress and cancel behaviour (include/resynthesizer.h), driving the CUDA passes through
 // include/rs_cuda.h.  There is no CPU synthesis path in this library.
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
@@ -24,11 +25,21 @@ thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-ta
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
 thread_local std::vector<uint64_t> t_timeline[6];                   // of the last engine() call (rs_keep_result)
 
+// point lists shorter than this are sorted on the host (orderings 2-8): a device sort costs two small copies and a sync
+std::atomic<size_t> g_device_sort_min{std::getenv("RS_DEVICE_SORT_MIN") ? (size_t)std::atoll(std::getenv("RS_DEVICE_SORT_MIN"))
+                                                                        : ((size_t)1 << 16)};
 std::atomic<unsigned long long> g_kernel_launches{0};  // every kernel any engine() call of this process launched
 
 double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" const char *rs_cuda_peek_error(void);
+void dbg(const char *where) {
+  static const bool on = std::getenv("RS_DEBUG") != nullptr;
+  if (!on) return;
+  if (const char *e = rs_cuda_peek_error()) std::fprintf(stderr, "[rs debug] pending CUDA error at %s: %s\n", where, e);
 }
 
 int ensure_device() {
@@ -67,6 +78,7 @@ extern "C" const char *rs_last_error(void) { return t_err.c_str(); }
 extern "C" void rs_get_stats(RsStats *out) { *out = t_stats; }
 extern "C" void rs_set_seed(unsigned int seed) { t_seed = seed; }
 extern "C" void rs_order_cache(int enabled) { rs_cuda_order_cache(enabled); }
+extern "C" void rs_set_device_sort_min(unsigned int n_points) { g_device_sort_min.store(n_points); }
 extern "C" unsigned long long rs_total_kernel_launches(void) { return g_kernel_launches.load(); }
 extern "C" void rs_keep_result(int yes) { t_keep_result = yes != 0; }
 extern "C" int rs_set_device(int ordinal) {
@@ -211,13 +223,16 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   desc.use_context = prm.matchContextType != 0;
   desc.patch_size = prm.patchSize; desc.max_probes = prm.maxProbeCount; desc.seed = t_seed;
   desc.n_passes = 6;
+  desc.ordered_visits = prm.matchContextType >= 2 ? 1 : 0;
   desc.terminate_fraction = 0.1;  // IMAGE_SYNTH_TERMINATE_FRACTION, a double (lib/refiner.h:111)
   const double t1 = now_ms();
 
   // Stage the images (asynchronous: host -> device, state init, corpus points, offsets table) and get the digest of
   // the target selection back: number of target points, their rows, and the key of the visit-order cache.
   RsJob *job = nullptr;
+  dbg("before create");
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
+  dbg("after create");
   RsTargetDigest dg;
   int rc = src.simple()
                ? rs_job_stage_simple(job, src.img->data, src.img->rowBytes, src.mask->data, src.mask->rowBytes,
@@ -225,6 +240,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
                : rs_job_stage(job, src.tpix, src.cpix, c256, m256, m512[0]);
   if (!rc) rc = rs_job_digest(job, &dg);
   if (rc) { t_err = rs_cuda_last_error(); rs_job_destroy(job); return RS_ERROR_CUDA; }
+  dbg("after stage+digest");
   const uint32_t n = dg.n;
   uint32_t pass_end[6];
   const uint32_t estimated = rs::pass_schedule(n, pass_end);
@@ -237,12 +253,22 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   key.h1 = dg.h1; key.h2 = dg.h2; key.n = n; key.tw = tw; key.th = th; key.mode = prm.matchContextType; key.seed = t_seed;
   static thread_local std::vector<uint32_t> targets;  // reused across calls: no page faults per job
   int hit = t_keep_result ? 0 : rs_job_bind_order(job, &dg, &key);
+  dbg("after bind");
   if (hit == 0) {
     if (t_keep_result) hit = rs_job_bind_order(job, &dg, nullptr) == 100 ? 100 : 0;  // sizes only; the order is wanted on the host
     if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
       const uint8_t *mask0 = src.simple() ? src.mask->data : src.tpix;
       const size_t pstride = src.simple() ? 1 : (size_t)bpp, rstride = src.simple() ? src.mask->rowBytes : (size_t)tw * bpp;
-      if (rs::collect_and_order(prm.matchContextType, mask0, tw, th, pstride, rstride, n, t_seed, targets) != 0 || targets.size() != n) {
+      // orderings 2-8 sort the points by a geometric key: the host computes the keys, the device sorts the pairs
+      const size_t device_sort_min = g_device_sort_min.load();
+      const rs::PairSorter sorter = [job, device_sort_min](uint32_t *keys, uint32_t *vals, size_t cnt) {
+        if (cnt < device_sort_min) return false;
+        dbg("before sort");
+        if (rs_job_sort_pairs(job, keys, vals, (uint32_t)cnt, 32) == 0) { dbg("after sort"); return true; }
+        if (std::getenv("RS_DEBUG")) std::fprintf(stderr, "rs_job_sort_pairs failed: %s\n", rs_cuda_last_error());
+        return false;
+      };
+      if (rs::collect_and_order(prm.matchContextType, mask0, tw, th, pstride, rstride, n, t_seed, targets, &sorter) != 0 || targets.size() != n) {
         t_err = "target point count differs between host and device";
         rc = 100;
       }
@@ -250,6 +276,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
     }
   }
   if (hit == 100) rc = 100;
+  dbg("after order");
   const double t2b = now_ms();
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
   if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, on_tick, &ts); }
@@ -271,6 +298,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
     rs_job_destroy(job);
     return RS_ERROR_CUDA;
   }
+  dbg("after run+download");
   RsJobCounters jc;
   rs_job_counters(job, &jc);
   if (t_keep_result)
@@ -279,6 +307,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
       t_timeline[p].resize(rs_job_timeline(job, p, t_timeline[p].data(), 512));
     }
   rs_job_destroy(job);
+  dbg("after destroy");
   const double t4 = now_ms();
   t_stats.visits = jc.visits; t_stats.evals = jc.evals; t_stats.evals_issued = jc.evals_issued;
   t_stats.compares = jc.compares; t_stats.offset_scans = jc.offset_scans; t_stats.heur_evals = jc.heur_evals;

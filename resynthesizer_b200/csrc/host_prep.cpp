@@ -322,13 +322,13 @@ static void parallel_ranges(size_t n, Body body) {
 // counted them).  For the shuffling modes the draws depend on that number and the seed only, so their producer thread
 // starts before the points are collected and the two overlap.
 int collect_and_order(int mode, const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride, size_t n_known,
-                      uint32_t seed, std::vector<uint32_t> &pts) {
+                      uint32_t seed, std::vector<uint32_t> &pts, const PairSorter *sorter) {
   if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
   constexpr size_t BLOCK = 1u << 16;
   if (mode > 1 || n_known < 4 * BLOCK) {
     collect_target_points_strided(mask0, w, h, pixel_stride, row_stride, pts);
     GRandMT prng(seed);
-    return order_target_points(mode, pts, prng);
+    return order_target_points(mode, pts, prng, sorter);
   }
   static thread_local std::vector<uint32_t> js;
   js.resize(n_known);
@@ -359,7 +359,7 @@ int collect_and_order(int mode, const uint8_t *mask0, int w, int h, size_t pixel
   return 0;
 }
 
-int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {
+int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng, const PairSorter *sorter) {
   const size_t n = pts.size();
   if (mode < 0 || mode > 8) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;
   if (mode <= 1) {  // not Fisher-Yates: every i swaps with a draw over the whole vector
@@ -421,10 +421,20 @@ int order_target_points(int mode, std::vector<uint32_t> &pts, GRandMT &prng) {
       std::reverse(keys.begin(), keys.end());
       for (size_t i = 0; i < n; i++) idx[i] = (uint32_t)(n - 1 - i);
     }
-    radix_sort_pairs(keys, idx);
-    std::vector<uint32_t> sorted(n);
-    for (size_t i = 0; i < n; i++) sorted[i] = pts[idx[i]];
-    pts.swap(sorted);
+    bool done = false;
+    if (sorter && *sorter) {
+      // the stable sort of (key, point) pairs is handed to the caller's sorter (the device, csrc/rs_kernels.cu): the
+      // points travel as the payload, in the same (possibly reversed) input order as the keys
+      std::vector<uint32_t> vals(n);
+      for (size_t i = 0; i < n; i++) vals[i] = pts[idx[i]];
+      if ((*sorter)(keys.data(), vals.data(), n)) { pts.swap(vals); done = true; }  // (keys and vals are untouched on failure)
+    }
+    if (!done) {
+      radix_sort_pairs(keys, idx);
+      std::vector<uint32_t> sorted(n);
+      for (size_t i = 0; i < n; i++) sorted[i] = pts[idx[i]];
+      pts.swap(sorted);
+    }
   }
   shuffle_bands(pts, prng);
   return 0;

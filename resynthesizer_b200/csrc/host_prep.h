@@ -4,6 +4,7 @@
 // tests/test_host_prep.py compares them with the oracle.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "../../include/resynthesizer.h"
@@ -45,10 +46,12 @@ bool has_target_point(const uint8_t *pix, int w, int h, int bpp);
 bool has_corpus_point(const uint8_t *pix, int w, int h, int bpp, const TFormatIndices &fi);
 
 // lib/orderTarget.h:268-343 (+ brushfire.h, engineTypes.h).  Returns 0 or IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE.
-int order_target_points(int match_context_type, std::vector<uint32_t> &pts, GRandMT &prng);
+// Stable ascending sort of n (key, value) pairs in place; false = not done (the host's own radix sort runs instead).
+using PairSorter = std::function<bool(uint32_t *keys, uint32_t *vals, size_t n)>;
+int order_target_points(int match_context_type, std::vector<uint32_t> &pts, GRandMT &prng, const PairSorter *sorter = nullptr);
 // Both steps for a pixmap with n_known selected pixels, overlapped where the mode allows; -1 if the count was wrong.
 int collect_and_order(int match_context_type, const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride,
-                      size_t n_known, uint32_t seed, std::vector<uint32_t> &pts);
+                      size_t n_known, uint32_t seed, std::vector<uint32_t> &pts, const PairSorter *sorter = nullptr);
 void collect_target_points_strided(const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride,
                                    std::vector<uint32_t> &out);
 

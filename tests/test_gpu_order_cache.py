@@ -95,3 +95,25 @@ def test_concurrent_jobs_share_a_fresh_entry():
                 assert (jb[2] == singles[i % 4]).all(), "job %d of repetition %d differs" % (i, rep)
     finally:
         api.order_cache(True)
+
+
+@pytest.mark.parametrize("mode", [2, 3, 4, 5, 6, 7, 8])
+def test_device_sort_equals_host_sort(mode):
+    """Orderings 2-8: sorting the (key, point) pairs on the device gives the same visit order, hence the same image,
+    sources and counters as the host's radix sort."""
+    api.order_cache(False)
+    api.keep_result(True)
+    try:
+        p, tp, cp = _job(31, 36, mode=mode)
+        api.set_device_sort_min(1 << 30)
+        a, sa = _run(p, tp, cp)
+        ta, srca = api.last_result()
+        api.set_device_sort_min(1)
+        b, sb = _run(p, tp, cp)
+        tb, srcb = api.last_result()
+        assert (ta == tb).all() and (srca == srcb).all() and (a == b).all()
+        assert sa["evals"] == sb["evals"] and sa["betters"] == sb["betters"]
+    finally:
+        api.set_device_sort_min(1 << 16)
+        api.keep_result(False)
+        api.order_cache(True)

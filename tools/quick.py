@@ -9,6 +9,7 @@ import bench  # noqa: E402
 from resynthesizer_b200 import api, build  # noqa: E402
 
 build.build()
+api.order_cache(False)   # every job orders its own points
 for name in sys.argv[1:]:
     w = bench.workload(name)
     fi = api.format_indices(w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
@@ -19,4 +20,6 @@ for name in sys.argv[1:]:
         st = api.last_stats()
         if rep and (best is None or st["ms_kernels"] < best["ms_kernels"]):
             best = st
-    print("%-16s kern %8.3f ms  passes %s  evals %.3g" % (name, best["ms_kernels"], " ".join("%.3f" % x for x in best["ms_pass"][:best["passes_run"]]), best["evals"]), flush=True)
+    print("%-16s kern %8.3f ms  passes %s  evals %.3g  [prep %.2f stage %.2f total %.2f ms]" % (
+        name, best["ms_kernels"], " ".join("%.3f" % x for x in best["ms_pass"][:best["passes_run"]]), best["evals"],
+        best["ms_prep"], best["ms_h2d"], best["ms_total"]), flush=True)
