@@ -142,6 +142,10 @@ void rs_order_cache(int enabled);
  * brushfire ray index needs libm's atan2 bit for bit), the pairs are sorted on the device when there are at least
  * n_points of them (default 65536; below, the host's radix sort is quicker than the copies).  Same result either way. */
 void rs_set_device_sort_min(unsigned int n_points);
+/* Orderings 0 and 1 are the reference's loop  for i: swap(a[i], a[rand(0,n)])  (lib/orderTarget.h:38-53).  The host makes
+ * the draws with the reference's PRNG stream; from n_points points on (default 32768) the device resolves the chain of
+ * swaps itself -- exactly, by walking it backwards for every position -- instead of the host swapping and uploading. */
+void rs_set_device_shuffle_min(unsigned int n_points);
 /* Throughput profile of the last engine() call on this thread (needs rs_keep_result(1)): ns from the start of
  * `pass` to the claim of its visit 4096 * i.  Returns the number of entries written. */
 unsigned int rs_get_timeline(unsigned int pass, unsigned long long *out_ns, unsigned int cap);

@@ -127,6 +127,11 @@ int rs_job_download_simple(RsJob *job, uint8_t *img, size_t img_row_bytes);
 int rs_job_bind_order(RsJob *job, const RsTargetDigest *digest, const RsOrderKey *key);
 int rs_job_set_order(RsJob *job, const uint32_t *ordered_points, const RsOrderKey *key);
 void rs_cuda_order_cache(int enabled);
+/* The shuffling orders (matchContextType 0, 1) built on the device, exactly: `draws` = the n = digest.n draws j_i of the
+ * reference's loop  for i: swap(a[i], a[j_i])  (lib/orderTarget.h:38-53), made by the host's PRNG stream.  The device
+ * compacts the target points, and finds what ends at each position by walking the chain of swaps backwards.  Replaces
+ * rs_job_set_order on a cache miss; ordered_out (or NULL) receives the order. */
+int rs_job_shuffle_order(RsJob *job, const uint32_t *draws, const RsOrderKey *key, uint32_t *ordered_out);
 /* Stable ascending radix sort of n (key, value) pairs on the low key_bits bits of the keys, host buffers in place, on a
  * side stream of the job (it runs beside the staging).  The sort step of the target orderings 2-8. */
 int rs_job_sort_pairs(RsJob *job, uint32_t *keys, uint32_t *vals, uint32_t n, int key_bits);

@@ -104,6 +104,11 @@ def set_device_sort_min(n_points):
     lib().rs_set_device_sort_min(int(n_points))
 
 
+def set_device_shuffle_min(n_points):
+    """Shuffling orders (matchContextType 0, 1) of at least n_points are resolved on the device."""
+    lib().rs_set_device_shuffle_min(int(n_points))
+
+
 def total_kernel_launches():
     L = lib()
     L.rs_total_kernel_launches.restype = C.c_ulonglong

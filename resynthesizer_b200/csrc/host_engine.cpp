@@ -28,6 +28,8 @@ thread_local std::vector<uint64_t> t_timeline[6];                   // of the la
 // point lists shorter than this are sorted on the host (orderings 2-8): a device sort costs two small copies and a sync
 std::atomic<size_t> g_device_sort_min{std::getenv("RS_DEVICE_SORT_MIN") ? (size_t)std::atoll(std::getenv("RS_DEVICE_SORT_MIN"))
                                                                         : ((size_t)1 << 16)};
+// shuffling orders (matchContextType 0, 1) of at least this many points are resolved on the device
+std::atomic<size_t> g_device_shuffle_min{(size_t)1 << 15};
 std::atomic<unsigned long long> g_kernel_launches{0};  // every kernel any engine() call of this process launched
 
 double now_ms() {
@@ -79,6 +81,7 @@ extern "C" void rs_get_stats(RsStats *out) { *out = t_stats; }
 extern "C" void rs_set_seed(unsigned int seed) { t_seed = seed; }
 extern "C" void rs_order_cache(int enabled) { rs_cuda_order_cache(enabled); }
 extern "C" void rs_set_device_sort_min(unsigned int n_points) { g_device_sort_min.store(n_points); }
+extern "C" void rs_set_device_shuffle_min(unsigned int n_points) { g_device_shuffle_min.store(n_points); }
 extern "C" unsigned long long rs_total_kernel_launches(void) { return g_kernel_launches.load(); }
 extern "C" void rs_keep_result(int yes) { t_keep_result = yes != 0; }
 extern "C" int rs_set_device(int ordinal) {
@@ -256,6 +259,17 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   dbg("after bind");
   if (hit == 0) {
     if (t_keep_result) hit = rs_job_bind_order(job, &dg, nullptr) == 100 ? 100 : 0;  // sizes only; the order is wanted on the host
+    if (hit == 0 && prm.matchContextType <= 1 && n >= g_device_shuffle_min.load()) {
+      // miss, shuffling order: the host only makes the draws (the reference's PRNG stream); the device compacts the
+      // target points and resolves the chain of swaps (rs_job_shuffle_order)
+      static thread_local std::vector<uint32_t> draws;
+      draws.resize(n);
+      rs::GRandMT prng(t_seed);
+      prng.fill_int_range(n, draws.data(), n);
+      if (t_keep_result) targets.resize(n);
+      rc = rs_job_shuffle_order(job, draws.data(), t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
+      hit = 2;
+    }
     if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
       const uint8_t *mask0 = src.simple() ? src.mask->data : src.tpix;
       const size_t pstride = src.simple() ? 1 : (size_t)bpp, rstride = src.simple() ? src.mask->rowBytes : (size_t)tw * bpp;

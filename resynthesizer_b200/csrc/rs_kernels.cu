@@ -1031,7 +1031,7 @@ struct Workspace {
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, simg, smask, smask2,
-      ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp;
+      ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
   void *pin_order = nullptr;  // pinned staging of a visit order
@@ -1079,7 +1079,7 @@ static void ws_free(Workspace *w) {
                    &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
                    &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts,
                    &w->simg, &w->smask, &w->smask2, &w->ord_keys_in, &w->ord_keys_out, &w->ord_vals_in, &w->ord_vals_out,
-                   &w->ord_tmp};
+                   &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
   if (w->pin_order) cudaFreeHost(w->pin_order);
@@ -1181,6 +1181,55 @@ __global__ void k_gen_offsets(int w, int h, uint32_t n, uint32_t *__restrict__ k
 }
 
 // ------------------------------------------------------------------------------------------------ the job
+// ---- the reference's shuffle on the device, exactly (lib/orderTarget.h:38-53, modes 0 and 1) ----
+// The reference runs  for i in [0,n): swap(a[i], a[j_i])  with j_i drawn over the WHOLE vector -- a sequential chain of
+// transpositions, not a Fisher-Yates shuffle.  What ends up at position p can still be found independently for every p
+// by walking the chain BACKWARDS: at time t the content of position x was last moved by the latest swap before t that
+// touches x, which is swap x itself (if x < t) or a swap i with j_i == x.  Follow it to where the content came from
+// and repeat until no earlier swap touches the position; the content is then the initial a[x].  Chains are short (2
+// hops on average, < 16 for a million points).  The swaps that target a position are found through the pairs (j_i, i)
+// sorted by j_i (stable radix sort: ascending i within a target).
+__global__ void k_iota(uint32_t *__restrict__ v, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+__global__ void k_run_heads(const uint32_t *__restrict__ sorted_j, uint32_t n, uint32_t *__restrict__ first) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && (k == 0 || sorted_j[k] != sorted_j[k - 1])) first[sorted_j[k]] = k;
+}
+__global__ void k_shuffle_trace(const uint32_t *__restrict__ draws, const uint32_t *__restrict__ sorted_j,
+                                const uint32_t *__restrict__ sorted_i, const uint32_t *__restrict__ first,
+                                const uint32_t *__restrict__ points, uint32_t n, uint32_t *__restrict__ ordered) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  uint32_t x = p, t = n;
+  while (true) {
+    // latest swap before t that targets x (j_i == x): its run in the sorted pairs is ascending in i
+    uint32_t best = 0xFFFFFFFFu;
+    const uint32_t k0 = first[x];
+    if (k0 != 0xFFFFFFFFu)
+      for (uint32_t k = k0; k < n && sorted_j[k] == x; k++) {
+        const uint32_t i = sorted_i[k];
+        if (i >= t) break;
+        best = i;
+      }
+    const bool own = x < t;  // swap x itself touches position x
+    if (best == 0xFFFFFFFFu && !own) break;
+    if (own && (best == 0xFFFFFFFFu || x >= best)) {  // the own swap is the latest (x == best: a self swap, no move)
+      t = x;
+      x = draws[x];
+    } else {
+      t = best;
+      x = best;
+    }
+  }
+  ordered[p] = points[x];
+}
+__global__ void k_target_flags(const uint8_t *__restrict__ raw, uint32_t n_px, int bpp, uint8_t *__restrict__ flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_px) flags[i] = raw[(size_t)i * bpp] != 0 ? 1 : 0;
+}
+
 // Visit orders kept on the device, keyed by what they are a function of.  A batch of jobs with the same selection
 // (frames of a video, a set of equally sized images with the same hole) orders its target points once.
 struct OrderEntry {
@@ -1706,6 +1755,93 @@ extern "C" int rs_job_sort_pairs(RsJob *j, uint32_t *keys, uint32_t *vals, uint3
   memcpy(keys, pin, bytes);
   memcpy(vals, pin + bytes, bytes);
   j->upload_launches += 2u + (uint32_t)((key_bits + 7) / 8);
+  return 0;
+}
+
+// Visit order of the shuffling modes (matchContextType 0, 1) built on the device from the host's draws j_i (the
+// reference's PRNG stream, n of them): target points compacted from the staged image, pairs sorted, chains traced.
+// With a key the order becomes a cache entry.  ordered_out (optional): the order back on the host.
+extern "C" int rs_job_shuffle_order(RsJob *j, const uint32_t *draws, const RsOrderKey *key, uint32_t *ordered_out) {
+  Workspace *w = j->ws;
+  RS_CHECK(cudaSetDevice(w->device));
+  const RsJobDesc &d = j->d;
+  const uint32_t n = j->nT;
+  const size_t bytes = (size_t)n * 4, tn = (size_t)d.tw * d.th;
+  cudaStream_t s = w->stream;
+  int rc = 0;
+  if ((rc = ws_ensure(w->ord_keys_in, bytes)) || (rc = ws_ensure(w->ord_keys_out, bytes)) || (rc = ws_ensure(w->ord_vals_in, bytes)) ||
+      (rc = ws_ensure(w->ord_vals_out, bytes)) || (rc = ws_ensure(w->ord_first, bytes)) || (rc = ws_ensure(w->ord_points, bytes + 4)) ||
+      (rc = ws_ensure(w->ord_flags, tn)))
+    return rc;
+  if (bytes > w->pin_order_cap) {
+    if (w->pin_order) cudaFreeHost(w->pin_order);
+    w->pin_order = nullptr; w->pin_order_cap = 0;
+    RS_CHECK(cudaHostAlloc(&w->pin_order, bytes + bytes / 8 + 4096, cudaHostAllocDefault));
+    w->pin_order_cap = bytes + bytes / 8 + 4096;
+  }
+  uint32_t *dst = nullptr;
+  j->order.reset();
+  std::shared_ptr<OrderEntry> entry;
+  if (key && g_order_cache_on.load()) {
+    entry = std::make_shared<OrderEntry>();
+    entry->key = *key; entry->device = w->device; entry->n = n;
+    RS_CHECK(cudaMalloc(&entry->dev, bytes));
+    RS_CHECK(cudaEventCreateWithFlags(&entry->ready, cudaEventDisableTiming));
+    dst = entry->dev;
+    j->order = entry;
+  } else {
+    if ((rc = ws_ensure(w->targets, bytes))) return rc;
+    dst = (uint32_t *)w->targets.p;
+  }
+  j->targets_dev = dst;
+  // the draws go up while the device compacts the target points
+  memcpy(w->pin_order, draws, bytes);
+  RS_CHECK(cudaMemcpyAsync(w->ord_keys_in.p, w->pin_order, bytes, cudaMemcpyHostToDevice, s));
+  const int T = 256;
+  k_target_flags<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_t.p, (uint32_t)tn, d.bpp, (uint8_t *)w->ord_flags.p);
+  thrust::counting_iterator<uint32_t> idx(0);
+  unsigned int *d_cnt = &((RsCtrl *)w->ctrl.p)->dg_sel;
+  size_t tmp = 0, tmp2 = 0;
+  RS_CHECK(cub::DeviceSelect::Flagged(nullptr, tmp, idx, (const uint8_t *)w->ord_flags.p, (uint32_t *)w->ord_points.p, d_cnt, (int)tn, s));
+  int bits = 1;
+  while (bits < 32 && ((n - 1) >> bits)) bits++;
+  RS_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (const uint32_t *)w->ord_keys_in.p, (uint32_t *)w->ord_keys_out.p,
+                                           (const uint32_t *)w->ord_vals_in.p, (uint32_t *)w->ord_vals_out.p, (int)n, 0, bits, s));
+  if ((rc = ws_ensure(w->ord_tmp, tmp > tmp2 ? tmp : tmp2))) return rc;
+  RS_CHECK(cub::DeviceSelect::Flagged(w->ord_tmp.p, tmp, idx, (const uint8_t *)w->ord_flags.p, (uint32_t *)w->ord_points.p, d_cnt, (int)tn, s));
+  k_pack_points<<<592, T, 0, s>>>((uint32_t *)w->ord_points.p, d_cnt, d.tw);
+  k_iota<<<(n + T - 1) / T, T, 0, s>>>((uint32_t *)w->ord_vals_in.p, n);
+  RS_CHECK(cub::DeviceRadixSort::SortPairs(w->ord_tmp.p, tmp2, (const uint32_t *)w->ord_keys_in.p, (uint32_t *)w->ord_keys_out.p,
+                                           (const uint32_t *)w->ord_vals_in.p, (uint32_t *)w->ord_vals_out.p, (int)n, 0, bits, s));
+  RS_CHECK(cudaMemsetAsync(w->ord_first.p, 0xFF, bytes, s));
+  k_run_heads<<<(n + T - 1) / T, T, 0, s>>>((const uint32_t *)w->ord_keys_out.p, n, (uint32_t *)w->ord_first.p);
+  k_shuffle_trace<<<(n + T - 1) / T, T, 0, s>>>((const uint32_t *)w->ord_keys_in.p, (const uint32_t *)w->ord_keys_out.p,
+                                               (const uint32_t *)w->ord_vals_out.p, (const uint32_t *)w->ord_first.p,
+                                               (const uint32_t *)w->ord_points.p, n, dst);
+  RS_CHECK(cudaGetLastError());
+  j->upload_launches += 8u + (uint32_t)((bits + 7) / 8);
+  if (entry) {
+    RS_CHECK(cudaEventRecord(entry->ready, s));
+    std::lock_guard<std::mutex> lk(g_order_mutex);
+    entry->stamp = ++g_order_clock;
+    g_orders.push_back(entry);
+    size_t total = 0;
+    for (auto &o : g_orders) total += (size_t)o->n * 4;
+    while (g_orders.size() > 16 || (total > ((size_t)1 << 30) && g_orders.size() > 1)) {
+      size_t lru = 0;
+      for (size_t i = 1; i < g_orders.size(); i++) if (g_orders[i]->stamp < g_orders[lru]->stamp) lru = i;
+      total -= (size_t)g_orders[lru]->n * 4;
+      g_orders.erase(g_orders.begin() + lru);
+    }
+  }
+  j->upload_launches += 1u;
+  k_scatter_order<<<(n + 255) / 256, 256, 0, s>>>(dst, n, d.tw, (uint32_t *)w->meta.p);
+  RS_CHECK(cudaGetLastError());
+  if (ordered_out) {
+    RS_CHECK(cudaMemcpyAsync(w->pin_order, dst, bytes, cudaMemcpyDeviceToHost, s));
+    RS_CHECK(cudaStreamSynchronize(s));
+    memcpy(ordered_out, w->pin_order, bytes);
+  }
   return 0;
 }
 

@@ -117,3 +117,25 @@ def test_device_sort_equals_host_sort(mode):
         api.set_device_sort_min(1 << 16)
         api.keep_result(False)
         api.order_cache(True)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("hole", [3, 40])
+def test_device_shuffle_equals_host_shuffle(mode, hole):
+    """Orderings 0/1: the chain of swaps resolved on the device gives the visit order the host's swap loop gives."""
+    api.order_cache(False)
+    api.keep_result(True)
+    try:
+        p, tp, cp = _job(33, hole, mode=mode)
+        api.set_device_shuffle_min(1 << 30)
+        a, sa = _run(p, tp, cp)
+        ta, srca = api.last_result()
+        api.set_device_shuffle_min(1)
+        b, sb = _run(p, tp, cp)
+        tb, srcb = api.last_result()
+        assert len(ta) == len(tb) and (ta == tb).all() and (srca == srcb).all() and (a == b).all()
+        assert sa["evals"] == sb["evals"] and sa["betters"] == sb["betters"]
+    finally:
+        api.set_device_shuffle_min(1 << 15)
+        api.keep_result(False)
+        api.order_cache(True)
