@@ -15,6 +15,9 @@ uint32_t rs_host_sorted_offsets(int tw, int th, int cw, int ch, int32_t *xy, uin
 /* replaces orderTargetPoints (lib/orderTarget.h:268-343) over n x,y pairs given in row-major scan order */
 int rs_host_order_targets(int match_context_type, int32_t *xy, uint32_t n, uint32_t seed);
 /* replaces prepare_repetition_parameters (lib/passes.h:67-93) */
+/* `count` successive g_rand_int_range(0, n) draws of the GRand stream seeded with `seed`: directly (via_raw_stream = 0)
+ * or through the early-started raw-word producer the engine uses (1).  Must be identical. */
+void rs_host_draws(uint32_t seed, uint32_t n, uint32_t count, uint32_t *out, int via_raw_stream);
 uint32_t rs_host_pass_schedule(uint32_t n_targets, uint32_t *ends6);
 #ifdef __cplusplus
 }

@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -232,6 +233,12 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
 
   // Stage the images (asynchronous: host -> device, state init, corpus points, offsets table) and get the digest of
   // the target selection back: number of target points, their rows, and the key of the visit-order cache.
+  // The shuffling orders need one PRNG draw per target point.  The raw words of the stream depend on the seed only, so a
+  // producer thread starts making them now, while the images are staged and counted (rejection rate < n / 2^32).
+  const size_t npx = (size_t)tw * th;
+  std::unique_ptr<rs::RawStream> raw;
+  if (prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26))
+    raw.reset(new rs::RawStream(t_seed, npx + npx / 32 + 65536));
   RsJob *job = nullptr;
   dbg("before create");
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
@@ -264,8 +271,12 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
       // target points and resolves the chain of swaps (rs_job_shuffle_order)
       static thread_local std::vector<uint32_t> draws;
       draws.resize(n);
-      rs::GRandMT prng(t_seed);
-      prng.fill_int_range(n, draws.data(), n);
+      if (raw) {
+        raw->reduce(n, draws.data(), n);
+      } else {
+        rs::GRandMT prng(t_seed);
+        prng.fill_int_range(n, draws.data(), n);
+      }
       if (t_keep_result) targets.resize(n);
       rc = rs_job_shuffle_order(job, draws.data(), t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
       hit = 2;
@@ -289,6 +300,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
       if (!rc) rc = rs_job_set_order(job, targets.data(), t_keep_result ? nullptr : &key);
     }
   }
+  raw.reset();
   if (hit == 100) rc = 100;
   dbg("after order");
   const double t2b = now_ms();
@@ -496,5 +508,14 @@ extern "C" int rs_host_order_targets(int mode, int32_t *xy, uint32_t n, uint32_t
   const int e = rs::order_target_points(mode, p, prng);
   for (uint32_t i = 0; i < n; i++) { xy[2 * i] = rs::unpack_x(p[i]); xy[2 * i + 1] = rs::unpack_y(p[i]); }
   return e;
+}
+extern "C" void rs_host_draws(uint32_t seed, uint32_t n, uint32_t count, uint32_t *out, int via_raw_stream) {
+  if (via_raw_stream) {
+    rs::RawStream r(seed, (size_t)count + count / 32 + 65536);
+    r.reduce(n, out, count);
+  } else {
+    rs::GRandMT g(seed);
+    g.fill_int_range(n, out, count);
+  }
 }
 extern "C" uint32_t rs_host_pass_schedule(uint32_t n, uint32_t *ends6) { return rs::pass_schedule(n, ends6); }

@@ -244,6 +244,63 @@ static void swaps_from_draws(uint32_t *a, size_t n, Fill fill) {
 }
 
 // lib/orderTarget.h:57-80: every i swaps with a draw from the band [i - half, i + half) clipped to the vector.
+void GRandMT::fill_raw(uint32_t *out, size_t count) {
+  size_t i = 0;
+  while (i < count) {
+    if (mti_ >= 624) refill();
+    const size_t take = std::min<size_t>((size_t)(624 - mti_), count - i);
+    std::memcpy(out + i, out_ + mti_, take * 4);
+    mti_ += (int)take;
+    i += take;
+  }
+}
+
+RawStream::RawStream(uint32_t seed, size_t max_words) : cap_(max_words), seed_(seed) {
+  static thread_local std::vector<uint32_t> storage;  // reused by the calling thread's next job
+  storage.resize(cap_);
+  buf_ = &storage;
+  uint32_t *b = storage.data();
+  th_ = std::thread([this, b]() {
+    GRandMT g(seed_);
+    constexpr size_t BLOCK = 624 * 64;
+    for (size_t off = 0; off < cap_ && !stop_.load(std::memory_order_relaxed); off += BLOCK) {
+      const size_t len = std::min(BLOCK, cap_ - off);
+      g.fill_raw(b + off, len);
+      ready_.store(off + len, std::memory_order_release);
+    }
+  });
+}
+RawStream::~RawStream() {
+  stop_.store(true);
+  if (th_.joinable()) th_.join();
+}
+void RawStream::reduce(uint32_t n, uint32_t *out, size_t count) {
+  if (n == 0) { for (size_t i = 0; i < count; i++) out[i] = 0; return; }
+  uint32_t leftover = (0x80000000u % n) * 2u;
+  if (leftover >= n) leftover -= n;
+  const uint32_t maxvalue = (n <= 0x80000000u) ? 0xffffffffu - leftover : n - 1u;
+  const FastMod fm(n);
+  size_t src = 0, i = 0;
+  const uint32_t *b = buf_->data();
+  while (i < count) {
+    size_t avail = ready_.load(std::memory_order_acquire);
+    if (avail <= src) {
+      if (src >= cap_) {  // out of prepared words (cannot happen with the caller's slack): finish from a fresh stream
+        GRandMT g(seed_);
+        std::vector<uint32_t> skip(4096);
+        for (size_t done = 0; done < cap_; done += skip.size()) g.fill_raw(skip.data(), std::min(skip.size(), cap_ - done));
+        g.fill_int_range(n, out + i, count - i);
+        return;
+      }
+      continue;
+    }
+    for (; src < avail && i < count; src++) {
+      const uint32_t v = b[src];
+      if (v <= maxvalue) out[i++] = fm.mod(v);  // rejection is rare (< 2^-12 per draw for n <= 2^20)
+    }
+  }
+}
+
 static void shuffle_bands(std::vector<uint32_t> &p, GRandMT &prng) {
   const int last = (int)p.size() - 1;
   const int half = (int)(p.size() * 0.1);  // IMAGE_SYNTH_BAND_FRACTION

@@ -4,7 +4,9 @@
 // tests/test_host_prep.py compares them with the oracle.
 #pragma once
 #include <cstdint>
+#include <atomic>
 #include <functional>
+#include <thread>
 #include <vector>
 
 #include "../../include/resynthesizer.h"
@@ -23,11 +25,29 @@ class GRandMT {
   uint32_t next32();
   uint32_t int_range(uint32_t n);  // g_rand_int_range(0, n)
   void fill_int_range(uint32_t n, uint32_t *out, size_t count);  // `count` successive int_range(n) draws
+  void fill_raw(uint32_t *out, size_t count);                    // `count` successive next32() words
  private:
   void refill();
   uint32_t mt_[624];
   uint32_t out_[624];  // tempered outputs of the current block
   int mti_;
+};
+
+// The raw 32-bit words of a GRand stream do not depend on the range they are later reduced to.  RawStream starts producing
+// them on its own thread as soon as the seed is known (before the number of target points is); reduce() then turns the
+// first words into `count` g_rand_int_range(0, n) draws exactly as GRandMT::fill_int_range would (same rejections).
+class RawStream {
+ public:
+  RawStream(uint32_t seed, size_t max_words);
+  ~RawStream();
+  void reduce(uint32_t n, uint32_t *out, size_t count);
+ private:
+  std::vector<uint32_t> *buf_;
+  std::atomic<size_t> ready_{0};
+  std::atomic<bool> stop_{false};
+  size_t cap_;
+  uint32_t seed_;
+  std::thread th_;
 };
 
 // lib/matchWeighting.h:142-204.  Tables over the signed difference, index 256+d, like the reference.

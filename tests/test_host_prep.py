@@ -107,3 +107,15 @@ def test_format_indices(built_oracle, built_lib):
         assert L.prepareImageFormatIndicesFromFormatType(C.byref(a), fmt) == 0 and a.total_bpp == bpp
     assert L.prepareImageFormatIndicesFromFormatType(C.byref(a), 666) == abi.IMAGE_SYNTH_ERROR_INVALID_IMAGE_FORMAT
     assert [L.countPixelelsPerPixelForFormat(f) for f in (0, 1, 2, 3, 9)] == [3, 4, 1, 2, 0]
+
+
+@pytest.mark.parametrize("n,count", [(1, 10), (1000, 5000), (1 << 20, 300000), (3000000, 200000), (2863311531, 150000)])
+def test_raw_stream_draws_equal_direct_draws(built_lib, n, count):
+    """The engine starts producing raw PRNG words before it knows how many target points there are and reduces them to
+    the range afterwards: the draws must be those of g_rand_int_range(0, n) in sequence, rejections included."""
+    L = api.lib()
+    L.rs_host_draws.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int]
+    a = np.zeros(count, np.uint32); b = np.zeros(count, np.uint32)
+    L.rs_host_draws(1198472, n, count, a.ctypes.data, 0)
+    L.rs_host_draws(1198472, n, count, b.ctypes.data, 1)
+    assert (a == b).all() and int(a.max()) < n
