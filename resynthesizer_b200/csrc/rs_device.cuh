@@ -92,6 +92,8 @@ struct RsDev {              // kernel argument (by value)
   unsigned long long *prober[3];  // [cw*ch] each: stamps of epochs = 0, 1, 2 (mod 3), see above
   const uint2 *nb_lists;    // pass-0 patches gathered up front by k_gather_pass0: [nT][kmax-1]
   const uint8_t *nb_counts; // [nT] patch size of each pass-0 visit
+  const uint2 *nb_later;    // patches of the passes >= 1 (every target point has a value by then, so they are the same in
+  const uint8_t *nb_later_counts;  // all of them): [nT][kmax-1] entries {offset, meta word of the pixel}, and sizes
   RsCtrl *ctrl;
   volatile unsigned int *host_ticks;  // mapped pinned: [6] highest tick index started per pass (+1)
   const volatile int *host_cancel;    // mapped pinned

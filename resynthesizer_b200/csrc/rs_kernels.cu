@@ -208,6 +208,43 @@ __global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__re
   if (lane == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
 }
 
+// From pass 1 on every target point has a value, so the patch of a target is the same in all later passes: the nearest
+// pixels that are usable context or target points at all.  Gathered once (beside pass 0, on the side stream); the pass
+// kernels then read 8 bytes per neighbour in one contiguous piece instead of scanning offsets and gathering a meta
+// word for each.  Entries {offset, meta word}: the meta word (visit index or context) drives the version arithmetic.
+__global__ void __launch_bounds__(256) k_gather_later(const RsDev J, uint2 *__restrict__ lists, uint8_t *__restrict__ counts) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  const uint32_t stride = J.kmax - 1u;
+  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < J.nT; v += nwarps) {
+    const uint32_t tpos = __ldg(J.targets + v);
+    const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
+    uint2 *out = lists + (size_t)v * stride;
+    uint32_t count = 1;
+    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
+      const uint32_t j = base + lane;
+      uint32_t o = 0, m = RS_NEVER;
+      if (j < J.nOff) {
+        o = __ldg(J.offsets + j);
+        int x = px + rs_off_x(o), y = py + rs_off_y(o);
+        bool in = true;
+        if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+        else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+        if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+        else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+        if (in) m = __ldg(J.meta + (uint32_t)y * (uint32_t)J.tw + (uint32_t)x);
+      }
+      const bool ok = m != RS_NEVER;
+      const unsigned b = __ballot_sync(RS_FULL, ok);
+      const uint32_t slot = count + __popc(b & lt);
+      if (ok && slot < J.kmax) out[slot - 1u] = make_uint2(o, m);
+      count += __popc(b);
+    }
+    if (lane == 0) counts[v] = (uint8_t)min(count, J.kmax);
+  }
+}
+
 // The first visits of pass 0 see almost no valued pixels and scan a long way down the offset table (all of it
 // when there is no context).  A whole CTA scans for one such visit: 1024 table entries per step, compacted in
 // table order through a shared-memory prefix over the 16 warps.
@@ -408,6 +445,19 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
       S.off[k] = e.x;
       S.q[k] = e.y & ~RS_TARGET_FLAG;
       S.aux[k] = (e.y & RS_TARGET_FLAG) ? 0u : RS_CTX_VALUED;
+    }
+  } else if (pass != 0u && J.nb_later != nullptr) {
+    // gathered once for all later passes by k_gather_later: offset + meta word; the pixel index follows from the offset
+    count = J.nb_later_counts[v];
+    const uint2 *lst = J.nb_later + (size_t)v * (J.kmax - 1u);
+    for (uint32_t k = 1u + lane; k < count; k += 32) {
+      const uint2 e = __ldcs(lst + (k - 1u));  // streamed: read once per pass
+      int x = px + rs_off_x(e.x), y = py + rs_off_y(e.x);
+      if (x < 0) x += J.tw; else if (x >= J.tw) x -= J.tw;  // only offsets that wrap (tiling) or stay inside were listed
+      if (y < 0) y += J.th; else if (y >= J.th) y -= J.th;
+      S.off[k] = e.x;
+      S.q[k] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+      S.aux[k] = e.y;
     }
   } else {
     for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
@@ -1027,10 +1077,10 @@ struct DevBuf {
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: work that may run beside the main stream's
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evLater = nullptr;
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
-      sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, simg, smask, smask2,
+      sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, nb_later, nb_later_counts, simg, smask, smask2,
       ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
@@ -1077,7 +1127,7 @@ static void ws_free(Workspace *w) {
   cudaSetDevice(w->device);
   DevBuf *all[] = {&w->raw_t, &w->raw_c, &w->corpus, &w->W, &w->meta, &w->tmaps, &w->targets, &w->cpts, &w->offsets,
                    &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
-                   &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts,
+                   &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts, &w->nb_later, &w->nb_later_counts,
                    &w->simg, &w->smask, &w->smask2, &w->ord_keys_in, &w->ord_keys_out, &w->ord_vals_in, &w->ord_vals_out,
                    &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
@@ -1095,6 +1145,7 @@ static void ws_free(Workspace *w) {
   if (w->evDone) cudaEventDestroy(w->evDone);
   if (w->evFork) cudaEventDestroy(w->evFork);
   if (w->evJoin) cudaEventDestroy(w->evJoin);
+  if (w->evLater) cudaEventDestroy(w->evLater);
   if (w->stream2) cudaStreamDestroy(w->stream2);
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;
@@ -1144,6 +1195,7 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking));
   WCHK(cudaEventCreateWithFlags(&w->evFork, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evJoin, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evLater, cudaEventDisableTiming));
   WCHK(cudaEventCreate(&w->ev0));
   WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
@@ -1256,6 +1308,7 @@ struct RsJob {
   const uint32_t *targets_dev = nullptr;  // the visit order on the device (cache entry or the workspace's buffer)
   bool want_sources = false;
   float ms_passes = 0.f;
+  bool later_lists = false;       // the patches of the passes >= 1 were gathered up front (k_gather_later)
   bool simple = false;            // staged by rs_job_stage_simple: results go back in the caller's image layout
   uint32_t launches = 0;          // pass-kernel launches of the last run
   uint32_t pass_launches[6] = {0, 0, 0, 0, 0, 0};
@@ -1587,6 +1640,8 @@ static int set_targets(RsJob *j, uint32_t n_targets, uint32_t y_min, uint32_t y_
   if (kmax > RS_MAX_NB) kmax = RS_MAX_NB;
   int rc = 0;
   if ((rc = ws_ensure(w->nb_lists, (size_t)n_targets * (kmax - 1) * sizeof(uint2))) || (rc = ws_ensure(w->nb_counts, n_targets)) ||
+      ((n_targets >= (1u << 21) || getenv("RS_LATER_LISTS_MIN")) &&
+       ((rc = ws_ensure(w->nb_later, (size_t)n_targets * (kmax - 1) * sizeof(uint2))) || (rc = ws_ensure(w->nb_later_counts, n_targets)))) ||
       (rc = ws_ensure(w->sources, (size_t)n_targets * 4)))
     return rc;
   j->out_bytes = (size_t)(y_max - y_min + 1) * d.tw * d.bpp + (size_t)n_targets * 4 + 512;
@@ -1881,6 +1936,8 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.prober[2] = (unsigned long long *)w->prober2.p;
   { const uint32_t e = (j->nT + 31u) / 32u; D.epoch_len = e < 64u ? 64u : e; }
   D.nb_lists = (const uint2 *)w->nb_lists.p; D.nb_counts = (const uint8_t *)w->nb_counts.p;
+  D.nb_later = j->later_lists ? (const uint2 *)w->nb_later.p : nullptr;
+  D.nb_later_counts = (const uint8_t *)w->nb_later_counts.p;
   D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
   D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch; D.cn = (uint32_t)d.cw * (uint32_t)d.ch;
   D.nT = j->nT; D.nOff = j->nOff;
@@ -1980,12 +2037,22 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     RS_CHECK(cudaStreamWaitEvent(w->stream2, w->evFork, 0));
     k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, &claims[1].v);
     RS_CHECK(cudaEventRecord(w->evJoin, w->stream2));
+    // (pays off when the meta words of the scan no longer sit in L1/L2 next to everything else: cfg4 98 -> 94 ms, cfg3
+    //  59.3 -> 58.2; a 1 Mi-target job loses 3 % to the extra kernel and the streamed lists, so small jobs keep scanning)
+    uint32_t later_min = 1u << 21;
+    if (const char *e = getenv("RS_LATER_LISTS_MIN")) later_min = (uint32_t)strtoul(e, nullptr, 10);  // tests, sweeps
+    j->later_lists = j->d.n_passes > 1 && j->nT >= later_min;
+    if (j->later_lists) {  // beside pass 0, needed from pass 1 on
+      k_gather_later<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_later.p, (uint8_t *)w->nb_later_counts.p);
+      RS_CHECK(cudaEventRecord(w->evLater, w->stream2));
+    }
     k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[0].v);
     RS_CHECK(cudaStreamWaitEvent(s, w->evJoin, 0));
   }
   RS_CHECK(cudaEventRecord(w->evG, s));
   uint32_t slot = 0;
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
+    if (p == 1 && j->later_lists) RS_CHECK(cudaStreamWaitEvent(s, w->evLater, 0));
     RsDev D = make_dev(j, p);
     Segment seg[4];
     const int nseg = plan_segments(j, p, seg);
@@ -2106,7 +2173,7 @@ extern "C" int rs_job_counters(RsJob *j, RsJobCounters *out) {
   out->n_corpus = c.n_corpus;
   out->ms_passes = j->ms_passes;
   out->ms_synth = j->ms_synth;
-  out->kernel_launches = j->upload_launches + 2u + j->launches + 1u;  // + pass-0 gather x2, passes, write-back
+  out->kernel_launches = j->upload_launches + 2u + (j->later_lists ? 1u : 0u) + j->launches + 1u;  // + gathers, passes, write-back
   for (uint32_t p = 0; p < c.passes_run && p < 6; p++) out->synth_launches_run += j->pass_launches[p];
   for (uint32_t p = 0; p < c.passes_run && p < 6; p++)
     out->ms_pass[p] = c.pass_end_ns[p] > c.tick_ns[p][0] ? (float)((c.pass_end_ns[p] - c.tick_ns[p][0]) * 1e-6) : 0.f;

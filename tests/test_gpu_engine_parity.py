@@ -140,3 +140,16 @@ def test_larger_job_is_deterministic_and_exact(built_oracle, built_lib):
 def test_render_texture_bench_shape_small(built_oracle, built_lib):
     """cfg2's shape at 1/8 scale: 128x128 target from a 64x64 corpus, ctx 0, 9/200 (dependency-heavy pass 0)."""
     _engine_case(128, 128, 64, 64, 3, 0, False, abi.make_params(0, 0, 0, 0.5, 0.117, 9, 200), True)
+
+
+@pytest.mark.parametrize("case", ["tiled_maps", "heal_alpha", "texture"])
+def test_patches_of_later_passes_gathered_up_front(built_oracle, built_lib, case, monkeypatch):
+    """Jobs of 2 Mi+ target points gather the patches of the passes >= 1 once (k_gather_later) instead of scanning the
+    offsets in every pass; here the same path is forced on small jobs and compared with the oracle bit for bit."""
+    monkeypatch.setenv("RS_LATER_LISTS_MIN", "1")
+    if case == "tiled_maps":
+        _engine_case(48, 40, 40, 36, 3, 3, False, abi.make_params(1, 1, 1, 0.5, 0.117, 9, 60), True)
+    elif case == "heal_alpha":
+        _engine_case(72, 60, 72, 60, 3, 0, True, abi.make_params(0, 0, 1, 0.5, 0.117, 30, 80), False)
+    else:
+        _engine_case(64, 48, 32, 32, 3, 0, False, abi.make_params(0, 1, 0, 0.0, 0.117, 16, 50), True)
