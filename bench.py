@@ -172,7 +172,8 @@ def cpu_reference_run(wname, scale, steps, warmup, procs, libname="ref_rand_1t")
 
 
 def reference_sample_scale(wname):
-    return {"cfg2": 0.25, "cfg1": 1.0, "cfg5": 0.25, "cfg3": 0.0625, "cfg4": 0.125}.get(wname, 1.0)
+    # bounded samples of the same workload: 10-30 s of CPU work in all (unthreaded + 8-thread build, or one job per core)
+    return {"cfg2": 0.5, "cfg1": 1.0, "cfg5": 0.25, "cfg3": 0.0625, "cfg4": 0.125}.get(wname, 1.0)
 
 
 def run_reference(a):
@@ -386,7 +387,7 @@ def run_ours(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
