@@ -37,8 +37,19 @@ UNIT = "px/s"
 
 
 # ------------------------------------------------------------------------------------------ workloads
+PROBES_OVERRIDE = 0
+
+
 def workload(name, seed_shift=0, scale=1.0):
     """Returns dict(params, fi_args, target pixmap builder inputs, n_color...)."""
+    w = _workload(name, seed_shift, scale)
+    if PROBES_OVERRIDE:
+        w["params"].maxProbeCount = PROBES_OVERRIDE
+        w["name"] = w["name"].replace("probes 200", "probes %d" % PROBES_OVERRIDE)
+    return w
+
+
+def _workload(name, seed_shift=0, scale=1.0):
     if name == "cfg2":      # render-texture 1024^2 from 256^2 corpus, ctx 0, 9/200
         t = int(1024 * scale)
         cor = G(256, 256, 3, 1 + seed_shift)
@@ -392,9 +403,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probes", type=int, default=0, help="override maxProbeCount (the cfg5 sweep of BASELINE.json: 50..1000)")
     ap.add_argument("--batch", type=int, default=1, help="jobs per step (rs_engine_batch); value is then wall-clock based")
     ap.add_argument("--slots", type=int, default=8, help="jobs in flight per GPU in batch mode")
     a = ap.parse_args()
+    global PROBES_OVERRIDE
+    PROBES_OVERRIDE = a.probes
     if a.impl == "reference":
         run_reference(a)
     else:
