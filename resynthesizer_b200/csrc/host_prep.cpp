@@ -18,7 +18,7 @@ GRandMT::GRandMT(uint32_t seed) {
 
 // Regenerates the 624-word state.  Three dependency-free segments (each reads only words that are already final),
 // so the compiler can vectorise them; then the whole block is tempered in place into out_[].
-void GRandMT::refill() {
+__attribute__((target_clones("avx2", "default"))) void GRandMT::refill() {
   uint32_t *mt = mt_;
   auto twist = [](uint32_t a, uint32_t b, uint32_t c) {
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
