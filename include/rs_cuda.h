@@ -132,6 +132,13 @@ void rs_cuda_order_cache(int enabled);
  * compacts the target points, and finds what ends at each position by walking the chain of swaps backwards.  Replaces
  * rs_job_set_order on a cache miss; ordered_out (or NULL) receives the order. */
 int rs_job_shuffle_order(RsJob *job, const uint32_t *draws, const RsOrderKey *key, uint32_t *ordered_out);
+/* The same from the RAW 32-bit words of the PRNG stream: rs_job_raw_buffer returns a pinned buffer for n_words words
+ * that the caller's producer fills (it can start before the number of target points is known);
+ * rs_job_shuffle_order_raw sends the first n_raw of them up and the device applies g_rand_int_range's rejection rule
+ * and modulo itself.  n_raw must leave room for the rejections (n / 2^32 per word); if fewer than digest.n words
+ * survive, the job is flagged faulty and rs_job_run returns an error. */
+uint32_t *rs_job_raw_buffer(RsJob *job, size_t n_words);
+int rs_job_shuffle_order_raw(RsJob *job, uint32_t n_raw, const RsOrderKey *key, uint32_t *ordered_out);
 /* Stable ascending radix sort of n (key, value) pairs on the low key_bits bits of the keys, host buffers in place, on a
  * side stream of the job (it runs beside the staging).  The sort step of the target orderings 2-8. */
 int rs_job_sort_pairs(RsJob *job, uint32_t *keys, uint32_t *vals, uint32_t n, int key_bits);

@@ -235,14 +235,18 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   // the target selection back: number of target points, their rows, and the key of the visit-order cache.
   // The shuffling orders need one PRNG draw per target point.  The raw words of the stream depend on the seed only, so a
   // producer thread starts making them now, while the images are staged and counted (rejection rate < n / 2^32).
-  const size_t npx = (size_t)tw * th;
-  std::unique_ptr<rs::RawStream> raw;
-  if (prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26))
-    raw.reset(new rs::RawStream(t_seed, npx + npx / 32 + 65536));
   RsJob *job = nullptr;
   dbg("before create");
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
   dbg("after create");
+  const size_t npx = (size_t)tw * th, raw_cap = npx + npx / 32 + 65536;
+  std::unique_ptr<rs::RawStream> raw;
+  bool raw_pinned = false;
+  if (prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26)) {
+    uint32_t *pinned = rs_job_raw_buffer(job, raw_cap);  // the producer writes where the H2D copy will read
+    raw_pinned = pinned != nullptr;
+    raw.reset(new rs::RawStream(t_seed, raw_cap, pinned));
+  }
   RsTargetDigest dg;
   int rc = src.simple()
                ? rs_job_stage_simple(job, src.img->data, src.img->rowBytes, src.mask->data, src.mask->rowBytes,
@@ -270,16 +274,25 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
       // miss, shuffling order: the host only makes the draws (the reference's PRNG stream); the device compacts the
       // target points and resolves the chain of swaps (rs_job_shuffle_order)
       static thread_local std::vector<uint32_t> draws;
-      draws.resize(n);
-      if (raw) {
+      if (!(raw && raw_pinned)) draws.resize(n);
+      if (raw && raw_pinned) {
+        // raw words straight from the producer's pinned buffer; rejection rule and modulo applied on the device
+        const size_t n_raw = std::min(raw_cap, (size_t)n + n / 32 + 65536);
+        raw->wait_ready(n_raw);
+        if (t_keep_result) targets.resize(n);
+        rc = rs_job_shuffle_order_raw(job, (uint32_t)n_raw, t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
+        hit = 2;
+      } else if (raw) {
         raw->reduce(n, draws.data(), n);
       } else {
         rs::GRandMT prng(t_seed);
         prng.fill_int_range(n, draws.data(), n);
       }
-      if (t_keep_result) targets.resize(n);
-      rc = rs_job_shuffle_order(job, draws.data(), t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
-      hit = 2;
+      if (hit != 2) {
+        if (t_keep_result) targets.resize(n);
+        rc = rs_job_shuffle_order(job, draws.data(), t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
+        hit = 2;
+      }
     }
     if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
       const uint8_t *mask0 = src.simple() ? src.mask->data : src.tpix;

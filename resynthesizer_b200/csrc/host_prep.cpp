@@ -255,11 +255,15 @@ void GRandMT::fill_raw(uint32_t *out, size_t count) {
   }
 }
 
-RawStream::RawStream(uint32_t seed, size_t max_words) : cap_(max_words), seed_(seed) {
-  static thread_local std::vector<uint32_t> storage;  // reused by the calling thread's next job
-  storage.resize(cap_);
-  buf_ = &storage;
-  uint32_t *b = storage.data();
+RawStream::RawStream(uint32_t seed, size_t max_words, uint32_t *external) : cap_(max_words), seed_(seed) {
+  if (external) {
+    buf_ = external;
+  } else {
+    static thread_local std::vector<uint32_t> storage;  // reused by the calling thread's next job
+    storage.resize(cap_);
+    buf_ = storage.data();
+  }
+  uint32_t *b = buf_;
   th_ = std::thread([this, b]() {
     GRandMT g(seed_);
     constexpr size_t BLOCK = 624 * 64;
@@ -274,6 +278,10 @@ RawStream::~RawStream() {
   stop_.store(true);
   if (th_.joinable()) th_.join();
 }
+void RawStream::wait_ready(size_t words) {
+  const size_t want = std::min(words, cap_);
+  while (ready_.load(std::memory_order_acquire) < want) { /* spin: the producer has been running since the job began */ }
+}
 void RawStream::reduce(uint32_t n, uint32_t *out, size_t count) {
   if (n == 0) { for (size_t i = 0; i < count; i++) out[i] = 0; return; }
   uint32_t leftover = (0x80000000u % n) * 2u;
@@ -281,7 +289,7 @@ void RawStream::reduce(uint32_t n, uint32_t *out, size_t count) {
   const uint32_t maxvalue = (n <= 0x80000000u) ? 0xffffffffu - leftover : n - 1u;
   const FastMod fm(n);
   size_t src = 0, i = 0;
-  const uint32_t *b = buf_->data();
+  const uint32_t *b = buf_;
   while (i < count) {
     size_t avail = ready_.load(std::memory_order_acquire);
     if (avail <= src) {

@@ -38,11 +38,13 @@ class GRandMT {
 // first words into `count` g_rand_int_range(0, n) draws exactly as GRandMT::fill_int_range would (same rejections).
 class RawStream {
  public:
-  RawStream(uint32_t seed, size_t max_words);
+  // external: caller-owned buffer of max_words words (e.g. pinned memory), else an internal per-thread buffer
+  RawStream(uint32_t seed, size_t max_words, uint32_t *external = nullptr);
   ~RawStream();
   void reduce(uint32_t n, uint32_t *out, size_t count);
+  void wait_ready(size_t words);  // until the first min(words, max_words) words are in the buffer
  private:
-  std::vector<uint32_t> *buf_;
+  uint32_t *buf_;
   std::atomic<size_t> ready_{0};
   std::atomic<bool> stop_{false};
   size_t cap_;

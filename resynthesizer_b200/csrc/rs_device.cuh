@@ -66,6 +66,7 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   unsigned long long dg_h1, dg_h2;        // digest of the target selection (k_target_digest), layout = RsTargetDigest
   unsigned int dg_n, dg_ymin, dg_ymax, dg_pad;
   unsigned int dg_sel;      // scratch counter of the target-point compaction (rs_job_shuffle_order)
+  unsigned int dg_acc;      // number of raw PRNG words the rejection rule accepted (rs_job_shuffle_order_raw)
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;
   unsigned long long pass_visits[6], sum_best[6];
   unsigned long long pass_end_ns[6];          // globaltimer when the last CTA of a pass left

@@ -1084,13 +1084,15 @@ struct Workspace {
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, nb_later, nb_later_counts, simg, smask, smask2,
-      ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags;
+      ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags, ord_raw;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
   void *pin_order = nullptr;  // pinned staging of a visit order
   size_t pin_order_cap = 0;
   void *pin_sort = nullptr;   // pinned staging of rs_job_sort_pairs
   size_t pin_sort_cap = 0;
+  void *pin_raw = nullptr;    // pinned buffer the host's PRNG producer fills (rs_job_raw_buffer)
+  size_t pin_raw_cap = 0;
   RsTargetDigest *h_digest = nullptr;  // pinned
   cudaEvent_t evDigest = nullptr;
   unsigned int *h_ticks = nullptr;
@@ -1132,11 +1134,12 @@ static void ws_free(Workspace *w) {
                    &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
                    &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts, &w->nb_later, &w->nb_later_counts,
                    &w->simg, &w->smask, &w->smask2, &w->ord_keys_in, &w->ord_keys_out, &w->ord_vals_in, &w->ord_vals_out,
-                   &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags};
+                   &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags, &w->ord_raw};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
   if (w->pin_order) cudaFreeHost(w->pin_order);
   if (w->pin_sort) cudaFreeHost(w->pin_sort);
+  if (w->pin_raw) cudaFreeHost(w->pin_raw);
   if (w->h_digest) cudaFreeHost(w->h_digest);
   if (w->evDigest) cudaEventDestroy(w->evDigest);
   if (w->h_ticks) cudaFreeHost(w->h_ticks);
@@ -1819,7 +1822,44 @@ extern "C" int rs_job_sort_pairs(RsJob *j, uint32_t *keys, uint32_t *vals, uint3
 // Visit order of the shuffling modes (matchContextType 0, 1) built on the device from the host's draws j_i (the
 // reference's PRNG stream, n of them): target points compacted from the staged image, pairs sorted, chains traced.
 // With a key the order becomes a cache entry.  ordered_out (optional): the order back on the host.
+// Range reduction of the raw PRNG words on the device: g_rand_int_range(0, n) accepts a word v iff v <= maxvalue (the
+// rejection rule of GLib's g_rand_int_range) and returns v % n; the accepted words keep their order.
+struct RsAccept {
+  uint32_t maxvalue;
+  __host__ __device__ bool operator()(const uint32_t &v) const { return v <= maxvalue; }
+};
+__global__ void k_reduce_draws(uint32_t *__restrict__ draws, const unsigned int *__restrict__ n_accepted, uint32_t n, RsCtrl *ctrl) {
+  if (*n_accepted < n) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&ctrl->fault, 1u); return; }  // too few words sent: fail loudly
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) draws[i] %= n;
+}
+
+static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *raw_pinned, uint32_t n_raw, const RsOrderKey *key,
+                              uint32_t *ordered_out);
 extern "C" int rs_job_shuffle_order(RsJob *j, const uint32_t *draws, const RsOrderKey *key, uint32_t *ordered_out) {
+  return shuffle_order_impl(j, draws, nullptr, 0, key, ordered_out);
+}
+// The same from RAW words of the PRNG stream (the first n_raw of them, in the pinned buffer rs_job_raw_buffer returned):
+// the device applies the rejection rule and the modulo itself.  n_raw must leave room for the rejections (probability
+// n / 2^32 per word); if fewer than n words survive the job is flagged faulty and rs_job_run returns an error.
+extern "C" int rs_job_shuffle_order_raw(RsJob *j, uint32_t n_raw, const RsOrderKey *key, uint32_t *ordered_out) {
+  if (!j->ws->pin_raw || (size_t)n_raw * 4 > j->ws->pin_raw_cap) { g_err = "rs_job_shuffle_order_raw: no raw buffer of that size"; return 100; }
+  return shuffle_order_impl(j, nullptr, (const uint32_t *)j->ws->pin_raw, n_raw, key, ordered_out);
+}
+// Pinned buffer for n_words raw PRNG words (the caller's producer thread fills it while the images are staged).
+extern "C" uint32_t *rs_job_raw_buffer(RsJob *j, size_t n_words) {
+  Workspace *w = j->ws;
+  if (cudaSetDevice(w->device) != cudaSuccess) return nullptr;
+  if (n_words * 4 > w->pin_raw_cap) {
+    if (w->pin_raw) cudaFreeHost(w->pin_raw);
+    w->pin_raw = nullptr; w->pin_raw_cap = 0;
+    if (cudaHostAlloc(&w->pin_raw, n_words * 4 + 4096, cudaHostAllocDefault) != cudaSuccess) { w->pin_raw = nullptr; return nullptr; }
+    w->pin_raw_cap = n_words * 4 + 4096;
+  }
+  return (uint32_t *)w->pin_raw;
+}
+static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *raw_pinned, uint32_t n_raw, const RsOrderKey *key,
+                              uint32_t *ordered_out) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   const RsJobDesc &d = j->d;
@@ -1827,6 +1867,8 @@ extern "C" int rs_job_shuffle_order(RsJob *j, const uint32_t *draws, const RsOrd
   const size_t bytes = (size_t)n * 4, tn = (size_t)d.tw * d.th;
   cudaStream_t s = w->stream;
   int rc = 0;
+  if (raw_pinned && n_raw < n) { g_err = "rs_job_shuffle_order_raw: fewer raw words than target points"; return 100; }
+  if (raw_pinned && (rc = ws_ensure(w->ord_raw, (size_t)n_raw * 4))) return rc;
   if ((rc = ws_ensure(w->ord_keys_in, bytes)) || (rc = ws_ensure(w->ord_keys_out, bytes)) || (rc = ws_ensure(w->ord_vals_in, bytes)) ||
       (rc = ws_ensure(w->ord_vals_out, bytes)) || (rc = ws_ensure(w->ord_first, bytes)) || (rc = ws_ensure(w->ord_points, bytes + 4)) ||
       (rc = ws_ensure(w->ord_flags, tn)))
@@ -1852,10 +1894,25 @@ extern "C" int rs_job_shuffle_order(RsJob *j, const uint32_t *draws, const RsOrd
     dst = (uint32_t *)w->targets.p;
   }
   j->targets_dev = dst;
-  // the draws go up while the device compacts the target points
-  memcpy(w->pin_order, draws, bytes);
-  RS_CHECK(cudaMemcpyAsync(w->ord_keys_in.p, w->pin_order, bytes, cudaMemcpyHostToDevice, s));
   const int T = 256;
+  size_t tmp3 = 0;
+  if (raw_pinned) {  // raw words up (already pinned), accepted ones compacted into the draw array, then reduced mod n
+    uint32_t leftover = (0x80000000u % n) * 2u;
+    if (leftover >= n) leftover -= n;
+    const RsAccept acc{(n <= 0x80000000u) ? 0xffffffffu - leftover : n - 1u};
+    // (the draw array takes up to n_raw words here; only the first n are used afterwards)
+    if ((rc = ws_ensure(w->ord_keys_in, (size_t)n_raw * 4))) return rc;
+    RS_CHECK(cudaMemcpyAsync(w->ord_raw.p, raw_pinned, (size_t)n_raw * 4, cudaMemcpyHostToDevice, s));
+    unsigned int *d_acc = &((RsCtrl *)w->ctrl.p)->dg_acc;
+    RS_CHECK(cub::DeviceSelect::If(nullptr, tmp3, (const uint32_t *)w->ord_raw.p, (uint32_t *)w->ord_keys_in.p, d_acc, (int)n_raw, acc, s));
+    if ((rc = ws_ensure(w->ord_tmp, tmp3))) return rc;
+    RS_CHECK(cub::DeviceSelect::If(w->ord_tmp.p, tmp3, (const uint32_t *)w->ord_raw.p, (uint32_t *)w->ord_keys_in.p, d_acc, (int)n_raw, acc, s));
+    k_reduce_draws<<<(n + T - 1) / T, T, 0, s>>>((uint32_t *)w->ord_keys_in.p, d_acc, n, (RsCtrl *)w->ctrl.p);
+    j->upload_launches += 3u;
+  } else {  // the draws go up while the device compacts the target points
+    memcpy(w->pin_order, draws, bytes);
+    RS_CHECK(cudaMemcpyAsync(w->ord_keys_in.p, w->pin_order, bytes, cudaMemcpyHostToDevice, s));
+  }
   k_target_flags<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_t.p, (uint32_t)tn, d.bpp, (uint8_t *)w->ord_flags.p);
   thrust::counting_iterator<uint32_t> idx(0);
   unsigned int *d_cnt = &((RsCtrl *)w->ctrl.p)->dg_sel;
