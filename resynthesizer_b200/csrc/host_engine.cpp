@@ -242,7 +242,8 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   const size_t npx = (size_t)tw * th, raw_cap = npx + npx / 32 + 65536;
   std::unique_ptr<rs::RawStream> raw;
   bool raw_pinned = false;
-  if (prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26)) {
+  if (prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26) &&
+      !std::getenv("RS_NO_RAW_STREAM")) {  // (the switch lets the tests take the host-reduced path below)
     uint32_t *pinned = rs_job_raw_buffer(job, raw_cap);  // the producer writes where the H2D copy will read
     raw_pinned = pinned != nullptr;
     raw.reset(new rs::RawStream(t_seed, raw_cap, pinned));

@@ -1739,9 +1739,19 @@ extern "C" int rs_job_stage_simple(RsJob *j, const uint8_t *img, size_t img_row_
 extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_bytes) {
   const Workspace *w = j->ws;
   if (!j->simple) { g_err = "rs_job_download_simple: the job was not staged by rs_job_stage_simple"; return 100; }
-  const size_t row_len = (size_t)j->d.tw * (j->d.bpp - 1);
-  for (uint32_t y = j->y_min; y <= j->y_max; y++)
-    memcpy(img + (size_t)y * img_row_bytes, (const uint8_t *)w->pin + (size_t)(y - j->y_min) * row_len, row_len);
+  const size_t row_len = (size_t)j->d.tw * (j->d.bpp - 1), rows = j->y_max - j->y_min + 1;
+  const uint8_t *src = (const uint8_t *)w->pin;
+  const uint32_t y0 = j->y_min;
+  unsigned hw = std::thread::hardware_concurrency();
+  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+  auto band = [=](size_t t) {
+    const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
+    for (size_t r = b; r < e; r++) memcpy(img + (size_t)(y0 + r) * img_row_bytes, src + r * row_len, row_len);
+  };
+  std::vector<std::thread> th;
+  for (size_t t = 1; t < nt; t++) th.emplace_back(band, t);
+  band(0);
+  for (auto &x : th) x.join();
   return 0;
 }
 extern "C" int rs_job_digest(RsJob *j, RsTargetDigest *out) {
@@ -2213,7 +2223,18 @@ extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sour
   const size_t row_bytes = (size_t)j->d.tw * j->d.bpp, rows_bytes = (size_t)(j->y_max - j->y_min + 1) * row_bytes;
   if (target_raw_out) {
     if (j->simple) { g_err = "rs_job_download: a job staged by rs_job_stage_simple returns its rows through rs_job_download_simple"; return 100; }
-    memcpy(target_raw_out + (size_t)j->y_min * row_bytes, w->pin, rows_bytes);
+    uint8_t *dst = target_raw_out + (size_t)j->y_min * row_bytes;
+    const uint8_t *src = (const uint8_t *)w->pin;
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+    const size_t per = (rows_bytes + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; t++) {
+      const size_t b = std::min(rows_bytes, t * per), e = std::min(rows_bytes, (t + 1) * per);
+      if (e > b) th.emplace_back([=]() { memcpy(dst + b, src + b, e - b); });
+    }
+    memcpy(dst, src, std::min(rows_bytes, per));
+    for (auto &x : th) x.join();
   }
   if (sources_out) {
     if (!j->want_sources) { g_err = "rs_job_download: sources were not requested before rs_job_run"; return 100; }

@@ -139,3 +139,30 @@ def test_device_shuffle_equals_host_shuffle(mode, hole):
         api.set_device_shuffle_min(1 << 15)
         api.keep_result(False)
         api.order_cache(True)
+
+
+@pytest.mark.parametrize("raw", [True, False])
+def test_device_shuffle_large(raw, monkeypatch):
+    """200 k target points: the device-resolved shuffle (from raw PRNG words reduced on the device, or from draws reduced
+    on the host) orders them exactly as the host's swap loop does."""
+    if not raw:
+        monkeypatch.setenv("RS_NO_RAW_STREAM", "1")
+    api.order_cache(False)
+    api.keep_result(True)
+    try:
+        img = G(640, 512, 3, 77)
+        m = np.zeros((512, 640), np.uint8); m[40:440, 60:560] = 255
+        p = abi.make_params(0, 0, 1, 0.5, 0.117, 9, 20)
+        tp = np.ascontiguousarray(np.concatenate([m[:, :, None], img], axis=2))
+        cp = np.ascontiguousarray(np.concatenate([(255 - m)[:, :, None], img], axis=2))
+        api.set_device_shuffle_min(1 << 30)
+        a, sa = _run(p, tp, cp)
+        ta, srca = api.last_result()
+        api.set_device_shuffle_min(1 << 15)
+        b, sb = _run(p, tp, cp)
+        tb, srcb = api.last_result()
+        assert len(ta) == 200000 and (ta == tb).all() and (srca == srcb).all() and (a == b).all()
+    finally:
+        api.set_device_shuffle_min(1 << 15)
+        api.keep_result(False)
+        api.order_cache(True)
