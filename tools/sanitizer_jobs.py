@@ -12,3 +12,16 @@ fi = api.format_indices(3,3,False,False,True); tp,cp = bench.pixmaps(w); assert 
 w = bench.workload("cfg2", 0, 0.0625)
 fi = api.format_indices(3,0,False,False,False); tp,cp = bench.pixmaps(w); assert api.engine(w["params"], fi, tp, cp) == 0
 print("ok", api.last_stats()["visits"])
+# the device-side ordering paths and the later-pass patch lists, forced on small jobs
+os.environ["RS_LATER_LISTS_MIN"] = "1"
+api.order_cache(False)
+api.set_device_shuffle_min(1); api.set_device_sort_min(1)
+for mode in (1, 2, 5):
+    out = img.copy(); p = abi.make_params(0, 0, mode, 0.5, 0.117, 16, 60)
+    assert api.image_synth(out, m, abi.T_RGB, p) == 0
+os.environ["RS_NO_RAW_STREAM"] = "1"
+out = img.copy(); assert api.image_synth(out, m, abi.T_RGB, abi.make_params(0, 0, 1, 0.5, 0.117, 16, 60)) == 0
+api.order_cache(True)
+out = img.copy(); assert api.image_synth(out, m, abi.T_RGB, None) == 0
+out = img.copy(); assert api.image_synth(out, m, abi.T_RGB, None) == 0 and api.last_stats()["order_cache_hit"] == 1
+print("ordering paths ok")
