@@ -252,6 +252,9 @@ __global__ void __launch_bounds__(256) k_gather_later(const RsDev J, uint2 *__re
 // when there is no context).  A whole CTA scans for one such visit: 1024 table entries per step, compacted in
 // table order through a shared-memory prefix over the 16 warps.
 #define RS_COOP_THREADS 512
+#ifndef RS_COOP_U
+#define RS_COOP_U 4       // table entries per thread and step (2, 4 and 8 are within 1 % of each other on B200)
+#endif
 __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsDev J, uint2 *__restrict__ lists,
                                                                      uint8_t *__restrict__ counts, uint32_t v_end,
                                                                      unsigned int *__restrict__ claim) {
@@ -270,11 +273,13 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
     const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
     uint2 *out = lists + (size_t)v * stride;
     uint32_t count = 1;  // CTA-uniform
-    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 2 * RS_COOP_THREADS) {
-      uint32_t o[2], q[2], m[2];
+    // One step = RS_COOP_U entries per thread, all of their loads in flight together: the first visits scan the whole
+    // table and a step's duration is two dependent round trips plus a barrier, however many entries it covers.
+    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += RS_COOP_U * RS_COOP_THREADS) {
+      uint32_t o[RS_COOP_U], q[RS_COOP_U], m[RS_COOP_U];
 #pragma unroll
-      for (int u = 0; u < 2; u++) {
-        const uint32_t j = base + warp * 64u + 32u * u + lane;
+      for (int u = 0; u < RS_COOP_U; u++) {
+        const uint32_t j = base + warp * (32u * RS_COOP_U) + 32u * u + lane;
         o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
         if (j < J.nOff) {
           o[u] = __ldg(J.offsets + j);
@@ -290,10 +295,15 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
           }
         }
       }
-      const bool ok0 = (m[0] == RS_CTX_VALUED) || (m[0] < v), ok1 = (m[1] == RS_CTX_VALUED) || (m[1] < v);
-      const unsigned b0 = __ballot_sync(RS_FULL, ok0), b1 = __ballot_sync(RS_FULL, ok1);
-      const int buf = (int)((base / (2 * RS_COOP_THREADS)) & 1u);
-      if (lane == 0) s_cnt[buf][warp] = __popc(b0) + __popc(b1);
+      unsigned bal[RS_COOP_U];
+      uint32_t mine = 0;
+#pragma unroll
+      for (int u = 0; u < RS_COOP_U; u++) {
+        bal[u] = __ballot_sync(RS_FULL, (m[u] == RS_CTX_VALUED) || (m[u] < v));
+        mine += __popc(bal[u]);
+      }
+      const int buf = (int)((base / (RS_COOP_U * RS_COOP_THREADS)) & 1u);
+      if (lane == 0) s_cnt[buf][warp] = mine;
       __syncthreads();
       uint32_t before = 0, total = 0;
 #pragma unroll
@@ -302,11 +312,16 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
         before += (w2 < (int)warp) ? c : 0u;
         total += c;
       }
-      const uint32_t slot0 = count + before + __popc(b0 & lt), slot1 = count + before + __popc(b0) + __popc(b1 & lt);
-      if (ok0 && slot0 < J.kmax) out[slot0 - 1u] = make_uint2(o[0], q[0] | (m[0] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
-      if (ok1 && slot1 < J.kmax) out[slot1 - 1u] = make_uint2(o[1], q[1] | (m[1] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+      uint32_t slot = count + before;  // table order within the step: warp, then u, then lane
+#pragma unroll
+      for (int u = 0; u < RS_COOP_U; u++) {
+        const bool ok = (bal[u] >> lane) & 1u;
+        const uint32_t sl = slot + __popc(bal[u] & lt);
+        if (ok && sl < J.kmax) out[sl - 1u] = make_uint2(o[u], q[u] | (m[u] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+        slot += __popc(bal[u]);
+      }
       count += total;
-      scans += (threadIdx.x == 0) ? 2ull * RS_COOP_THREADS : 0ull;
+      scans += (threadIdx.x == 0) ? (unsigned long long)RS_COOP_U * RS_COOP_THREADS : 0ull;
     }
     if (threadIdx.x == 0) counts[v] = (uint8_t)min(count, J.kmax);
     __syncthreads();  // s_v is rewritten by the next claim
