@@ -878,6 +878,7 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
 struct TeamShared {
   unsigned long long best;
   uint32_t hsum[RS_MAX_NB];
+  uint32_t hcnt[RS_MAX_NB];  // chunks of each heuristic candidate added so far
   uint32_t v, K, nHeur, alive;
   uint32_t win_pt, win_col;  // corpus point and colour of the winning probe, written by the lane that evaluated it
 };
@@ -894,7 +895,7 @@ __device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
 //   ---------------------------------------------------------------- barrier B
 //   heuristic CANDIDATES                        table lookups of the first chunk -> partial sum
 //   ---------------------------------------------------------------- barrier C
-//   all warps: (heuristic candidate, chunk) pairs                     -> barrier D -> warp 0: best heuristic -> E
+//   all warps: (heuristic candidate, chunk) pairs; a candidate's last chunk enters it in the shared best -> barrier D
 //   all warps: probes continue from their second chunk, early-out against the shared best; rest of the probes
 //   ---------------------------------------------------------------- barrier F
 //   the lane that owns the winning probe publishes its point + colour -> barrier G -> warp 0 commits
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       uint32_t Kc = 0;
       if (ok) Kc = rs_visit_geometry<MAPS>(J, S, vc, __ldg(J.targets + vc));
       if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = vc; TS.K = Kc; TS.nHeur = 0u; TS.best = ~0ull; TS.win_pt = RS_NO_SRC; }
-      for (uint32_t i = lane; i < RS_MAX_NB; i += 32) TS.hsum[i] = 0u;
+      for (uint32_t i = lane; i < RS_MAX_NB; i += 32) { TS.hsum[i] = 0u; TS.hcnt[i] = 0u; }
     }
     rs_team_sync(bar_id, T);  // A
     if (!TS.alive) break;
@@ -962,22 +963,13 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       for (uint32_t t = tid; t < nHeur * nch; t += T) {
         const uint32_t ci = t / nch, j = t % nch;
         atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, S.q, K, ci, j, st));
+        __threadfence_block();
+        // the lane that adds a candidate's last chunk holds its full sum: it enters "first candidate with the minimum
+        // full sum" directly (packed sum << 32 | index, atomicMin) -- no barrier and no scan by warp 0 in between
+        if (atomicAdd(&TS.hcnt[ci], 1u) + 1u == nch)
+          atomicMin(&TS.best, ((unsigned long long)atomicAdd(&TS.hsum[ci], 0u) << 32) | ci);
       }
       rs_team_sync(bar_id, T);  // D
-      if (wt == 0) {  // first candidate with the minimum full sum
-        unsigned long long key = ~0ull;
-        for (uint32_t i = lane; i < nHeur; i += 32) {
-          const unsigned long long k2 = ((unsigned long long)TS.hsum[i] << 32) | i;
-          key = k2 < key ? k2 : key;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long other = __shfl_xor_sync(RS_FULL, key, o);
-          key = other < key ? other : key;
-        }
-        if (lane == 0) TS.best = key;
-      }
-      rs_team_sync(bar_id, T);  // E
     }
     // ---- random probes, early-out against the shared best (sum << 32 | index, atomicMin): the fetched-ahead ones
     //      resume after their first chunk, the rest (probes >= nPre) run from the start
