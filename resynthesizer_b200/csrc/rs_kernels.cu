@@ -837,19 +837,17 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
     if (nHeur) {
       const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = 0xFFFFFFFFu / nch + 1u;
-      for (uint32_t i = lane; i < nHeur; i += 32) hsum[i] = 0u;
+      hsum[lane] = 0u;        // (nHeur <= RS_MAX_NB = 64: two slots per lane cover every candidate)
+      hsum[lane + 32u] = 0u;
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
         const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
         atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, hcol, K, ci, j, st));
       }
       __syncwarp();
-      uint32_t msum = 0xFFFFFFFFu;
-      for (uint32_t i = lane; i < nHeur; i += 32) msum = min(msum, hsum[i]);
-      msum = __reduce_min_sync(RS_FULL, msum);
-      int midx = 0x7FFFFFFF;
-      for (uint32_t i = lane; i < nHeur; i += 32) midx = (hsum[i] == msum) ? min(midx, (int)i) : midx;
-      midx = __reduce_min_sync(RS_FULL, midx);
+      const uint32_t h0 = lane < nHeur ? hsum[lane] : 0xFFFFFFFFu, h1 = lane + 32u < nHeur ? hsum[lane + 32u] : 0xFFFFFFFFu;
+      const uint32_t msum = __reduce_min_sync(RS_FULL, min(h0, h1));
+      const int midx = __reduce_min_sync(RS_FULL, (h0 == msum) ? (int)lane : ((h1 == msum) ? (int)lane + 32 : 0x7FFFFFFF));
       bestSum = msum;
       bestIdx = midx;
     }
