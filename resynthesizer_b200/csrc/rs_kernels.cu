@@ -630,7 +630,10 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
     const uint32_t k = lane + 32u * rnd;
     const uint32_t c = mycand[rnd];
     bool valid = (c != RS_NO_SRC);
-    if (valid) {
+    if (rnd == 0) {  // an earlier neighbour proposing the same point: lanes are neighbours here, one MATCH finds them
+      const unsigned same = __match_any_sync(RS_FULL, c);
+      if (pskip[0] || (same & lt)) valid = false;
+    } else if (valid) {
       bool skip = pskip[rnd];
       for (uint32_t k2 = 0; k2 < k && !skip; k2++) skip = (S.q[k2] == c);
       if (skip) valid = false;
