@@ -654,17 +654,50 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
   __syncwarp();
 }
 
+// One warp: merge the stamps of visit v into the recentProber array of its epoch (c0/c1: this lane's candidates
+// lane and lane + 32 of the list; the first stampEnd of the list are stamped), then publish the visit as complete.
+__device__ __forceinline__ void rs_visit_stamps(const RsDev &J, RsCtrl *ctrl, const uint32_t v, const uint32_t epoch_idx,
+                                                const uint32_t my_base, const uint32_t hide_from, const uint32_t stampEnd,
+                                                const uint32_t c0, const uint32_t c1) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t pass = J.pass, stp = ((pass + 1u) << 29) | v;
+  if (stampEnd > 0u && hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
+    if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
+    __syncwarp();
+  }
+#pragma unroll
+  for (int rnd = 0; rnd < 2; rnd++) {
+    if (lane + 32u * rnd < stampEnd) {
+      const uint32_t c = rnd ? c1 : c0;
+      unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+      unsigned long long old = rs_ld_state(pp);
+      while (true) {
+        const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
+        const unsigned long long nw = (hi >= my_base) ? (((unsigned long long)max(hi, stp) << 32) | lo)
+                                                        : (((unsigned long long)stp << 32) | hi);
+        if (nw == old) break;
+        const unsigned long long prev = atomicCAS(pp, old, nw);
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+  }
+  __syncwarp();
+  // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
+  if (lane == 0)
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->epoch_done[pass][epoch_idx].v) : "memory");
+}
+
 // One warp: commit the winner (lib/synthesize.h:620-639), merge the heuristic-2 stamps, publish completion.
 // hcol[i] = colour of heuristic candidate i (fetched with its first chunk).  For a winning probe: win_pt = its corpus
 // point if the distance phase tracked it (else RS_NO_SRC: looked up from the probe's index), win_col = its colour if
 // have_col (else fetched here).
-template <bool MAPS>
+template <bool MAPS, bool STAMPS = true>
 __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, const Visit &V,
                                                 uint32_t bestSum, int bestIdx, uint32_t win_pt, uint32_t win_col,
                                                 bool have_col) {
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t pass = J.pass, v = V.v, nHeur = V.nHeur;
-  const uint32_t tag = (pass + 1u) << 29;
   const uint32_t *candlist = S.aux, *hcol = S.q;
   const uint32_t epoch_idx = S.vis.epoch_idx, my_base = S.vis.my_base;
   const bool bettered = bestIdx != 0x7FFFFFFF;
@@ -702,31 +735,34 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
     S.st.heur += min(nHeur, seq_evals);
     S.st.perfect += (bettered && bestSum == 0u) ? 1u : 0u;
   }
-  // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
-  const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
-  if (stampEnd > 0u && S.vis.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
-    if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
-    __syncwarp();
-  }
-  for (uint32_t i = lane; i < stampEnd; i += 32) {
-    const uint32_t c = candlist[i];
-    unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
-    const uint32_t stp = tag | v;
-    unsigned long long old = rs_ld_state(pp);
-    while (true) {
-      const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
-      const unsigned long long nw = (hi >= my_base) ? (((unsigned long long)max(hi, stp) << 32) | lo)
-                                                      : (((unsigned long long)stp << 32) | hi);
-      if (nw == old) break;
-      const unsigned long long prev = atomicCAS(pp, old, nw);
-      if (prev == old) break;
-      old = prev;
+  if (STAMPS) {  // (the throughput kernel: this warp does it all; same merge as rs_visit_stamps, list read in place)
+    // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
+    const uint32_t tag = (pass + 1u) << 29;
+    const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
+    if (stampEnd > 0u && S.vis.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
+      if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
+      __syncwarp();
     }
+    for (uint32_t i = lane; i < stampEnd; i += 32) {
+      const uint32_t c = candlist[i];
+      unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+      const uint32_t stp = tag | v;
+      unsigned long long old = rs_ld_state(pp);
+      while (true) {
+        const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
+        const unsigned long long nw = (hi >= my_base) ? (((unsigned long long)max(hi, stp) << 32) | lo)
+                                                        : (((unsigned long long)stp << 32) | hi);
+        if (nw == old) break;
+        const unsigned long long prev = atomicCAS(pp, old, nw);
+        if (prev == old) break;
+        old = prev;
+      }
+    }
+    __syncwarp();
+    // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
+    if (lane == 0)
+      asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->epoch_done[pass][epoch_idx].v) : "memory");
   }
-  __syncwarp();
-  // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
-  if (lane == 0)
-    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->epoch_done[pass][epoch_idx].v) : "memory");
 }
 
 // Whole CTA, at kernel end: flush the per-warp counters; the last CTA out decides whether later passes run
@@ -1018,13 +1054,24 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       }
     }
     rs_team_sync(bar_id, T);  // F
-    if (mykey == TS.best && mykey != ~0ull) { TS.win_pt = mypt; TS.win_col = mycol; }
+    const unsigned long long key = TS.best;  // final; warp 0 resets it for the next visit only after barrier G
+    if (mykey == key && mykey != ~0ull) { TS.win_pt = mypt; TS.win_col = mycol; }
+    // warp 1 merges the visit's stamps while warp 0 commits and claims the next visit: what it needs leaves the
+    // scratch (which warp 0 is about to reuse) before the barrier
+    uint32_t sc0 = 0, sc1 = 0;
+    if (wt == 1) {
+      sc0 = lane < nHeur ? S.aux[lane] : 0u;
+      sc1 = lane + 32u < nHeur ? S.aux[lane + 32u] : 0u;
+    }
     rs_team_sync(bar_id, T);  // G
+    const uint32_t bestSum = (key == ~0ull) ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
+    const int bestIdx = (key == ~0ull) ? 0x7FFFFFFF : (int)(uint32_t)key;
     if (wt == 0) {
-      const unsigned long long key = TS.best;
-      const uint32_t bestSum = (key == ~0ull) ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
-      const int bestIdx = (key == ~0ull) ? 0x7FFFFFFF : (int)(uint32_t)key;
-      rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx, TS.win_pt, TS.win_col, true);
+      rs_visit_finish<MAPS, false>(J, ctrl, S, V, bestSum, bestIdx, TS.win_pt, TS.win_col, true);
+    } else if (wt == 1) {
+      const uint32_t stampEnd = (bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
+      const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;  // as in rs_visit_candidates
+      rs_visit_stamps(J, ctrl, v, epoch_idx, ((pass + 1u) << 29) | epoch0, epoch_idx ? epoch0 - J.epoch_len : 0u, stampEnd, sc0, sc1);
     }
   }
   __syncwarp();
