@@ -162,12 +162,22 @@ struct PixelSource {
   bool simple() const { return img != nullptr; }
 };
 
+// Any non-zero byte in p[0..n): 64 bytes per step (a byte loop with an early exit costs a millisecond on the two
+// megabytes of mask above a centred hole in a 2048x2048 image -- more than a pass of the synthesis itself).
+bool any_nonzero(const uint8_t *p, size_t n) {
+  size_t i = 0;
+  for (; i + 64 <= n; i += 64) {
+    uint64_t a[8];
+    std::memcpy(a, p + i, 64);
+    if (a[0] | a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7]) return true;
+  }
+  for (; i < n; i++) if (p[i]) return true;
+  return false;
+}
 bool any_target(const PixelSource &s) {
   if (!s.simple()) return rs::has_target_point(s.tpix, s.tw, s.th, s.bpp);
-  for (int y = 0; y < s.th; y++) {
-    const uint8_t *row = s.mask->data + (size_t)y * s.mask->rowBytes;
-    for (int x = 0; x < s.tw; x++) if (row[x]) return true;
-  }
+  for (int y = 0; y < s.th; y++)
+    if (any_nonzero(s.mask->data + (size_t)y * s.mask->rowBytes, (size_t)s.tw)) return true;
   return false;
 }
 bool any_corpus(const PixelSource &s, const TFormatIndices &fi) {

@@ -61,6 +61,30 @@ def test_reference_error_codes_without_cuda(built_lib):
     assert api.image_synth(img.copy(), mask, abi.T_RGB, p) == abi.IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE
 
 
+def test_selection_scan_finds_a_single_selected_byte_anywhere(built_lib):
+    # the empty-target check reads the mask 64 bytes at a time with a byte tail: one selected pixel at any position of
+    # a row whose width is not a multiple of 64 must be seen (whatever follows -- success or "no CUDA device" -- it is
+    # not EMPTY_TARGET), and the padding of a mask with rowBytes > width must not count
+    L = api.lib()
+    w, h, row_bytes = 131, 5, 192
+    img = G(w, h, 3, 2)
+    cb = abi.PROGRESS_CB(lambda pct, ctx: None)
+
+    def call(mask_rows):
+        im, cancel = img.copy(), C.c_int(0)
+        ib = abi.ImageBuffer(im.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, w * 3)
+        mb = abi.ImageBuffer(mask_rows.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, row_bytes)
+        return L.imageSynth(C.byref(ib), C.byref(mb), abi.T_RGB, None, cb, None, C.byref(cancel))
+
+    padded = np.zeros((h, row_bytes), np.uint8)
+    padded[:, w:] = 255
+    assert call(padded) == abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+    for x in (0, 63, 64, 127, 128, 130):
+        m = padded.copy()
+        m[h - 1, x] = 1
+        assert call(m) != abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+
+
 def test_map_helpers(built_lib):
     L = api.lib()
     pm, bm = abi.Map(), abi.Map()
