@@ -173,6 +173,13 @@ void rs_cuda_release_cached(void);
  * such load per neighbour compare, so this is its practical ceiling on this GPU. */
 int rs_cuda_gather_rate(size_t buffer_bytes, int elem_bytes, int repeats, double *loads_per_s);
 
+/* The launch plan of one pass (host logic only, no device needed): a pass runs as up to four persistent launches over
+ * consecutive segments of the visit order; widths4[k] = warps per visit of segment k (8, 4, 2: latency kernel
+ * k_synth_pass_team; 1: throughput kernel k_synth_pass), ends4[k] = its end (exclusive; the last one is pass_end).
+ * ordered_visits as in RsJobDesc.  Returns the number of segments. */
+int rs_cuda_plan_pass(uint32_t n_targets, uint32_t pass_end, int ordered_visits, int patch_size, uint32_t pass,
+                      uint32_t *ends4, uint32_t *widths4);
+
 int rs_bestfit_batch(const RsJobDesc *desc, const uint8_t *corpus_raw,
                      const uint32_t *color_lut256, const uint32_t *map_lut256, uint32_t map_lut_max,
                      uint32_t n_visits, const uint32_t *nb_begin, const uint32_t *nb_offsets,

@@ -126,6 +126,16 @@ def gather_rate(buffer_bytes, elem_bytes=4, repeats=3):
     return out.value
 
 
+def plan_pass(n_targets, pass_end, patch_size, pass_index, ordered_visits=False):
+    """Launch plan of one pass: [(segment end, warps per visit)], 1 warp = the throughput kernel (rs_cuda_plan_pass)."""
+    L = lib()
+    L.rs_cuda_plan_pass.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.rs_cuda_plan_pass.restype = C.c_int
+    ends, widths = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+    k = L.rs_cuda_plan_pass(int(n_targets), int(pass_end), int(bool(ordered_visits)), int(patch_size), int(pass_index), ends, widths)
+    return [(int(ends[i]), int(widths[i])) for i in range(k)]
+
+
 def last_timeline(pass_index):
     """ns from the start of `pass_index` to the claim of its visit 4096*i, for the last engine() call made with
     keep_result(True); empty if the pass did not run."""

@@ -2083,27 +2083,25 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
 // launch each, whose width shrinks as the pass fills in.  Thresholds from sweeps on B200 (profiles/); RS_TEAM_P0 /
 // RS_TEAM_PN force one width for a whole pass, RS_SEG_P0="end:width,end:width,..." forces the pass-0 plan.
 struct Segment { uint32_t end; unsigned width; };
-static unsigned pass_width(const RsJob *j, uint32_t p) {
-  const uint32_t n = j->nT;
+static unsigned pass_width(uint32_t n, uint32_t p) {
   if (n <= 32768u) return 8;
   if (n <= 200000u) return p == 0 ? 8 : 4;
   if (n <= 600000u) return p == 0 ? 4 : 2;
   return 1;
 }
-static int plan_segments(const RsJob *j, uint32_t p, Segment *out /*[4]*/) {
-  const uint32_t end = j->d.pass_end[p];
+static int plan_segments(uint32_t n_targets, uint32_t end, int ordered_visits, int patch_size, uint32_t p, Segment *out /*[4]*/) {
   const char *e = getenv(p == 0 ? "RS_TEAM_P0" : "RS_TEAM_PN");
   if (e) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) { out[0] = {end, (unsigned)w}; return 1; } }
-  const unsigned base = pass_width(j, p);
+  const unsigned base = pass_width(n_targets, p);
   if (p != 0) { out[0] = {end, base}; return 1; }
-  if (j->d.ordered_visits && !getenv("RS_SEG_P0")) {
+  if (ordered_visits && !getenv("RS_SEG_P0")) {
     // A spatially sorted order (inwards, outwards, by rows...) keeps pass 0 a narrow dependency front from its first visit
     // to its last: latency mode throughout (1 Mi targets: 11.8 ms at 4 warps per visit, 20.0 with the shuffle's plan).
     out[0] = {end, base > 4u ? base : 4u};
     return 1;
   }
   Segment plan[4] = {{16384u, 8u}, {65536u, 4u}, {262144u, 2u}, {0xFFFFFFFFu, 1u}};
-  if (j->d.patch_size < RS_CHUNK_SWITCH_K) {  // small patches depend on fewer earlier visits: the pass widens sooner
+  if (patch_size < RS_CHUNK_SWITCH_K) {  // small patches depend on fewer earlier visits: the pass widens sooner
     plan[0].end = 8192u; plan[1].end = 24576u; plan[2].end = 65536u;  // (cfg2 4.33 -> 4.08 ms, cfg4 86.8 -> 85.4)
   }
   if (const char *sp = getenv("RS_SEG_P0")) {  // "end:width,..." ; the last entry runs to the end of the pass
@@ -2130,6 +2128,15 @@ static int plan_segments(const RsJob *j, uint32_t p, Segment *out /*[4]*/) {
   }
   if (n == 0) out[n++] = {end, base};
   out[n - 1].end = end;
+  return n;
+}
+
+// The launch plan of one pass, for tests and tools (no device needed): segment ends and warps per visit (1 = throughput kernel).
+extern "C" int rs_cuda_plan_pass(uint32_t n_targets, uint32_t pass_end, int ordered_visits, int patch_size, uint32_t pass,
+                                 uint32_t *ends4, uint32_t *widths4) {
+  Segment seg[4];
+  const int n = plan_segments(n_targets, pass_end, ordered_visits, patch_size, pass, seg);
+  for (int k = 0; k < n; k++) { ends4[k] = seg[k].end; widths4[k] = seg[k].width; }
   return n;
 }
 
@@ -2183,7 +2190,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     if (p == 1 && j->later_lists) RS_CHECK(cudaStreamWaitEvent(s, w->evLater, 0));
     RsDev D = make_dev(j, p);
     Segment seg[4];
-    const int nseg = plan_segments(j, p, seg);
+    const int nseg = plan_segments(j->nT, j->d.pass_end[p], j->d.ordered_visits, j->d.patch_size, p, seg);
     uint32_t begin = 0;
     j->pass_launches[p] = (uint32_t)nseg;
     for (int k = 0; k < nseg; k++) {
