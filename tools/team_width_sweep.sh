@@ -1,3 +1,6 @@
+#!/bin/bash
+# Sweep of team widths (RS_TEAM_PN) and pass-0 segment plans (RS_SEG_P0) over a set of workloads; run on a GPU box
+# from the repo root: bash tools/team_width_sweep.sh   (see DESIGN.md section 8.4 for the results that set the defaults)
 W="cfg2 cfg5 heal:2048:1024 heal:1024:384 heal:2048:512"
 echo "== default"; python tools/quick.py $W cfg1
 echo "== PN=8"; RS_TEAM_PN=8 python tools/quick.py cfg5 heal:1024:384 heal:2048:512
