@@ -264,7 +264,12 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
                                      src.mask2 ? src.mask2->data : nullptr, src.mask2 ? src.mask2->rowBytes : 0, c256, m256, m512[0])
                : rs_job_stage(job, src.tpix, src.cpix, c256, m256, m512[0]);
   if (!rc) rc = rs_job_digest(job, &dg);
-  if (rc) { t_err = rs_cuda_last_error(); rs_job_destroy(job); return RS_ERROR_CUDA; }
+  if (rc) {
+    t_err = rs_cuda_last_error();
+    raw.reset();  // the producer writes into the job's pinned buffer: stop it before the workspace goes back to the pool
+    rs_job_destroy(job);
+    return RS_ERROR_CUDA;
+  }
   dbg("after stage+digest");
   const uint32_t n = dg.n;
   uint32_t pass_end[6];

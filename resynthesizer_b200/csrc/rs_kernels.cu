@@ -1382,6 +1382,7 @@ extern "C" void rs_job_destroy(RsJob *j) {
   if (j->ws) {
     cudaSetDevice(j->ws->device);
     cudaStreamSynchronize(j->ws->stream);
+    if (j->ws->stream2) cudaStreamSynchronize(j->ws->stream2);  // (joined into the main stream on the good path; an error may leave it running)
     ws_release(j->ws);
   }
   delete j;
