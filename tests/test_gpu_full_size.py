@@ -1,5 +1,11 @@
-"""-m gpu: BASELINE.json's full-size configurations, checked through size-independent properties (the oracle
-needs minutes to hours at these sizes):
+"""-m gpu: BASELINE.json's full-size configurations.
+
+cfg1, cfg2 and cfg5 are compared BIT FOR BIT with the oracle (oracle/resynth_port.c in GPU mode needs 0.3 s, 4 s and
+8 s for them on one host core): every pixel, every source, every counter, under the default launch plans -- for cfg2
+that is the segmented pass 0 (teams of 8/4/2 warps, then the throughput kernel) and the throughput kernel in pass 1.
+cfg3 and cfg4 (minutes on the oracle; their counters are pinned in profiles/algorithmic_counts.json, produced by
+tools/algorithmic_counts.py) are compared with those committed oracle counters and, like all of them, checked
+through size-independent properties:
   * every synthesised target pixel carries exactly the colour of the corpus pixel recorded as its source;
   * every source is a legal corpus point (mask 0xFF, not transparent);
   * context pixels, alpha and map channels are untouched;
@@ -73,3 +79,73 @@ def test_cfg3_large_hole_rgba_full_size(built_lib):
     _check(w, fi, before, tp, cp, st, txy, sxy)
     # random probes never pick transparent corpus pixels; the transparent band is not a valued context either
     assert st["n_corpus"] == int(((cp[:, :, 0] == 0xFF) & (cp[:, :, fi.alpha_bip] != 0)).sum())
+
+
+# ---------------------------------------------------------------------------------- bit-exact against the oracle
+import json
+import os
+
+from oracle import refdriver as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COUNTER_KEYS = ("passes_run", "betters", "sum_best", "visits", "pass_visits", "evals", "perfect", "heur_evals")
+
+
+@pytest.mark.parametrize("wname", ["cfg1", "cfg2", "cfg5"])
+def test_full_size_bit_exact_vs_oracle(built_oracle, built_lib, wname):
+    """The BASELINE-size job under the DEFAULT launch plan == the sequential oracle: pixels, sources, counters."""
+    w, fi, before, tp, cp, st, txy, sxy = _run(wname)
+    port = R.load_port(R.GPU_MODE, 1198472)
+    want = before.copy()
+    assert R.engine(port, w["params"], R.format_indices(port, w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0),
+                    want, cp) == 0
+    ps = R.port_stats(port)
+    t_ref, s_ref = R.port_last_result(port)
+    assert (txy == t_ref).all(), "visit order differs from the oracle's"
+    assert int((tp != want).any(axis=2).sum()) == 0
+    assert (sxy == s_ref).all()
+    for k in COUNTER_KEYS:
+        assert st[k] == ps[k], (k, st[k], ps[k])
+
+
+@pytest.mark.parametrize("wname", ["cfg1", "cfg2", "cfg5"])
+def test_simple_and_batch_paths_equal_oracle_at_full_size(built_oracle, built_lib, wname):
+    """The same jobs through the paths bench.py times: imageSynth() (heal configurations) and rs_engine_batch."""
+    w = bench.workload(wname)
+    fi = api.format_indices(w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
+    port = R.load_port(R.GPU_MODE, 1198472)
+    tp, cp = bench.pixmaps(w)
+    want = tp.copy()
+    assert R.engine(port, w["params"], fi, want, cp) == 0
+    api.set_seed(1198472)
+    if "simple" in w:
+        img = w["tgt"].copy()
+        assert api.image_synth(img, w["tmask"], w["simple"], w["params"]) == 0
+        assert (img == want[:, :, 1:1 + img.shape[2]]).all()
+    jobs = [(w["params"], fi, tp.copy(), cp) for _ in range(3)]
+    assert not any(api.engine_batch(jobs, 2))
+    for jb in jobs:
+        assert (jb[2] == want).all()
+
+
+@pytest.mark.parametrize("wname", ["cfg3", "cfg4"])
+def test_large_configs_equal_committed_oracle_counters(built_lib, wname):
+    """cfg3 / cfg4: the oracle needs minutes, so its counters were taken once (tools/algorithmic_counts.py) and are
+    committed; visits, evals, betters, sum of best distances and perfect matches of the CUDA run must equal them."""
+    path = os.path.join(ROOT, "profiles", "algorithmic_counts.json")
+    if not os.path.exists(path) or wname not in json.load(open(path)):
+        pytest.skip("no committed oracle counters for %s" % wname)
+    ps = json.load(open(path))[wname]
+    w = bench.workload(wname)
+    assert ps["workload"] == w["name"]
+    api.set_seed(1198472)
+    if "simple" in w:
+        img = w["tgt"].copy()
+        assert api.image_synth(img, w["tmask"], w["simple"], w["params"]) == 0
+    else:
+        fi = api.format_indices(w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
+        tp, cp = bench.pixmaps(w)
+        assert api.engine(w["params"], fi, tp, cp) == 0
+    st = api.last_stats()
+    for k in COUNTER_KEYS:
+        assert st[k] == ps[k], (k, st[k], ps[k])

@@ -1,0 +1,176 @@
+"""-m gpu: EVERY variant of the pass kernels against the oracle, bit for bit.
+
+The launch plan of a pass (throughput kernel = one warp per visit, or teams of 2/4/8 warps per visit; pass 0 cut into
+segments of shrinking width; chunk size 2 or 3; corpus in shared memory or in L2) follows the job size, so small jobs
+under the default plan only ever run the 8-wide team kernel.  Here the knobs RS_TEAM_P0 / RS_TEAM_PN / RS_SEG_P0 /
+RS_CHUNK / RS_SMEM_CORPUS force each variant on jobs the oracle finishes in seconds, and pixels, sources, betters,
+sum of best distances, evals and perfect matches must all equal oracle/resynth_port.c in GPU mode
+(lib/synthesize.h:426-642 restated sequentially)."""
+import numpy as np
+import pytest
+
+from oracle import refdriver as R
+from resynthesizer_b200 import abi, api
+from resynthesizer_b200.synthetic import G, centered_mask
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(kind):
+    """(params, n_color, n_map, alpha, target pixmap, corpus pixmap)"""
+    if kind == "heal30":        # CH=3 kernels, context, K=30
+        img = G(112, 96, 3, 41)
+        m = centered_mask(112, 96, 44, 40)
+        return (abi.make_params(0, 0, 1, 0.5, 0.117, 30, 120), 3, 0, False,
+                R.build_pixmap(m, img), R.build_pixmap(255 - m, img))
+    if kind == "texture9":      # CH=2 kernels, no context, K=9, small corpus (the render-texture shape)
+        tgt = np.full((96, 96, 3), 255, np.uint8)
+        cor = G(48, 40, 3, 42)
+        cm = np.full((40, 48), 255, np.uint8); cm[:2, :7] = 0
+        return (abi.make_params(0, 0, 0, 0.5, 0.117, 9, 150), 3, 0, False,
+                R.build_pixmap(np.full((96, 96), 255, np.uint8), tgt), R.build_pixmap(cm, cor))
+    if kind == "texture9_tiled":
+        tgt = np.full((80, 72, 3), 255, np.uint8)
+        cor = G(64, 64, 3, 43)
+        return (abi.make_params(1, 1, 0, 0.5, 0.117, 9, 100), 3, 0, False,
+                R.build_pixmap(np.full((80, 72), 255, np.uint8), tgt), R.build_pixmap(np.full((64, 64), 255, np.uint8), cor))
+    if kind == "maps9":         # MAPS kernels, CH=2
+        tgt = G(72, 64, 3, 44); cor = G(56, 60, 3, 45)
+        full_t = np.full((64, 72), 255, np.uint8); full_c = np.full((60, 56), 255, np.uint8)
+        return (abi.make_params(1, 1, 1, 0.5, 0.117, 9, 100), 3, 3, False,
+                R.build_pixmap(full_t, tgt, None, G(72, 64, 3, 46)), R.build_pixmap(full_c, cor, None, G(56, 60, 3, 47)))
+    if kind == "maps20_alpha":  # MAPS kernels, CH=3, alpha channel, gray map
+        tgt = G(64, 64, 3, 48); cor = G(64, 48, 3, 49)
+        tm = centered_mask(64, 64, 40, 36)
+        ta = np.full((64, 64), 255, np.uint8); ta[::7, ::5] = 0
+        ca = np.full((48, 64), 255, np.uint8); ca[::6, ::4] = 0
+        return (abi.make_params(0, 0, 1, 0.3, 0.117, 20, 90), 3, 1, True,
+                R.build_pixmap(tm, tgt, ta, G(64, 64, 1, 50)), R.build_pixmap(np.full((48, 64), 255, np.uint8), cor, ca, G(64, 48, 1, 51)))
+    if kind == "gray16":
+        img = G(90, 70, 1, 52)
+        m = centered_mask(90, 70, 30, 30)
+        return (abi.make_params(0, 0, 2, 0.5, 0.117, 16, 80), 1, 0, False,
+                R.build_pixmap(m, img), R.build_pixmap(255 - m, img))
+    raise KeyError(kind)
+
+
+def _check(kind, seed=1198472):
+    params, n_color, n_map, alpha, tp, cp = _case(kind)
+    port = R.load_port(R.GPU_MODE, seed)
+    fi = R.format_indices(port, n_color, n_map, alpha, alpha, n_map > 0)
+    want = tp.copy()
+    assert R.engine(port, params, fi, want, cp) == 0
+    ps = R.port_stats(port)
+    t_ref, s_ref = R.port_last_result(port)
+    api.set_seed(seed)
+    api.order_cache(False)
+    api.keep_result(True)
+    try:
+        got = tp.copy()
+        assert api.engine(params, fi, got, cp) == 0
+        st = api.last_stats()
+        t_gpu, s_gpu = api.last_result()
+    finally:
+        api.keep_result(False)
+        api.order_cache(True)
+    assert (t_gpu == t_ref).all(), "visit order differs"
+    nd = int((got != want).any(axis=2).sum())
+    assert nd == 0, "%d pixels differ from the oracle" % nd
+    assert (s_gpu == s_ref).all(), "%d sources differ" % int((s_gpu != s_ref).any(axis=1).sum())
+    for k in ("passes_run", "betters", "sum_best", "visits", "pass_visits", "evals", "perfect", "heur_evals"):
+        assert st[k] == ps[k], (k, st[k], ps[k])
+    return st
+
+
+KINDS = ["heal30", "texture9", "texture9_tiled", "maps9", "maps20_alpha", "gray16"]
+
+
+@pytest.mark.parametrize("width", [1, 2, 4, 8])
+@pytest.mark.parametrize("kind", KINDS)
+def test_every_width_in_every_pass(built_oracle, built_lib, monkeypatch, kind, width):
+    """k_synth_pass (width 1) and k_synth_pass_team (2/4/8) for pass 0 AND the later passes."""
+    monkeypatch.setenv("RS_TEAM_P0", str(width))
+    monkeypatch.setenv("RS_TEAM_PN", str(width))
+    _check(kind)
+
+
+@pytest.mark.parametrize("p0,pn", [(8, 1), (1, 8), (4, 2), (2, 4)])
+def test_mixed_widths(built_oracle, built_lib, monkeypatch, p0, pn):
+    monkeypatch.setenv("RS_TEAM_P0", str(p0))
+    monkeypatch.setenv("RS_TEAM_PN", str(pn))
+    _check("heal30")
+    _check("texture9")
+
+
+@pytest.mark.parametrize("plan", ["512:8,2048:4,6000:2,0:1", "100:2,101:8,3000:1,0:4", "64:1,0:8", "4000:4,0:1"])
+@pytest.mark.parametrize("kind", ["texture9", "heal30", "maps9"])
+def test_multi_segment_pass0(built_oracle, built_lib, monkeypatch, plan, kind):
+    """Pass 0 cut into launches of different widths (plan_segments): visits hand over between kernels mid-pass."""
+    monkeypatch.setenv("RS_SEG_P0", plan)
+    monkeypatch.setenv("RS_TEAM_PN", "1")
+    _check(kind)
+
+
+@pytest.mark.parametrize("chunk", [2, 3])
+@pytest.mark.parametrize("width", [1, 4])
+def test_chunk_size_override(built_oracle, built_lib, monkeypatch, chunk, width):
+    """Both chunk sizes (neighbours per early-out check) on both patch-size classes."""
+    monkeypatch.setenv("RS_CHUNK", str(chunk))
+    monkeypatch.setenv("RS_TEAM_P0", str(width))
+    monkeypatch.setenv("RS_TEAM_PN", str(width))
+    _check("heal30")
+    _check("texture9")
+    _check("maps9")
+
+
+@pytest.mark.parametrize("width", [1, 2, 8])
+def test_smem_corpus_off_equals_on(built_oracle, built_lib, monkeypatch, width):
+    """Small corpora are staged into (distributed) shared memory by TMA; RS_SMEM_CORPUS=0 forces the L2 path.  Both
+    must equal the oracle."""
+    monkeypatch.setenv("RS_TEAM_P0", str(width))
+    monkeypatch.setenv("RS_TEAM_PN", str(width))
+    for flag in ("0", "1"):
+        monkeypatch.setenv("RS_SMEM_CORPUS", flag)
+        _check("texture9")
+        _check("texture9_tiled")
+        _check("gray16")
+
+
+@pytest.mark.parametrize("width", [1, 2, 4, 8])
+def test_later_lists_with_every_width(built_oracle, built_lib, monkeypatch, width):
+    monkeypatch.setenv("RS_LATER_LISTS_MIN", "1")
+    monkeypatch.setenv("RS_TEAM_P0", str(width))
+    monkeypatch.setenv("RS_TEAM_PN", str(width))
+    _check("heal30")
+    _check("maps9")
+
+
+def test_mid_size_default_plans(built_oracle, built_lib):
+    """Default plans of the size classes between 'always 8 wide' and 'segments + throughput kernel'
+    (pass_width: <= 32 Ki: 8/8; <= 200 k: 8/4; <= 600 k: 4/2): a 240x200 hole (48 000 targets) and a 512x512 texture
+    (262 144 targets)."""
+    img = G(400, 320, 3, 61)
+    m = centered_mask(400, 320, 240, 200)
+    port = R.load_port(R.GPU_MODE)
+    p = abi.make_params(0, 0, 1, 0.5, 0.117, 12, 40)
+    e_ref, want = R.image_synth(port, img, m, abi.T_RGB, p)
+    ps = R.port_stats(port)
+    got = img.copy()
+    api.set_seed(1198472)
+    assert api.image_synth(got, m, abi.T_RGB, p) == 0 and e_ref == 0
+    st = api.last_stats()
+    assert (got == want).all() and st["evals"] == ps["evals"] and st["betters"] == ps["betters"] and st["sum_best"] == ps["sum_best"]
+
+    tgt = np.full((512, 512, 3), 255, np.uint8)
+    cor = G(128, 128, 3, 62)
+    fi = R.format_indices(port, 3, 0, False, False, False)
+    tp = R.build_pixmap(np.full((512, 512), 255, np.uint8), tgt)
+    cp = R.build_pixmap(np.full((128, 128), 255, np.uint8), cor)
+    p = abi.make_params(0, 0, 0, 0.5, 0.117, 9, 60)
+    want = tp.copy()
+    assert R.engine(port, p, fi, want, cp) == 0
+    ps = R.port_stats(port)
+    got = tp.copy()
+    assert api.engine(p, fi, got, cp) == 0
+    st = api.last_stats()
+    assert (got == want).all() and st["evals"] == ps["evals"] and st["betters"] == ps["betters"] and st["sum_best"] == ps["sum_best"]

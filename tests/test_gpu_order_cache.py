@@ -166,3 +166,37 @@ def test_device_shuffle_large(raw, monkeypatch):
         api.set_device_shuffle_min(1 << 15)
         api.keep_result(False)
         api.order_cache(True)
+
+
+@pytest.mark.parametrize("mode", list(range(9)))
+def test_device_resolved_order_equals_oracle_order(mode):
+    """The visit order as the DEVICE paths resolve it (modes 0/1: chain of swaps traced on the device from raw PRNG
+    words; modes 2-8: pair sort on the device) against the oracle's orderTargetPoints restatement (port_order,
+    lib/orderTarget.h:268-343), directly, on 200 000 points."""
+    from oracle import refdriver as R
+    import subprocess, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "oracle"), "port"])
+    port = R.load_port(R.REF_MODE)
+    api.order_cache(False)
+    api.keep_result(True)
+    try:
+        img = G(640, 512, 3, 78)
+        m = np.zeros((512, 640), np.uint8); m[40:440, 60:560] = 255
+        m[100:140, 200:260] = 0           # a hole in the selection: bounding box and rays are not trivial
+        n = int((m != 0).sum())
+        p = abi.make_params(0, 0, mode, 0.5, 0.117, 4, 2)
+        tp = np.ascontiguousarray(np.concatenate([m[:, :, None], img], axis=2))
+        cp = np.ascontiguousarray(np.concatenate([(255 - m)[:, :, None], img], axis=2))
+        api.set_device_shuffle_min(1 << 15)
+        api.set_device_sort_min(1 << 16)
+        api.set_seed(1198472)
+        _run(p, tp, cp)
+        t_gpu, _ = api.last_result()
+        ys, xs = np.nonzero(m)
+        pts = np.stack([xs, ys], axis=1).astype(np.int32).copy()       # row-major, as the engine collects them
+        assert port.port_order(mode, pts.ctypes.data, n, 1198472) == 0
+        assert len(t_gpu) == n and (t_gpu == pts).all()
+    finally:
+        api.keep_result(False)
+        api.order_cache(True)
