@@ -2,21 +2,23 @@
 """bench.py -- synthesized target px/s (and patch-distance evals/s) of the synthesis hot path.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
-  python bench.py --impl reference --gpus N ...            # the reference's CPU engine (oracle/_ref)
+  python bench.py --impl reference --gpus N ...            # the reference's CPU engine (oracle/_ref), same config
 
-One "step" = one complete synthesis job (all passes) of the workload on each rank.  Default workload is
-BASELINE.json configs[1]: render-texture, a 1024x1024 target synthesised from a 256x256 synthetic corpus
-tile, no context matching (matchContextType 0, no tiling), the render-texture script's 9 neighbours / 200
-probes (PluginScripts/plugin-render-texture.py:175), through the full API engine().
+One "step" = one complete synthesis job (all passes) of the workload on each rank.  The default workload is the
+largest single-GPU configuration of BASELINE.json, configs[2]: large-hole inpaint of a 4096x4096 RGBA image, 25 %
+masked (centred 2048x2048), alpha weighting, defaults (30 neighbours / 200 probes), all six refiner passes, through
+imageSynth().  It does not sit on the 10 % stop rule's knife edge (both engines run all six passes, so both arms do
+the same 4.05 visits per target pixel), which makes px/s comparable between the arms; every line also carries
+visits/s and evals/s, the equal-work rates.  The other BASELINE configurations ride along as sub-records
+("configs"), and configuration 5 -- the FIXED batch of 64 heal jobs dealt over the ranks, with its probe-count
+sweep -- as "cfg5_batch" (strong scaling; the headline is weak scaling: one job stream per GPU).
 
-  value  = target px/s with inputs resident in HBM: n_targets / CUDA-event time from "upload complete" to
-           "last pass done" on the job's stream (whole job: N ranks x K steps, max over ranks).
-  e2e    = the same metric through the reference-facing C-ABI call engine() with HOST buffers: host prep,
-           H2D, passes, D2H, write-back all inside the timed region.
-Multi-GPU: independent jobs per rank (a job does not shard), no data-path collective, "scaling": "weak".
+  value  = target px/s with inputs resident in HBM: n_targets / CUDA-event time of the job's kernels on the job's
+           stream (pass-0 patch gather + every pass), whole job: N ranks x K steps, max over ranks.
+  e2e    = the same metric through the reference-facing C-ABI call with HOST buffers: host prep, H2D, ordering,
+           passes, D2H, write-back all inside the timed region.
 """
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -34,6 +36,9 @@ from resynthesizer_b200.synthetic import G, centered_mask  # noqa: E402
 
 METRIC = "synthesized target px/s"
 UNIT = "px/s"
+DTYPE = "u8/u32 integer"
+DEFAULT_WORKLOAD = "cfg3"
+SEED = 1198472   # the reference seeds its PRNG with this constant in every engine() call (lib/engine.c:643)
 
 
 # ------------------------------------------------------------------------------------------ workloads
@@ -108,6 +113,15 @@ def pixmaps(w):
     return np.ascontiguousarray(np.concatenate(tparts, axis=2)), np.ascontiguousarray(np.concatenate(cparts, axis=2))
 
 
+def api_name(w):
+    return "imageSynth() simple API" if "simple" in w else "engine() full API"
+
+
+def config_of(w):
+    """The `config` object of a line: identical in both arms (what the driver compares)."""
+    return {"workload": w["name"], "api": api_name(w)}
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     def __init__(self, index):
@@ -151,6 +165,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def visits_of(n, passes_run):
+    """Visits the pass schedule (lib/passes.h:67-93) makes in `passes_run` passes over n target points."""
+    ends = [n, n]
+    for _ in range(4):
+        ends.append(ends[-1] * 3 // 4)
+    return sum(ends[:passes_run])
+
+
 def _ref_worker(args):
     libname, wname, scale, seed_shift, steps = args
     from oracle import refdriver as R
@@ -160,31 +182,54 @@ def _ref_worker(args):
     times = []
     n = int((w["tmask"] != 0).sum())
     for _ in range(steps):
-        tp, cp = pixmaps(w)
         t0 = time.perf_counter()
-        err = R.engine(lib, w["params"], fi, tp, cp)
+        if "simple" in w:   # the same entry point our arm times for this workload
+            err, _out = R.image_synth(lib, w["tgt"], w["tmask"], w["simple"], w["params"])
+        else:
+            tp, cp = pixmaps(w)
+            t0 = time.perf_counter()
+            err = R.engine(lib, w["params"], fi, tp, cp)
         times.append(time.perf_counter() - t0)
         assert err == 0
     return n, times
 
 
 def cpu_reference_run(wname, scale, steps, warmup, procs, libname="ref_rand_1t"):
-    """Runs `procs` independent sample jobs per step on the host cores with the compiled reference."""
+    """Runs `procs` identical sample jobs per step, one per host core, with the compiled reference."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(procs) as pool:
         if warmup:
-            pool.map(_ref_worker, [(libname, wname, scale, i, 1) for i in range(procs)])
+            pool.map(_ref_worker, [(libname, wname, scale, 0, warmup) for _ in range(procs)])
         t0 = time.perf_counter()
-        res = pool.map(_ref_worker, [(libname, wname, scale, i, steps) for i in range(procs)])
+        res = pool.map(_ref_worker, [(libname, wname, scale, 0, steps) for _ in range(procs)])
         wall = time.perf_counter() - t0
     n = res[0][0]
     return dict(px_per_s=procs * steps * n / wall, wall=wall, n=n, per_job_s=float(np.mean([np.mean(r[1]) for r in res])))
 
 
+def reference_counters(wname, scale):
+    """Visits / evals / passes of ONE reference job of the sample: the C restatement in the reference's own semantics
+    with the standalone build's libc-rand stream (oracle RAND_MODE, pinned to libref_rand_1t output for output in
+    tests/test_port_vs_ref.py) -- the compiled reference itself keeps no counters."""
+    from oracle import refdriver as R
+    port = R.load_port(R.RAND_MODE)
+    w = workload(wname, 0, scale)
+    if "simple" in w:
+        err, _ = R.image_synth(port, w["tgt"], w["tmask"], w["simple"], w["params"])
+    else:
+        fi = R.format_indices(port, w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
+        tp, cp = pixmaps(w)
+        err = R.engine(port, w["params"], fi, tp, cp)
+    assert err == 0
+    return R.port_stats(port)
+
+
 def reference_sample_scale(wname):
-    # bounded samples of the same workload: 10-30 s of CPU work in all (unthreaded + 8-thread build, or one job per core)
-    return {"cfg2": 0.5, "cfg1": 1.0, "cfg5": 0.25, "cfg3": 0.0625, "cfg4": 0.125}.get(wname, 1.0)
+    # Bounded samples of the same workload.  Sized so that the sample runs the same number of passes as the full job
+    # (checked below) and one step is a few seconds per core; cfg2 is run in full (its 1024^2 job stops after 2 passes,
+    # its 512^2 sample after 3: not like for like, hence no scaling).
+    return {"cfg2": 1.0, "cfg1": 1.0, "cfg5": 0.5, "cfg3": 0.125, "cfg4": 0.125}.get(wname, 1.0)
 
 
 def run_reference(a):
@@ -196,20 +241,205 @@ def run_reference(a):
         return
     procs = max(1, min(os.cpu_count() or 1, 64))
     scale = reference_sample_scale(a.workload)
+    w_full = workload(a.workload)
     w = workload(a.workload, 0, scale)
-    r = cpu_reference_run(a.workload, scale, a.steps, min(a.warmup, 1), procs)
-    sample = "%s; %d independent jobs (one per host core) x %d steps, unthreaded reference build (libref_rand_1t)" % (w["name"], procs, a.steps)
+    r = cpu_reference_run(a.workload, scale, a.steps, a.warmup, procs)
+    ctr = reference_counters(a.workload, scale)
+    n = r["n"]
+    step_s = r["wall"] / a.steps
+    sample = ("%s; each step = %d identical jobs, one per host core, complete (all passes) through the unthreaded "
+              "reference build (oracle/_ref/libref_rand_1t.so); counters of one job from the oracle port in the same "
+              "semantics" % (w["name"], procs))
     line = {"metric": METRIC, "value": r["px_per_s"], "unit": UNIT, "impl": "reference", "n_gpus": a.gpus,
-            "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": 1000.0 * r["wall"] / a.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer",
-            "data": "synthetic", "config": {"workload": workload(a.workload)["name"], "sample": sample},
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1000.0 * step_s,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
+            "data": "synthetic", "config": config_of(w_full), "sample": sample,
+            # equal-work keys (the same ones our arm prints): px/s compares like with like when visits_per_px agree
+            "passes_run": ctr["passes_run"], "visits_per_px": ctr["visits"] / n, "evals_per_visit": ctr["evals"] / ctr["visits"],
+            "visits_per_step": procs * ctr["visits"], "evals_per_step": procs * ctr["evals"],
+            "visits_per_s": procs * ctr["visits"] / step_s, "evals_per_s": procs * ctr["evals"] / step_s,
+            "compares_per_s": procs * ctr["compares"] / step_s,
             "cpu_baseline": {"value": r["px_per_s"], "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
-            "e2e": {"value": r["px_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": r["px_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "visits_per_s": procs * ctr["visits"] / step_s, "evals_per_s": procs * ctr["evals"] / step_s},
             "gpu_launches": 0, "per_job_seconds": r["per_job_s"]}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def algorithmic_counts(key):
+    p = os.path.join(ROOT, "profiles", "algorithmic_counts.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(key)
+
+
+def algorithmic_bytes(c, w):
+    """SURVEY.md section 8d, from the counters of the SEQUENTIAL algorithm (oracle): per neighbour compare bpp bytes of
+    corpus; per scanned offset 8 + 1 (offset + hasValue); per visit K x (bpp + 8) (neighbour pixel + sourceOf) and the
+    commit (colour bytes + 8 + 1); per heuristic candidate 4 + 4 (recentProber read + write); per probe drawn 8
+    (corpusPoints lookup)."""
+    bpp = w["bpp"]
+    K = max(2, w["params"].patchSize)
+    probes_drawn = c["evals"] - c["heur_evals"]
+    return (c["compares"] * bpp + c["offset_scans"] * 9 + c["visits"] * (K * (bpp + 8) + w["n_color"] + 9) +
+            (c["heur_evals"] + c["heur_skips"]) * 8 + probes_drawn * 8)
+
+
+def roofline_of(w, wname, stats, steps, api, gather=True):
+    """Roofline record of the synthesis kernels of `steps` identical jobs (their stats in `stats`)."""
+    key = wname + (":%d" % PROBES_OVERRIDE if PROBES_OVERRIDE and PROBES_OVERRIDE != 200 else "")
+    oc = algorithmic_counts(key)
+    dev = {k: stats[-1][k] for k in ("visits", "evals", "compares", "offset_scans", "heur_evals", "heur_skips")}
+    if oc is not None and (oc["visits"], oc["evals"]) == (dev["visits"], dev["evals"]):
+        counts, src = oc, "profiles/algorithmic_counts.json (sequential oracle; visits and evals equal the device's)"
+    else:
+        counts, src = dev, ("the device's own counters (compares as issued by the chunked parallel early-out: an upper "
+                            "bound of the sequential algorithm's)" + ("" if oc is None else "; the oracle's visit/eval counts differ!"))
+    algo = algorithmic_bytes(counts, w)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "MEASURED_PEAKS.json hbm_gbs (measured, burst)"
+    else:
+        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
+    kern_s = float(np.mean([s["ms_kernels"] for s in stats])) / 1000.0
+    launches = int(np.mean([s["synth_launches_run"] for s in stats])) + 2   # pass launches that did work + the two pass-0 gathers
+    achieved = algo / kern_s / 1e9
+    traffic = bound = None
+    tp_path = os.path.join(ROOT, "profiles", "traffic_%s.json" % wname)
+    if os.path.exists(tp_path):
+        t = json.load(open(tp_path))
+        traffic = t.get("dram_bytes_per_launch")
+        bound = t.get("bound")
+    rec = {"bound": bound or "hbm", "kernel": "k_synth_pass / k_synth_pass_team (all pass launches + pass-0 patch gather of one job)",
+           "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+           "peak_source": peak_src, "counts_source": src,
+           "algorithmic_bytes_per_job": algo, "algorithmic_bytes_per_launch": algo / launches,
+           "ms_kernels_per_job": 1000.0 * kern_s, "avg_launch_ms": 1000.0 * kern_s / launches, "launches_per_job": launches,
+           "counts": {k: counts[k] for k in ("visits", "evals", "compares", "offset_scans", "heur_evals", "heur_skips")},
+           "compares_issued": dev["compares"],
+           "formula": "compares*bpp + offset_scans*9 + visits*(K*(bpp+8) + n_color+9) + (heur_evals+heur_skips)*8 + "
+                      "(evals-heur_evals)*8, bpp=%d K=%d; achieved = that / ms_kernels" % (w["bpp"], max(2, w["params"].patchSize))}
+    if gather:
+        # the access pattern's own ceiling: random corpus-pixel gathers from a corpus-sized buffer, measured now
+        elem = 8 if w["n_map"] else 4
+        nbytes = w["cor"].shape[0] * w["cor"].shape[1] * elem
+        g = api.gather_rate(nbytes, elem, 7)
+        rec["l2_gather"] = {"loads_per_s": g, "compares_per_s": counts["compares"] / kern_s,
+                            "frac": counts["compares"] / kern_s / g,
+                            "what": "uniformly random %d-byte loads from a %d-byte buffer (rs_cuda_gather_rate: the throughput "
+                                    "kernel's launch shape and L1 carve-out, >= 20 ms launches, median of 7): the access "
+                                    "pattern of one neighbour compare" % (elem, nbytes)}
+    return rec
+
+
+class Runner:
+    """One workload through the public API, with host buffers, L2 flushed before every job."""
+
+    def __init__(self, api, torch, w, fi):
+        self.api, self.torch, self.w, self.fi = api, torch, w, fi
+        self.n = int((w["tmask"] != 0).sum())
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+        rows = np.flatnonzero(w["tmask"].any(axis=1))
+        n_rows = int(rows[-1] - rows[0] + 1)
+        if "simple" in w:
+            self.h2d = w["tgt"].nbytes + w["tmask"].nbytes + 4 * self.n      # image + mask planes and the PRNG draws of the order
+            self.d2h = n_rows * w["tmask"].shape[1] * (w["bpp"] - 1)          # the rows that hold target points
+        else:
+            tp, cp = pixmaps(w)
+            self.h2d = tp.nbytes + cp.nbytes + 4 * self.n
+            self.d2h = n_rows * w["tmask"].shape[1] * w["bpp"]
+
+    def step(self):
+        api, w = self.api, self.w
+        api.set_seed(SEED)
+        if "simple" in w:
+            img = w["tgt"].copy()
+            self.flush.fill_(1)
+            self.torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            err = api.image_synth(img, w["tmask"], w["simple"], w["params"])
+            wall = time.perf_counter() - t0
+        else:
+            tp, cp = pixmaps(w)
+            self.flush.fill_(1)
+            self.torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            err = api.engine(w["params"], self.fi, tp, cp)
+            wall = time.perf_counter() - t0
+        assert err == 0
+        return wall, api.last_stats()
+
+
+def sub_record(api, torch, wname, steps, warmup):
+    """A short run of another BASELINE configuration, same definitions as the headline."""
+    w = workload(wname)
+    fi = api.format_indices(w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
+    r = Runner(api, torch, w, fi)
+    for _ in range(warmup):
+        r.step()
+    walls, stats = [], []
+    for _ in range(steps):
+        wall, st = r.step()
+        walls.append(wall); stats.append(st)
+    kern_s = sum(s["ms_kernels"] for s in stats) / 1000.0
+    visits = stats[-1]["visits"]; evals = stats[-1]["evals"]
+    rf = roofline_of(w, wname, stats, steps, api, gather=False)
+    return {"workload": w["name"], "api": api_name(w), "steps": steps, "warmup": warmup,
+            "value": steps * r.n / kern_s, "unit": UNIT, "e2e": steps * r.n / sum(walls),
+            "ms_kernels": 1000.0 * kern_s / steps, "ms_e2e": 1000.0 * sum(walls) / steps,
+            "ms_pass": [float(np.mean([s["ms_pass"][p] for s in stats])) for p in range(6)],
+            "passes_run": stats[-1]["passes_run"], "visits_per_px": visits / r.n, "evals_per_visit": evals / max(visits, 1),
+            "visits_per_s": steps * visits / kern_s, "evals_per_s": steps * evals / kern_s,
+            "roofline": {k: rf[k] for k in ("bound", "achieved", "peak", "frac", "traffic", "counts_source", "algorithmic_bytes_per_job")}}
+
+
+def cfg5_batch_record(api, torch, dist, rank, local, world, n_jobs, probe_list, slots):
+    """BASELINE.json config 5: a FIXED batch of `n_jobs` independent 2048x2048 heal jobs (images G(2048,2048,3,100+k),
+    the same centred 256x256 hole) dealt round robin over the ranks (strong scaling), once per probe count.  Every rank
+    runs its share through rs_image_synth_batch() -- host buffers in, healed images out -- and the time of a sweep
+    point is the slowest rank's wall clock between two barriers."""
+    from concurrent.futures import ThreadPoolExecutor
+    mine = sharding.deal_round_robin(n_jobs, world, rank)
+    m = centered_mask(2048, 2048, 256, 256)
+    with ThreadPoolExecutor(4) as ex:
+        pristine = list(ex.map(lambda k: G(2048, 2048, 3, 100 + k), mine))
+    work = [p.copy() for p in pristine]
+    masks = [m] * len(mine)
+    n_px = int((m != 0).sum())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    api.order_cache(True)   # same selection in every job of the batch: its target points are ordered once per GPU
+    out = {}
+    for probes in probe_list:
+        prm = abi.default_params()
+        prm.maxProbeCount = probes
+        for rep in range(2):   # rep 0: warm-up (workspaces, order cache), rep 1: timed
+            for dst, src in zip(work, pristine):
+                np.copyto(dst, src)
+            barrier()
+            t0 = time.perf_counter()
+            errs = api.image_synth_batch(work, masks, abi.T_RGB, prm, devices=[local], slots=slots) if work else []
+            t_rank = time.perf_counter() - t0
+            barrier()
+            t_all = time.perf_counter() - t0
+            assert not any(errs)
+        t_all, t_rank = sharding.max_over_ranks([t_all, t_rank], device="cuda")
+        changed = all((wk != pr).any() for wk, pr in zip(work, pristine))
+        ok = sharding.sum_over_ranks([0.0 if changed else 1.0], device="cuda")[0] == 0.0
+        out[str(probes)] = {"px_per_s": n_jobs * n_px / t_all, "ms_per_job": 1000.0 * t_all / n_jobs,
+                            "ms_batch": 1000.0 * t_all, "every_image_healed": bool(ok)}
+    api.order_cache(False)
+    return {"workload": "cfg5: %d heal jobs 2048x2048 RGB, 256x256 hole, ctx1, patch 30, dealt round robin over %d GPU(s)" % (n_jobs, world),
+            "api": "rs_image_synth_batch() = imageSynth() per image; host buffers in and out; visit-order cache on",
+            "jobs": n_jobs, "jobs_per_rank": [len(sharding.deal_round_robin(n_jobs, world, r)) for r in range(world)],
+            "slots_per_gpu": slots, "scaling": "strong", "unit": UNIT, "timing": "wall clock between barriers, max over ranks",
+            "h2d_bytes_per_job": int(pristine[0].nbytes + m.nbytes) if pristine else 0,
+            "d2h_bytes_per_job": 256 * 2048 * 3, "probes": out}
+
 
 def run_ours(a):
     import torch
@@ -234,53 +464,14 @@ def run_ours(a):
 
     w = workload(a.workload)   # the same job on every rank: weak scaling compares like with like
     fi = api.format_indices(w["n_color"], w["n_map"], w["alpha"], w["alpha"], w["n_map"] > 0)
-    n = int((w["tmask"] != 0).sum())
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    runner = Runner(api, torch, w, fi)
+    n = runner.n
 
-    B = max(1, a.batch)
-
-    def one_step(seed):
-        api.set_seed(seed)
-        if B == 1 and "simple" in w:
-            # the heal configurations are imageSynth() jobs (BASELINE.json configs 1, 3, 5): one image + mask, host buffers
-            img = w["tgt"].copy()
-            flush.fill_(seed & 0xFF)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            err = api.image_synth(img, w["tmask"], w["simple"], w["params"])
-            wall = time.perf_counter() - t0
-            assert err == 0
-            return wall, api.last_stats(), img, w["tmask"]
-        if B == 1:
-            tp, cp = pixmaps(w)
-            flush.fill_(seed & 0xFF)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            err = api.engine(w["params"], fi, tp, cp)
-            wall = time.perf_counter() - t0
-            assert err == 0
-            return wall, api.last_stats(), tp, cp
-        # a step = a batch of B independent jobs kept `slots` at a time on this GPU (rs_engine_batch)
-        jobs = [(w["params"], fi) + pixmaps(w) for _ in range(B)]
-        flush.fill_(seed & 0xFF)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        errs = api.engine_batch(jobs, a.slots)
-        wall = time.perf_counter() - t0
-        assert not any(errs)
-        st = {k: 0 for k in ("evals", "evals_issued", "compares", "visits", "offset_scans")}
-        st.update(ms_kernels=wall * 1000.0, ms_synth=wall * 1000.0, ms_prep=0.0, ms_h2d=0.0, ms_d2h=0.0, passes_run=0,
-                  ms_pass=[0.0] * 6, kernel_launches=0, synth_launches_run=0,
-                  n_corpus=int((w["cmask"] == 255).sum()))
-        return wall, st, jobs[0][2], jobs[0][3]
-
-    # The reference seeds its PRNG with the same constant in every engine() call (lib/engine.c:643); so does every step.
     # The device-side cache of visit orders (a job with the same selection, size, context type and seed reuses the
     # order of the first one) is OFF for the headline numbers: every timed job orders its target points itself.
-    SEED = 1198472
-    api.order_cache(B > 1)   # batch mode IS the cache's use case (same selection in every job of the batch): on, and said so
+    api.order_cache(False)
     for i in range(a.warmup):
-        one_step(SEED)
+        runner.step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -288,13 +479,9 @@ def run_ours(a):
     launches0 = api.total_kernel_launches()
     t_begin = time.perf_counter()
     walls, stats = [], []
-    h2d = d2h = 0
     for i in range(a.steps):
-        wall, st, tp, cp = one_step(SEED)
+        wall, st = runner.step()
         walls.append(wall); stats.append(st)
-        h2d = tp.nbytes + cp.nbytes + 4 * n      # both pixmaps (or image + mask) and the visit order
-        d2h = int((np.flatnonzero(w["tmask"].any(axis=1))[[0, -1]] * [-1, 1]).sum() + 1) * w["tmask"].shape[1] * (
-            (w["bpp"] - 1) if "simple" in w and B == 1 else w["bpp"])   # the rows that hold target points
     barrier()
     t_total = time.perf_counter() - t_begin
     n_launches = api.total_kernel_launches() - launches0
@@ -302,86 +489,74 @@ def run_ours(a):
 
     # the same job stream with the order cache on (what a batch of same-shaped jobs or the frames of a clip see)
     cached_walls = []
-    if B == 1:
+    if not a.quick:
         api.order_cache(True)
-        one_step(SEED)
+        runner.step()
         for i in range(max(3, a.steps // 4)):
-            cached_walls.append(one_step(SEED)[0])
+            cached_walls.append(runner.step()[0])
         api.order_cache(False)
 
     kern_s = sum(s["ms_kernels"] for s in stats) / 1000.0
     e2e_s = sum(walls)
     # the only communication of the multi-GPU path: max over ranks of three timing scalars
     kern_s, e2e_s, t_total = sharding.max_over_ranks([kern_s, e2e_s, t_total], device="cuda")
-    total_px = world * a.steps * n * B
+    total_px = world * a.steps * n
     evals = sum(s["evals"] for s in stats); issued = sum(s["evals_issued"] for s in stats)
     compares = sum(s["compares"] for s in stats); visits = sum(s["visits"] for s in stats)
-    scans = sum(s["offset_scans"] for s in stats)
+
+    # BASELINE config 5, dealt over the ranks (all ranks take part), and the other configurations (rank 0, one GPU)
+    batch = None
+    if not a.quick and a.cfg5_jobs > 0:
+        batch = cfg5_batch_record(api, torch, dist, rank, local, world, a.cfg5_jobs,
+                                  [int(p) for p in a.cfg5_probes.split(",") if p], a.slots)
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
+    subs = {}
+    if not a.quick and world == 1:
+        for name in ("cfg1", "cfg2", "cfg4", "cfg5"):
+            if name != a.workload:
+                subs[name] = sub_record(api, torch, name, 5, 2)
+        if a.workload != DEFAULT_WORKLOAD:
+            subs[DEFAULT_WORKLOAD] = sub_record(api, torch, DEFAULT_WORKLOAD, 5, 2)
 
-    # ---- roofline of the dominant kernel (k_synth_pass / k_synth_pass_team): algorithmic bytes per SURVEY.md section 8d.
-    # Duration = CUDA events on the job's stream around the pass kernels alone; launches = the pass-kernel launches
-    # that did work (passes after the 10 % stop rule exit immediately and are not counted).
-    bpp = w["bpp"]
-    K = max(2, w["params"].patchSize)
-    P = w["params"].maxProbeCount
-    fixed = scans * (4 + 4) + visits * (K * (8 + (4 if w["n_map"] else 0)) + K * 8 + P * 4 + 8 + 4)
-    algo_bytes = compares * bpp + fixed
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak = json.load(open(peaks_path))["hbm_gbs"]; peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)"
-    else:
-        peak = 6650.0; peak_src = "fallback 6.65 TB/s (B200_PROFILING.md)"
-    synth_s = sum(s["ms_synth"] for s in stats) / 1000.0
-    launches_pass = max(1, sum(s["synth_launches_run"] for s in stats))
-    achieved = algo_bytes / synth_s / 1e9
-    traffic = None
-    tp_path = os.path.join(ROOT, "profiles", "traffic_%s.json" % a.workload)
-    if os.path.exists(tp_path):
-        traffic = json.load(open(tp_path)).get("dram_bytes_per_launch")
-    # the access pattern's own ceiling: random corpus-pixel gathers from a corpus-sized buffer, measured now
-    elem = 8 if w["n_map"] else 4
-    gather = api.gather_rate(w["cor"].shape[0] * w["cor"].shape[1] * elem, elem)
-    roofline = {"bound": "hbm", "kernel": "k_synth_pass(+_team)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes / launches_pass,
-                "avg_launch_ms": 1000.0 * synth_s / launches_pass, "launches": launches_pass,
-                "gather_ceiling": {"loads_per_s": gather, "compares_per_s": compares / synth_s,
-                                   "frac": compares / synth_s / gather,
-                                   "what": "uniformly random %d-byte loads from a %d-byte buffer (rs_cuda_gather_rate), "
-                                           "the access pattern of one neighbour compare" % (elem, w["cor"].shape[0] * w["cor"].shape[1] * elem)},
-                "note": "bytes = neighbour-compares x %d B corpus pixel + per-visit fixed part; the working set is "
-                        "L2-resident, so DRAM traffic is far below the algorithmic bytes and the HBM fraction is small "
-                        "by construction; the gather ceiling is the bound that applies" % bpp}
+    roofline = roofline_of(w, a.workload, stats, a.steps, api)
 
-    # ---- CPU baseline beside it: the compiled reference on a bounded sample of the same workload
+    # ---- CPU baseline beside it: the compiled reference on a bounded sample of the same workload (rank 0, N = 1)
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_rand_1t.so")):
             scale = reference_sample_scale(a.workload)
             r1 = cpu_reference_run(a.workload, scale, 1, 0, 1, "ref_rand_1t")
             r8 = cpu_reference_run(a.workload, scale, 1, 0, 1, "ref_rand_8t")
+            ctr = reference_counters(a.workload, scale)
             best, cores, which = (r1, 1, "unthreaded") if r1["px_per_s"] >= r8["px_per_s"] else (r8, 8, "8-thread refiner")
             cpu = {"value": best["px_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": "%s, one job, reference %s build; unthreaded %.0f px/s, threaded(8) %.0f px/s" %
-                             (workload(a.workload, 0, scale)["name"], which, r1["px_per_s"], r8["px_per_s"])}
+                   "sample": "%s, one complete job, reference %s build; unthreaded %.0f px/s, threaded(8) %.0f px/s" %
+                             (workload(a.workload, 0, scale)["name"], which, r1["px_per_s"], r8["px_per_s"]),
+                   "passes_run": ctr["passes_run"], "visits_per_px": ctr["visits"] / best["n"],
+                   "visits_per_s": ctr["visits"] / best["per_job_s"], "evals_per_s": ctr["evals"] / best["per_job_s"]}
         else:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
 
     line = {"metric": METRIC, "value": total_px / kern_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000.0 * t_total / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
-            "config": {"workload": w["name"] + (" x %d jobs per step, %d in flight, visit-order cache on" % (B, a.slots) if B > 1 else ""),
-                       "parallelism": "independent jobs, %d GPU(s)" % world,
-                       "l2": "256 MiB flush between steps",
-                       "api": "imageSynth() simple API" if ("simple" in w and B == 1) else "engine() full API"},
-            "evals_per_s": world * evals / kern_s, "evals_issued_per_s": world * issued / kern_s,
-            "compares_per_s": world * compares / kern_s, "compares_per_eval_issued": compares / max(issued, 1),
-            "passes_run": stats[-1]["passes_run"], "visits_per_step": visits / a.steps,
-            "e2e": {"value": total_px / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": config_of(w),
+            "parallelism": "independent jobs, one job stream per GPU, %d GPU(s), no collective on the data path" % world,
+            "l2": "256 MiB flush before every job",
+            # equal-work keys (also printed by --impl reference)
+            "passes_run": stats[-1]["passes_run"], "visits_per_px": visits / a.steps / n,
+            "evals_per_visit": evals / max(visits, 1),
+            "visits_per_step": world * visits / a.steps, "evals_per_step": world * evals / a.steps,
+            "visits_per_s": world * visits / kern_s, "evals_per_s": world * evals / kern_s,
+            "evals_issued_per_s": world * issued / kern_s, "compares_per_s": world * compares / kern_s,
+            "compares_per_eval_issued": compares / max(issued, 1),
+            "e2e": {"value": total_px / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(runner.h2d), "d2h_bytes_per_step": int(runner.d2h),
+                    "visits_per_s": world * visits / e2e_s, "evals_per_s": world * evals / e2e_s,
+                    "ms_call": 1000.0 * e2e_s / a.steps,
                     "ms_prep": float(np.mean([s["ms_prep"] for s in stats])), "ms_h2d": float(np.mean([s["ms_h2d"] for s in stats])),
                     "ms_kernels": float(np.mean([s["ms_kernels"] for s in stats])), "ms_d2h": float(np.mean([s["ms_d2h"] for s in stats]))},
             "ms_pass": [float(np.mean([s["ms_pass"][p] for s in stats])) for p in range(6)],
@@ -389,23 +564,27 @@ def run_ours(a):
                                   "what": "same call with the visit-order cache on (rank 0, %d jobs): the target order of an "
                                           "identical selection is reused from the device" % len(cached_walls)}
                                  if cached_walls else None),
-            "gpu_launches": int(n_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+            "gpu_launches": int(n_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "configs": subs or None, "cfg5_batch": batch}
     print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--probes", type=int, default=0, help="override maxProbeCount (the cfg5 sweep of BASELINE.json: 50..1000)")
-    ap.add_argument("--batch", type=int, default=1, help="jobs per step (rs_engine_batch); value is then wall-clock based")
-    ap.add_argument("--slots", type=int, default=8, help="jobs in flight per GPU in batch mode")
+    ap.add_argument("--quick", action="store_true", help="headline only: no sub-records, no cfg5 batch, no cached-order leg")
+    ap.add_argument("--probes", type=int, default=0, help="override maxProbeCount of the headline workload")
+    ap.add_argument("--cfg5-jobs", type=int, default=64, help="jobs of the cfg5 batch record (0 = skip)")
+    ap.add_argument("--cfg5-probes", default="50,100,200,500,1000", help="probe counts of the cfg5 sweep")
+    ap.add_argument("--slots", type=int, default=3, help="jobs in flight per GPU in the cfg5 batch")
     a = ap.parse_args()
     global PROBES_OVERRIDE
     PROBES_OVERRIDE = a.probes

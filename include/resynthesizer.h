@@ -160,6 +160,21 @@ unsigned long long rs_total_kernel_launches(void);
  * Returns 0 if every job returned 0, else the first non-zero code. */
 int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
                     Map *const *targetMaps, Map *const *corpusMaps, int slots, int *errors_out);
+/* The same batch dealt over several GPUs of the box from ONE process (a job never shards, a batch does; no collective):
+ * `devices[0..n_devices)` are CUDA ordinals (n_devices 0 / devices NULL: the calling thread's device).  Every device
+ * gets `slots` host threads; all of them pull the next job from one queue, longest estimated job first, so a device
+ * that finishes early takes more.  What the reference's callers do with a loop over engine()
+ * (PluginScripts/plugin-heal-selection.py:148 per image) becomes one call.  rs_last_error() holds the text of the first
+ * failed job. */
+int rs_engine_batch_multi(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
+                          Map *const *targetMaps, Map *const *corpusMaps, int n_devices, const int *devices, int slots,
+                          int *errors_out);
+/* The batch call for simple-API jobs: imageSynth(images[i], masks[i], format, params, ...) for every i, or imageSynth2
+ * where masks2 (may be NULL) holds an explicit corpus mask for that job; params NULL = defaults.  Images change in place
+ * exactly as imageSynth() changes them.  Same dealing as rs_engine_batch_multi. */
+int rs_image_synth_batch(int n_jobs, ImageBuffer *const *images, ImageBuffer *const *masks, ImageBuffer *const *masks2,
+                         TImageFormat format, const TImageSynthParameters *params, int n_devices, const int *devices,
+                         int slots, int *errors_out);
 /* rs_keep_result(1): engine() calls on this thread also fetch what rs_get_last_result() returns (off by default). */
 void rs_keep_result(int yes);
 /* Visit order and final source (best corpus point) of each target point of the last engine() call on this

@@ -81,6 +81,9 @@ typedef int (*RsTickFn)(void *ctx, uint32_t pass, uint32_t index);
 const char *rs_cuda_last_error(void);
 int rs_cuda_set_device(int ordinal);
 int rs_cuda_device_count(void);
+/* Host cores this process may use for helper threads: hardware cores / LOCAL_WORLD_SIZE (one process per GPU under
+ * torchrun), or RS_HOST_THREADS. */
+unsigned rs_host_cores(void);
 /* Number of jobs the caller intends to keep in flight per device (default 1).  With k > 1 every job's persistent
  * kernels take ceil(1/k) of the SMs so that k jobs run side by side instead of queueing behind each other. */
 void rs_cuda_set_job_slots(int slots);

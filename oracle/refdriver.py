@@ -25,6 +25,12 @@ def load(name):
     return abi.bind(C.CDLL(path))
 
 
+def have(name):
+    """True when that library has been built (oracle/_ref needs /root/reference at build time)."""
+    return os.path.exists(os.path.join(HERE, "_port", "libresynth_port.so") if name == "port"
+                          else os.path.join(HERE, "_ref", "lib%s.so" % name))
+
+
 class Progress:
     def __init__(self, cancel_after=None):
         self.percents = []

@@ -257,8 +257,42 @@ def device_sorted_offsets(tw, th, cw, ch):
     return np.stack([x, y], axis=1)
 
 
-def engine_batch(jobs, slots=4):
-    """rs_engine_batch(): jobs = list of (params, fi, target_pixmap, corpus_pixmap); pixmaps change in place.
+def image_synth_batch(images, masks, fmt, params=None, devices=None, slots=4, masks2=None):
+    """rs_image_synth_batch(): imageSynth() (or imageSynth2() where masks2[i] is given) for every image of the batch,
+    dealt over `devices` (CUDA ordinals; None = this thread's device) from one process; images change in place.
+    Returns the list of per-job error codes."""
+    L = lib()
+    n = len(images)
+    IB = (C.POINTER(abi.ImageBuffer) * n)()
+    MB = (C.POINTER(abi.ImageBuffer) * n)()
+    M2 = (C.POINTER(abi.ImageBuffer) * n)() if masks2 is not None else None
+    keep = []
+
+    def buf(a, row_channels):
+        b = abi.ImageBuffer(a.ctypes.data_as(C.POINTER(C.c_ubyte)), a.shape[1], a.shape[0], a.shape[1] * row_channels)
+        keep.append((a, b))
+        return C.pointer(b)
+    for i in range(n):
+        im = images[i]
+        assert im.dtype == np.uint8 and im.ndim == 3 and im.flags["C_CONTIGUOUS"]
+        IB[i] = buf(im, im.shape[2])
+        MB[i] = buf(np.ascontiguousarray(masks[i], dtype=np.uint8), 1)
+        if M2 is not None and masks2[i] is not None:
+            M2[i] = buf(np.ascontiguousarray(masks2[i], dtype=np.uint8), 1)
+    errs = (C.c_int * n)()
+    nd = len(devices) if devices else 0
+    dv = (C.c_int * max(nd, 1))(*(devices or [0]))
+    L.rs_image_synth_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_void_p]
+    rc = L.rs_image_synth_batch(n, IB, MB, M2, fmt, C.byref(params) if params is not None else None, nd,
+                                dv if nd else None, int(slots), errs)
+    _check(rc)
+    return list(errs)
+
+
+def engine_batch(jobs, slots=4, devices=None):
+    """rs_engine_batch() / rs_engine_batch_multi(): jobs = list of (params, fi, target_pixmap, corpus_pixmap); pixmaps
+    change in place.  devices: CUDA ordinals the batch is dealt over (None = this thread's device).
     Returns the list of per-job error codes."""
     L = lib()
     n = len(jobs)
@@ -273,7 +307,13 @@ def engine_batch(jobs, slots=4):
         keep.append((fi, tm, cm, k1, k2))
         FI[i] = C.pointer(fi); TM[i] = C.pointer(tm); CM[i] = C.pointer(cm)
     errs = (C.c_int * n)()
-    L.rs_engine_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
-    rc = L.rs_engine_batch(n, P, FI, TM, CM, int(slots), errs)
+    if devices:
+        dv = (C.c_int * len(devices))(*devices)
+        L.rs_engine_batch_multi.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_int, C.c_void_p]
+        rc = L.rs_engine_batch_multi(n, P, FI, TM, CM, len(devices), dv, int(slots), errs)
+    else:
+        L.rs_engine_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        rc = L.rs_engine_batch(n, P, FI, TM, CM, int(slots), errs)
     _check(rc)
     return list(errs)

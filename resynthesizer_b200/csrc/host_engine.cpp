@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
+#include <functional>
 #include <memory>
 #include <string>
 #include <thread>
@@ -259,6 +261,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
     raw.reset(new rs::RawStream(t_seed, raw_cap, pinned));
   }
   RsTargetDigest dg;
+  const char *host_fault = nullptr;  // a failure detected by this layer (not by the CUDA layer)
   int rc = src.simple()
                ? rs_job_stage_simple(job, src.img->data, src.img->rowBytes, src.mask->data, src.mask->rowBytes,
                                      src.mask2 ? src.mask2->data : nullptr, src.mask2 ? src.mask2->rowBytes : 0, c256, m256, m512[0])
@@ -323,7 +326,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
         return false;
       };
       if (rs::collect_and_order(prm.matchContextType, mask0, tw, th, pstride, rstride, n, t_seed, targets, &sorter) != 0 || targets.size() != n) {
-        t_err = "target point count differs between host and device";
+        host_fault = "target point count differs between host and device";
         rc = 100;
       }
       if (!rc) rc = rs_job_set_order(job, targets.data(), t_keep_result ? nullptr : &key);
@@ -349,7 +352,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
     if (!rc && src.simple() && write_back) rc = rs_job_download_simple(job, src.img->data, src.img->rowBytes);
   }
   if (rc) {
-    t_err = rs_cuda_last_error();
+    t_err = host_fault ? host_fault : rs_cuda_last_error();  // the CUDA layer's text only when the failure was its own
     rs_job_destroy(job);
     return RS_ERROR_CUDA;
   }
@@ -393,50 +396,158 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
 }
 
 // ------------------------------------------------------------------------------- batch of independent jobs
+// The reference's users loop over engine() / imageSynth() (PluginScripts/plugin-heal-selection.py:148 once per image);
+// a job never shards (a visit reads pixels written by arbitrary earlier visits), a batch does.  The dealer below runs
+// ONE queue of jobs over `n_devices` GPUs of the box from one process: every device gets `slots` host threads (each
+// with its own workspace and stream on that device), every thread pulls the next job from the queue -- longest jobs
+// first when their estimated costs differ -- so a GPU that finishes early takes more.  No collective, no peer copies:
+// jobs are independent.
 extern "C" void rs_cuda_set_job_slots(int slots);
-extern "C" int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
-                               Map *const *targetMaps, Map *const *corpusMaps, int slots, int *errors_out) {
-  if (n_jobs <= 0) return 0;
-  if (slots < 1) slots = 1;
-  if (slots > n_jobs) slots = n_jobs;
-  {  // Side-by-side jobs pay off while a job is latency-bound (few thousand target points: B200 sweeps in profiles/);
-     // from ~16 k points on a job fills the GPU by itself and more than a few in flight only overlap host work and
-     // copies with kernels.  Estimate the size of the first job from a sparse sample of its mask.
-    const Map *m = targetMaps[0];
-    const uint8_t *pix = reinterpret_cast<const uint8_t *>(m->data->data);
-    const size_t npx = (size_t)m->width * m->height, step = 61;
-    size_t hits = 0;
-    for (size_t i = 0; i < npx; i += step) hits += pix[i * m->depth] != 0;
-    const size_t n_est = hits * step;
-    const int cap = n_est >= 200000 ? 2 : (n_est >= 16384 ? 4 : 8);
-    if (slots > cap) slots = cap;
+namespace {
+struct BatchPlan {
+  int n_jobs = 0, n_devices = 1, slots = 1;
+  bool share_sms = true;     // side-by-side jobs each take 1/slots of the SMs; false: every job launches full-width
+                             // grids and the jobs in flight only overlap their copies and host work with kernels
+  const int *devices = nullptr;
+  std::vector<double> cost;  // per job: ~ target points x (patch + probes); empty = all equal
+};
+// Estimated target points of a selection from a sparse sample of its mask bytes (stride `px_stride` bytes).
+size_t estimate_targets(const uint8_t *mask0, size_t npx, size_t px_stride) {
+  const size_t step = 61;
+  size_t hits = 0;
+  for (size_t i = 0; i < npx; i += step) hits += mask0[i * px_stride] != 0;
+  return hits * step;
+}
+// Jobs in flight per device.  Side-by-side jobs (each on 1/slots of the SMs) pay off while a job is latency-bound (a
+// few thousand target points: B200 sweeps in profiles/); from ~16 k points on a job fills the GPU by itself and more
+// than a few in flight only overlap host work and copies with kernels.
+int cap_slots(int slots, size_t n_est) {
+  const int cap = n_est >= 200000 ? 2 : (n_est >= 16384 ? 4 : 8);
+  return slots > cap ? cap : (slots < 1 ? 1 : slots);
+}
+// Jobs of 16 k+ target points fill the GPU on their own: in a batch they keep full-width grids (the persistent kernels
+// of the next job move in as the tail of the previous one drains) and only staging, ordering and read-back overlap.
+bool share_sms_for(size_t n_est) {
+  if (const char *e = std::getenv("RS_BATCH_SHARE")) return std::atoi(e) != 0;
+  return n_est < 16384;
+}
+int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int *errors_out) {
+  const int n_jobs = plan.n_jobs;
+  int n_dev = rs_cuda_device_count();
+  if (n_dev <= 0) { t_err = "no CUDA device available (this library has no CPU path)"; return RS_ERROR_CUDA; }
+  std::vector<int> devices;
+  if (plan.devices && plan.n_devices > 0) {
+    for (int d = 0; d < plan.n_devices; d++) {
+      if (plan.devices[d] < 0 || plan.devices[d] >= n_dev) { t_err = "batch: device ordinal out of range"; return RS_ERROR_CUDA; }
+      devices.push_back(plan.devices[d]);
+    }
+  } else {
+    if (int e = ensure_device()) return e;
+    devices.push_back(t_device >= 0 ? t_device : 0);
   }
-  if (int e = ensure_device()) return e;
-  int device = 0;
-  if (const char *e = std::getenv("RESYNTH_CUDA_DEVICE")) device = std::atoi(e);
-  device = t_device >= 0 ? t_device : device;
+  int slots = plan.slots < 1 ? 1 : plan.slots;
+  const int threads_wanted = (int)devices.size() * slots;
+  if (threads_wanted > n_jobs) slots = (n_jobs + (int)devices.size() - 1) / (int)devices.size();
+  // queue order: longest-processing-time first (stable), the classic greedy for unequal independent jobs
+  std::vector<int> order(n_jobs);
+  for (int i = 0; i < n_jobs; i++) order[i] = i;
+  if (!plan.cost.empty())
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plan.cost[a] > plan.cost[b]; });
   const uint32_t seed = t_seed;
   std::vector<int> errs(n_jobs, 0);
+  std::vector<std::string> texts(n_jobs);
   std::atomic<int> next{0};
-  rs_cuda_set_job_slots(slots);
-  auto worker = [&]() {
-    rs_set_device(device);
+  rs_cuda_set_job_slots(plan.share_sms ? slots : 1);
+  auto worker = [&](int device) {
+    if (rs_set_device(device)) {  // this device takes no jobs; the others drain the queue
+      return;
+    }
     rs_set_seed(seed);
-    int dummy_cancel = 0;
-    for (int i = next.fetch_add(1); i < n_jobs; i = next.fetch_add(1))
-      errs[i] = engine(params[i], indices[i], targetMaps[i], corpusMaps[i], [](int, void *) {}, nullptr, &dummy_cancel);
+    for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) {
+      const int i = order[k];
+      errs[i] = run_one(i);
+      if (errs[i]) texts[i] = t_err;  // thread-local text: keep it past the thread's end
+    }
   };
+  const int caller_device = t_device;
+  const bool caller_chosen = t_device_chosen;
   std::vector<std::thread> pool;
-  for (int t = 1; t < slots; t++) pool.emplace_back(worker);
-  worker();
+  for (size_t d = 0; d < devices.size(); d++)
+    for (int t = 0; t < slots; t++)
+      if (!(d == 0 && t == 0)) pool.emplace_back(worker, devices[d]);
+  worker(devices[0]);
   for (auto &t : pool) t.join();
   rs_cuda_set_job_slots(1);
+  if (caller_chosen && caller_device >= 0) rs_set_device(caller_device);  // the calling thread keeps the device it had
   int first = 0;
+  if (next.load() < n_jobs) { t_err = "batch: no usable device"; first = RS_ERROR_CUDA; }
   for (int i = 0; i < n_jobs; i++) {
     if (errors_out) errors_out[i] = errs[i];
-    if (!first && errs[i]) first = errs[i];
+    if (!first && errs[i]) { first = errs[i]; t_err = texts[i]; }
   }
   return first;
+}
+}  // namespace
+
+extern "C" int rs_engine_batch_multi(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
+                                     Map *const *targetMaps, Map *const *corpusMaps, int n_devices, const int *devices,
+                                     int slots, int *errors_out) {
+  if (n_jobs <= 0) return 0;
+  BatchPlan plan;
+  plan.n_jobs = n_jobs; plan.n_devices = n_devices; plan.devices = devices;
+  plan.cost.resize(n_jobs);
+  size_t n_max = 0;
+  bool equal = true;
+  for (int i = 0; i < n_jobs; i++) {
+    const Map *m = targetMaps[i];
+    const size_t n_est = estimate_targets(reinterpret_cast<const uint8_t *>(m->data->data), (size_t)m->width * m->height, m->depth);
+    plan.cost[i] = (double)n_est * (double)(params[i].patchSize + params[i].maxProbeCount);
+    if (n_est > n_max) n_max = n_est;
+    if (plan.cost[i] != plan.cost[0]) equal = false;
+  }
+  if (equal) plan.cost.clear();
+  plan.slots = cap_slots(slots, n_max);
+  plan.share_sms = share_sms_for(n_max);
+  return run_batch(plan, [&](int i) {
+    int dummy_cancel = 0;
+    return engine(params[i], indices[i], targetMaps[i], corpusMaps[i], [](int, void *) {}, nullptr, &dummy_cancel);
+  }, errors_out);
+}
+extern "C" int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
+                               Map *const *targetMaps, Map *const *corpusMaps, int slots, int *errors_out) {
+  return rs_engine_batch_multi(n_jobs, params, indices, targetMaps, corpusMaps, 0, nullptr, slots, errors_out);
+}
+// The same for simple-API jobs: imageSynth() (masks2 == NULL) or imageSynth2() per image.
+extern "C" int rs_image_synth_batch(int n_jobs, ImageBuffer *const *images, ImageBuffer *const *masks,
+                                    ImageBuffer *const *masks2, TImageFormat format, const TImageSynthParameters *params,
+                                    int n_devices, const int *devices, int slots, int *errors_out) {
+  if (n_jobs <= 0) return 0;
+  TImageSynthParameters prm;
+  if (params) prm = *params; else setDefaultParams(&prm);
+  BatchPlan plan;
+  plan.n_jobs = n_jobs; plan.n_devices = n_devices; plan.devices = devices;
+  plan.cost.resize(n_jobs);
+  size_t n_max = 0;
+  bool equal = true;
+  for (int i = 0; i < n_jobs; i++) {
+    const ImageBuffer *m = masks[i];
+    size_t hits = 0;  // sparse sample, row by row (rows may be padded)
+    for (unsigned y = 0; y < m->height; y += 7)
+      for (unsigned x = y % 5; x < m->width; x += 9) hits += m->data[(size_t)y * m->rowBytes + x] != 0;
+    const size_t n_est = hits * 63;
+    plan.cost[i] = (double)n_est;
+    if (n_est > n_max) n_max = n_est;
+    if (plan.cost[i] != plan.cost[0]) equal = false;
+  }
+  if (equal) plan.cost.clear();
+  plan.slots = cap_slots(slots, n_max);
+  plan.share_sms = share_sms_for(n_max);
+  return run_batch(plan, [&](int i) {
+    int dummy_cancel = 0;
+    TImageSynthParameters p = prm;
+    return masks2 && masks2[i] ? imageSynth2(images[i], masks[i], masks2[i], format, &p, [](int, void *) {}, nullptr, &dummy_cancel)
+                               : imageSynth(images[i], masks[i], format, &p, [](int, void *) {}, nullptr, &dummy_cancel);
+  }, errors_out);
 }
 
 // ------------------------------------------------------------------------------- simple API (one image)

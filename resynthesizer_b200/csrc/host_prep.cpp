@@ -104,7 +104,7 @@ void collect_target_points(const uint8_t *pix, int w, int h, int bpp, std::vecto
 void collect_target_points_strided(const uint8_t *mask0, int w, int h, size_t pixel_stride, size_t row_stride,
                                    std::vector<uint32_t> &out) {
   const size_t npx = (size_t)w * h;
-  unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = rs_host_cores();
   const int nt = npx < ((size_t)1 << 19) ? 1 : (int)std::min<unsigned>(npx < ((size_t)1 << 21) ? 4u : 8u, hw ? hw : 1u);
   if (nt <= 1) {
     out.clear();
@@ -373,7 +373,7 @@ static void radix_sort_pairs(std::vector<uint32_t> &keys, std::vector<uint32_t> 
 // Runs body(begin, end) over [0, n) on up to 8 threads (one for small n).
 template <class Body>
 static void parallel_ranges(size_t n, Body body) {
-  unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = rs_host_cores();
   size_t nt = n < ((size_t)1 << 17) ? 1 : std::min<size_t>(8, hw ? hw : 1);
   if (nt <= 1) { body((size_t)0, n, (size_t)0); return; }
   std::vector<std::thread> th;

@@ -11,6 +11,8 @@
 
 #include "../../include/resynthesizer.h"
 
+extern "C" unsigned rs_host_cores(void);  // cores this process may use for helper threads (csrc/rs_kernels.cu)
+
 namespace rs {
 
 // Points are packed x | y << 16 (coordinates < 32768) all the way from the scan to the device.

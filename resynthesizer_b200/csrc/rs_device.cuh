@@ -47,7 +47,12 @@
 #ifndef RS_CHUNK_SWITCH_K
 #define RS_CHUNK_SWITCH_K 16
 #endif
-#define RS_LUT_WORDS (256 * 32)
+// Copies of each metric-table entry, one per lane group (lane % RS_LUT_REP picks the column): 32 = no two lanes ever
+// share a bank, 8 = a quarter of the shared memory for occasional 2-way conflicts.
+#ifndef RS_LUT_REP
+#define RS_LUT_REP 32
+#endif
+#define RS_LUT_WORDS (256 * RS_LUT_REP)
 #define RS_MAX_LAUNCHES 16   // pass-kernel launches per job: 6 passes, the first ones cut into up to 4 segments
 #define RS_TIMELINE 320      // progress ticks per pass whose start time is kept (4096 visits each)
 #define RS_MAX_EPOCHS 40     // epochs per pass: ceil(n / max(64, ceil(n/32))) <= 32
@@ -88,6 +93,8 @@ struct RsDev {              // kernel argument (by value)
   const uint32_t *tmaps;
   const uint32_t *targets;
   const uint32_t *corpus_pts;
+  const uint32_t *cbits;    // bitmap of the usable corpus pixels, row-major, 32 per word (or nullptr: table only)
+  const uint32_t *csamples; // linear index of usable corpus pixel 32 * j
   const uint32_t *offsets;
   const uint32_t *lut_rep;  // [2][256][32] colour then map metric, replicated per lane (bank-conflict free)
   unsigned long long *prober[3];  // [cw*ch] each: stamps of epochs = 0, 1, 2 (mod 3), see above
@@ -109,6 +116,7 @@ struct RsDev {              // kernel argument (by value)
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
   uint32_t ends[6];
   int htile, vtile;
+  uint32_t cw_inv;          // floor(2^32 / cw): quotient estimate for rs_corpus_point (one correction step makes it exact)
   double terminate_fraction;
 };
 
@@ -127,6 +135,43 @@ __host__ __device__ __forceinline__ uint32_t rs_probe_hash_visit(uint32_t seed, 
   return rs_mix32(h ^ (index * 0x85EBCA6Bu + 0x165667B1u));
 }
 __device__ __forceinline__ uint32_t rs_range(uint32_t r, uint32_t n) { return __umulhi(r, n); }
+__device__ __forceinline__ uint32_t rs_nth_set_bit(uint32_t x, uint32_t r) {  // position of the r-th (0-based) set bit of x
+  uint32_t pos = 0, c;
+  c = __popc(x & 0xFFFFu); if (r >= c) { r -= c; pos += 16; x >>= 16; }
+  c = __popc(x & 0xFFu);   if (r >= c) { r -= c; pos += 8;  x >>= 8; }
+  c = __popc(x & 0xFu);    if (r >= c) { r -= c; pos += 4;  x >>= 4; }
+  c = __popc(x & 0x3u);    if (r >= c) { r -= c; pos += 2;  x >>= 2; }
+  c = x & 1u;              if (r >= c) { pos += 1; }
+  return pos;
+}
+// The idx-th corpus point (lib/engine.c:400-431: row-major list of the usable corpus pixels), packed x | y << 16.  When
+// EVERY corpus pixel is usable (nC == cw * ch: texture tiles, whole-image corpora) the list is the identity and the
+// point follows from the index -- no table lookup, and the table stays out of L1.
+__device__ __forceinline__ uint32_t rs_corpus_point(const RsDev &J, uint32_t nC, uint32_t idx) {
+  if (nC == J.cn) {
+    uint32_t y = __umulhi(idx, J.cw_inv), x = idx - y * (uint32_t)J.cw;  // y is exact or one short (idx < 2^32)
+    if (x >= (uint32_t)J.cw) { x -= (uint32_t)J.cw; y++; }
+    return x | (y << 16);
+  }
+  if (J.cbits != nullptr && nC >= (J.cn >> 2)) {
+    // Dense selections (a quarter or more of the pixels usable: an image minus its hole): the point table is tens of
+    // megabytes of one-sector DRAM misses, the bitmap and its samples stay in L2.  From the sample at or before idx,
+    // count set bits word by word (32 usable pixels span 2-5 words at these densities).  Same point, bit for bit.
+    uint32_t r = idx & 31u;
+    const uint32_t p = __ldg(J.csamples + (idx >> 5));
+    uint32_t wi = p >> 5, x = __ldg(J.cbits + wi) & (0xFFFFFFFFu << (p & 31u)), c = __popc(x);
+    while (r >= c) {
+      r -= c;
+      x = __ldg(J.cbits + ++wi);
+      c = __popc(x);
+    }
+    const uint32_t pos = (wi << 5) + rs_nth_set_bit(x, r);
+    uint32_t y = __umulhi(pos, J.cw_inv), xx = pos - y * (uint32_t)J.cw;
+    if (xx >= (uint32_t)J.cw) { xx -= (uint32_t)J.cw; y++; }
+    return xx | (y << 16);
+  }
+  return __ldg(J.corpus_pts + idx);
+}
 
 // ---- single-copy-atomic 64-bit state word access (coherent at L2, no fence needed) ----
 __device__ __forceinline__ unsigned long long rs_ld_state(const unsigned long long *p) {
@@ -209,10 +254,10 @@ __device__ __forceinline__ uint32_t rs_lds_u32(unsigned shared_addr) {
   return v;
 }
 // Sum of the three table entries selected by bytes 0..2 of d; `col` = shared-space address of THIS LANE's column of
-// a replicated table (row stride 128 B, so the 32 lanes of a warp never share a bank).
+// a replicated table (row stride RS_LUT_REP words; with 32 copies the lanes of a warp never share a bank).
 __device__ __forceinline__ uint32_t rs_lut3(unsigned col, uint32_t d) {
-  return rs_lds_u32(col + __byte_perm(d, 0, 0x4440) * 128u) + rs_lds_u32(col + __byte_perm(d, 0, 0x4441) * 128u) +
-         rs_lds_u32(col + __byte_perm(d, 0, 0x4442) * 128u);
+  return rs_lds_u32(col + __byte_perm(d, 0, 0x4440) * (RS_LUT_REP * 4u)) + rs_lds_u32(col + __byte_perm(d, 0, 0x4441) * (RS_LUT_REP * 4u)) +
+         rs_lds_u32(col + __byte_perm(d, 0, 0x4442) * (RS_LUT_REP * 4u));
 }
 
 // ---- CH neighbour compares of one candidate: the body of computeBestFit's loop for neighbours k0.. ----

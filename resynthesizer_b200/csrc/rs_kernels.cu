@@ -22,6 +22,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
 #include "../../include/rs_cuda.h"
@@ -48,6 +49,32 @@ extern "C" const char *rs_cuda_peek_error(void) {
 extern "C" int rs_cuda_set_device(int ordinal) {
   RS_CHECK(cudaSetDevice(ordinal));
   return 0;
+}
+// Frees and evictions may run on a thread that is working on another device: they select the owning device for the
+// call and put the caller's back (the current device is per-thread state that ws_acquire and the launches rely on).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) cudaSetDevice(device); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+// Host cores this process may use for its own helper threads (staging copies, ordering keys): the machine's cores
+// divided among the processes that share it -- one process per GPU under torchrun (LOCAL_WORLD_SIZE), where 8 ranks
+// x 4 staging threads + 8 PRNG producers on 32 cores slowed one another's copies (SCALE_r01: e2e 0.93 at 8 GPUs).
+// RS_HOST_THREADS overrides.
+extern "C" unsigned rs_host_cores(void) {
+  static const unsigned cached = []() -> unsigned {
+    if (const char *e = getenv("RS_HOST_THREADS")) { const int v = atoi(e); if (v > 0) return (unsigned)v; }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    unsigned procs = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) procs = (unsigned)v; }
+    const unsigned c = hw / procs;
+    return c ? c : 1u;
+  }();
+  return cached;
 }
 extern "C" int rs_cuda_device_count(void) {
   int n = 0;
@@ -107,8 +134,8 @@ __global__ void k_replicate_lut(const uint32_t *__restrict__ c256, const uint32_
                                 uint32_t *__restrict__ rep) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < RS_LUT_WORDS) {
-    rep[i] = c256[i >> 5];
-    rep[RS_LUT_WORDS + i] = m256[i >> 5];
+    rep[i] = c256[i / RS_LUT_REP];
+    rep[RS_LUT_WORDS + i] = m256[i / RS_LUT_REP];
   }
 }
 
@@ -362,17 +389,25 @@ struct Visit {         // the visit a warp is working on (warp-uniform registers
   uint32_t v, K, nHeur;
 };
 
-template <bool MAPS>
+// NB = the most neighbours a patch can have in this instantiation: 64 (the reference's limit, lib/engine.c:591) or 16 for
+// the small patches of the texture scripts (9 neighbours: render-texture, map-style).  The small variant takes a warp's
+// scratch from 2.0 KB to 0.85 KB, i.e. the throughput kernel's CTA from 96 KB to 59 KB of shared memory -- and what
+// shared memory does not take is L1: a 256 KB corpus tile then mostly stays in the SM's own cache.
+template <bool MAPS, int NB>
 struct __align__(16) WarpScratch {
-  RsNb nb[RS_NB_SLOTS];                   // the patch as the distance loop reads it (rs_device.cuh), padded to whole chunks
-  uint32_t map[MAPS ? RS_NB_SLOTS : 4];   // neighbour map bytes
-  uint32_t off[RS_MAX_NB];   // neighbour offsets (packed int16 pair), ascending distance; [0] = (0,0).  Dead once the
+  static constexpr int kSlots = NB + RS_CHUNK_MAX;         // distance records: the patch padded to whole chunks
+  static constexpr int kLaneSlots = NB < 64 ? 32 : 64;     // arrays that are also indexed by lane (+ 32)
+  RsNb nb[kSlots];                        // the patch as the distance loop reads it (rs_device.cuh), padded to whole chunks
+  uint32_t map[MAPS ? kSlots : 4];        // neighbour map bytes
+  uint32_t off[kLaneSlots];  // neighbour offsets (packed int16 pair), ascending distance; [0] = (0,0).  Dead once the
                              // heuristic candidates exist: reused as the full patch distance of each of them (hsum)
-  uint32_t q[RS_MAX_NB];     // neighbour pixel index, later: packed heuristic candidate or RS_NO_SRC
-  uint32_t aux[RS_MAX_NB];   // neighbour meta, later: neighbour source, later: compacted candidate list
+  uint32_t q[kLaneSlots];    // neighbour pixel index, later: packed heuristic candidate or RS_NO_SRC
+  uint32_t aux[kLaneSlots];  // neighbour meta, later: neighbour source, later: compacted candidate list
   VisitShared vis;
   WarpStats st;
 };
+#define RS_NB_SMALL 16
+#define RS_NB_FULL RS_MAX_NB
 
 // Stage the replicated metric tables with one TMA bulk copy per table (whole CTA calls this).
 template <bool MAPS>
@@ -438,8 +473,8 @@ __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uin
 //
 // (1) One warp: gather the patch of visit v (target point tpos): S.off / S.q / S.aux(meta) and the geometry half of
 // the distance records S.nb[k].{lin,dx,pen}, padded to whole chunks.  Returns K.
-template <bool MAPS>
-__device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS> &S, const uint32_t v, const uint32_t tpos) {
+template <bool MAPS, int NB>
+__device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t tpos) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass;
@@ -513,7 +548,7 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
   {  // geometry half of the distance records, padded to whole chunks with records that cost nothing
     // (whole chunks of the launched kernel's size, and a continuation chunk of the team kernel may start at any k < K)
     const uint32_t nch = (K + J.chunk - 2u) / J.chunk;
-    const uint32_t kpad = min((uint32_t)RS_NB_SLOTS, max(1u + (nch ? nch : 1u) * J.chunk, K + (uint32_t)RS_CHUNK_MAX));
+    const uint32_t kpad = min((uint32_t)WarpScratch<MAPS, NB>::kSlots, max(1u + (nch ? nch : 1u) * J.chunk, K + (uint32_t)RS_CHUNK_MAX));
     for (uint32_t k = lane; k < kpad; k += 32) {
       RsNb r;
       if (k < K) {
@@ -535,8 +570,8 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
 
 // (2) One warp: wait for exactly the versions the sequential order would see, then read them (one 64-bit load each):
 // colours into S.nb[k].pix (+ S.map), sources into S.aux.
-template <bool MAPS>
-__device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS> &S, const uint32_t v, const uint32_t K) {
+template <bool MAPS, int NB>
+__device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t K) {
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t pass = J.pass, pass_end = J.pass_end;
   for (uint32_t k = lane; k < K; k += 32) {
@@ -564,8 +599,8 @@ __device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS
 }
 
 // (3) One warp: the heuristic candidate list S.aux[0..nHeur) of visit v, and what rs_visit_finish needs (S.vis).
-template <bool MAPS>
-__device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, Visit &V,
+template <bool MAPS, int NB>
+__device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS, NB> &S, Visit &V,
                                                     const uint32_t v, const uint32_t K) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
@@ -579,9 +614,10 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
   const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
   const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
   const uint32_t hide_base = tag | hide_from;
+  constexpr int NR = NB > 32 ? 2 : 1;  // rounds of 32 neighbours
   uint32_t mycand[2];
 #pragma unroll
-  for (int rnd = 0; rnd < 2; rnd++) {
+  for (int rnd = 0; rnd < NR; rnd++) {
     const uint32_t k = lane + 32u * rnd;
     uint32_t c = RS_NO_SRC;
     if (k < K) {
@@ -604,7 +640,7 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
   for (int attempt = 0; attempt < 2; attempt++) {
     bool any = false;
 #pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
+    for (int rnd = 0; rnd < NR; rnd++) {
       const uint32_t c = mycand[rnd];
       pskip[rnd] = false;
       if (c != RS_NO_SRC) {
@@ -626,7 +662,7 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
   }
   uint32_t nHeur = 0, nSkips = 0;
 #pragma unroll
-  for (int rnd = 0; rnd < 2; rnd++) {
+  for (int rnd = 0; rnd < NR; rnd++) {
     const uint32_t k = lane + 32u * rnd;
     const uint32_t c = mycand[rnd];
     bool valid = (c != RS_NO_SRC);
@@ -692,8 +728,8 @@ __device__ __forceinline__ void rs_visit_stamps(const RsDev &J, RsCtrl *ctrl, co
 // hcol[i] = colour of heuristic candidate i (fetched with its first chunk).  For a winning probe: win_pt = its corpus
 // point if the distance phase tracked it (else RS_NO_SRC: looked up from the probe's index), win_col = its colour if
 // have_col (else fetched here).
-template <bool MAPS, bool STAMPS = true>
-__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS> &S, const Visit &V,
+template <bool STAMPS = true, bool MAPS, int NB>
+__device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS, NB> &S, const Visit &V,
                                                 uint32_t bestSum, int bestIdx, uint32_t win_pt, uint32_t win_col,
                                                 bool have_col) {
   const unsigned lane = threadIdx.x & 31u;
@@ -716,7 +752,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
         bp = win_pt;
         bcol = win_col;
       } else {
-        bp = __ldg(J.corpus_pts + rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
+        bp = rs_corpus_point(J, J.ctrl->n_corpus, rs_range(rs_probe_hash(J.seed, pass, v, (uint32_t)bestIdx - nHeur), J.ctrl->n_corpus));
       }
       if (bp != src) {
         if (!heur && !(have_col && win_pt != RS_NO_SRC)) {
@@ -802,8 +838,8 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, L
 }
 
 // One (heuristic candidate, chunk j) pair of the patch distance; chunk 0 also carries the target point's own terms.
-template <bool MAPS, int CH>
-__device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, unsigned lutm, const WarpScratch<MAPS> &S,
+template <bool MAPS, int CH, int NB>
+__device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, unsigned lutm, const WarpScratch<MAPS, NB> &S,
                                                  uint32_t *hcol, uint32_t K, uint32_t ci, uint32_t j, LaneStats &st) {
   const uint32_t c = S.aux[ci];
   const int cx = (int)(c & 0xFFFFu);
@@ -829,29 +865,29 @@ struct PassSmem {  // carve-up of the dynamic shared memory of the pass kernels
   void *scratch;
   uint64_t *bar;
 };
-template <bool MAPS, int NSCRATCH>
+template <bool MAPS, int NB, int NSCRATCH>
 __device__ __forceinline__ PassSmem rs_pass_smem(const RsDev &J, unsigned char *smem_raw) {
   uint32_t *lutc = reinterpret_cast<uint32_t *>(smem_raw);
   uint32_t *lutm = lutc + RS_LUT_WORDS;  // only staged when MAPS
   const unsigned lut_bytes = (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u;
   PassSmem P;
   P.scratch = smem_raw + lut_bytes;
-  P.bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch<MAPS>) * NSCRATCH);
+  P.bar = reinterpret_cast<uint64_t *>(smem_raw + lut_bytes + sizeof(WarpScratch<MAPS, NB>) * NSCRATCH);
   rs_stage_tables<MAPS>(J, lutc, lutm, P.bar);
-  P.lutc = (unsigned)__cvta_generic_to_shared(lutc) + (threadIdx.x & 31u) * 4u;
-  P.lutm = (unsigned)__cvta_generic_to_shared(lutm) + (threadIdx.x & 31u) * 4u;
+  P.lutc = (unsigned)__cvta_generic_to_shared(lutc) + (threadIdx.x & (RS_LUT_REP - 1u)) * 4u;
+  P.lutm = (unsigned)__cvta_generic_to_shared(lutm) + (threadIdx.x & (RS_LUT_REP - 1u)) * 4u;
   return P;
 }
 
 // ---- throughput mode: one warp per visit -------------------------------------------------------------------
-template <bool MAPS, int CH>
+template <bool MAPS, int CH, int NB>
 __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass(const RsDev J) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
   if (rs_ld_u32_relaxed(&ctrl->stop)) return;
-  const PassSmem P = rs_pass_smem<MAPS, RS_TP_WARPS>(J, smem_raw);
+  const PassSmem P = rs_pass_smem<MAPS, NB, RS_TP_WARPS>(J, smem_raw);
   const unsigned lutc = P.lutc, lutm = P.lutm;
-  WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[threadIdx.x >> 5];
+  WarpScratch<MAPS, NB> &S = reinterpret_cast<WarpScratch<MAPS, NB> *>(P.scratch)[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
   LaneStats st;
   Visit V;
@@ -860,9 +896,9 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
   while (v < J.seg_end) {
     {
-      const uint32_t Kv = rs_visit_geometry<MAPS>(J, S, v, tpos);
-      rs_visit_values<MAPS>(J, S, v, Kv);
-      rs_visit_candidates<MAPS>(J, ctrl, S, V, v, Kv);
+      const uint32_t Kv = rs_visit_geometry(J, S, v, tpos);
+      rs_visit_values(J, S, v, Kv);
+      rs_visit_candidates(J, ctrl, S, V, v, Kv);
     }
     // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
     uint32_t bestSum = 0xFFFFFFFFu, bestLin = RS_NO_SRC;
@@ -870,21 +906,20 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     uint32_t *hsum = S.off;  // offsets are dead by now (WarpScratch)
     uint32_t *hcol = S.q;    // so are the per-neighbour candidates: colour of each heuristic candidate
     const uint32_t nHeur = V.nHeur, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus, K = V.K;
-    const uint32_t *cpts = J.corpus_pts;
     const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
     // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
     // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
     if (nHeur) {
       const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = 0xFFFFFFFFu / nch + 1u;
-      hsum[lane] = 0u;        // (nHeur <= RS_MAX_NB = 64: two slots per lane cover every candidate)
-      hsum[lane + 32u] = 0u;
+      hsum[lane] = 0u;        // (nHeur <= NB <= 64: two slots per lane cover every candidate)
+      if (NB > 32) hsum[lane + 32u] = 0u;
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
         const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
-        atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, hcol, K, ci, j, st));
+        atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH, NB>(J, lutc, lutm, S, hcol, K, ci, j, st));
       }
       __syncwarp();
-      const uint32_t h0 = lane < nHeur ? hsum[lane] : 0xFFFFFFFFu, h1 = lane + 32u < nHeur ? hsum[lane + 32u] : 0xFFFFFFFFu;
+      const uint32_t h0 = lane < nHeur ? hsum[lane] : 0xFFFFFFFFu, h1 = (NB > 32 && lane + 32u < nHeur) ? hsum[lane + 32u] : 0xFFFFFFFFu;
       const uint32_t msum = __reduce_min_sync(RS_FULL, min(h0, h1));
       const int midx = __reduce_min_sync(RS_FULL, (h0 == msum) ? (int)lane : ((h1 == msum) ? (int)lane + 32 : 0x7FFFFFFF));
       bestSum = msum;
@@ -892,9 +927,9 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     }
     if (bestSum != 0u)
       rs_eval_range<MAPS, CH>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
-                          [&](int i) { return __ldg(cpts + rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
+                          [&](int i) { return rs_corpus_point(J, nC, rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
                           bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued);
-    rs_visit_finish<MAPS>(J, ctrl, S, V, bestSum, bestIdx,
+    rs_visit_finish(J, ctrl, S, V, bestSum, bestIdx,
                           bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
                           0u, false);
     const uint32_t v_next = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
@@ -938,19 +973,19 @@ __device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
 //   the lane that owns the winning probe publishes its point + colour -> barrier G -> warp 0 commits
 // So the gathers of every probe's first chunk, and the colour a winning probe commits, are fetched while the visit
 // is still waiting for its dependencies; none of them is on the critical path.
-template <bool MAPS, int CH>
+template <bool MAPS, int CH, int NB>
 __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const RsDev J, const unsigned W) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
   if (rs_ld_u32_relaxed(&ctrl->stop)) return;
-  const PassSmem P = rs_pass_smem<MAPS, RS_TEAM_SLOTS>(J, smem_raw);
+  const PassSmem P = rs_pass_smem<MAPS, NB, RS_TEAM_SLOTS>(J, smem_raw);
   const unsigned lutc = P.lutc, lutm = P.lutm;
   TeamShared *tshared = reinterpret_cast<TeamShared *>(P.bar + 2);
 
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned team = warp / W, wt = warp % W, T = W * 32u, tid = wt * 32u + lane;
   const unsigned bar_id = 1u + team;
-  WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[team];
+  WarpScratch<MAPS, NB> &S = reinterpret_cast<WarpScratch<MAPS, NB> *>(P.scratch)[team];
   TeamShared &TS = tshared[team];
   const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
   const uint32_t nPre = min(J.probes, T - 32u);  // probes fetched ahead, one per lane of warps 1..W-1
@@ -962,7 +997,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       const uint32_t vc = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
       const bool ok = vc < J.seg_end;
       uint32_t Kc = 0;
-      if (ok) Kc = rs_visit_geometry<MAPS>(J, S, vc, __ldg(J.targets + vc));
+      if (ok) Kc = rs_visit_geometry(J, S, vc, __ldg(J.targets + vc));
       if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = vc; TS.K = Kc; TS.nHeur = 0u; TS.best = ~0ull; TS.win_pt = RS_NO_SRC; }
       for (uint32_t i = lane; i < RS_MAX_NB; i += 32) { TS.hsum[i] = 0u; TS.hcnt[i] = 0u; }
     }
@@ -975,9 +1010,9 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     uint32_t pc = 0, pclin = 0, pown_x = 0, pown_y = 0, ppartial = 0, cp[CH], cm[CH];
     int pcx = 0;
     if (wt == 0) {
-      rs_visit_values<MAPS>(J, S, v, K);
+      rs_visit_values(J, S, v, K);
     } else if (pre) {
-      pc = __ldg(J.corpus_pts + rs_range(rs_mix32(hv + (tid - 32u) * 0xC2B2AE35u), nC));
+      pc = rs_corpus_point(J, nC, rs_range(rs_mix32(hv + (tid - 32u) * 0xC2B2AE35u), nC));
       pcx = (int)(pc & 0xFFFFu);
       pclin = (pc >> 16) * (uint32_t)J.cw + (uint32_t)pcx;
       if (MAPS) { const uint2 t = __ldg(J.corpus8 + pclin); pown_x = t.x; pown_y = t.y; }
@@ -986,7 +1021,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     }
     rs_team_sync(bar_id, T);  // B
     if (wt == 0) {
-      rs_visit_candidates<MAPS>(J, ctrl, S, V, v, K);
+      rs_visit_candidates(J, ctrl, S, V, v, K);
       if (lane == 0) TS.nHeur = V.nHeur;
     } else if (pre) {
       ppartial = rs_chunk_reduce<MAPS, CH>(lutc, lutm, S.nb, S.map, 1u, cp, cm);
@@ -999,7 +1034,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     if (nHeur) {
       for (uint32_t t = tid; t < nHeur * nch; t += T) {
         const uint32_t ci = t / nch, j = t % nch;
-        atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH>(J, lutc, lutm, S, S.q, K, ci, j, st));
+        atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH, NB>(J, lutc, lutm, S, S.q, K, ci, j, st));
         __threadfence_block();
         // the lane that adds a candidate's last chunk holds its full sum: it enters "first candidate with the minimum
         // full sum" directly (packed sum << 32 | index, atomicMin) -- no barrier and no scan by warp 0 in between
@@ -1030,7 +1065,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       }
       for (uint32_t j = nPre + tid; j < J.probes; j += T) {
         if ((uint32_t)(*vbest >> 32) == 0u) break;  // perfect match: nothing later is evaluated (synthesize.h:599)
-        const uint32_t c = __ldg(J.corpus_pts + rs_range(rs_mix32(hv + j * 0xC2B2AE35u), nC));
+        const uint32_t c = rs_corpus_point(J, nC, rs_range(rs_mix32(hv + j * 0xC2B2AE35u), nC));
         const int cx = (int)(c & 0xFFFFu);
         const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx;
         const unsigned long long idx = (unsigned long long)(nHeur + j);
@@ -1061,13 +1096,13 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     uint32_t sc0 = 0, sc1 = 0;
     if (wt == 1) {
       sc0 = lane < nHeur ? S.aux[lane] : 0u;
-      sc1 = lane + 32u < nHeur ? S.aux[lane + 32u] : 0u;
+      sc1 = (NB > 32 && lane + 32u < nHeur) ? S.aux[lane + 32u] : 0u;
     }
     rs_team_sync(bar_id, T);  // G
     const uint32_t bestSum = (key == ~0ull) ? 0xFFFFFFFFu : (uint32_t)(key >> 32);
     const int bestIdx = (key == ~0ull) ? 0x7FFFFFFF : (int)(uint32_t)key;
     if (wt == 0) {
-      rs_visit_finish<MAPS, false>(J, ctrl, S, V, bestSum, bestIdx, TS.win_pt, TS.win_col, true);
+      rs_visit_finish<false>(J, ctrl, S, V, bestSum, bestIdx, TS.win_pt, TS.win_col, true);
     } else if (wt == 1) {
       const uint32_t stampEnd = (bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
       const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;  // as in rs_visit_candidates
@@ -1086,9 +1121,9 @@ __global__ void __launch_bounds__(RS_BF_WARPS * 32, 2)
                     int n_map, int map_bip, const uint32_t *__restrict__ cand_begin, const uint32_t *__restrict__ cands,
                     uint32_t *__restrict__ best_sum, int32_t *__restrict__ best_index) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const PassSmem P = rs_pass_smem<MAPS, RS_BF_WARPS>(J, smem_raw);
+  const PassSmem P = rs_pass_smem<MAPS, RS_NB_FULL, RS_BF_WARPS>(J, smem_raw);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  WarpScratch<MAPS> &S = reinterpret_cast<WarpScratch<MAPS> *>(P.scratch)[warp];
+  WarpScratch<MAPS, RS_NB_FULL> &S = reinterpret_cast<WarpScratch<MAPS, RS_NB_FULL> *>(P.scratch)[warp];
   for (uint32_t v = blockIdx.x * RS_BF_WARPS + warp; v < n_visits; v += gridDim.x * RS_BF_WARPS) {
     const uint32_t nb0 = nb_begin[v], K = min(nb_begin[v + 1] - nb0, (uint32_t)RS_MAX_NB);
     const uint32_t nchr = (K + RS_CHUNK_SMALL - 2u) / RS_CHUNK_SMALL, kpad = 1u + (nchr ? nchr : 1u) * RS_CHUNK_SMALL;
@@ -1132,6 +1167,12 @@ struct DevBuf {
   void *p = nullptr;
   size_t cap = 0;
 };
+struct PassVariant {
+  void (*tp)(const RsDev) = nullptr;                    // k_synth_pass<maps, chunk, nb>
+  void (*team)(const RsDev, const unsigned) = nullptr;  // k_synth_pass_team<maps, chunk, nb>
+  size_t smem_tp = 0, smem_team = 0;
+  int grid = 0, grid_team = 0;                          // persistent grids: resident CTAs per SM x SMs
+};
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: work that may run beside the main stream's
@@ -1139,7 +1180,8 @@ struct Workspace {
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, nb_later, nb_later_counts, simg, smask, smask2,
-      ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags, ord_raw;
+      ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags, ord_raw,
+      cbits, ccounts, cbefore, csamples;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
   void *pin_order = nullptr;  // pinned staging of a visit order
@@ -1155,8 +1197,7 @@ struct Workspace {
   RsCtrl *h_ctrl = nullptr;
   int off_w = 0, off_h = 0;  // dimensions the resident offsets table was built for
   uint32_t off_n = 0;
-  int grid[4] = {0, 0, 0, 0};       // persistent grid of k_synth_pass<maps, chunk>: index 2 * maps + (chunk == large)
-  int grid_team[4] = {0, 0, 0, 0};  // persistent grid of k_synth_pass_team, likewise
+  PassVariant variant[8];  // the pass-kernel instantiations and their persistent grids, index = rs_variant()
 };
 static std::atomic<int> g_job_slots{1};
 extern "C" void rs_cuda_set_job_slots(int slots) { g_job_slots.store(slots < 1 ? 1 : slots); }
@@ -1184,12 +1225,13 @@ static int ws_ensure_pinned(Workspace *w, size_t bytes) {
   return 0;
 }
 static void ws_free(Workspace *w) {
-  cudaSetDevice(w->device);
+  DeviceGuard guard(w->device);
   DevBuf *all[] = {&w->raw_t, &w->raw_c, &w->corpus, &w->W, &w->meta, &w->tmaps, &w->targets, &w->cpts, &w->offsets,
                    &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
                    &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts, &w->nb_later, &w->nb_later_counts,
                    &w->simg, &w->smask, &w->smask2, &w->ord_keys_in, &w->ord_keys_out, &w->ord_vals_in, &w->ord_vals_out,
-                   &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags, &w->ord_raw};
+                   &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags, &w->ord_raw, &w->cbits, &w->ccounts, &w->cbefore,
+                   &w->csamples};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
   if (w->pin_order) cudaFreeHost(w->pin_order);
@@ -1212,23 +1254,38 @@ static void ws_free(Workspace *w) {
   delete w;
 }
 
-static size_t pass_smem(bool maps, int scratch_slots) {
-  const size_t scratch = maps ? sizeof(WarpScratch<true>) : sizeof(WarpScratch<false>);
-  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + scratch * scratch_slots + 16 + sizeof(TeamShared) * RS_TEAM_SLOTS;
+static size_t scratch_bytes(bool maps, bool nb_full) {
+  return maps ? (nb_full ? sizeof(WarpScratch<true, RS_NB_FULL>) : sizeof(WarpScratch<true, RS_NB_SMALL>))
+              : (nb_full ? sizeof(WarpScratch<false, RS_NB_FULL>) : sizeof(WarpScratch<false, RS_NB_SMALL>));
 }
-template <bool MAPS, int CH>
+static size_t pass_smem(bool maps, int scratch_slots, bool nb_full = true) {
+  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + scratch_bytes(maps, nb_full) * scratch_slots + 16 + sizeof(TeamShared) * RS_TEAM_SLOTS;
+}
+// The instantiations of the two pass kernels: map channels x chunk size x scratch size (index = rs_variant()).
+static int rs_variant(bool maps, bool chunk_large, bool nb_full) { return (maps ? 4 : 0) + (chunk_large ? 2 : 0) + (nb_full ? 1 : 0); }
+template <bool MAPS, int CH, int NB>
 static int configure_pass_kernel(Workspace *w) {
-  const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
+  const bool full = NB == RS_NB_FULL;
+  const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS, full), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS, full);
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
   int per_sm = 0, per_sm_team = 0, sms = 0;
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH>, RS_TP_WARPS * 32, smem_tp));
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS, CH>, RS_TEAM_WARPS * 32, smem_team));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB>, RS_TP_WARPS * 32, smem_tp));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS, CH, NB>, RS_TEAM_WARPS * 32, smem_team));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
   if (per_sm < 1 || per_sm_team < 1) { g_err = "the pass kernels do not fit on an SM"; return 100; }
-  const int slot = (MAPS ? 2 : 0) + (CH == RS_CHUNK_LARGE ? 1 : 0);
-  w->grid[slot] = per_sm * sms;
-  w->grid_team[slot] = per_sm_team * sms;
+  // what shared memory does not take stays L1: ask for no more than the resident CTAs need
+  // (percent of the 228 KB an SM can give to shared memory; every resident CTA also takes 1 KB of system space)
+  const size_t sm_max = 233472;
+  const int carve_tp = (int)std::min<size_t>(100, ((smem_tp + 1024) * per_sm * 100 + sm_max - 1) / sm_max);
+  const int carve_team = (int)std::min<size_t>(100, ((smem_team + 1024) * per_sm_team * 100 + sm_max - 1) / sm_max);
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_team));
+  PassVariant &V = w->variant[rs_variant(MAPS, CH == RS_CHUNK_LARGE, full)];
+  V.tp = k_synth_pass<MAPS, CH, NB>;
+  V.team = k_synth_pass_team<MAPS, CH, NB>;
+  V.smem_tp = smem_tp; V.smem_team = smem_team;
+  V.grid = per_sm * sms; V.grid_team = per_sm_team * sms;
   return 0;
 }
 
@@ -1246,10 +1303,14 @@ static int ws_acquire(Workspace **out) {
   }
   Workspace *w = new Workspace();
   w->device = dev;
-  int rc = configure_pass_kernel<false, RS_CHUNK_SMALL>(w);
-  if (!rc) rc = configure_pass_kernel<false, RS_CHUNK_LARGE>(w);
-  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_SMALL>(w);
-  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_LARGE>(w);
+  int rc = configure_pass_kernel<false, RS_CHUNK_SMALL, RS_NB_SMALL>(w);
+  if (!rc) rc = configure_pass_kernel<false, RS_CHUNK_SMALL, RS_NB_FULL>(w);
+  if (!rc) rc = configure_pass_kernel<false, RS_CHUNK_LARGE, RS_NB_SMALL>(w);
+  if (!rc) rc = configure_pass_kernel<false, RS_CHUNK_LARGE, RS_NB_FULL>(w);
+  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_SMALL, RS_NB_SMALL>(w);
+  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_SMALL, RS_NB_FULL>(w);
+  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_LARGE, RS_NB_SMALL>(w);
+  if (!rc) rc = configure_pass_kernel<true, RS_CHUNK_LARGE, RS_NB_FULL>(w);
   if (rc) { delete w; return rc; }
 #define WCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); ws_free(w); return 100; } } while (0)
   WCHK(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
@@ -1353,7 +1414,7 @@ struct OrderEntry {
   unsigned long long stamp = 0;
   cudaEvent_t ready = nullptr;  // recorded behind the upload on the creating job's stream: other streams wait on it
   ~OrderEntry() {
-    cudaSetDevice(device);
+    DeviceGuard guard(device);
     if (ready) cudaEventDestroy(ready);
     if (dev) cudaFree(dev);
   }
@@ -1371,6 +1432,7 @@ struct RsJob {
   float ms_passes = 0.f;
   bool later_lists = false;       // the patches of the passes >= 1 were gathered up front (k_gather_later)
   bool simple = false;            // staged by rs_job_stage_simple: results go back in the caller's image layout
+  bool corpus_bits = false;       // the device built the corpus-point bitmap + samples (rs_corpus_point's select path)
   uint32_t launches = 0;          // pass-kernel launches of the last run
   uint32_t pass_launches[6] = {0, 0, 0, 0, 0, 0};
   uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
@@ -1437,6 +1499,24 @@ __global__ void k_corpus_flags(const uint8_t *__restrict__ raw, uint32_t n_px, i
   const uint8_t *p = raw + (size_t)i * bpp;
   flags[i] = (p[0] == 0xFFu && (!alpha_source || p[alpha_bip] != 0)) ? 1 : 0;
 }
+// The same list without the list: a bitmap of the usable corpus pixels (row-major) and, for every 32nd usable pixel, its
+// linear index.  rs_corpus_point() then finds point idx by a short scan from sample idx / 32 -- two or three words of a
+// bitmap that stays in L2 instead of one 4-byte load from a table of tens of megabytes that never does (4096^2 inpaint:
+// 46 MB of points, one DRAM sector per probe, a quarter of the pass kernels' DRAM traffic).
+__global__ void k_corpus_bits(const uint8_t *__restrict__ flags, uint32_t n_px, uint32_t *__restrict__ bits,
+                              uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // launched over n_px rounded up to whole words
+  const uint32_t wd = __ballot_sync(RS_FULL, i < n_px && flags[i] != 0);
+  if ((threadIdx.x & 31u) == 0u) { bits[i >> 5] = wd; counts[i >> 5] = __popc(wd); }
+}
+__global__ void k_corpus_samples(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ before, uint32_t n_words,
+                                 uint32_t *__restrict__ samples) {
+  const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= n_words) return;
+  const uint32_t wd = bits[wi], b = before[wi], c = __popc(wd);
+  const uint32_t first = (b + 31u) & ~31u;  // the only multiple of 32 this word's points [b, b + c) can contain
+  if (c && first < b + c) samples[first >> 5] = (wi << 5) + rs_nth_set_bit(wd, first - b);
+}
 __global__ void k_pack_points(uint32_t *__restrict__ pts, const unsigned int *__restrict__ n_ptr, int w) {
   const uint32_t n = *n_ptr;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1485,7 +1565,52 @@ static unsigned long long g_order_clock = 0;
 static std::atomic<int> g_order_cache_on{1};
 extern "C" void rs_cuda_order_cache(int enabled) {
   g_order_cache_on.store(enabled ? 1 : 0);
-  if (!enabled) { std::lock_guard<std::mutex> lk(g_order_mutex); g_orders.clear(); }
+  if (!enabled) {  // entries are released (cudaFree: a device-wide sync) after the mutex is dropped
+    std::vector<std::shared_ptr<OrderEntry>> dropped;
+    { std::lock_guard<std::mutex> lk(g_order_mutex); dropped.swap(g_orders); }
+  }
+}
+// A new cache entry for n points on `device`, or nullptr when the device has no room for it even after the cached
+// orders of that device were dropped: the job then keeps its order in the workspace, uncached.
+static std::shared_ptr<OrderEntry> order_entry_alloc(const RsOrderKey &key, int device, uint32_t n) {
+  auto entry = std::make_shared<OrderEntry>();
+  entry->key = key; entry->device = device; entry->n = n;
+  const size_t bytes = (size_t)n * 4;
+  if (cudaMalloc(&entry->dev, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    std::vector<std::shared_ptr<OrderEntry>> dropped;
+    {
+      std::lock_guard<std::mutex> lk(g_order_mutex);
+      for (size_t i = 0; i < g_orders.size();)
+        if (g_orders[i]->device == device) { dropped.push_back(g_orders[i]); g_orders.erase(g_orders.begin() + i); } else i++;
+    }
+    dropped.clear();
+    entry->dev = nullptr;
+    if (cudaMalloc(&entry->dev, bytes) != cudaSuccess) { cudaGetLastError(); entry->dev = nullptr; return nullptr; }
+  }
+  if (cudaEventCreateWithFlags(&entry->ready, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return entry;
+}
+// Makes the entry visible to other jobs (its `ready` event has been recorded) and evicts the least recently used
+// ones: at most 16 entries / 1 GiB per device.  The evicted entries are freed after the mutex is dropped.
+static void order_cache_publish(const std::shared_ptr<OrderEntry> &entry) {
+  std::vector<std::shared_ptr<OrderEntry>> evicted;
+  {
+    std::lock_guard<std::mutex> lk(g_order_mutex);
+    entry->stamp = ++g_order_clock;
+    g_orders.push_back(entry);
+    while (true) {
+      size_t count = 0, total = 0, lru = g_orders.size();
+      for (size_t i = 0; i < g_orders.size(); i++) {
+        if (g_orders[i]->device != entry->device) continue;
+        count++; total += (size_t)g_orders[i]->n * 4;
+        if (g_orders[i] != entry && (lru == g_orders.size() || g_orders[i]->stamp < g_orders[lru]->stamp)) lru = i;
+      }
+      if (lru == g_orders.size() || !(count > 16 || total > ((size_t)1 << 30))) break;
+      evicted.push_back(g_orders[lru]);
+      g_orders.erase(g_orders.begin() + lru);
+    }
+  }
 }
 static bool key_equal(const RsOrderKey &a, const RsOrderKey &b) {
   return a.h1 == b.h1 && a.h2 == b.h2 && a.n == b.n && a.tw == b.tw && a.th == b.th && a.mode == b.mode && a.seed == b.seed;
@@ -1523,7 +1648,7 @@ static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t b
     RS_CHECK(cudaMemcpyAsync(dev, pin, bytes, cudaMemcpyHostToDevice, s));
     return 0;
   }
-  unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = rs_host_cores();
   const size_t nt = std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
   for (size_t off = 0; off < bytes; off += PIECE * nt) {
     const size_t len = std::min(bytes - off, PIECE * nt);
@@ -1548,7 +1673,7 @@ static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t b
 static int stage_rows_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t rows, size_t row_len, size_t src_stride,
                                 cudaStream_t s) {
   if (src_stride == row_len) return stage_to_device(dev, pin, src, rows * row_len, s);
-  unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = rs_host_cores();
   const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
   auto band = [=](size_t t) {
     const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
@@ -1580,6 +1705,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
   const size_t tn = (size_t)d.tw * d.th, cn = (size_t)d.cw * d.ch;
   cudaStream_t s = w->stream;
   j->nC = corpus_points ? n_corpus : 0;
+  j->corpus_bits = false;
   j->penalty = 65535u * (uint32_t)d.n_color + map_lut_max * (uint32_t)d.n_map;
   const size_t cap_cpts = corpus_points ? (size_t)n_corpus : cn;
   int rc = 0;
@@ -1653,6 +1779,21 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     RS_CHECK(cub::DeviceSelect::Flagged(w->sort_tmp.p, tmp, idx, (const uint8_t *)w->sort_keys_in.p, (uint32_t *)w->cpts.p,
                                         d_ncorpus, (int)cn, s));
     k_pack_points<<<592, T, 0, s>>>((uint32_t *)w->cpts.p, d_ncorpus, d.cw);
+    // bitmap + every-32nd-point samples of the same selection (rs_corpus_point picks by density at run time)
+    const uint32_t n_words = (uint32_t)((cn + 31) / 32);
+    if ((rc = ws_ensure(w->cbits, (size_t)(n_words + 2) * 4)) || (rc = ws_ensure(w->ccounts, (size_t)n_words * 4)) ||
+        (rc = ws_ensure(w->cbefore, (size_t)n_words * 4)) || (rc = ws_ensure(w->csamples, (size_t)(n_words + 1) * 4)))
+      return rc;
+    k_corpus_bits<<<(n_words * 32u + T - 1) / T, T, 0, s>>>((const uint8_t *)w->sort_keys_in.p, (uint32_t)cn, (uint32_t *)w->cbits.p,
+                                                          (uint32_t *)w->ccounts.p);
+    RS_CHECK(cudaMemsetAsync((uint32_t *)w->cbits.p + n_words, 0, 8, s));  // the scan may peek one word past the end
+    size_t tmp_scan = 0;
+    RS_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t *)w->ccounts.p, (uint32_t *)w->cbefore.p, (int)n_words, s));
+    if ((rc = ws_ensure(w->sort_tmp, tmp_scan > tmp ? tmp_scan : tmp))) return rc;
+    RS_CHECK(cub::DeviceScan::ExclusiveSum(w->sort_tmp.p, tmp_scan, (const uint32_t *)w->ccounts.p, (uint32_t *)w->cbefore.p, (int)n_words, s));
+    k_corpus_samples<<<(n_words + T - 1) / T, T, 0, s>>>((const uint32_t *)w->cbits.p, (const uint32_t *)w->cbefore.p, n_words,
+                                                       (uint32_t *)w->csamples.p);
+    j->corpus_bits = true;
   }
   if (offsets) {
     if ((rc = ws_ensure(w->offsets, sz_off))) return rc;
@@ -1682,7 +1823,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
   k_replicate_lut<<<(RS_LUT_WORDS + T - 1) / T, T, 0, s>>>((const uint32_t *)w->lut256.p, (const uint32_t *)w->lut256.p + 256,
                                                          (uint32_t *)w->lut_rep.p);
   RS_CHECK(cudaGetLastError());
-  j->upload_launches += 3u + (corpus_points ? 0u : 4u) + (built_offsets ? 1u + (uint32_t)((offset_sort_bits + 7) / 8) + 2u : 0u);
+  j->upload_launches += 3u + (corpus_points ? 0u : 7u) + (built_offsets ? 1u + (uint32_t)((offset_sort_bits + 7) / 8) + 2u : 0u);
   for (int p = 0; p < 6; p++) w->h_ticks[p] = 0;
   *w->h_cancel = 0;
   return 0;
@@ -1736,11 +1877,8 @@ static int upload_order_impl(RsJob *j, const uint32_t *targets, const RsOrderKey
   uint32_t *dst = nullptr;
   j->order.reset();
   std::shared_ptr<OrderEntry> entry;
-  if (key && g_order_cache_on.load()) {  // the uploaded order becomes a cache entry
-    entry = std::make_shared<OrderEntry>();
-    entry->key = *key; entry->device = w->device; entry->n = j->nT;
-    RS_CHECK(cudaMalloc(&entry->dev, bytes));
-    RS_CHECK(cudaEventCreateWithFlags(&entry->ready, cudaEventDisableTiming));
+  if (key && g_order_cache_on.load()) entry = order_entry_alloc(*key, w->device, j->nT);  // the uploaded order becomes a cache entry
+  if (entry) {
     dst = entry->dev;
     j->order = entry;
   } else {
@@ -1754,17 +1892,7 @@ static int upload_order_impl(RsJob *j, const uint32_t *targets, const RsOrderKey
     // visible to other jobs only once the event that follows its upload exists: a job on another stream that hits this
     // entry makes its stream wait for that event before reading the order
     RS_CHECK(cudaEventRecord(entry->ready, w->stream));
-    std::lock_guard<std::mutex> lk(g_order_mutex);
-    entry->stamp = ++g_order_clock;
-    g_orders.push_back(entry);
-    size_t total = 0;
-    for (auto &o : g_orders) total += (size_t)o->n * 4;
-    while (g_orders.size() > 16 || (total > ((size_t)1 << 30) && g_orders.size() > 1)) {  // evict the least recently used
-      size_t lru = 0;
-      for (size_t i = 1; i < g_orders.size(); i++) if (g_orders[i]->stamp < g_orders[lru]->stamp) lru = i;
-      total -= (size_t)g_orders[lru]->n * 4;
-      g_orders.erase(g_orders.begin() + lru);
-    }
+    order_cache_publish(entry);
   }
   j->upload_launches += 1u;
   k_scatter_order<<<(j->nT + 255) / 256, 256, 0, w->stream>>>(dst, j->nT, j->d.tw, (uint32_t *)w->meta.p);
@@ -1798,7 +1926,7 @@ extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_byt
   const size_t row_len = (size_t)j->d.tw * (j->d.bpp - 1), rows = j->y_max - j->y_min + 1;
   const uint8_t *src = (const uint8_t *)w->pin;
   const uint32_t y0 = j->y_min;
-  unsigned hw = std::thread::hardware_concurrency();
+  unsigned hw = rs_host_cores();
   const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
   auto band = [=](size_t t) {
     const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
@@ -1895,7 +2023,9 @@ struct RsAccept {
   __host__ __device__ bool operator()(const uint32_t &v) const { return v <= maxvalue; }
 };
 __global__ void k_reduce_draws(uint32_t *__restrict__ draws, const unsigned int *__restrict__ n_accepted, uint32_t n, RsCtrl *ctrl) {
-  if (*n_accepted < n) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&ctrl->fault, 1u); return; }  // too few words sent: fail loudly
+  // too few words sent: fail loudly (rs_job_run reports the fault) -- but the kernels queued behind this one still
+  // index with the draws, so they are reduced into range regardless
+  if (*n_accepted < n && blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&ctrl->fault, 1u);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) draws[i] %= n;
 }
@@ -1948,11 +2078,8 @@ static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *r
   uint32_t *dst = nullptr;
   j->order.reset();
   std::shared_ptr<OrderEntry> entry;
-  if (key && g_order_cache_on.load()) {
-    entry = std::make_shared<OrderEntry>();
-    entry->key = *key; entry->device = w->device; entry->n = n;
-    RS_CHECK(cudaMalloc(&entry->dev, bytes));
-    RS_CHECK(cudaEventCreateWithFlags(&entry->ready, cudaEventDisableTiming));
+  if (key && g_order_cache_on.load()) entry = order_entry_alloc(*key, w->device, n);
+  if (entry) {
     dst = entry->dev;
     j->order = entry;
   } else {
@@ -2003,17 +2130,7 @@ static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *r
   j->upload_launches += 8u + (uint32_t)((bits + 7) / 8);
   if (entry) {
     RS_CHECK(cudaEventRecord(entry->ready, s));
-    std::lock_guard<std::mutex> lk(g_order_mutex);
-    entry->stamp = ++g_order_clock;
-    g_orders.push_back(entry);
-    size_t total = 0;
-    for (auto &o : g_orders) total += (size_t)o->n * 4;
-    while (g_orders.size() > 16 || (total > ((size_t)1 << 30) && g_orders.size() > 1)) {
-      size_t lru = 0;
-      for (size_t i = 1; i < g_orders.size(); i++) if (g_orders[i]->stamp < g_orders[lru]->stamp) lru = i;
-      total -= (size_t)g_orders[lru]->n * 4;
-      g_orders.erase(g_orders.begin() + lru);
-    }
+    order_cache_publish(entry);
   }
   j->upload_launches += 1u;
   k_scatter_order<<<(n + 255) / 256, 256, 0, s>>>(dst, n, d.tw, (uint32_t *)w->meta.p);
@@ -2057,6 +2174,8 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.W = (unsigned long long *)w->W.p; D.meta = (const uint32_t *)w->meta.p;
   D.tmaps = j->maps ? (const uint32_t *)w->tmaps.p : nullptr;
   D.targets = j->targets_dev; D.corpus_pts = (const uint32_t *)w->cpts.p;
+  D.cbits = j->corpus_bits && !getenv("RS_NO_CORPUS_BITS") ? (const uint32_t *)w->cbits.p : nullptr;
+  D.csamples = (const uint32_t *)w->csamples.p;
   D.offsets = (const uint32_t *)w->offsets.p; D.lut_rep = (const uint32_t *)w->lut_rep.p;
   D.prober[0] = (unsigned long long *)w->prober0.p; D.prober[1] = (unsigned long long *)w->prober1.p;
   D.prober[2] = (unsigned long long *)w->prober2.p;
@@ -2073,6 +2192,7 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.pass = pass; D.pass_end = d.pass_end[pass];
   for (int p = 0; p < 6; p++) D.ends[p] = d.pass_end[p];
   D.htile = d.htile; D.vtile = d.vtile; D.terminate_fraction = d.terminate_fraction;
+  D.cw_inv = d.cw > 1 ? (uint32_t)(0x100000000ull / (uint32_t)d.cw) : 0xFFFFFFFFu;
   return D;
 }
 
@@ -2148,8 +2268,11 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   uint32_t kmax_run = j->d.patch_size < 2 ? 2 : j->d.patch_size;
   bool large = kmax_run >= RS_CHUNK_SWITCH_K;
   if (const char *e = getenv("RS_CHUNK")) large = atoi(e) >= RS_CHUNK_LARGE;
-  const int gslot = (j->maps ? 2 : 0) + (large ? 1 : 0);
-  int grid = w->grid[gslot], grid_team = w->grid_team[gslot];
+  // patches of at most RS_NB_SMALL neighbours run the small-scratch instantiation (more of the SM's memory stays L1)
+  bool nb_full = kmax_run > RS_NB_SMALL;
+  if (const char *e = getenv("RS_NB_FULL")) nb_full = nb_full || atoi(e) != 0;
+  const PassVariant &PV = w->variant[rs_variant(j->maps, large, nb_full)];
+  int grid = PV.grid, grid_team = PV.grid_team;
   {  // several jobs sharing the device: each persistent grid takes its share of the SMs (rs_cuda_set_job_slots)
     const int slots = g_job_slots.load();
     if (slots > 1) {
@@ -2158,7 +2281,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     }
     if (const char *e = getenv("RS_GRID_CAP")) { const int c = atoi(e); if (c > 0 && c < grid) grid = c; if (c > 0 && c < grid_team) grid_team = c; }
   }
-  const size_t smem_tp = pass_smem(j->maps, RS_TP_WARPS), smem_team = pass_smem(j->maps, RS_TEAM_SLOTS);
+  const size_t smem_tp = PV.smem_tp, smem_team = PV.smem_team;
   RS_CHECK(cudaEventRecord(w->ev0, s));
   {  // all pass-0 patches, dependency-free
     RsDev D0 = make_dev(j, 0);
@@ -2198,17 +2321,8 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
       const unsigned W = seg[k].width;
       D.chunk = large ? RS_CHUNK_LARGE : RS_CHUNK_SMALL;
-      if (W <= 1) {
-        if (j->maps) { if (large) k_synth_pass<true, RS_CHUNK_LARGE><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
-                       else k_synth_pass<true, RS_CHUNK_SMALL><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D); }
-        else { if (large) k_synth_pass<false, RS_CHUNK_LARGE><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
-               else k_synth_pass<false, RS_CHUNK_SMALL><<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D); }
-      } else {
-        if (j->maps) { if (large) k_synth_pass_team<true, RS_CHUNK_LARGE><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
-                       else k_synth_pass_team<true, RS_CHUNK_SMALL><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W); }
-        else { if (large) k_synth_pass_team<false, RS_CHUNK_LARGE><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
-               else k_synth_pass_team<false, RS_CHUNK_SMALL><<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W); }
-      }
+      if (W <= 1) PV.tp<<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+      else PV.team<<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
       begin = seg[k].end;
     }
   }
@@ -2238,6 +2352,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   // Host side of the progress/cancel contract: replay ticks in order while the device runs.
   uint32_t emitted[6] = {0, 0, 0, 0, 0, 0};  // ticks already forwarded per pass
   bool cancelled = false;
+  uint32_t cancel_pass = 0, cancel_index = 0;
   unsigned idle_spins = 0;
   auto emit_upto = [&](uint32_t p, uint32_t upto) {
     while (emitted[p] < upto) {
@@ -2245,6 +2360,8 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       emitted[p]++;
       if (tick && !cancelled && tick(tick_ctx, p, idx)) {
         cancelled = true;
+        cancel_pass = p;
+        cancel_index = idx;
         *(volatile int *)w->h_cancel = 1;
       }
     }
@@ -2273,6 +2390,15 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     const unsigned long long started = w->h_ctrl->pass_visits[p];
     if (started) emit_upto(p, (uint32_t)((started - 1ull) / 4096ull + 1ull));
   }
+  if (cancelled && tick && cancel_pass + 1u < j->d.n_passes) {
+    // What the reference does after a cancel (lib/synthesize.h:493-497, lib/refiner.h:75-121): the cancelled synthesize()
+    // call returns the betters it had; unless that is below the stop fraction the next pass starts, ticks at its index
+    // 0, sees the flag and returns no betters -- which ends the pass loop.  So exactly one more tick, or none.
+    // (A cancel at index 0 means no visit of that pass counted; otherwise the device's count stands in for the
+    //  reference's -- it includes the visits that were already in flight beyond the cancelled tick.)
+    const float frac = cancel_index == 0u ? 0.f : (float)w->h_ctrl->betters[cancel_pass] / (float)j->nT;
+    if (!((double)frac < j->d.terminate_fraction)) tick(tick_ctx, cancel_pass + 1u, 0u);
+  }
   if (w->h_ctrl->fault) {
     g_err = "rs_job_run: a visit waited more than 10 s for another one (inconsistent inputs); the result is invalid";
     return 100;
@@ -2291,7 +2417,7 @@ extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sour
     if (j->simple) { g_err = "rs_job_download: a job staged by rs_job_stage_simple returns its rows through rs_job_download_simple"; return 100; }
     uint8_t *dst = target_raw_out + (size_t)j->y_min * row_bytes;
     const uint8_t *src = (const uint8_t *)w->pin;
-    unsigned hw = std::thread::hardware_concurrency();
+    unsigned hw = rs_host_cores();
     const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
     const size_t per = (rows_bytes + nt - 1) / nt;
     std::vector<std::thread> th;
@@ -2354,9 +2480,13 @@ extern "C" int rs_job_read_offsets(RsJob *j, uint32_t *out, uint32_t cap) {
 // What the distance loop is made of: independent, uniformly random aligned loads of one corpus pixel (4 or 8 bytes)
 // from a buffer the size of a corpus.  Gives the rate this GPU sustains for that access pattern (L1/L2 sector
 // gathers), the practical ceiling of neighbour compares per second.
+// Pinned down so that two runs agree: the launch shape and the shared-memory carve-out of the throughput kernel (one
+// 1024-thread CTA per SM, the same dynamic shared memory, hence the same L1 size -- a 256 KB corpus is L1-resident or
+// not depending on exactly that), launches of >= 20 ms each, the median of `repeats` (>= 5) of them after a warm-up.
 template <typename T>
 __global__ void __launch_bounds__(1024, 1) k_gather_rate(const T *__restrict__ buf, uint32_t n_elems, uint32_t iters,
                                                          unsigned long long *__restrict__ sink) {
+  extern __shared__ __align__(16) unsigned char gr_smem[];
   uint32_t h = rs_mix32(blockIdx.x * 1024u + threadIdx.x + 0x9E3779B9u);
   unsigned long long acc = 0;
   for (uint32_t i = 0; i < iters; i++) {
@@ -2370,7 +2500,7 @@ __global__ void __launch_bounds__(1024, 1) k_gather_rate(const T *__restrict__ b
                               : (unsigned long long)((const uint32_t *)&v)[0];
     }
   }
-  if (acc == 0x123456789ull) *sink = acc;  // keep the loads alive
+  if (acc == 0x123456789ull) { *sink = acc; gr_smem[threadIdx.x] = 1; }  // keep the loads (and the carve-out) alive
 }
 extern "C" int rs_cuda_gather_rate(size_t buffer_bytes, int elem_bytes, int repeats, double *loads_per_s) {
   if (elem_bytes != 4 && elem_bytes != 8) { g_err = "rs_cuda_gather_rate: element size must be 4 or 8"; return 100; }
@@ -2379,27 +2509,37 @@ extern "C" int rs_cuda_gather_rate(size_t buffer_bytes, int elem_bytes, int repe
   unsigned long long *sink = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   int sms = 148, dev = 0, rc = 0;
-  float best = 1e30f;
-  const uint32_t iters = 256;
+  uint32_t iters = 256;
+  std::vector<float> times;
+  if (repeats < 5) repeats = 5;
+  const size_t smem = pass_smem(elem_bytes == 8, RS_TP_WARPS);
 #define GCHK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); rc = 100; goto out; } } while (0)
   GCHK(cudaGetDevice(&dev));
   GCHK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  GCHK(cudaFuncSetAttribute(k_gather_rate<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  GCHK(cudaFuncSetAttribute(k_gather_rate<uint2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   GCHK(cudaMalloc(&buf, (size_t)n * elem_bytes));
   GCHK(cudaMalloc(&sink, 8));
   GCHK(cudaMemset(buf, 1, (size_t)n * elem_bytes));
   GCHK(cudaEventCreate(&e0));
   GCHK(cudaEventCreate(&e1));
-  for (int r = 0; r < repeats + 1; r++) {
+  for (int r = -2; r < repeats; r++) {  // r = -2: warm-up; r = -1: calibrates the launch length to >= 20 ms
     GCHK(cudaEventRecord(e0));
-    if (elem_bytes == 4) k_gather_rate<uint32_t><<<sms, 1024>>>((const uint32_t *)buf, n, iters, sink);
-    else k_gather_rate<uint2><<<sms, 1024>>>((const uint2 *)buf, n, iters, sink);
+    if (elem_bytes == 4) k_gather_rate<uint32_t><<<sms, 1024, smem>>>((const uint32_t *)buf, n, iters, sink);
+    else k_gather_rate<uint2><<<sms, 1024, smem>>>((const uint2 *)buf, n, iters, sink);
     GCHK(cudaEventRecord(e1));
     GCHK(cudaEventSynchronize(e1));
     float ms = 0.f;
     GCHK(cudaEventElapsedTime(&ms, e0, e1));
-    if (r > 0 && ms < best) best = ms;
+    if (r == -1) {
+      const double scale = ms > 0.f ? 20.0 / ms : 1.0;
+      if (scale > 1.0) iters = (uint32_t)std::min(1.0e7, iters * scale + 1.0);
+    } else if (r >= 0) {
+      times.push_back(ms / (float)iters);
+    }
   }
-  *loads_per_s = (double)sms * 1024.0 * iters * 8.0 / (best * 1e-3);
+  std::sort(times.begin(), times.end());
+  *loads_per_s = (double)sms * 1024.0 * 8.0 / ((double)times[times.size() / 2] * 1e-3);
 out:
 #undef GCHK
   if (e0) cudaEventDestroy(e0);

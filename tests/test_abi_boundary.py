@@ -111,6 +111,41 @@ def test_no_cpu_fallback_when_cuda_is_absent(built_lib):
     assert (img == before).all()
 
 
+def test_host_cores_divides_the_box_among_local_ranks(built_lib):
+    """rs_host_cores(): helper threads a process may use = cores / LOCAL_WORLD_SIZE (one process per GPU), >= 1."""
+    import subprocess
+    import sys
+    code = ("import ctypes, sys; L = ctypes.CDLL(sys.argv[1]); L.rs_host_cores.restype = ctypes.c_uint; "
+            "print(L.rs_host_cores(), L.rs_host_cores())")
+    def cores(**env):
+        e = dict(os.environ); e.pop("LOCAL_WORLD_SIZE", None); e.pop("RS_HOST_THREADS", None); e.update(env)
+        out = subprocess.run([sys.executable, "-c", code, api.LIB_PATH], env=e, capture_output=True, text=True, timeout=60)
+        a, b = out.stdout.split()
+        assert a == b
+        return int(a)
+    hw = os.cpu_count() or 1
+    assert cores() == hw
+    assert cores(LOCAL_WORLD_SIZE="8") == max(1, hw // 8)
+    assert cores(LOCAL_WORLD_SIZE="8", RS_HOST_THREADS="3") == 3
+
+
+def test_batch_calls_fail_loudly_without_cuda(built_lib):
+    """The batch dealers (rs_image_synth_batch / rs_engine_batch_multi) have no CPU path either: without a device every
+    job reports the CUDA-layer error, the images stay untouched, and rs_last_error() says why."""
+    if api.lib().rs_cuda_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    imgs = [G(16, 12, 3, k) for k in range(3)]
+    before = [i.copy() for i in imgs]
+    masks = [centered_mask(16, 12, 4, 4)] * 3
+    with pytest.raises(api.ResynthError) as e:
+        api.image_synth_batch(imgs, masks, abi.T_RGB, None, devices=None, slots=2)
+    assert "CUDA" in str(e.value)
+    with pytest.raises(api.ResynthError):
+        api.image_synth_batch(imgs, masks, abi.T_RGB, None, devices=[0, 1], slots=2)   # ordinals out of range
+    assert all((a == b).all() for a, b in zip(imgs, before))
+    assert api.image_synth_batch([], [], abi.T_RGB) == []                               # an empty batch is a no-op
+
+
 def test_product_sources_do_not_reference_the_oracle():
     for dirpath, _d, files in os.walk(os.path.join(ROOT, "resynthesizer_b200")):
         for f in files:

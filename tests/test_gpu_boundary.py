@@ -62,6 +62,27 @@ def test_cancel_leaves_image_untouched(built_lib):
     assert api.image_synth(out2, mask, abi.T_RGB, None) == 0 and (out2 != img).any()
 
 
+@pytest.mark.parametrize("cancel_after", [1, 2, 4, 6])
+def test_cancelled_progress_sequence_equals_reference(built_oracle, built_lib, cancel_after):
+    """After a cancel the reference's pass loop goes on (lib/refiner.h:75-121): the cancelled pass returns its betters so
+    far; unless they are under the stop fraction the next pass starts, ticks once at index 0 (synthesize.h:493-497) and
+    ends the loop with no betters.  Same callback sequence from the CUDA engine, the port and the compiled reference."""
+    img = G(200, 160, 3, 3)
+    mask = centered_mask(200, 160, 120, 100)                      # 12000 targets: ticks at 0, 4096, 8192 in pass 0
+    seqs = []
+    for lib in (R.load_port(R.GPU_MODE), R.load_port(R.REF_MODE)) + ((R.load("ref_mt_1t"),) if R.have("ref_mt_1t") else ()):
+        pr = R.Progress(cancel_after=cancel_after)
+        err, out = R.image_synth(lib, img, mask, abi.T_RGB, None, pr)
+        assert err == 0 and (out == img).all()
+        seqs.append(pr.percents)
+    got = img.copy()
+    err, percents = api.image_synth(got, mask, abi.T_RGB, None, cancel_after=cancel_after, return_progress=True)
+    assert err == 0 and (got == img).all()
+    for s_ in seqs:
+        assert percents == s_, (percents, seqs)
+    assert len(percents) in (cancel_after, cancel_after + 1)
+
+
 def test_row_padding_and_imagesynth2(built_oracle, built_lib):
     L = api.lib()
     img = G(40, 30, 3, 8)

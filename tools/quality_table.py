@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Reference-anchored whole-image quality of the CUDA engine on the reference's own golden recipes.
+
+For each recipe of oracle/goldens.py (what Test/testResynth.py:216-408 feeds plug_in_resynthesizer), the CUDA engine is
+run with several seeds and set beside the REFERENCE algorithm's own seed-to-seed spread on the same recipe
+(tests/golden/recipe_ref_spread.json, made by tests/golden/make_recipe_spread.py from the oracle in reference mode):
+whole-image PSNR against the reference's golden image, mean best-match distance of the last pass, passes run.
+Writes a markdown table (and the raw numbers as JSON) -- MEASUREMENT INFRASTRUCTURE, needs a GPU and
+oracle/_ref/recipe_images.npz.
+
+  python tools/quality_table.py --out gpurun_out/r02_quality
+"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import goldens  # noqa: E402
+from resynthesizer_b200 import api, build  # noqa: E402
+
+GPU_SEEDS = [1198472, 7, 99, 2024, 31337, 424242]
+
+
+def psnr(a, b):
+    d = a.astype(np.float64) - b.astype(np.float64)
+    mse = float((d ** 2).mean())
+    return 99.0 if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))
+
+
+def run_recipe(name, seed):
+    _exact, fn = goldens.CASES[name]
+    api.set_seed(seed)
+    out = fn(api.lib())
+    st = api.last_stats()
+    p = st["passes_run"] - 1
+    return out, st["sum_best"][p] / max(st["pass_visits"][p], 1), st["passes_run"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/quality")
+    a = ap.parse_args()
+    build.build()
+    api.order_cache(False)
+    spread = json.load(open(os.path.join(ROOT, "tests", "golden", "recipe_ref_spread.json")))
+    rows, raw = [], {}
+    for name in goldens.CASES:
+        gold = goldens.load_golden(name)
+        ref = spread[name]
+        ps, mb, passes = [], [], []
+        exact = None
+        for seed in GPU_SEEDS:
+            out, best, npass = run_recipe(name, seed)
+            ps.append(psnr(out, gold)); mb.append(best); passes.append(npass)
+            if seed == GPU_SEEDS[0]:
+                exact = hashlib.sha1(np.ascontiguousarray(out).tobytes()).hexdigest() == ref["gpu_mode_sha1"]
+        rps = [p for p in ref["psnr_vs_golden"] if p is not None]
+        raw[name] = {"gpu_psnr": ps, "gpu_mean_best": mb, "gpu_passes": passes, "equals_oracle_gpu_mode": exact}
+        rows.append("| %s | %.2f ± %.2f | %.2f ± %.2f | %+.2f | %.0f ± %.0f | %.0f ± %.0f | %+.1f %% | %s | %s | %s |" % (
+            name, np.mean(rps), np.std(rps), np.mean(ps), np.std(ps), (np.mean(ps) - np.mean(rps)) / max(np.std(rps), 1e-9),
+            np.mean(ref["mean_best"]), np.std(ref["mean_best"]), np.mean(mb), np.std(mb),
+            100.0 * (np.mean(mb) / np.mean(ref["mean_best"]) - 1.0),
+            "/".join(str(x) for x in sorted(set(ref["passes"]))), "/".join(str(x) for x in sorted(set(passes))),
+            "yes" if exact else "NO"))
+    hdr = ("| recipe | PSNR vs golden, reference seeds (dB) | PSNR vs golden, CUDA seeds (dB) | Δ in σ_ref | mean best distance, reference | "
+           "mean best distance, CUDA | Δ | passes ref | passes CUDA | CUDA == oracle GPU mode |\n|---|---|---|---|---|---|---|---|---|---|")
+    text = ("Reference seeds: %d runs of the reference algorithm (oracle reference mode) per recipe, the golden's own seed excluded from the "
+            "PSNR column; CUDA: %d seeds.\n\n" % (len(spread[next(iter(spread))]["seeds"]), len(GPU_SEEDS))) + hdr + "\n" + "\n".join(rows) + "\n"
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    open(a.out + ".md", "w").write(text)
+    json.dump(raw, open(a.out + ".json", "w"), indent=1)
+    print(text)
+
+
+if __name__ == "__main__":
+    main()
