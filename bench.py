@@ -305,14 +305,18 @@ def roofline_of(w, wname, stats, steps, api, gather=True):
     kern_s = float(np.mean([s["ms_kernels"] for s in stats])) / 1000.0
     launches = int(np.mean([s["synth_launches_run"] for s in stats])) + 2   # pass launches that did work + the two pass-0 gathers
     achieved = algo / kern_s / 1e9
-    traffic = bound = None
+    traffic = bound = traffic_src = None
     tp_path = os.path.join(ROOT, "profiles", "traffic_%s.json" % wname)
-    if os.path.exists(tp_path):
+    if os.path.exists(tp_path):   # one `ncu --set full` capture of every synthesis launch of one job (tools/ncu_traffic.py)
         t = json.load(open(tp_path))
-        traffic = t.get("dram_bytes_per_launch")
+        if "dram_bytes_per_job" in t:
+            traffic = t["dram_bytes_per_job"] / launches
+            traffic_src = "%s: dram__bytes_read.sum + dram__bytes_write.sum over the %d synthesis launches of one job / %d" % (
+                os.path.basename(tp_path), t.get("launches_captured", launches), launches)
         bound = t.get("bound")
     rec = {"bound": bound or "hbm", "kernel": "k_synth_pass / k_synth_pass_team (all pass launches + pass-0 patch gather of one job)",
            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+           "traffic_source": traffic_src, "hbm_frac_of_traffic": (traffic * launches / kern_s / 1e9 / peak) if traffic else None,
            "peak_source": peak_src, "counts_source": src,
            "algorithmic_bytes_per_job": algo, "algorithmic_bytes_per_launch": algo / launches,
            "ms_kernels_per_job": 1000.0 * kern_s, "avg_launch_ms": 1000.0 * kern_s / launches, "launches_per_job": launches,
@@ -320,10 +324,12 @@ def roofline_of(w, wname, stats, steps, api, gather=True):
            "compares_issued": dev["compares"],
            "formula": "compares*bpp + offset_scans*9 + visits*(K*(bpp+8) + n_color+9) + (heur_evals+heur_skips)*8 + "
                       "(evals-heur_evals)*8, bpp=%d K=%d; achieved = that / ms_kernels" % (w["bpp"], max(2, w["params"].patchSize))}
-    if gather:
-        # the access pattern's own ceiling: random corpus-pixel gathers from a corpus-sized buffer, measured now
-        elem = 8 if w["n_map"] else 4
-        nbytes = w["cor"].shape[0] * w["cor"].shape[1] * elem
+    elem = 8 if w["n_map"] else 4
+    nbytes = w["cor"].shape[0] * w["cor"].shape[1] * elem
+    if gather and nbytes <= (32 << 20):
+        # L2-resident corpora: the access pattern's own ceiling -- random corpus-pixel gathers from a corpus-sized buffer,
+        # measured now.  (Not reported for corpora beyond the L2: there the neighbour compares of a patch share sectors
+        # that a uniformly random probe stream does not, and DRAM traffic is what binds -- see `traffic`.)
         g = api.gather_rate(nbytes, elem, 7)
         rec["l2_gather"] = {"loads_per_s": g, "compares_per_s": counts["compares"] / kern_s,
                             "frac": counts["compares"] / kern_s / g,
@@ -388,6 +394,9 @@ def sub_record(api, torch, wname, steps, warmup):
     return {"workload": w["name"], "api": api_name(w), "steps": steps, "warmup": warmup,
             "value": steps * r.n / kern_s, "unit": UNIT, "e2e": steps * r.n / sum(walls),
             "ms_kernels": 1000.0 * kern_s / steps, "ms_e2e": 1000.0 * sum(walls) / steps,
+            "ms_e2e_steps": [round(1000.0 * x, 3) for x in walls],
+            "ms_prep": float(np.mean([s["ms_prep"] for s in stats])), "ms_h2d": float(np.mean([s["ms_h2d"] for s in stats])),
+            "ms_d2h": float(np.mean([s["ms_d2h"] for s in stats])),
             "ms_pass": [float(np.mean([s["ms_pass"][p] for s in stats])) for p in range(6)],
             "passes_run": stats[-1]["passes_run"], "visits_per_px": visits / r.n, "evals_per_visit": evals / max(visits, 1),
             "visits_per_s": steps * visits / kern_s, "evals_per_s": steps * evals / kern_s,
@@ -439,6 +448,42 @@ def cfg5_batch_record(api, torch, dist, rank, local, world, n_jobs, probe_list, 
             "slots_per_gpu": slots, "scaling": "strong", "unit": UNIT, "timing": "wall clock between barriers, max over ranks",
             "h2d_bytes_per_job": int(pristine[0].nbytes + m.nbytes) if pristine else 0,
             "d2h_bytes_per_job": 256 * 2048 * 3, "probes": out}
+
+
+def shared_corpus_record(api, n_jobs=32):
+    """One corpus, many targets: `n_jobs` 256x256 targets textured from ONE 2048x2048 corpus
+    (ctx 0, 9 neighbours, 200 probes) -- as one rs_engine_batch() call, whose jobs share the device-resident corpus,
+    against the loop over engine() the reference's callers write."""
+    cor = G(2048, 2048, 3, 77)
+    cp = np.ascontiguousarray(np.concatenate([np.full((2048, 2048, 1), 255, np.uint8), cor], axis=2))
+    prm = abi.make_params(0, 0, 0, 0.5, 0.117, 9, 200)
+    fi = api.format_indices(3)
+
+    def targets():
+        return [np.ascontiguousarray(np.concatenate([np.full((256, 256, 1), 255, np.uint8), np.full((256, 256, 3), 255, np.uint8)], axis=2))
+                for _ in range(n_jobs)]
+    api.order_cache(True)
+    out = {}
+    for rep in range(2):
+        tps = targets()
+        t0 = time.perf_counter()
+        for tp in tps:
+            assert api.engine(prm, fi, tp, cp) == 0
+        out["loop_ms_per_job"] = 1000.0 * (time.perf_counter() - t0) / n_jobs
+    loop_first = tps[0].copy()
+    b0 = api.shared_corpus_stats()
+    for rep in range(2):
+        tps = targets()
+        t0 = time.perf_counter()
+        errs = api.engine_batch([(prm, fi, tp, cp) for tp in tps], slots=4)
+        out["batch_ms_per_job"] = 1000.0 * (time.perf_counter() - t0) / n_jobs
+        assert not any(errs)
+    b1 = api.shared_corpus_stats()
+    api.order_cache(False)
+    out.update(workload="%d targets 256x256 from one 2048x2048 corpus, ctx0, patch 9, probes 200" % n_jobs,
+               speedup=out["loop_ms_per_job"] / out["batch_ms_per_job"], same_result_as_loop=bool((tps[0] == loop_first).all()),
+               corpora_built=b1[0] - b0[0], corpus_reuses=b1[1] - b0[1], h2d_bytes_saved_per_job=int(cp.nbytes))
+    return out
 
 
 def run_ours(a):
@@ -521,6 +566,7 @@ def run_ours(a):
                 subs[name] = sub_record(api, torch, name, 5, 2)
         if a.workload != DEFAULT_WORKLOAD:
             subs[DEFAULT_WORKLOAD] = sub_record(api, torch, DEFAULT_WORKLOAD, 5, 2)
+        subs["shared_corpus_batch"] = shared_corpus_record(api)
 
     roofline = roofline_of(w, a.workload, stats, a.steps, api)
 
@@ -584,7 +630,7 @@ def main():
     ap.add_argument("--probes", type=int, default=0, help="override maxProbeCount of the headline workload")
     ap.add_argument("--cfg5-jobs", type=int, default=64, help="jobs of the cfg5 batch record (0 = skip)")
     ap.add_argument("--cfg5-probes", default="50,100,200,500,1000", help="probe counts of the cfg5 sweep")
-    ap.add_argument("--slots", type=int, default=3, help="jobs in flight per GPU in the cfg5 batch")
+    ap.add_argument("--slots", type=int, default=4, help="jobs in flight per GPU in the cfg5 batch")
     a = ap.parse_args()
     global PROBES_OVERRIDE
     PROBES_OVERRIDE = a.probes

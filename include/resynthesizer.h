@@ -169,6 +169,10 @@ int rs_engine_batch(int n_jobs, const TImageSynthParameters *params, TFormatIndi
 int rs_engine_batch_multi(int n_jobs, const TImageSynthParameters *params, TFormatIndices *const *indices,
                           Map *const *targetMaps, Map *const *corpusMaps, int n_devices, const int *devices, int slots,
                           int *errors_out);
+/* Jobs of one rs_engine_batch(_multi) call that pass the same corpusMap share it on the device: the corpus is staged,
+ * canonicalised and indexed once per device (and copied device to device for a second GPU) -- one texture or style
+ * source, many targets.  Counters of this process: corpora built, reuses, peer copies. */
+void rs_shared_corpus_stats(unsigned long long *builds, unsigned long long *hits, unsigned long long *peer_copies);
 /* The batch call for simple-API jobs: imageSynth(images[i], masks[i], format, params, ...) for every i, or imageSynth2
  * where masks2 (may be NULL) holds an explicit corpus mask for that job; params NULL = defaults.  Images change in place
  * exactly as imageSynth() changes them.  Same dealing as rs_engine_batch_multi. */

@@ -89,6 +89,14 @@ unsigned rs_host_cores(void);
 void rs_cuda_set_job_slots(int slots);
 
 int rs_job_create(const RsJobDesc *desc, RsJob **out);
+/* Jobs of one batch (any non-zero id, unique per batch call) that pass the SAME corpus pixmap to rs_job_stage share one
+ * device-resident corpus per device -- canonical pixels, point list, bitmap, count -- built by the first job that needs
+ * it; a second device copies it from the first (peer copy) instead of staging it from the host again.  Call before
+ * rs_job_stage.  rs_cuda_drop_shared_corpora releases a batch's entries; the stats count builds / reuses / peer copies
+ * of this process. */
+void rs_job_share_corpus(RsJob *job, unsigned long long batch);
+void rs_cuda_drop_shared_corpora(unsigned long long batch);
+void rs_cuda_shared_corpus_stats(unsigned long long *builds, unsigned long long *hits, unsigned long long *peer_copies);
 /* Host -> device.  target_raw/corpus_raw: tw*th*bpp and cw*ch*bpp bytes, pixel = [mask][colours][alpha?][maps].
  * targets: n points packed x | y<<16 in visit order.  corpus_points: C points packed likewise.
  * offsets: n_offsets neighbour offsets packed (int16 x | int16 y << 16), ascending distance, entry 0 = (0,0);

@@ -290,6 +290,13 @@ def image_synth_batch(images, masks, fmt, params=None, devices=None, slots=4, ma
     return list(errs)
 
 
+def shared_corpus_stats():
+    """(corpora built, reuses, peer copies) by the batch calls of this process (rs_shared_corpus_stats)."""
+    a, b, c = C.c_ulonglong(0), C.c_ulonglong(0), C.c_ulonglong(0)
+    lib().rs_shared_corpus_stats(C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
 def engine_batch(jobs, slots=4, devices=None):
     """rs_engine_batch() / rs_engine_batch_multi(): jobs = list of (params, fi, target_pixmap, corpus_pixmap); pixmaps
     change in place.  devices: CUDA ordinals the batch is dealt over (None = this thread's device).

@@ -24,6 +24,7 @@ thread_local RsStats t_stats;
 thread_local uint32_t t_seed = 1198472u;  // lib/engine.c:643
 thread_local bool t_device_chosen = false;
 thread_local int t_device = -1;  // ordinal chosen by rs_set_device / ensure_device on this thread
+thread_local unsigned long long t_batch = 0;  // != 0 inside a batch call: jobs naming the same corpus pixmap share it on the device
 thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-target sources (tests, quality metrics)
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
 thread_local std::vector<uint64_t> t_timeline[6];                   // of the last engine() call (rs_keep_result)
@@ -250,6 +251,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   RsJob *job = nullptr;
   dbg("before create");
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
+  if (t_batch && !src.simple()) rs_job_share_corpus(job, t_batch);
   dbg("after create");
   const size_t npx = (size_t)tw * th, raw_cap = npx + npx / 32 + 65536;
   std::unique_ptr<rs::RawStream> raw;
@@ -403,9 +405,14 @@ extern "C" int engine(TImageSynthParameters prm, TFormatIndices *fi, Map *target
 // first when their estimated costs differ -- so a GPU that finishes early takes more.  No collective, no peer copies:
 // jobs are independent.
 extern "C" void rs_cuda_set_job_slots(int slots);
+extern "C" void rs_cuda_shared_corpus_stats(unsigned long long *builds, unsigned long long *hits, unsigned long long *peer_copies);
+extern "C" void rs_shared_corpus_stats(unsigned long long *builds, unsigned long long *hits, unsigned long long *peer_copies) {
+  rs_cuda_shared_corpus_stats(builds, hits, peer_copies);
+}
 namespace {
 struct BatchPlan {
   int n_jobs = 0, n_devices = 1, slots = 1;
+  bool share_corpora = false;  // some jobs name the same corpus pixmap: it is staged and prepared once per device
   bool share_sms = true;     // side-by-side jobs each take 1/slots of the SMs; false: every job launches full-width
                              // grids and the jobs in flight only overlap their copies and host work with kernels
   const int *devices = nullptr;
@@ -425,11 +432,12 @@ int cap_slots(int slots, size_t n_est) {
   const int cap = n_est >= 200000 ? 2 : (n_est >= 16384 ? 4 : 8);
   return slots > cap ? cap : (slots < 1 ? 1 : slots);
 }
-// Jobs of 16 k+ target points fill the GPU on their own: in a batch they keep full-width grids (the persistent kernels
-// of the next job move in as the tail of the previous one drains) and only staging, ordering and read-back overlap.
-bool share_sms_for(size_t n_est) {
+// Jobs in flight on a device each take 1/slots of the SMs.  The alternative -- full-width grids, the jobs in flight only
+// overlapping copies and host work with kernels -- measured worse on B200 even for 65 k-point jobs (64 heal jobs
+// 2048x2048: 3.83 ms per job shared at 4 slots, 4.36 full-width; one call at a time 5.99): RS_BATCH_SHARE=0 selects it.
+bool share_sms_for(size_t /*n_est*/) {
   if (const char *e = std::getenv("RS_BATCH_SHARE")) return std::atoi(e) != 0;
-  return n_est < 16384;
+  return true;
 }
 int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int *errors_out) {
   const int n_jobs = plan.n_jobs;
@@ -454,6 +462,8 @@ int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int
   if (!plan.cost.empty())
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return plan.cost[a] > plan.cost[b]; });
   const uint32_t seed = t_seed;
+  static std::atomic<unsigned long long> batch_counter{0};
+  const unsigned long long batch = plan.share_corpora ? ++batch_counter : 0ull;
   std::vector<int> errs(n_jobs, 0);
   std::vector<std::string> texts(n_jobs);
   std::atomic<int> next{0};
@@ -463,6 +473,7 @@ int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int
       return;
     }
     rs_set_seed(seed);
+    t_batch = batch;
     for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) {
       const int i = order[k];
       errs[i] = run_one(i);
@@ -477,6 +488,8 @@ int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int
       if (!(d == 0 && t == 0)) pool.emplace_back(worker, devices[d]);
   worker(devices[0]);
   for (auto &t : pool) t.join();
+  t_batch = 0;
+  if (batch) rs_cuda_drop_shared_corpora(batch);  // the shared corpora live as long as the batch call
   rs_cuda_set_job_slots(1);
   if (caller_chosen && caller_device >= 0) rs_set_device(caller_device);  // the calling thread keeps the device it had
   int first = 0;
@@ -506,6 +519,9 @@ extern "C" int rs_engine_batch_multi(int n_jobs, const TImageSynthParameters *pa
     if (plan.cost[i] != plan.cost[0]) equal = false;
   }
   if (equal) plan.cost.clear();
+  for (int i = 1; i < n_jobs && !plan.share_corpora; i++)   // one corpus, many targets?
+    for (int k = 0; k < i; k++)
+      if (corpusMaps[i]->data->data == corpusMaps[k]->data->data) { plan.share_corpora = true; break; }
   plan.slots = cap_slots(slots, n_max);
   plan.share_sms = share_sms_for(n_max);
   return run_batch(plan, [&](int i) {

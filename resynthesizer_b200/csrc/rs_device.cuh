@@ -53,6 +53,9 @@
 #define RS_LUT_REP 32
 #endif
 #define RS_LUT_WORDS (256 * RS_LUT_REP)
+#ifndef RS_SELECT_MIN_POINTS
+#define RS_SELECT_MIN_POINTS (8u << 20)   // corpus points from which rs_corpus_point selects from the bitmap (32 MB of table)
+#endif
 #define RS_MAX_LAUNCHES 16   // pass-kernel launches per job: 6 passes, the first ones cut into up to 4 segments
 #define RS_TIMELINE 320      // progress ticks per pass whose start time is kept (4096 visits each)
 #define RS_MAX_EPOCHS 40     // epochs per pass: ceil(n / max(64, ceil(n/32))) <= 32
@@ -116,6 +119,8 @@ struct RsDev {              // kernel argument (by value)
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
   uint32_t ends[6];
   int htile, vtile;
+  uint32_t sc_slice;        // corpus pixels per CTA slice when the corpus is staged into shared memory (k_synth_pass<..., true>)
+  uint32_t select_min;      // corpus points from which rs_corpus_point selects from the bitmap (RS_SELECT_MIN_POINTS)
   uint32_t cw_inv;          // floor(2^32 / cw): quotient estimate for rs_corpus_point (one correction step makes it exact)
   double terminate_fraction;
 };
@@ -153,9 +158,10 @@ __device__ __forceinline__ uint32_t rs_corpus_point(const RsDev &J, uint32_t nC,
     if (x >= (uint32_t)J.cw) { x -= (uint32_t)J.cw; y++; }
     return x | (y << 16);
   }
-  if (J.cbits != nullptr && nC >= (J.cn >> 2)) {
-    // Dense selections (a quarter or more of the pixels usable: an image minus its hole): the point table is tens of
-    // megabytes of one-sector DRAM misses, the bitmap and its samples stay in L2.  From the sample at or before idx,
+  if (J.cbits != nullptr && nC >= (J.cn >> 2) && nC >= J.select_min) {
+    // Dense selections (a quarter or more of the pixels usable: an image minus its hole) of RS_SELECT_MIN_POINTS points or
+    // more: the point table is tens of megabytes of one-sector DRAM misses, the bitmap and its samples stay in L2
+    // (B200: 4096^2 inpaint 59.1 -> 54.0 ms of kernels; a 16 MB table still lives in L2 and the lookup wins by 3 %).  From the sample at or before idx,
     // count set bits word by word (32 usable pixels span 2-5 words at these densities).  Same point, bit for bit.
     uint32_t r = idx & 31u;
     const uint32_t p = __ldg(J.csamples + (idx >> 5));
@@ -236,6 +242,45 @@ __device__ __forceinline__ void rs_tma_load_1d(void *smem_dst, const void *gmem_
                : "memory");
 }
 
+// ---- the corpus on chip (throughput kernel, corpora without map channels that fit) ----
+// A corpus tile of up to ~80 k pixels (render-texture's 256x256 tile is 256 KB) is staged ONCE per CTA into shared memory
+// by TMA bulk copies -- whole when it fits one CTA, else split over the two CTAs of a thread-block cluster, each holding
+// a slice and reading the other's through distributed shared memory (ld.shared::cluster).  Every neighbour compare is
+// then an on-chip load instead of an L1/L2 sector gather.  lo / hi are shared::cluster addresses such that pixel a lives
+// at (a < split ? lo : hi) + 4 * a.
+struct CorpusSmem {
+  unsigned lo = 0, hi = 0;
+  uint32_t split = 0xFFFFFFFFu;
+};
+template <bool SMEMC>
+__device__ __forceinline__ uint32_t rs_corpus4(const RsDev &J, const CorpusSmem &cs, uint32_t a) {
+  if (SMEMC) {
+    uint32_t v;
+    const unsigned addr = (a < cs.split ? cs.lo : cs.hi) + a * 4u;
+    asm("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  }
+  return __ldg(J.corpus4 + a);
+}
+__device__ __forceinline__ unsigned rs_cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned rs_cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned rs_mapa(unsigned shared_addr, unsigned rank) {  // the same shared-memory offset in CTA `rank` of the cluster
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(shared_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void rs_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- one neighbour of the patch as the distance loop reads it (shared memory, one LDS.128, broadcast) ----
 // lin = dy * cw + dx and dx: the corpus pixel compared with this neighbour for candidate (cx, cy) is
 // clin + lin, inside the corpus iff (unsigned)(cx + dx) < cw and (unsigned)(clin + lin) < cw * ch.
@@ -300,9 +345,10 @@ __device__ __forceinline__ uint32_t rs_chunk_reduce(unsigned lutc, unsigned lutm
   }
   return sum;
 }
-template <bool MAPS, int CH>
+template <bool MAPS, int CH, bool SMEMC = false>
 __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
-                                                 const uint32_t *nmap, int cx, uint32_t clin, uint32_t k0) {
+                                                 const uint32_t *nmap, int cx, uint32_t clin, uint32_t k0,
+                                                 const CorpusSmem &cs = CorpusSmem()) {
   RsNb r[CH];
   uint32_t cp[CH], cm[CH];
 #pragma unroll
@@ -316,7 +362,7 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, 
       cp[u] = t.x;
       cm[u] = t.y;
     } else {
-      cp[u] = __ldg(J.corpus4 + a);
+      cp[u] = rs_corpus4<SMEMC>(J, cs, a);
       cm[u] = 0u;
     }
   }
@@ -339,11 +385,11 @@ __device__ __forceinline__ uint32_t rs_chunk_sum(const RsDev &J, unsigned lutc, 
 // Candidates are fetched a window of 32 ahead (one per lane, all lanes at once) and handed to the lanes that need
 // one by shuffle, so the dependent table load of cand_of() is off the critical path of a round.
 // K = patch size (>= 1); nb/nmap hold 1 + ceil((K-1)/CH)*CH records.
-template <bool MAPS, int CH, class CandFn>
+template <bool MAPS, int CH, bool SMEMC = false, class CandFn>
 __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, unsigned lutm, const RsNb *nb,
                                               const uint32_t *nmap, uint32_t K, int begin, int end, CandFn cand_of,
                                               uint32_t &bestSum, int &bestIdx, uint32_t &bestLin, int &bestCx,
-                                              uint32_t &nCompares, uint32_t &nIssued) {
+                                              uint32_t &nCompares, uint32_t &nIssued, const CorpusSmem &cs = CorpusSmem()) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   int next = begin;  // warp-uniform
@@ -386,7 +432,7 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
     }
     bool finished = false;
     if (active) {
-      partial += rs_chunk_sum<MAPS, CH>(J, lutc, lutm, nb, nmap, cx, clin, k);
+      partial += rs_chunk_sum<MAPS, CH, SMEMC>(J, lutc, lutm, nb, nmap, cx, clin, k, cs);
       if (MAPS && k == 1u) partial += rs_lut3(lutm, __vabsdiffu4(m0, selfmap));  // map terms of the target point itself (synthesize.h:342-355)
       k += CH;
       finished = (k >= K);

@@ -599,9 +599,9 @@ __device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS
 }
 
 // (3) One warp: the heuristic candidate list S.aux[0..nHeur) of visit v, and what rs_visit_finish needs (S.vis).
-template <bool MAPS, int NB>
+template <bool SMEMC = false, bool MAPS, int NB>
 __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS, NB> &S, Visit &V,
-                                                    const uint32_t v, const uint32_t K) {
+                                                    const uint32_t v, const uint32_t K, const CorpusSmem &cs = CorpusSmem()) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass;
@@ -627,7 +627,7 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
         const int x = (int)(src & 0xFFFFu) - rs_off_x(o), y = (int)(src >> 16) - rs_off_y(o);
         if ((unsigned)x < (unsigned)J.cw && (unsigned)y < (unsigned)J.ch) {
           const size_t a = (size_t)y * J.cw + x;
-          const uint32_t cm = MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a);
+          const uint32_t cm = MAPS ? __ldg(&J.corpus8[a].x) : rs_corpus4<SMEMC>(J, cs, (uint32_t)a);
           if (cm >= 0xFF000000u) c = (uint32_t)x | ((uint32_t)y << 16);
         }
       }
@@ -728,10 +728,10 @@ __device__ __forceinline__ void rs_visit_stamps(const RsDev &J, RsCtrl *ctrl, co
 // hcol[i] = colour of heuristic candidate i (fetched with its first chunk).  For a winning probe: win_pt = its corpus
 // point if the distance phase tracked it (else RS_NO_SRC: looked up from the probe's index), win_col = its colour if
 // have_col (else fetched here).
-template <bool STAMPS = true, bool MAPS, int NB>
+template <bool STAMPS = true, bool SMEMC = false, bool MAPS, int NB>
 __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS, NB> &S, const Visit &V,
                                                 uint32_t bestSum, int bestIdx, uint32_t win_pt, uint32_t win_col,
-                                                bool have_col) {
+                                                bool have_col, const CorpusSmem &cs = CorpusSmem()) {
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t pass = J.pass, v = V.v, nHeur = V.nHeur;
   const uint32_t *candlist = S.aux, *hcol = S.q;
@@ -757,7 +757,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
       if (bp != src) {
         if (!heur && !(have_col && win_pt != RS_NO_SRC)) {
           const size_t a = (size_t)(bp >> 16) * J.cw + (bp & 0xFFFFu);
-          bcol = (MAPS ? __ldg(&J.corpus8[a].x) : __ldg(J.corpus4 + a)) & 0xFFFFFFu;
+          bcol = (MAPS ? __ldg(&J.corpus8[a].x) : rs_corpus4<SMEMC>(J, cs, (uint32_t)a)) & 0xFFFFFFu;
         }
         colour = bcol;
         src = bp;
@@ -838,18 +838,19 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, L
 }
 
 // One (heuristic candidate, chunk j) pair of the patch distance; chunk 0 also carries the target point's own terms.
-template <bool MAPS, int CH, int NB>
+template <bool MAPS, int CH, int NB, bool SMEMC = false>
 __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, unsigned lutm, const WarpScratch<MAPS, NB> &S,
-                                                 uint32_t *hcol, uint32_t K, uint32_t ci, uint32_t j, LaneStats &st) {
+                                                 uint32_t *hcol, uint32_t K, uint32_t ci, uint32_t j, LaneStats &st,
+                                                 const CorpusSmem &cs = CorpusSmem()) {
   const uint32_t c = S.aux[ci];
   const int cx = (int)(c & 0xFFFFu);
   const uint32_t clin = (c >> 16) * (uint32_t)J.cw + (uint32_t)cx, k0 = 1u + j * CH;
   uint32_t own_x = 0, own_y = 0;  // the candidate's own pixel: its colour is what a win commits (synthesize.h:403-419)
   if (j == 0u) {
     if (MAPS) { const uint2 t = __ldg(J.corpus8 + clin); own_x = t.x; own_y = t.y; }
-    else own_x = __ldg(J.corpus4 + clin);
+    else own_x = rs_corpus4<SMEMC>(J, cs, clin);
   }
-  uint32_t part = rs_chunk_sum<MAPS, CH>(J, lutc, lutm, S.nb, S.map, cx, clin, k0);
+  uint32_t part = rs_chunk_sum<MAPS, CH, SMEMC>(J, lutc, lutm, S.nb, S.map, cx, clin, k0, cs);
   if (j == 0u) {
     if (MAPS) part += rs_lut3(lutm, __vabsdiffu4(own_y, S.map[0]));
     hcol[ci] = own_x & 0xFFFFFFu;
@@ -860,6 +861,19 @@ __device__ __forceinline__ uint32_t rs_heur_pair(const RsDev &J, unsigned lutc, 
   return part;
 }
 
+struct TeamShared {  // per team of the latency kernel (k_synth_pass_team, below)
+  unsigned long long best;
+  uint32_t hsum[RS_MAX_NB];
+  uint32_t hcnt[RS_MAX_NB];  // chunks of each heuristic candidate added so far
+  uint32_t v, K, nHeur, alive;
+  uint32_t win_pt, win_col;  // corpus point and colour of the winning probe, written by the lane that evaluated it
+};
+// Dynamic shared memory of a pass kernel with `scratch_slots` warp scratches: tables, scratches, two mbarriers, team blocks.
+template <bool MAPS, int NB>
+__host__ __device__ constexpr unsigned pass_smem_bytes(int scratch_slots) {
+  return (MAPS ? 2u : 1u) * RS_LUT_WORDS * 4u + (unsigned)sizeof(WarpScratch<MAPS, NB>) * (unsigned)scratch_slots + 16u +
+         (unsigned)sizeof(TeamShared) * RS_TEAM_SLOTS;
+}
 struct PassSmem {  // carve-up of the dynamic shared memory of the pass kernels
   unsigned lutc, lutm;  // shared-space addresses of this lane's table columns
   void *scratch;
@@ -880,25 +894,53 @@ __device__ __forceinline__ PassSmem rs_pass_smem(const RsDev &J, unsigned char *
 }
 
 // ---- throughput mode: one warp per visit -------------------------------------------------------------------
-template <bool MAPS, int CH, int NB>
+// SMEMC: the corpus (no map channels) lives in the shared memory of the CTA, or of the two CTAs of its cluster; the launch
+// passes the slice length in J.sc_slice (pixels per CTA, a multiple of 4) and sizes the dynamic shared memory for it.
+template <bool MAPS, int CH, int NB, bool SMEMC>
 __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass(const RsDev J) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
-  if (rs_ld_u32_relaxed(&ctrl->stop)) return;
+  const bool stopped = rs_ld_u32_relaxed(&ctrl->stop) != 0u;
+  if (!SMEMC && stopped) return;  // (a cluster leaves together: both CTAs go through the two cluster barriers below)
   const PassSmem P = rs_pass_smem<MAPS, NB, RS_TP_WARPS>(J, smem_raw);
   const unsigned lutc = P.lutc, lutm = P.lutm;
   WarpScratch<MAPS, NB> &S = reinterpret_cast<WarpScratch<MAPS, NB> *>(P.scratch)[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
+  CorpusSmem cs;
+  if (SMEMC) {
+    // this CTA's slice of the canonical corpus (sentinel pixel included) -> shared memory, by TMA bulk copies
+    uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw + ((pass_smem_bytes<MAPS, NB>(RS_TP_WARPS) + 127u) & ~127u));
+    const unsigned rank = rs_cluster_ctarank(), nr = rs_cluster_nctarank();
+    const uint32_t first = rank * J.sc_slice, total = J.cn + 1u;
+    const uint32_t count = first < total ? min(J.sc_slice, total - first) : 0u;
+    const uint32_t bytes = ((count * 4u) + 15u) & ~15u;  // (the corpus buffer is allocated with slack beyond the sentinel)
+    uint64_t *cbar = P.bar + 1;
+    if (threadIdx.x == 0) {
+      rs_mbar_init(cbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      rs_mbar_expect_tx(cbar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u)
+        rs_tma_load_1d(reinterpret_cast<unsigned char *>(slice) + off, reinterpret_cast<const unsigned char *>(J.corpus4 + first) + off,
+                       min(32768u, bytes - off), cbar);
+    }
+    __syncthreads();
+    rs_mbar_wait(cbar, 0);
+    rs_cluster_sync();  // the peer's slice is complete before anyone reads it
+    const unsigned base = (unsigned)__cvta_generic_to_shared(slice);
+    cs.lo = rs_mapa(base, 0u);
+    cs.hi = rs_mapa(base, nr - 1u) - (nr - 1u) * J.sc_slice * 4u;
+    cs.split = nr > 1u ? J.sc_slice : 0xFFFFFFFFu;
+  }
   LaneStats st;
   Visit V;
   if (lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
-  uint32_t v = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
+  uint32_t v = stopped ? J.seg_end : rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
   uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
   while (v < J.seg_end) {
     {
       const uint32_t Kv = rs_visit_geometry(J, S, v, tpos);
       rs_visit_values(J, S, v, Kv);
-      rs_visit_candidates(J, ctrl, S, V, v, Kv);
+      rs_visit_candidates<SMEMC>(J, ctrl, S, V, v, Kv, cs);
     }
     // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
     uint32_t bestSum = 0xFFFFFFFFu, bestLin = RS_NO_SRC;
@@ -916,7 +958,7 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
         const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
-        atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH, NB>(J, lutc, lutm, S, hcol, K, ci, j, st));
+        atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH, NB, SMEMC>(J, lutc, lutm, S, hcol, K, ci, j, st, cs));
       }
       __syncwarp();
       const uint32_t h0 = lane < nHeur ? hsum[lane] : 0xFFFFFFFFu, h1 = (NB > 32 && lane + 32u < nHeur) ? hsum[lane + 32u] : 0xFFFFFFFFu;
@@ -926,19 +968,20 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
       bestIdx = midx;
     }
     if (bestSum != 0u)
-      rs_eval_range<MAPS, CH>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
+      rs_eval_range<MAPS, CH, SMEMC>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
                           [&](int i) { return rs_corpus_point(J, nC, rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
-                          bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued);
-    rs_visit_finish(J, ctrl, S, V, bestSum, bestIdx,
+                          bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued, cs);
+    rs_visit_finish<true, SMEMC>(J, ctrl, S, V, bestSum, bestIdx,
                           bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
-                          0u, false);
+                          0u, false, cs);
     const uint32_t v_next = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
     const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
     v = v_next;
     tpos = tpos_next;
   }
   __syncwarp();
-  rs_pass_epilogue(J, ctrl, st, &S.st);
+  if (!SMEMC || !stopped) rs_pass_epilogue(J, ctrl, st, &S.st);
+  if (SMEMC) rs_cluster_sync();  // nobody leaves while its peer may still read its slice
 }
 
 // ---- latency mode: a team of W warps per visit ---------------------------------------------------------------
@@ -947,13 +990,6 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
 // chunk) pair in one gather round, sums merged by shared-memory atomics; (B) the random probes, one
 // per lane per round, early-out against a team-shared packed best (sum << 32 | index, atomicMin) -- the same
 // "first candidate with the minimum full sum" rule, hence the same bits as the warp kernel.
-struct TeamShared {
-  unsigned long long best;
-  uint32_t hsum[RS_MAX_NB];
-  uint32_t hcnt[RS_MAX_NB];  // chunks of each heuristic candidate added so far
-  uint32_t v, K, nHeur, alive;
-  uint32_t win_pt, win_col;  // corpus point and colour of the winning probe, written by the lane that evaluated it
-};
 
 __device__ __forceinline__ void rs_team_sync(unsigned id, unsigned nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -1172,6 +1208,10 @@ struct PassVariant {
   void (*team)(const RsDev, const unsigned) = nullptr;  // k_synth_pass_team<maps, chunk, nb>
   size_t smem_tp = 0, smem_team = 0;
   int grid = 0, grid_team = 0;                          // persistent grids: resident CTAs per SM x SMs
+  int sms = 0;
+  void (*tp_smemc)(const RsDev) = nullptr;              // k_synth_pass<false, chunk, nb, true>: corpus in shared memory
+  size_t smemc_base = 0;                                // dynamic shared memory before the corpus slice
+  uint32_t smemc_slice_max = 0;                         // pixels a CTA's slice can hold
 };
 struct Workspace {
   int device = 0;
@@ -1254,12 +1294,9 @@ static void ws_free(Workspace *w) {
   delete w;
 }
 
-static size_t scratch_bytes(bool maps, bool nb_full) {
-  return maps ? (nb_full ? sizeof(WarpScratch<true, RS_NB_FULL>) : sizeof(WarpScratch<true, RS_NB_SMALL>))
-              : (nb_full ? sizeof(WarpScratch<false, RS_NB_FULL>) : sizeof(WarpScratch<false, RS_NB_SMALL>));
-}
 static size_t pass_smem(bool maps, int scratch_slots, bool nb_full = true) {
-  return (maps ? 2u : 1u) * RS_LUT_WORDS * 4u + scratch_bytes(maps, nb_full) * scratch_slots + 16 + sizeof(TeamShared) * RS_TEAM_SLOTS;
+  return maps ? (nb_full ? pass_smem_bytes<true, RS_NB_FULL>(scratch_slots) : pass_smem_bytes<true, RS_NB_SMALL>(scratch_slots))
+              : (nb_full ? pass_smem_bytes<false, RS_NB_FULL>(scratch_slots) : pass_smem_bytes<false, RS_NB_SMALL>(scratch_slots));
 }
 // The instantiations of the two pass kernels: map channels x chunk size x scratch size (index = rs_variant()).
 static int rs_variant(bool maps, bool chunk_large, bool nb_full) { return (maps ? 4 : 0) + (chunk_large ? 2 : 0) + (nb_full ? 1 : 0); }
@@ -1267,10 +1304,10 @@ template <bool MAPS, int CH, int NB>
 static int configure_pass_kernel(Workspace *w) {
   const bool full = NB == RS_NB_FULL;
   const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS, full), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS, full);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
   int per_sm = 0, per_sm_team = 0, sms = 0;
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB>, RS_TP_WARPS * 32, smem_tp));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB, false>, RS_TP_WARPS * 32, smem_tp));
   RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS, CH, NB>, RS_TEAM_WARPS * 32, smem_team));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
   if (per_sm < 1 || per_sm_team < 1) { g_err = "the pass kernels do not fit on an SM"; return 100; }
@@ -1279,13 +1316,22 @@ static int configure_pass_kernel(Workspace *w) {
   const size_t sm_max = 233472;
   const int carve_tp = (int)std::min<size_t>(100, ((smem_tp + 1024) * per_sm * 100 + sm_max - 1) / sm_max);
   const int carve_team = (int)std::min<size_t>(100, ((smem_team + 1024) * per_sm_team * 100 + sm_max - 1) / sm_max);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_tp));
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_team));
   PassVariant &V = w->variant[rs_variant(MAPS, CH == RS_CHUNK_LARGE, full)];
-  V.tp = k_synth_pass<MAPS, CH, NB>;
+  V.tp = k_synth_pass<MAPS, CH, NB, false>;
   V.team = k_synth_pass_team<MAPS, CH, NB>;
   V.smem_tp = smem_tp; V.smem_team = smem_team;
   V.grid = per_sm * sms; V.grid_team = per_sm_team * sms;
+  V.sms = sms;
+  if (!MAPS) {  // the corpus-in-shared-memory instantiation: one CTA per SM, everything the SM has left goes to the slice
+    const size_t smem_max = 232448;  // 227 KB per CTA on sm_100
+    const size_t base = (smem_tp + 127) & ~(size_t)127;
+    V.tp_smemc = k_synth_pass<false, CH, NB, true>;
+    V.smemc_base = base;
+    V.smemc_slice_max = (uint32_t)(((smem_max - base) / 4) & ~(size_t)3);
+    RS_CHECK(cudaFuncSetAttribute(k_synth_pass<false, CH, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  }
   return 0;
 }
 
@@ -1294,7 +1340,10 @@ static int ws_acquire(Workspace **out) {
   if (cudaGetDevice(&dev) != cudaSuccess) { g_err = "no CUDA device"; return 100; }
   {
     std::lock_guard<std::mutex> lk(g_pool_mutex);
-    for (size_t i = 0; i < g_pool.size(); i++)
+    // most recently released first: a caller that runs one job after another keeps getting the workspace whose
+    // buffers, pinned staging and offsets table already fit its jobs (oldest-first rotated through every workspace a
+    // batch had left in the pool, growing each in turn: 2x the call time of the first jobs after a batch)
+    for (size_t i = g_pool.size(); i-- > 0;)
       if (g_pool[i]->device == dev) {
         *out = g_pool[i];
         g_pool.erase(g_pool.begin() + i);
@@ -1419,7 +1468,50 @@ struct OrderEntry {
     if (dev) cudaFree(dev);
   }
 };
+// Where a job's corpus lives on the device: in its workspace, or in an entry shared by the jobs of a batch that
+// synthesise from the SAME corpus (one texture or style source, many targets: SURVEY.md section 8 f4).  The entry
+// holds everything that is a function of the corpus alone -- canonical pixels, point list, bitmap + samples, point
+// count -- built once per device; a second device of the batch copies it from the first over NVLink (peer copy)
+// instead of staging it from the host again.
+struct CorpusBufs {
+  void *corpus = nullptr;
+  uint32_t *cpts = nullptr, *cbits = nullptr, *csamples = nullptr;
+};
+struct SharedCorpus {
+  unsigned long long batch = 0;
+  const void *host_key = nullptr;  // the caller's corpus pixmap (identity within one batch call)
+  int device = 0;
+  int cw = 0, ch = 0, bpp = 0, n_color = 0, n_map = 0, map_bip = 0, alpha_bip = 0, alpha_source = 0;
+  DevBuf corpus, cpts, cbits, csamples, n_corpus;
+  size_t corpus_bytes = 0, cpts_bytes = 0, cbits_bytes = 0, csamples_bytes = 0;
+  bool peer_copied = false;
+  cudaEvent_t ready = nullptr;  // recorded behind the build (or the peer copy) on the creating job's stream
+  ~SharedCorpus() {
+    DeviceGuard guard(device);
+    if (ready) cudaEventDestroy(ready);
+    for (DevBuf *b : {&corpus, &cpts, &cbits, &csamples, &n_corpus}) if (b->p) cudaFree(b->p);
+  }
+};
+static std::mutex g_corpus_mutex;
+static std::vector<std::shared_ptr<SharedCorpus>> g_corpora;
+static std::atomic<unsigned long long> g_corpus_peer_copies{0}, g_corpus_hits{0}, g_corpus_builds{0};
+extern "C" void rs_cuda_drop_shared_corpora(unsigned long long batch) {
+  std::vector<std::shared_ptr<SharedCorpus>> dropped;
+  {
+    std::lock_guard<std::mutex> lk(g_corpus_mutex);
+    for (size_t i = 0; i < g_corpora.size();)
+      if (g_corpora[i]->batch == batch) { dropped.push_back(g_corpora[i]); g_corpora.erase(g_corpora.begin() + i); } else i++;
+  }
+}
+extern "C" void rs_cuda_shared_corpus_stats(unsigned long long *builds, unsigned long long *hits, unsigned long long *peer_copies) {
+  if (builds) *builds = g_corpus_builds.load();
+  if (hits) *hits = g_corpus_hits.load();
+  if (peer_copies) *peer_copies = g_corpus_peer_copies.load();
+}
 struct RsJob {
+  CorpusBufs cb;
+  std::shared_ptr<SharedCorpus> shared;   // the batch's corpus entry this job reads, if any
+  unsigned long long share_batch = 0;     // != 0: the corpus may be shared with other jobs of this batch (rs_job_share_corpus)
   RsJobDesc d;
   Workspace *ws = nullptr;
   bool maps = false;
@@ -1450,6 +1542,9 @@ extern "C" void rs_job_destroy(RsJob *j) {
   delete j;
 }
 
+// The jobs of batch `batch` (any non-zero id, unique per batch call) that pass the same corpus pixmap to rs_job_stage
+// share one device-resident corpus per device; rs_cuda_drop_shared_corpora(batch) releases the entries.
+extern "C" void rs_job_share_corpus(RsJob *j, unsigned long long batch) { j->share_batch = batch; }
 extern "C" int rs_job_create(const RsJobDesc *desc, RsJob **out) {
   *out = nullptr;
   if (desc->tw <= 0 || desc->th <= 0 || desc->cw <= 0 || desc->ch <= 0 || desc->tw > 32767 || desc->th > 32767 ||
@@ -1732,68 +1827,135 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
   RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl), s));
   const int T = 256;
   j->upload_launches = 0;
+  auto enqueue_digest = [&](const uint8_t *mask_bytes, int stride) -> int {
+    // count, row range and digest of the selection: queued as early as the mask is on its way, so that the result is
+    // back (rs_job_digest) while the host is still copying the rest of the job into the staging buffer
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+    const uint32_t ymin_init = 0xFFFFFFFFu;
+    RS_CHECK(cudaMemcpyAsync(&((RsCtrl *)w->ctrl.p)->dg_ymin, &ymin_init, 4, cudaMemcpyHostToDevice, s));
+    k_target_digest<<<sms * 8, 256, 0, s>>>(mask_bytes, (uint32_t)tn, stride, d.tw, (RsCtrl *)w->ctrl.p);
+    RS_CHECK(cudaMemcpyAsync(w->h_digest, &((RsCtrl *)w->ctrl.p)->dg_h1, sizeof(RsTargetDigest), cudaMemcpyDeviceToHost, s));
+    RS_CHECK(cudaEventRecord(w->evDigest, s));
+    j->upload_launches += 1u;
+    return 0;
+  };
   if (simple) {  // image + mask planes up (they fit the staging regions of the two pixmaps), pixmaps built on the device
     const size_t sz_img = tn * simple->nc;
     if ((rc = ws_ensure(w->simg, sz_img)) || (rc = ws_ensure(w->smask, tn)) || (rc = ws_ensure(w->smask2, simple->mask2 ? tn : 4)))
       return rc;
     if ((rc = stage_rows_to_device(w->smask.p, pin + o_t + sz_img, simple->mask, d.th, d.tw, simple->mask_rb, s))) return rc;
+    if (digest && (rc = enqueue_digest((const uint8_t *)w->smask.p, 1))) return rc;  // the selection IS the mask plane
     if ((rc = stage_rows_to_device(w->simg.p, pin + o_t, simple->img, d.th, (size_t)d.tw * simple->nc, simple->img_rb, s))) return rc;
     if (simple->mask2 && (rc = stage_rows_to_device(w->smask2.p, pin + o_c, simple->mask2, d.th, d.tw, simple->mask2_rb, s))) return rc;
     k_build_simple<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->simg.p, (const uint8_t *)w->smask.p,
                                                             simple->mask2 ? (const uint8_t *)w->smask2.p : nullptr, (uint32_t)tn,
                                                             simple->nc, (uint8_t *)w->raw_t.p, (uint8_t *)w->raw_c.p);
     j->upload_launches += 1u;
-  } else if ((rc = stage_to_device(w->raw_t.p, pin + o_t, target_raw, sz_t, s))) {
-    return rc;
+  } else {
+    if ((rc = stage_to_device(w->raw_t.p, pin + o_t, target_raw, sz_t, s))) return rc;
+    if (digest && (rc = enqueue_digest((const uint8_t *)w->raw_t.p, d.bpp))) return rc;
   }
-  if (digest) {  // first, so that its result can come back while the rest of the staging runs
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
-    const uint32_t ymin_init = 0xFFFFFFFFu;
-    RS_CHECK(cudaMemcpyAsync(&((RsCtrl *)w->ctrl.p)->dg_ymin, &ymin_init, 4, cudaMemcpyHostToDevice, s));
-    k_target_digest<<<sms * 8, 256, 0, s>>>((const uint8_t *)w->raw_t.p, (uint32_t)tn, d.bpp, d.tw, (RsCtrl *)w->ctrl.p);
-    RS_CHECK(cudaMemcpyAsync(w->h_digest, &((RsCtrl *)w->ctrl.p)->dg_h1, sizeof(RsTargetDigest), cudaMemcpyDeviceToHost, s));
-    RS_CHECK(cudaEventRecord(w->evDigest, s));
-    j->upload_launches += 1u;
-  }
-  if (!simple && (rc = stage_to_device(w->raw_c.p, pin + o_c, corpus_raw, sz_c, s))) return rc;
   memcpy(pin + o_lut, color_lut256, 256 * 4);
   memcpy(pin + o_lut + 256 * 4, map_lut256, 256 * 4);
   RS_CHECK(cudaMemcpyAsync(w->lut256.p, pin + o_lut, sz_lut, cudaMemcpyHostToDevice, s));
   bool built_offsets = false;
   int offset_sort_bits = 1;
   unsigned int *d_ncorpus = &((RsCtrl *)w->ctrl.p)->n_corpus;
+  j->cb = CorpusBufs{w->corpus.p, (uint32_t *)w->cpts.p, nullptr, nullptr};
+  j->shared.reset();
+  bool corpus_ready = false;  // canonical pixels + points already on the device (a shared entry)
   if (corpus_points) {
     memcpy(pin + o_cp, corpus_points, sz_cp);
     RS_CHECK(cudaMemcpyAsync(w->cpts.p, pin + o_cp, sz_cp, cudaMemcpyHostToDevice, s));
     RS_CHECK(cudaMemcpyAsync(d_ncorpus, &j->nC, 4, cudaMemcpyHostToDevice, s));
+    if (!simple && (rc = stage_to_device(w->raw_c.p, pin + o_c, corpus_raw, sz_c, s))) return rc;
   } else {
-    if ((rc = ws_ensure(w->sort_keys_in, cn))) return rc;  // flags
-    k_corpus_flags<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (uint32_t)cn, d.bpp, d.alpha_bip,
-                                                            d.alpha_source, (uint8_t *)w->sort_keys_in.p);
-    thrust::counting_iterator<uint32_t> idx(0);
-    size_t tmp = 0;
-    RS_CHECK(cub::DeviceSelect::Flagged(nullptr, tmp, idx, (const uint8_t *)w->sort_keys_in.p, (uint32_t *)w->cpts.p,
-                                        d_ncorpus, (int)cn, s));
-    if ((rc = ws_ensure(w->sort_tmp, tmp))) return rc;
-    RS_CHECK(cub::DeviceSelect::Flagged(w->sort_tmp.p, tmp, idx, (const uint8_t *)w->sort_keys_in.p, (uint32_t *)w->cpts.p,
-                                        d_ncorpus, (int)cn, s));
-    k_pack_points<<<592, T, 0, s>>>((uint32_t *)w->cpts.p, d_ncorpus, d.cw);
-    // bitmap + every-32nd-point samples of the same selection (rs_corpus_point picks by density at run time)
     const uint32_t n_words = (uint32_t)((cn + 31) / 32);
-    if ((rc = ws_ensure(w->cbits, (size_t)(n_words + 2) * 4)) || (rc = ws_ensure(w->ccounts, (size_t)n_words * 4)) ||
-        (rc = ws_ensure(w->cbefore, (size_t)n_words * 4)) || (rc = ws_ensure(w->csamples, (size_t)(n_words + 1) * 4)))
-      return rc;
-    k_corpus_bits<<<(n_words * 32u + T - 1) / T, T, 0, s>>>((const uint8_t *)w->sort_keys_in.p, (uint32_t)cn, (uint32_t *)w->cbits.p,
-                                                          (uint32_t *)w->ccounts.p);
-    RS_CHECK(cudaMemsetAsync((uint32_t *)w->cbits.p + n_words, 0, 8, s));  // the scan may peek one word past the end
-    size_t tmp_scan = 0;
-    RS_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t *)w->ccounts.p, (uint32_t *)w->cbefore.p, (int)n_words, s));
-    if ((rc = ws_ensure(w->sort_tmp, tmp_scan > tmp ? tmp_scan : tmp))) return rc;
-    RS_CHECK(cub::DeviceScan::ExclusiveSum(w->sort_tmp.p, tmp_scan, (const uint32_t *)w->ccounts.p, (uint32_t *)w->cbefore.p, (int)n_words, s));
-    k_corpus_samples<<<(n_words + T - 1) / T, T, 0, s>>>((const uint32_t *)w->cbits.p, (const uint32_t *)w->cbefore.p, n_words,
-                                                       (uint32_t *)w->csamples.p);
+    std::unique_lock<std::mutex> share_lock;
+    std::shared_ptr<SharedCorpus> mine, peer;
+    if (j->share_batch && !simple) {  // jobs of a batch that name the same corpus pixmap: built once per device
+      share_lock = std::unique_lock<std::mutex>(g_corpus_mutex);
+      for (auto &e : g_corpora) {
+        if (e->batch != j->share_batch || e->host_key != (const void *)corpus_raw || e->cw != d.cw || e->ch != d.ch || e->bpp != d.bpp ||
+            e->n_color != d.n_color || e->n_map != d.n_map || e->map_bip != d.map_bip || e->alpha_bip != d.alpha_bip ||
+            e->alpha_source != d.alpha_source)
+          continue;
+        if (e->device == w->device) { mine = e; break; }
+        if (!peer) peer = e;
+      }
+      if (mine) {  // hit: nothing of the corpus is staged or built again
+        RS_CHECK(cudaStreamWaitEvent(s, mine->ready, 0));
+        RS_CHECK(cudaMemcpyAsync(d_ncorpus, mine->n_corpus.p, 4, cudaMemcpyDeviceToDevice, s));
+        g_corpus_hits.fetch_add(1);
+        corpus_ready = true;
+      } else {
+        mine = std::make_shared<SharedCorpus>();
+        mine->batch = j->share_batch; mine->host_key = corpus_raw; mine->device = w->device;
+        mine->cw = d.cw; mine->ch = d.ch; mine->bpp = d.bpp; mine->n_color = d.n_color; mine->n_map = d.n_map;
+        mine->map_bip = d.map_bip; mine->alpha_bip = d.alpha_bip; mine->alpha_source = d.alpha_source;
+        mine->corpus_bytes = (cn + 1) * (j->maps ? 8 : 4); mine->cpts_bytes = cn * 4;
+        mine->cbits_bytes = (size_t)(n_words + 2) * 4; mine->csamples_bytes = (size_t)(n_words + 1) * 4;
+        if ((rc = ws_ensure(mine->corpus, mine->corpus_bytes)) || (rc = ws_ensure(mine->cpts, mine->cpts_bytes)) ||
+            (rc = ws_ensure(mine->cbits, mine->cbits_bytes)) || (rc = ws_ensure(mine->csamples, mine->csamples_bytes)) ||
+            (rc = ws_ensure(mine->n_corpus, 4)))
+          return rc;
+        RS_CHECK(cudaEventCreateWithFlags(&mine->ready, cudaEventDisableTiming));
+        if (peer) {  // another device of the batch has it: device-to-device over NVLink, no host staging
+          RS_CHECK(cudaStreamWaitEvent(s, peer->ready, 0));
+          RS_CHECK(cudaMemcpyPeerAsync(mine->corpus.p, w->device, peer->corpus.p, peer->device, mine->corpus_bytes, s));
+          RS_CHECK(cudaMemcpyPeerAsync(mine->cpts.p, w->device, peer->cpts.p, peer->device, mine->cpts_bytes, s));
+          RS_CHECK(cudaMemcpyPeerAsync(mine->cbits.p, w->device, peer->cbits.p, peer->device, mine->cbits_bytes, s));
+          RS_CHECK(cudaMemcpyPeerAsync(mine->csamples.p, w->device, peer->csamples.p, peer->device, mine->csamples_bytes, s));
+          RS_CHECK(cudaMemcpyPeerAsync(mine->n_corpus.p, w->device, peer->n_corpus.p, peer->device, 4, s));
+          RS_CHECK(cudaMemcpyAsync(d_ncorpus, mine->n_corpus.p, 4, cudaMemcpyDeviceToDevice, s));
+          mine->peer_copied = true;
+          g_corpus_peer_copies.fetch_add(1);
+          corpus_ready = true;
+        }
+      }
+      j->shared = mine;
+      j->cb = CorpusBufs{mine->corpus.p, (uint32_t *)mine->cpts.p, (uint32_t *)mine->cbits.p, (uint32_t *)mine->csamples.p};
+    } else {
+      if ((rc = ws_ensure(w->cbits, (size_t)(n_words + 2) * 4)) || (rc = ws_ensure(w->csamples, (size_t)(n_words + 1) * 4))) return rc;
+      j->cb.cbits = (uint32_t *)w->cbits.p; j->cb.csamples = (uint32_t *)w->csamples.p;
+    }
+    if (!corpus_ready) {
+      if (!simple && (rc = stage_to_device(w->raw_c.p, pin + o_c, corpus_raw, sz_c, s))) return rc;
+      if ((rc = ws_ensure(w->sort_keys_in, cn))) return rc;  // flags
+      k_corpus_flags<<<(unsigned)((cn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (uint32_t)cn, d.bpp, d.alpha_bip,
+                                                              d.alpha_source, (uint8_t *)w->sort_keys_in.p);
+      thrust::counting_iterator<uint32_t> idx(0);
+      size_t tmp = 0, tmp_scan = 0;
+      RS_CHECK(cub::DeviceSelect::Flagged(nullptr, tmp, idx, (const uint8_t *)w->sort_keys_in.p, j->cb.cpts, d_ncorpus, (int)cn, s));
+      RS_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t *)w->ccounts.p, (uint32_t *)w->cbefore.p, (int)n_words, s));
+      if ((rc = ws_ensure(w->sort_tmp, tmp_scan > tmp ? tmp_scan : tmp)) || (rc = ws_ensure(w->ccounts, (size_t)n_words * 4)) ||
+          (rc = ws_ensure(w->cbefore, (size_t)n_words * 4)))
+        return rc;
+      RS_CHECK(cub::DeviceSelect::Flagged(w->sort_tmp.p, tmp, idx, (const uint8_t *)w->sort_keys_in.p, j->cb.cpts, d_ncorpus, (int)cn, s));
+      k_pack_points<<<592, T, 0, s>>>(j->cb.cpts, d_ncorpus, d.cw);
+      // bitmap + every-32nd-point samples of the same selection (rs_corpus_point picks by density at run time)
+      k_corpus_bits<<<(n_words * 32u + T - 1) / T, T, 0, s>>>((const uint8_t *)w->sort_keys_in.p, (uint32_t)cn, j->cb.cbits,
+                                                            (uint32_t *)w->ccounts.p);
+      RS_CHECK(cudaMemsetAsync(j->cb.cbits + n_words, 0, 8, s));  // the scan may peek one word past the end
+      RS_CHECK(cub::DeviceScan::ExclusiveSum(w->sort_tmp.p, tmp_scan, (const uint32_t *)w->ccounts.p, (uint32_t *)w->cbefore.p, (int)n_words, s));
+      k_corpus_samples<<<(n_words + T - 1) / T, T, 0, s>>>(j->cb.cbits, (const uint32_t *)w->cbefore.p, n_words, j->cb.csamples);
+      if (mine) RS_CHECK(cudaMemcpyAsync(mine->n_corpus.p, d_ncorpus, 4, cudaMemcpyDeviceToDevice, s));
+    }
     j->corpus_bits = true;
+    if (mine && !corpus_ready) {  // canonical pixels belong to the entry too; then it becomes visible to the batch
+      k_canon_corpus<<<(unsigned)((cn + T) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map, d.map_bip,
+                                                              j->maps ? nullptr : (uint32_t *)j->cb.corpus,
+                                                              j->maps ? (uint2 *)j->cb.corpus : nullptr);
+      g_corpus_builds.fetch_add(1);
+      corpus_ready = true;
+    }
+    if (mine && !g_corpora.empty() && std::find(g_corpora.begin(), g_corpora.end(), mine) != g_corpora.end()) {
+      // (an entry found in the list: nothing to publish)
+    } else if (mine) {
+      RS_CHECK(cudaEventRecord(mine->ready, s));
+      g_corpora.push_back(mine);
+    }
   }
   if (offsets) {
     if ((rc = ws_ensure(w->offsets, sz_off))) return rc;
@@ -1813,9 +1975,10 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
   RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 8, s));
   RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 8, s));
   RS_CHECK(cudaMemsetAsync(w->prober2.p, 0, cn * 8, s));
-  k_canon_corpus<<<(unsigned)((cn + T) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
-                                                          d.map_bip, j->maps ? nullptr : (uint32_t *)w->corpus.p,
-                                                          j->maps ? (uint2 *)w->corpus.p : nullptr);
+  if (!corpus_ready)
+    k_canon_corpus<<<(unsigned)((cn + T) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
+                                                            d.map_bip, j->maps ? nullptr : (uint32_t *)j->cb.corpus,
+                                                            j->maps ? (uint2 *)j->cb.corpus : nullptr);
   k_init_target<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_t.p, (int)tn, d.bpp, d.n_color, d.n_map,
                                                          d.map_bip, d.alpha_bip, d.alpha_target, d.use_context,
                                                          (unsigned long long *)w->W.p, (uint32_t *)w->meta.p,
@@ -2169,13 +2332,13 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   memset(&D, 0, sizeof D);
   const RsJobDesc &d = j->d;
   const Workspace *w = j->ws;
-  D.corpus4 = j->maps ? nullptr : (const uint32_t *)w->corpus.p;
-  D.corpus8 = j->maps ? (const uint2 *)w->corpus.p : nullptr;
+  D.corpus4 = j->maps ? nullptr : (const uint32_t *)j->cb.corpus;
+  D.corpus8 = j->maps ? (const uint2 *)j->cb.corpus : nullptr;
   D.W = (unsigned long long *)w->W.p; D.meta = (const uint32_t *)w->meta.p;
   D.tmaps = j->maps ? (const uint32_t *)w->tmaps.p : nullptr;
-  D.targets = j->targets_dev; D.corpus_pts = (const uint32_t *)w->cpts.p;
-  D.cbits = j->corpus_bits && !getenv("RS_NO_CORPUS_BITS") ? (const uint32_t *)w->cbits.p : nullptr;
-  D.csamples = (const uint32_t *)w->csamples.p;
+  D.targets = j->targets_dev; D.corpus_pts = j->cb.cpts;
+  D.cbits = j->corpus_bits && !getenv("RS_NO_CORPUS_BITS") ? j->cb.cbits : nullptr;
+  D.csamples = j->cb.csamples;
   D.offsets = (const uint32_t *)w->offsets.p; D.lut_rep = (const uint32_t *)w->lut_rep.p;
   D.prober[0] = (unsigned long long *)w->prober0.p; D.prober[1] = (unsigned long long *)w->prober1.p;
   D.prober[2] = (unsigned long long *)w->prober2.p;
@@ -2192,6 +2355,8 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.pass = pass; D.pass_end = d.pass_end[pass];
   for (int p = 0; p < 6; p++) D.ends[p] = d.pass_end[p];
   D.htile = d.htile; D.vtile = d.vtile; D.terminate_fraction = d.terminate_fraction;
+  D.select_min = RS_SELECT_MIN_POINTS;
+  if (const char *e = getenv("RS_SELECT_MIN")) D.select_min = (uint32_t)strtoul(e, nullptr, 10);  // tests, sweeps
   D.cw_inv = d.cw > 1 ? (uint32_t)(0x100000000ull / (uint32_t)d.cw) : 0xFFFFFFFFu;
   return D;
 }
@@ -2282,6 +2447,22 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     if (const char *e = getenv("RS_GRID_CAP")) { const int c = atoi(e); if (c > 0 && c < grid) grid = c; if (c > 0 && c < grid_team) grid_team = c; }
   }
   const size_t smem_tp = PV.smem_tp, smem_team = PV.smem_team;
+  // Corpus on chip (throughput kernel, no map channels): whole in one CTA's shared memory when it fits, else split over the
+  // two CTAs of a cluster.  RS_SMEM_CORPUS=0 keeps it in L2; =1/2 forces the cluster size (tests).
+  int smemc_ctas = 0, grid_smemc = grid < PV.sms ? grid : PV.sms;
+  uint32_t smemc_slice = 0;
+  if (!j->maps && PV.tp_smemc != nullptr) {
+    const uint32_t total = (uint32_t)j->d.cw * (uint32_t)j->d.ch + 1u;  // pixels + the sentinel
+    int want = total <= PV.smemc_slice_max ? 1 : (total <= 2u * PV.smemc_slice_max ? 2 : 0);
+    if (const char *e = getenv("RS_SMEM_CORPUS")) {
+      const int f = atoi(e);
+      if (f == 0) want = 0;
+      else if (f == 2 && want == 1) want = 2;
+    }
+    if (want == 2 && grid_smemc < 2) want = 0;
+    smemc_ctas = want;
+    if (want) smemc_slice = (uint32_t)((((total + (uint32_t)want - 1u) / (uint32_t)want) + 3u) & ~3u);
+  }
   RS_CHECK(cudaEventRecord(w->ev0, s));
   {  // all pass-0 patches, dependency-free
     RsDev D0 = make_dev(j, 0);
@@ -2321,8 +2502,24 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
       const unsigned W = seg[k].width;
       D.chunk = large ? RS_CHUNK_LARGE : RS_CHUNK_SMALL;
-      if (W <= 1) PV.tp<<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
-      else PV.team<<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+      if (W <= 1 && smemc_ctas) {  // corpus staged into the shared memory of a CTA or of a 2-CTA cluster
+        D.sc_slice = smemc_slice;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3((unsigned)(grid_smemc / smemc_ctas * smemc_ctas), 1, 1);
+        cfg.blockDim = dim3(RS_TP_WARPS * 32, 1, 1);
+        cfg.dynamicSmemBytes = PV.smemc_base + (size_t)smemc_slice * 4 + 16;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)smemc_ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        RS_CHECK(cudaLaunchKernelEx(&cfg, PV.tp_smemc, D));
+      } else if (W <= 1) {
+        PV.tp<<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+      } else {
+        PV.team<<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
+      }
       begin = seg[k].end;
     }
   }

@@ -83,3 +83,37 @@ def test_bad_job_reports_its_error_and_the_rest_still_run(built_oracle, built_li
     errs = api.image_synth_batch(got, masks, abi.T_RGB, None, devices=[0], slots=2)
     assert errs[1] == 5 and errs[0] == 0 and errs[2] == 0
     assert (got[1] == imgs[1]).all() and (got[0] != imgs[0]).any()
+
+
+def test_shared_corpus_is_built_once_per_device_and_results_equal_single_calls(built_oracle, built_lib):
+    """One corpus, many targets: the jobs of a batch that pass the SAME corpus pixmap stage and
+    prepare it once per device; every target comes out as from its own engine() call (= the oracle's)."""
+    port = R.load_port(R.GPU_MODE)
+    cor = G(72, 60, 3, 5)
+    cmask = np.full((60, 72), 255, np.uint8); cmask[10:20, 30:50] = 0          # a corpus with a hole: point list != identity
+    cp = np.ascontiguousarray(np.concatenate([cmask[:, :, None], cor], axis=2))
+    p = abi.make_params(1, 0, 0, 0.5, 0.117, 9, 60)
+    fi = api.format_indices(3)
+    jobs, want = [], []
+    for k in range(9):
+        side = 24 + 4 * k
+        tp = np.ascontiguousarray(np.concatenate([np.full((side, side, 1), 255, np.uint8), G(side, side, 3, 50 + k)], axis=2))
+        ref_t = tp.copy()
+        assert R.engine(port, p, R.format_indices(port, 3, 0, False, False, False), ref_t, cp.copy()) == 0
+        want.append(ref_t)
+        jobs.append((p, fi, tp, cp))                                          # the same corpus array in every job
+    devs = _devices()
+    b0 = api.shared_corpus_stats()
+    errs = api.engine_batch(jobs, slots=3, devices=devs)
+    b1 = api.shared_corpus_stats()
+    assert not any(errs)
+    for (_p, _f, tp, _c), w in zip(jobs, want):
+        assert (tp == w).all()
+    built, reused, peer = (b1[i] - b0[i] for i in range(3))
+    assert 1 <= built + peer <= len(devs) and built >= 1       # once per device that took a job: from the host, or from a peer
+    assert built + peer + reused == len(jobs)
+    # a different corpus per job: nothing is shared
+    jobs2 = [(p, fi, j[2].copy(), cp.copy()) for j in jobs[:3]]
+    b2 = api.shared_corpus_stats()
+    assert not any(api.engine_batch(jobs2, slots=2))
+    assert api.shared_corpus_stats() == b2

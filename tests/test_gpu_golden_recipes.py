@@ -6,15 +6,14 @@ Two claims per recipe:
       its semantics (oracle GPU mode) on the reference's real test images -- digest committed in
       tests/golden/recipe_ref_spread.json by tests/golden/make_recipe_spread.py;
   (2) statistical, against the REFERENCE algorithm itself (the sequential PRNG stream and the live recentProber map
-      cannot be followed in parallel): over GPU_SEEDS runs, the CUDA engine's whole-image PSNR
-      against the reference's golden image and its mean best-match distance of the last pass lie within the
-      reference's own seed-to-seed spread on that recipe (8 seeds of the oracle in reference mode, which reproduces
-      the goldens at the reference's seed):
-          mean_gpu(PSNR)      >= mean_ref(PSNR)      - TOL_SIGMA * sigma_ref(PSNR)      - PSNR_FLOOR_DB
-          mean_gpu(mean best) <= mean_ref(mean best) + TOL_SIGMA * sigma_ref(mean best) + BEST_FLOOR * mean_ref
-      The floors are what the table in profiles/r02_quality_goldens.md justifies and nothing more: on recipes whose
-      reference spread is a fraction of a percent (whole-image texture transfer: sigma 0.1-0.9 % of the mean over
-      100 k+ visits) the bounded-staleness prober shifts the mean best distance by up to that much.
+      cannot be followed in parallel).  Tolerance, as SURVEY.md section 8c proposes it, with the
+      reference distribution taken from 8 seeds of the oracle in reference mode (which reproduces the goldens at the
+      reference's seed) on the same recipe, and NO extra slack:
+          whole-image PSNR against the reference's golden image   >= mean_ref - 2 sigma_ref
+          mean best-match distance over the last pass that ran    <= mean_ref + 2 sigma_ref
+      held by the MEDIAN of the CUDA engine's GPU_SEEDS runs (the last-pass mean of a 5000-pixel heal is heavy-tailed:
+      one seed in six lands a few bad pixels, in the reference's own runs as well) and by at least 4 of the 6 runs
+      individually.  Measured table: profiles/r02_quality_goldens.md.
 Needs oracle/_ref/recipe_images.npz (packed by build() where /root/reference exists; travels with the snapshot)."""
 import hashlib
 import json
@@ -31,8 +30,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SPREAD = json.load(open(os.path.join(ROOT, "tests", "golden", "recipe_ref_spread.json")))
 GPU_SEEDS = [1198472, 7, 99, 2024, 31337, 424242]
 TOL_SIGMA = 2.0
-PSNR_FLOOR_DB = 0.1
-BEST_FLOOR = 0.03
+MIN_RUNS_WITHIN = 4
 
 needs_images = pytest.mark.skipif(not goldens.available(), reason="oracle/_ref/recipe_images.npz not packed (build() without /root/reference)")
 
@@ -67,6 +65,10 @@ def test_recipe_on_cuda_engine(built_lib, name):
         mb.append(st["sum_best"][p] / max(st["pass_visits"][p], 1))
     # (2) within the reference's own seed-to-seed spread
     rps = [x for x in ref["psnr_vs_golden"] if x is not None]
-    assert np.mean(ps) >= np.mean(rps) - TOL_SIGMA * np.std(rps) - PSNR_FLOOR_DB, (np.mean(ps), np.mean(rps), np.std(rps))
     rmb = ref["mean_best"]
-    assert np.mean(mb) <= np.mean(rmb) + TOL_SIGMA * np.std(rmb) + BEST_FLOOR * np.mean(rmb), (np.mean(mb), np.mean(rmb), np.std(rmb))
+    psnr_bound = np.mean(rps) - TOL_SIGMA * np.std(rps)
+    best_bound = np.mean(rmb) + TOL_SIGMA * np.std(rmb)
+    assert np.median(ps) >= psnr_bound, (ps, psnr_bound)
+    assert np.median(mb) <= best_bound, (mb, best_bound)
+    assert sum(p >= psnr_bound for p in ps) >= MIN_RUNS_WITHIN, (ps, psnr_bound)
+    assert sum(b <= best_bound for b in mb) >= MIN_RUNS_WITHIN, (mb, best_bound)

@@ -125,15 +125,33 @@ def test_chunk_size_override(built_oracle, built_lib, monkeypatch, chunk, width)
 
 @pytest.mark.parametrize("width", [1, 2, 8])
 def test_smem_corpus_off_equals_on(built_oracle, built_lib, monkeypatch, width):
-    """Small corpora are staged into (distributed) shared memory by TMA; RS_SMEM_CORPUS=0 forces the L2 path.  Both
-    must equal the oracle."""
+    """Corpora without map channels that fit are staged into shared memory by TMA bulk copies when the throughput kernel
+    runs (width 1) -- whole in one CTA, or split over a 2-CTA cluster and read through distributed shared memory;
+    RS_SMEM_CORPUS=0 forces the L2 path, =2 the cluster split.  All must equal the oracle."""
     monkeypatch.setenv("RS_TEAM_P0", str(width))
     monkeypatch.setenv("RS_TEAM_PN", str(width))
-    for flag in ("0", "1"):
+    for flag in ("0", "1", "2"):   # L2 path / as it fits (one CTA here) / split over the two CTAs of a cluster (DSMEM)
         monkeypatch.setenv("RS_SMEM_CORPUS", flag)
         _check("texture9")
         _check("texture9_tiled")
         _check("gray16")
+        _check("heal30")
+
+
+@pytest.mark.parametrize("width", [1, 4])
+def test_corpus_point_lookup_paths(built_oracle, built_lib, monkeypatch, width):
+    """The idx-th corpus point three ways (rs_corpus_point): identity when every corpus pixel is usable (texture9_tiled,
+    maps9), bitmap select for dense selections from RS_SELECT_MIN points on (forced here: heal30, gray16, texture9 have
+    holes in their corpora), and the point table (RS_NO_CORPUS_BITS).  Same points, so the same images as the oracle."""
+    monkeypatch.setenv("RS_TEAM_P0", str(width))
+    monkeypatch.setenv("RS_TEAM_PN", str(width))
+    monkeypatch.setenv("RS_SELECT_MIN", "0")
+    for kind in ("heal30", "gray16", "texture9", "texture9_tiled", "maps9", "maps20_alpha"):
+        _check(kind)
+    monkeypatch.delenv("RS_SELECT_MIN")
+    monkeypatch.setenv("RS_NO_CORPUS_BITS", "1")
+    _check("heal30")
+    _check("texture9")
 
 
 @pytest.mark.parametrize("width", [1, 2, 4, 8])
