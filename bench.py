@@ -70,6 +70,12 @@ def _workload(name, seed_shift=0, scale=1.0):
         return dict(name="cfg1 heal %dx%d, %dx%d hole, ctx1, patch 30, probes 200" % (s, s, s // 8, s // 8),
                     params=abi.default_params(), n_color=3, n_map=0, alpha=False,
                     tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4, simple=abi.T_RGB)
+    if name == "cfg1_brick":  # BASELINE configs[0] on the real image it names (Test/in_images/brick.png, packed by build())
+        img = np.load(os.path.join(ROOT, "baseline", "_ref", "brick_512.npy"))
+        m = centered_mask(512, 512, 64, 64)
+        return dict(name="cfg1 heal brick.png 512x512, 64x64 hole, ctx1, patch 30, probes 200",
+                    params=abi.default_params(), n_color=3, n_map=0, alpha=False,
+                    tmask=m, tgt=img, cmask=255 - m, cor=img, bpp=4, simple=abi.T_RGB)
     if name == "cfg5":      # one heal job of the batch config: 2048^2, 256^2 hole, 30/200
         s = int(2048 * scale)
         img = G(s, s, 3, 100 + seed_shift)
@@ -305,16 +311,18 @@ def roofline_of(w, wname, stats, steps, api, gather=True):
     kern_s = float(np.mean([s["ms_kernels"] for s in stats])) / 1000.0
     launches = int(np.mean([s["synth_launches_run"] for s in stats])) + 2   # pass launches that did work + the two pass-0 gathers
     achieved = algo / kern_s / 1e9
-    traffic = bound = traffic_src = None
+    traffic = bound = traffic_src = limiter = None
     tp_path = os.path.join(ROOT, "profiles", "traffic_%s.json" % wname)
     if os.path.exists(tp_path):   # one `ncu --set full` capture of every synthesis launch of one job (tools/ncu_traffic.py)
         t = json.load(open(tp_path))
         if "dram_bytes_per_job" in t:
+            launches = int(t.get("launches_captured", launches))   # every launch that did work, as ncu saw them (incl. k_gather_later)
             traffic = t["dram_bytes_per_job"] / launches
             traffic_src = "%s: dram__bytes_read.sum + dram__bytes_write.sum over the %d synthesis launches of one job / %d" % (
                 os.path.basename(tp_path), t.get("launches_captured", launches), launches)
         bound = t.get("bound")
-    rec = {"bound": bound or "hbm", "kernel": "k_synth_pass / k_synth_pass_team (all pass launches + pass-0 patch gather of one job)",
+        limiter = t.get("limiter")
+    rec = {"bound": bound or "hbm", "limiter": limiter, "kernel": "k_synth_pass / k_synth_pass_team (all pass launches + pass-0 patch gather of one job)",
            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
            "traffic_source": traffic_src, "hbm_frac_of_traffic": (traffic * launches / kern_s / 1e9 / peak) if traffic else None,
            "peak_source": peak_src, "counts_source": src,
@@ -561,7 +569,10 @@ def run_ours(a):
         return
     subs = {}
     if not a.quick and world == 1:
-        for name in ("cfg1", "cfg2", "cfg4", "cfg5"):
+        names = ["cfg1", "cfg2", "cfg4", "cfg5"]
+        if os.path.exists(os.path.join(ROOT, "baseline", "_ref", "brick_512.npy")):
+            names.insert(1, "cfg1_brick")
+        for name in names:
             if name != a.workload:
                 subs[name] = sub_record(api, torch, name, 5, 2)
         if a.workload != DEFAULT_WORKLOAD:

@@ -27,6 +27,11 @@ def main():
     os.makedirs(os.path.dirname(goldens.PACK), exist_ok=True)
     np.savez_compressed(goldens.PACK, **d)
     print("wrote %s (%d arrays, %.1f MB)" % (goldens.PACK, len(d), os.path.getsize(goldens.PACK) / 1e6))
+    # BASELINE.json configs[0] names a real image of Test/in_images: bench.py's "cfg1_brick" sub-record reads this copy
+    # (git-ignored like the pack; bench.py never touches oracle/ outside its CPU-baseline legs)
+    bdir = os.path.join(ROOT, "baseline", "_ref")
+    os.makedirs(bdir, exist_ok=True)
+    np.save(os.path.join(bdir, "brick_512.npy"), d["in/brick"])
     return 0
 
 
