@@ -97,7 +97,7 @@ struct RsDev {              // kernel argument (by value)
   const uint32_t *targets;
   const uint32_t *corpus_pts;
   const uint32_t *cbits;    // bitmap of the usable corpus pixels, row-major, 32 per word (or nullptr: table only)
-  const uint32_t *csamples; // linear index of usable corpus pixel 32 * j
+  const uint2 *csamples;    // {linear index p of usable corpus pixel 16 * j, bitmap window of pixels p .. p + 31}
   const uint32_t *offsets;
   const uint32_t *lut_rep;  // [2][256][32] colour then map metric, replicated per lane (bank-conflict free)
   unsigned long long *prober[3];  // [cw*ch] each: stamps of epochs = 0, 1, 2 (mod 3), see above
@@ -161,17 +161,24 @@ __device__ __forceinline__ uint32_t rs_corpus_point(const RsDev &J, uint32_t nC,
   if (J.cbits != nullptr && nC >= (J.cn >> 2) && nC >= J.select_min) {
     // Dense selections (a quarter or more of the pixels usable: an image minus its hole) of RS_SELECT_MIN_POINTS points or
     // more: the point table is tens of megabytes of one-sector DRAM misses, the bitmap and its samples stay in L2
-    // (B200: 4096^2 inpaint 59.1 -> 54.0 ms of kernels; a 16 MB table still lives in L2 and the lookup wins by 3 %).  From the sample at or before idx,
-    // count set bits word by word (32 usable pixels span 2-5 words at these densities).  Same point, bit for bit.
-    uint32_t r = idx & 31u;
-    const uint32_t p = __ldg(J.csamples + (idx >> 5));
-    uint32_t wi = p >> 5, x = __ldg(J.cbits + wi) & (0xFFFFFFFFu << (p & 31u)), c = __popc(x);
-    while (r >= c) {
+    // (B200: 4096^2 inpaint 59.1 -> 54.0 ms of kernels; a 16 MB table still lives in L2 and the lookup wins by 3 %).
+    uint32_t r = idx & 15u, pos;
+    const uint2 e = __ldg(J.csamples + (idx >> 4));
+    uint32_t c = __popc(e.y);
+    if (r < c) {
+      pos = e.x + rs_nth_set_bit(e.y, r);
+    } else {  // sparser than 16 usable pixels in 32 here: go on in the bitmap behind the window
+      const uint32_t q = e.x + 32u;
+      uint32_t wi = q >> 5, x = __ldg(J.cbits + wi) & (0xFFFFFFFFu << (q & 31u));
       r -= c;
-      x = __ldg(J.cbits + ++wi);
       c = __popc(x);
+      while (r >= c) {
+        r -= c;
+        x = __ldg(J.cbits + ++wi);
+        c = __popc(x);
+      }
+      pos = (wi << 5) + rs_nth_set_bit(x, r);
     }
-    const uint32_t pos = (wi << 5) + rs_nth_set_bit(x, r);
     uint32_t y = __umulhi(pos, J.cw_inv), xx = pos - y * (uint32_t)J.cw;
     if (xx >= (uint32_t)J.cw) { xx -= (uint32_t)J.cw; y++; }
     return xx | (y << 16);

@@ -1475,7 +1475,8 @@ struct OrderEntry {
 // instead of staging it from the host again.
 struct CorpusBufs {
   void *corpus = nullptr;
-  uint32_t *cpts = nullptr, *cbits = nullptr, *csamples = nullptr;
+  uint32_t *cpts = nullptr, *cbits = nullptr;
+  uint2 *csamples = nullptr;
 };
 struct SharedCorpus {
   unsigned long long batch = 0;
@@ -1594,10 +1595,11 @@ __global__ void k_corpus_flags(const uint8_t *__restrict__ raw, uint32_t n_px, i
   const uint8_t *p = raw + (size_t)i * bpp;
   flags[i] = (p[0] == 0xFFu && (!alpha_source || p[alpha_bip] != 0)) ? 1 : 0;
 }
-// The same list without the list: a bitmap of the usable corpus pixels (row-major) and, for every 32nd usable pixel, its
-// linear index.  rs_corpus_point() then finds point idx by a short scan from sample idx / 32 -- two or three words of a
-// bitmap that stays in L2 instead of one 4-byte load from a table of tens of megabytes that never does (4096^2 inpaint:
-// 46 MB of points, one DRAM sector per probe, a quarter of the pass kernels' DRAM traffic).
+// The same list without the list: a bitmap of the usable corpus pixels (row-major) and, for every 16th usable pixel, its
+// linear index p together with the bitmap window of pixels p .. p + 31.  rs_corpus_point() finds point idx in the window
+// of sample idx / 16 -- ONE 8-byte load from a table that stays in L2 wherever at least half of the pixels are usable,
+// a short bitmap scan elsewhere -- instead of one 4-byte load from a table of tens of megabytes that never stays
+// (4096^2 inpaint: 46 MB of points, one DRAM sector per probe: 45 GB of DRAM reads per pass where 13 GB remain).
 __global__ void k_corpus_bits(const uint8_t *__restrict__ flags, uint32_t n_px, uint32_t *__restrict__ bits,
                               uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // launched over n_px rounded up to whole words
@@ -1605,12 +1607,16 @@ __global__ void k_corpus_bits(const uint8_t *__restrict__ flags, uint32_t n_px, 
   if ((threadIdx.x & 31u) == 0u) { bits[i >> 5] = wd; counts[i >> 5] = __popc(wd); }
 }
 __global__ void k_corpus_samples(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ before, uint32_t n_words,
-                                 uint32_t *__restrict__ samples) {
+                                 uint2 *__restrict__ samples) {
   const uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x;
   if (wi >= n_words) return;
   const uint32_t wd = bits[wi], b = before[wi], c = __popc(wd);
-  const uint32_t first = (b + 31u) & ~31u;  // the only multiple of 32 this word's points [b, b + c) can contain
-  if (c && first < b + c) samples[first >> 5] = (wi << 5) + rs_nth_set_bit(wd, first - b);
+  // the multiples of 16 among this word's points [b, b + c): at most two
+  for (uint32_t first = (b + 15u) & ~15u; c && first < b + c; first += 16u) {
+    const uint32_t s = rs_nth_set_bit(wd, first - b), p = (wi << 5) + s;
+    const uint32_t win = (wd >> s) | (s ? (bits[wi + 1] << (32u - s)) : 0u);  // usable-pixel bits of pixels p .. p + 31
+    samples[first >> 4] = make_uint2(p, win);
+  }
 }
 __global__ void k_pack_points(uint32_t *__restrict__ pts, const unsigned int *__restrict__ n_ptr, int w) {
   const uint32_t n = *n_ptr;
@@ -1895,7 +1901,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
         mine->cw = d.cw; mine->ch = d.ch; mine->bpp = d.bpp; mine->n_color = d.n_color; mine->n_map = d.n_map;
         mine->map_bip = d.map_bip; mine->alpha_bip = d.alpha_bip; mine->alpha_source = d.alpha_source;
         mine->corpus_bytes = (cn + 1) * (j->maps ? 8 : 4); mine->cpts_bytes = cn * 4;
-        mine->cbits_bytes = (size_t)(n_words + 2) * 4; mine->csamples_bytes = (size_t)(n_words + 1) * 4;
+        mine->cbits_bytes = (size_t)(n_words + 2) * 4; mine->csamples_bytes = (size_t)(2 * n_words + 2) * 8;
         if ((rc = ws_ensure(mine->corpus, mine->corpus_bytes)) || (rc = ws_ensure(mine->cpts, mine->cpts_bytes)) ||
             (rc = ws_ensure(mine->cbits, mine->cbits_bytes)) || (rc = ws_ensure(mine->csamples, mine->csamples_bytes)) ||
             (rc = ws_ensure(mine->n_corpus, 4)))
@@ -1915,10 +1921,10 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
         }
       }
       j->shared = mine;
-      j->cb = CorpusBufs{mine->corpus.p, (uint32_t *)mine->cpts.p, (uint32_t *)mine->cbits.p, (uint32_t *)mine->csamples.p};
+      j->cb = CorpusBufs{mine->corpus.p, (uint32_t *)mine->cpts.p, (uint32_t *)mine->cbits.p, (uint2 *)mine->csamples.p};
     } else {
-      if ((rc = ws_ensure(w->cbits, (size_t)(n_words + 2) * 4)) || (rc = ws_ensure(w->csamples, (size_t)(n_words + 1) * 4))) return rc;
-      j->cb.cbits = (uint32_t *)w->cbits.p; j->cb.csamples = (uint32_t *)w->csamples.p;
+      if ((rc = ws_ensure(w->cbits, (size_t)(n_words + 2) * 4)) || (rc = ws_ensure(w->csamples, (size_t)(2 * n_words + 2) * 8))) return rc;
+      j->cb.cbits = (uint32_t *)w->cbits.p; j->cb.csamples = (uint2 *)w->csamples.p;
     }
     if (!corpus_ready) {
       if (!simple && (rc = stage_to_device(w->raw_c.p, pin + o_c, corpus_raw, sz_c, s))) return rc;
