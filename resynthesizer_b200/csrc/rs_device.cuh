@@ -36,8 +36,12 @@
 // Neighbours gathered per lane between two early-out checks (template parameter CH of the distance code).  More per
 // check = more gathers in flight and fewer rounds for long patches, but more wasted compares for short ones; B200
 // sweeps (profiles/): 2 for patches below RS_CHUNK_SWITCH_K neighbours, 3 from there on.
+#ifndef RS_CHUNK_SMALL
 #define RS_CHUNK_SMALL 2
+#endif
+#ifndef RS_CHUNK_LARGE
 #define RS_CHUNK_LARGE 3
+#endif
 #define RS_CHUNK_MAX 8
 // Latency mode (team kernel): after a probe's first chunk the rest of its patch is walked RS_CHUNK_CONT neighbours at a
 // time -- lanes are plentiful there and what counts is the number of dependent gather rounds, not wasted compares.
