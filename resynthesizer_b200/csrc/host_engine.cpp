@@ -24,6 +24,7 @@ thread_local RsStats t_stats;
 thread_local uint32_t t_seed = 1198472u;  // lib/engine.c:643
 thread_local bool t_device_chosen = false;
 thread_local int t_device = -1;  // ordinal chosen by rs_set_device / ensure_device on this thread
+thread_local bool t_quiet = false;  // batch workers: no progress callback to serve, rs_job_run may sleep instead of polling
 thread_local unsigned long long t_batch = 0;  // != 0 inside a batch call: jobs naming the same corpus pixmap share it on the device
 thread_local bool t_keep_result = false;  // rs_keep_result(): also fetch per-target sources (tests, quality metrics)
 thread_local std::vector<uint32_t> t_last_sources, t_last_targets;  // of the last engine() call, visit order
@@ -339,7 +340,7 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   dbg("after order");
   const double t2b = now_ms();
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
-  if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, on_tick, &ts); }
+  if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, t_quiet ? nullptr : on_tick, &ts); }
   const double t3 = now_ms();
   if (!rc) {
     // engine() mutates the colour bytes of targetMap in place (lib/synthesize.h:403-419); alpha and maps untouched
@@ -474,6 +475,7 @@ int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int
     }
     rs_set_seed(seed);
     t_batch = batch;
+    t_quiet = std::getenv("RS_BATCH_POLL") == nullptr;
     for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) {
       const int i = order[k];
       errs[i] = run_one(i);
@@ -489,6 +491,7 @@ int run_batch(const BatchPlan &plan, const std::function<int(int)> &run_one, int
   worker(devices[0]);
   for (auto &t : pool) t.join();
   t_batch = 0;
+  t_quiet = false;
   if (batch) rs_cuda_drop_shared_corpora(batch);  // the shared corpora live as long as the batch call
   rs_cuda_set_job_slots(1);
   if (caller_chosen && caller_device >= 0) rs_set_device(caller_device);  // the calling thread keeps the device it had

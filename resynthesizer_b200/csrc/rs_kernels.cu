@@ -1370,7 +1370,7 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreate(&w->ev0));
   WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
-  WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming | cudaEventBlockingSync));
   WCHK(cudaEventCreateWithFlags(&w->evDigest, cudaEventDisableTiming));
   WCHK(cudaHostAlloc(&w->h_digest, sizeof(RsTargetDigest), cudaHostAllocDefault));
   WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
@@ -2569,7 +2569,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       }
     }
   };
-  while (true) {
+  while (tick != nullptr) {  // (no progress callback to serve -- a batch job: wait below without polling the driver)
     cudaError_t q = cudaEventQuery(w->evDone);
     if (q == cudaSuccess) break;
     if (q != cudaErrorNotReady) { g_err = std::string("rs_job_run: ") + cudaGetErrorString(q); return 100; }
@@ -2587,6 +2587,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       idle_spins = 0;
     }
   }
+  if (tick == nullptr) RS_CHECK(cudaEventSynchronize(w->evDone));  // blocking: the thread sleeps, the driver is left to the others
   RS_CHECK(cudaStreamSynchronize(s));
   // final, exact replay from the device's own counters: visits [0, pass_visits) of each pass were started
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
