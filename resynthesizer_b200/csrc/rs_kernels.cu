@@ -1750,7 +1750,7 @@ static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t b
     return 0;
   }
   unsigned hw = rs_host_cores();
-  const size_t nt = std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+  const size_t nt = std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
   for (size_t off = 0; off < bytes; off += PIECE * nt) {
     const size_t len = std::min(bytes - off, PIECE * nt);
     if (nt > 1 && len > PIECE) {
@@ -1775,7 +1775,7 @@ static int stage_rows_to_device(void *dev, uint8_t *pin, const uint8_t *src, siz
                                 cudaStream_t s) {
   if (src_stride == row_len) return stage_to_device(dev, pin, src, rows * row_len, s);
   unsigned hw = rs_host_cores();
-  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
   auto band = [=](size_t t) {
     const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
     for (size_t y = b; y < e; y++) memcpy(pin + y * row_len, src + y * src_stride, row_len);
@@ -2096,7 +2096,7 @@ extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_byt
   const uint8_t *src = (const uint8_t *)w->pin;
   const uint32_t y0 = j->y_min;
   unsigned hw = rs_host_cores();
-  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
   auto band = [=](size_t t) {
     const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
     for (size_t r = b; r < e; r++) memcpy(img + (size_t)(y0 + r) * img_row_bytes, src + r * row_len, row_len);
@@ -2622,7 +2622,7 @@ extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sour
     uint8_t *dst = target_raw_out + (size_t)j->y_min * row_bytes;
     const uint8_t *src = (const uint8_t *)w->pin;
     unsigned hw = rs_host_cores();
-    const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 1 ? hw / 2 : 1);
+    const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
     const size_t per = (rows_bytes + nt - 1) / nt;
     std::vector<std::thread> th;
     for (size_t t = 1; t < nt; t++) {
