@@ -380,6 +380,9 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   t_stats.ms_d2h = (float)(t4 - t3); t_stats.ms_total = (float)(t4 - t0);
   for (int p = 0; p < 6; p++) t_stats.ms_pass[p] = jc.ms_pass[p];
   g_kernel_launches.fetch_add(jc.kernel_launches);
+  if (std::getenv("RS_DEBUG"))  // where the call went, host clock: the run phase includes whatever of the upload was still queued
+    std::fprintf(stderr, "[rs debug] call %.2f ms: prep %.2f | stage+digest %.2f | order %.2f | run %.2f (kernels %.2f) | read-back %.2f\n",
+                 t4 - t0, t1 - t0, t2 - t1, t2b - t2, t3 - t2b, (double)jc.ms_passes, t4 - t3);
   t_stats.ms_synth = jc.ms_synth; t_stats.kernel_launches = jc.kernel_launches; t_stats.synth_launches_run = jc.synth_launches_run;
   return 0;  // success, also when cancelled (lib/engine.c:689)
 }
