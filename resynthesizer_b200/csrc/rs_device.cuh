@@ -14,7 +14,8 @@
 //            usable as neighbour, RS_NEVER otherwise
 //   prober   recentProberMap (lib/engine.c:314-327), deterministic bounded-staleness version of the reference's
 //            live map.  A pass is cut into epochs of epoch_len visits; a visit of epoch e sees the stamps of
-//            earlier passes and of epochs <= e-2 of its own pass.  Three arrays (epoch mod 3), each one 64-bit
+//            earlier passes and of epochs <= e-2 of its own pass.  Three arrays (epoch mod 3; interleaved per corpus
+//            pixel, 32 bytes = one sector for all three), each one 64-bit
 //            word per corpus pixel holding two stamps ((pass+1) << 29 | index; 0 = never): hi = newest stamp
 //            written to this array, lo = newest stamp of an earlier epoch than hi's.  A visit of epoch e stamps
 //            only array e%3, by 64-bit CAS, and only once every visit of epochs <= e-2 has completed; so each
@@ -43,6 +44,10 @@
 #define RS_CHUNK_LARGE 3
 #endif
 #define RS_CHUNK_MAX 8
+// Chunks a surviving candidate runs through per round of the throughput kernel's distance loop (rs_eval_range).
+#ifndef RS_EVAL_CHUNKS_PER_ROUND
+#define RS_EVAL_CHUNKS_PER_ROUND 1
+#endif
 // Latency mode (team kernel): after a probe's first chunk the rest of its patch is walked RS_CHUNK_CONT neighbours at a
 // time -- lanes are plentiful there and what counts is the number of dependent gather rounds, not wasted compares.
 #ifndef RS_CHUNK_CONT
@@ -89,6 +94,7 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   RsLine epoch_wm[6];       // per pass: number of leading epochs that are complete (what waiters poll)
   RsLine epoch_done[6][RS_MAX_EPOCHS];  // per pass and epoch: visits completed (state word + stamps published)
   RsLine claims[2];         // work counters of the pass-0 gather kernels
+  RsLine n_ctx;             // context pixels usable as neighbours in the whole target image (k_ctx_blocks)
 };
 #define RS_CTRL_COPY_BYTES offsetof(RsCtrl, next)
 
@@ -104,15 +110,18 @@ struct RsDev {              // kernel argument (by value)
   const uint2 *csamples;    // {linear index p of usable corpus pixel 16 * j, bitmap window of pixels p .. p + 31}
   const uint32_t *offsets;
   const uint32_t *lut_rep;  // [2][256][32] colour then map metric, replicated per lane (bank-conflict free)
-  unsigned long long *prober[3];  // [cw*ch] each: stamps of epochs = 0, 1, 2 (mod 3), see above
+  unsigned long long *prober;     // [cw*ch][4]: stamps of epochs = 0, 1, 2 (mod 3) of a corpus pixel (+ 1 pad word), see above
   const uint2 *nb_lists;    // pass-0 patches gathered up front by k_gather_pass0: [nT][kmax-1]
   const uint8_t *nb_counts; // [nT] patch size of each pass-0 visit
   const uint2 *nb_later;    // patches of the passes >= 1 (every target point has a value by then, so they are the same in
   const uint8_t *nb_later_counts;  // all of them): [nT][kmax-1] entries {offset, meta word of the pixel}, and sizes
+  const uint32_t *ctx_blocks;  // usable context pixels per 32x32 block of the target image, [gh][gw] (k_ctx_blocks), or nullptr
   RsCtrl *ctrl;
   volatile unsigned int *host_ticks;  // mapped pinned: [6] highest tick index started per pass (+1)
   const volatile int *host_cancel;    // mapped pinned
   int tw, th, cw, ch;
+  int ow, oh;               // the offsets table holds every (x, y) with |x| < ow, |y| < oh (0: a caller's partial table)
+  int gw, gh;               // blocks per row / column of ctx_blocks
   uint32_t cn;              // cw * ch = index of the sentinel corpus pixel
   uint32_t nT, nOff;
   uint32_t kmax, probes, seed, penalty;
@@ -121,6 +130,7 @@ struct RsDev {              // kernel argument (by value)
   uint32_t slot, last_seg;      // index of this launch's counters in RsCtrl; last launch of its pass?
   uint32_t chunk;               // CH the launched kernel was instantiated with (patch padding follows it)
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
+  uint32_t epoch_inv;       // floor(2^32 / epoch_len)
   uint32_t ends[6];
   int htile, vtile;
   uint32_t sc_slice;        // corpus pixels per CTA slice when the corpus is staged into shared memory (k_synth_pass<..., true>)
@@ -169,7 +179,9 @@ __device__ __forceinline__ uint32_t rs_corpus_point(const RsDev &J, uint32_t nC,
     uint32_t r = idx & 15u, pos;
     const uint2 e = __ldg(J.csamples + (idx >> 4));
     uint32_t c = __popc(e.y);
-    if (r < c) {
+    if (e.y == 0xFFFFFFFFu) {  // away from the edges of the selection every window is full: nothing to search
+      pos = e.x + r;
+    } else if (r < c) {
       pos = e.x + rs_nth_set_bit(e.y, r);
     } else {  // sparser than 16 usable pixels in 32 here: go on in the bitmap behind the window
       const uint32_t q = e.x + 32u;
@@ -194,6 +206,11 @@ __device__ __forceinline__ uint32_t rs_corpus_point(const RsDev &J, uint32_t nC,
 __device__ __forceinline__ unsigned long long rs_ld_state(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ ulonglong2 rs_ld_state2(const unsigned long long *p) {  // two adjacent words (16-byte aligned), each atomic
+  ulonglong2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void rs_st_state(unsigned long long *p, unsigned long long v) {
@@ -447,6 +464,14 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
       if (MAPS && k == 1u) partial += rs_lut3(lutm, __vabsdiffu4(m0, selfmap));  // map terms of the target point itself (synthesize.h:342-355)
       k += CH;
       finished = (k >= K);
+#if RS_EVAL_CHUNKS_PER_ROUND > 1
+      // a candidate that survives its chunk goes on at once instead of through another round of hand-outs and votes
+      if (!finished && !(partial > bestSum || (partial == bestSum && myIdx > bestIdx))) {
+        partial += rs_chunk_sum<MAPS, CH, SMEMC>(J, lutc, lutm, nb, nmap, cx, clin, k, cs);
+        k += CH;
+        finished = (k >= K);
+      }
+#endif
     }
     const bool worse = active && (partial > bestSum || (partial == bestSum && myIdx > bestIdx));
     const bool propose = active && finished && !worse;

@@ -163,15 +163,15 @@ __global__ void k_writeback(const unsigned long long *__restrict__ W, const uint
 // Output per visit: count-1 entries {packed offset, pixel index | target flag << 31}.
 #define RS_TARGET_FLAG 0x80000000u
 __global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__restrict__ lists, uint8_t *__restrict__ counts,
-                                                      unsigned int *__restrict__ claim) {
+                                                      const uint32_t v_begin, const uint32_t v_end) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t stride = J.kmax - 1u;
   unsigned long long scans = 0;
-  // static striding: the long scans were taken by k_gather_pass0_coop, the rest are short and uniform
-  const uint32_t first = *claim;  // = number of visits the cooperative kernel handles
+  // static striding: the long scans of the first visits are not in this range (k_gather_pass0_sparse / _coop), the rest
+  // are short and uniform
   const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t v = first + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < J.nT; v += nwarps) {
+  for (uint32_t v = v_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < v_end; v += nwarps) {
     const uint32_t tpos = __ldg(J.targets + v);
     const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
     uint2 *out = lists + (size_t)v * stride;
@@ -284,8 +284,9 @@ __global__ void __launch_bounds__(256) k_gather_later(const RsDev J, uint2 *__re
 #endif
 __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsDev J, uint2 *__restrict__ lists,
                                                                      uint8_t *__restrict__ counts, uint32_t v_end,
-                                                                     unsigned int *__restrict__ claim) {
+                                                                     unsigned int *__restrict__ claim, const int only_if_ctx) {
   __shared__ uint32_t s_cnt[2][RS_COOP_THREADS / 32];
+  if (only_if_ctx && J.ctrl->n_ctx.v == 0u) return;  // (k_gather_pass0_sparse took these visits)
   __shared__ uint32_t s_v;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt = (1u << lane) - 1u;
@@ -356,8 +357,218 @@ __global__ void __launch_bounds__(RS_COOP_THREADS) k_gather_pass0_coop(const RsD
   if (threadIdx.x == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
 }
 
+// ---- the same patches without the scan: nearest valued pixels by search, for the first visits of pass 0 ----
+// The scan above tests EVERY offset in table order until K-1 valued pixels have turned up.  For the first visits of a
+// large hole that is a disc of millions of empty pixels (all 16 Mi table entries for the first visits of a job without
+// context: render-texture, map-style), although the valued pixels are few and known: the v points visited before v, and
+// the context.  k_gather_pass0_sparse finds the same K-1 entries -- the K-1 smallest offsets in TABLE ORDER whose pixel
+// is valued -- by search:
+//   table order = ascending (x^2 + y^2, rank of (x, y) in reverse row-major order), k_gen_offsets below; that pair is the
+//   64-bit key of an offset, and the patch is the K-1 smallest keys among the valued pixels in reach (|x| < ow, |y| < oh);
+//   (A) a short scan of the first RS_SPARSE_PROBE table entries settles the visits whose surroundings are already dense;
+//   (B) every earlier target point (and, when tiling, its wrapped aliases: the scan meets a pixel once per offset that
+//       reaches it) goes through a sorted top-(K-1) list kept in shared memory by the warp;
+//   (C) context pixels: 32x32 blocks of the target image in rings around the visit's block, nearest ring first; a block
+//       without context (k_ctx_blocks) or farther away than the list's last entry is skipped, a ring that lies farther
+//       away ends the search.  Tiling with context is left to the scan (k_gather_pass0_coop).
+// Same lists bit for bit (the parity suite compares whole images); cfg4's 27 ms and cfg3's 3.8 ms of scanning become < 0.3.
+#define RS_SPARSE_WARPS 8
+#define RS_SPARSE_PROBE 512u  // table entries scanned first (RS_SPARSE_PROBE=n overrides at run time; 0: always search)
+struct SparseList {  // the K-1 best entries so far, ascending key
+  unsigned long long key[64];
+  uint2 pay[64];     // {packed offset, pixel index | target flag}
+};
+__device__ __forceinline__ unsigned long long rs_offset_key(const RsDev &J, int dx, int dy) {
+  const uint32_t d2 = (uint32_t)(dx * dx + dy * dy);
+  const uint32_t tie = (uint32_t)(J.oh - 1 - dy) * (uint32_t)(2 * J.ow - 1) + (uint32_t)(J.ow - 1 - dx);
+  return ((unsigned long long)d2 << 32) | tie;
+}
+// One warp, all lanes with the same entry: insert it; n = entries held, tau = key of the (K-1)-th entry once n == K1.
+__device__ __forceinline__ void rs_sparse_insert(SparseList &L, uint32_t &n, unsigned long long &tau, const uint32_t K1,
+                                                 const unsigned long long nk, const uint2 np) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long e0 = lane < n ? L.key[lane] : ~0ull, e1 = lane + 32u < n ? L.key[lane + 32u] : ~0ull;
+  const uint32_t pos = __popc(__ballot_sync(RS_FULL, e0 < nk)) + __popc(__ballot_sync(RS_FULL, e1 < nk));
+  if (pos >= K1) return;
+  const uint2 p0 = L.pay[lane], p1 = L.pay[lane + 32u];
+  __syncwarp();
+  if (lane >= pos && lane < n && lane + 1u < K1) { L.key[lane + 1u] = e0; L.pay[lane + 1u] = p0; }
+  if (lane + 32u >= pos && lane + 32u < n && lane + 33u < K1) { L.key[lane + 33u] = e1; L.pay[lane + 33u] = p1; }
+  if (lane == 0) { L.key[pos] = nk; L.pay[pos] = np; }
+  __syncwarp();
+  n = min(n + 1u, K1);
+  tau = (n == K1) ? L.key[K1 - 1u] : ~0ull;
+}
+// One warp: the lanes with `cand` offer (key, pay); those still under tau enter the list, in lane order.
+__device__ __forceinline__ void rs_sparse_offer(SparseList &L, uint32_t &n, unsigned long long &tau, const uint32_t K1,
+                                                bool cand, unsigned long long key, uint2 pay) {
+  unsigned b = __ballot_sync(RS_FULL, cand && key < tau);
+  while (b) {
+    const int src = __ffs(b) - 1;
+    b &= b - 1u;
+    const unsigned long long nk = __shfl_sync(RS_FULL, key, src);
+    const uint2 np = make_uint2(__shfl_sync(RS_FULL, pay.x, src), __shfl_sync(RS_FULL, pay.y, src));
+    if (nk < tau) rs_sparse_insert(L, n, tau, K1, nk, np);
+  }
+}
+// Usable context pixels per 32x32 block of the target image, and their total.
+__global__ void __launch_bounds__(256) k_ctx_blocks(const uint32_t *__restrict__ meta, int tw, int th, int gw, int gh,
+                                                    uint32_t *__restrict__ blocks, unsigned int *__restrict__ total) {
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t nb = (uint32_t)gw * (uint32_t)gh, nwarps = gridDim.x * (blockDim.x >> 5);
+  uint32_t sum = 0;
+  for (uint32_t b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); b < nb; b += nwarps) {
+    const int bx = (int)(b % (uint32_t)gw), by = (int)(b / (uint32_t)gw), x = 32 * bx + (int)lane;
+    uint32_t c = 0;
+    for (int r = 0; r < 32; r++) {
+      const int y = 32 * by + r;
+      if (y < th && x < tw) c += (__ldg(meta + (size_t)y * tw + x) == RS_CTX_VALUED) ? 1u : 0u;
+    }
+    c = __reduce_add_sync(RS_FULL, c);
+    if (lane == 0) blocks[b] = c;
+    sum += c;
+  }
+  if (lane == 0 && sum) atomicAdd(total, sum);
+}
+__global__ void __launch_bounds__(RS_SPARSE_WARPS * 32) k_gather_pass0_sparse(const RsDev J, uint2 *__restrict__ lists,
+                                                                              uint8_t *__restrict__ counts, uint32_t v_end,
+                                                                              unsigned int *__restrict__ claim, const uint32_t probe) {
+  __shared__ SparseList s_list[RS_SPARSE_WARPS];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt = (1u << lane) - 1u;
+  SparseList &L = s_list[threadIdx.x >> 5];
+  const uint32_t K1 = J.kmax - 1u, stride = K1;
+  const uint32_t n_ctx = J.ctx_blocks != nullptr ? J.ctrl->n_ctx.v : 0u;
+  const bool tiled = J.htile || J.vtile;
+  if (tiled && n_ctx) return;  // wrapped context: k_gather_pass0_coop scans for these visits
+  unsigned long long scans = 0;
+  while (true) {
+    uint32_t v = 0;
+    if (lane == 0) v = atomicAdd(claim, 1u);
+    v = __shfl_sync(RS_FULL, v, 0);
+    if (v >= v_end) break;
+    v = v_end - 1u - v;  // the visits with the most earlier points first
+    const uint32_t tpos = __ldg(J.targets + v);
+    const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
+    uint2 *out = lists + (size_t)v * stride;
+    // ---- (A) the head of the table, scanned
+    {
+      uint32_t count = 1;
+      for (uint32_t base = 1; base < probe && base < J.nOff && count < J.kmax; base += 128) {
+        uint32_t o[4], q[4], m[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const uint32_t j = base + 32u * u + lane;
+          o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
+          if (j < J.nOff) {
+            o[u] = __ldg(J.offsets + j);
+            int x = px + rs_off_x(o[u]), y = py + rs_off_y(o[u]);
+            bool in = true;
+            if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+            else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+            if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+            else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+            if (in) {
+              q[u] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+              m[u] = __ldg(J.meta + q[u]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const bool ok = (m[u] == RS_CTX_VALUED) || (m[u] < v);
+          const unsigned b = __ballot_sync(RS_FULL, ok);
+          const uint32_t slot = count + __popc(b & lt);
+          if (ok && slot < J.kmax) out[slot - 1u] = make_uint2(o[u], q[u] | (m[u] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+          count += __popc(b);
+        }
+        scans += 128;
+      }
+      if (count >= J.kmax || (probe >= J.nOff && probe > 1u)) {
+        if (lane == 0) counts[v] = (uint8_t)min(count, J.kmax);
+        continue;
+      }
+    }
+    // ---- (B) the earlier target points
+    uint32_t n = 0;
+    unsigned long long tau = ~0ull;
+    __syncwarp();
+    for (uint32_t i0 = 0; i0 < v; i0 += 32) {
+      const uint32_t i = i0 + lane;
+      const bool have = i < v;
+      const uint32_t t = have ? __ldg(J.targets + i) : 0u;
+      const int qx = (int)(t & 0xFFFFu), qy = (int)(t >> 16);
+      const int dx1 = qx - px, dy1 = qy - py;
+      const uint32_t qf = ((uint32_t)qy * (uint32_t)J.tw + (uint32_t)qx) | RS_TARGET_FLAG;
+      for (int ay = 0; ay <= (J.vtile ? 1 : 0); ay++)
+        for (int ax = 0; ax <= (J.htile ? 1 : 0); ax++) {
+          const int dx = ax ? (dx1 > 0 ? dx1 - J.tw : dx1 + J.tw) : dx1, dy = ay ? (dy1 > 0 ? dy1 - J.th : dy1 + J.th) : dy1;
+          const bool ok = have && !(ax && dx1 == 0) && !(ay && dy1 == 0) && abs(dx) < J.ow && abs(dy) < J.oh;
+          rs_sparse_offer(L, n, tau, K1, ok, rs_offset_key(J, dx, dy),
+                          make_uint2(((uint32_t)dx & 0xFFFFu) | ((uint32_t)dy << 16), qf));
+        }
+    }
+    scans += v;
+    // ---- (C) context pixels, block rings outwards
+    if (n_ctx) {
+      const int bx0 = px >> 5, by0 = py >> 5;
+      const int rmax = max(max(bx0, J.gw - 1 - bx0), max(by0, J.gh - 1 - by0));
+      for (int r = 0; r <= rmax; r++) {
+        if (r >= 1 && n == K1) {  // every pixel of ring r is at least 32 (r - 1) + 1 away
+          const unsigned long long md = 32ull * (unsigned)(r - 1) + 1ull;
+          if (md * md > (tau >> 32)) break;
+        }
+        const int nblk = r ? 8 * r : 1, top = 2 * r + 1, side = 2 * r - 1;
+        for (int t0 = 0; t0 < nblk; t0 += 32) {
+          const int t = t0 + (int)lane;
+          int bx = bx0, by = by0;
+          if (r) {
+            if (t < top) { by = by0 - r; bx = bx0 - r + t; }
+            else if (t < 2 * top) { by = by0 + r; bx = bx0 - r + (t - top); }
+            else if (t < 2 * top + side) { bx = bx0 - r; by = by0 - r + 1 + (t - 2 * top); }
+            else { bx = bx0 + r; by = by0 - r + 1 + (t - 2 * top - side); }
+          }
+          uint32_t md2 = 0;
+          bool want = t < nblk && bx >= 0 && bx < J.gw && by >= 0 && by < J.gh;
+          if (want) want = __ldg(J.ctx_blocks + (size_t)by * J.gw + bx) != 0u;
+          if (want) {
+            const int ddx = max(0, max(32 * bx - px, px - (32 * bx + 31))), ddy = max(0, max(32 * by - py, py - (32 * by + 31)));
+            md2 = (uint32_t)(ddx * ddx + ddy * ddy);
+            want = n < K1 || md2 <= (uint32_t)(tau >> 32);
+          }
+          unsigned wb = __ballot_sync(RS_FULL, want);
+          while (wb) {
+            const int src = __ffs(wb) - 1;
+            wb &= wb - 1u;
+            const int sbx = __shfl_sync(RS_FULL, bx, src), sby = __shfl_sync(RS_FULL, by, src);
+            const uint32_t smd2 = __shfl_sync(RS_FULL, md2, src);
+            if (n == K1 && smd2 > (uint32_t)(tau >> 32)) continue;
+            const bool up = 32 * sby + 31 < py;  // a block above the visit: its bottom rows are the near ones
+            const int x = 32 * sbx + (int)lane, dx = x - px;
+            for (int rr = 0; rr < 32; rr++) {
+              const int y = 32 * sby + (up ? 31 - rr : rr), dy = y - py;
+              if (y >= J.th) continue;
+              if (n == K1 && (uint32_t)(dy * dy) > (uint32_t)(tau >> 32)) continue;
+              const uint32_t q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+              const bool ok = x < J.tw && abs(dx) < J.ow && abs(dy) < J.oh && __ldg(J.meta + q) == RS_CTX_VALUED;
+              rs_sparse_offer(L, n, tau, K1, ok, rs_offset_key(J, dx, dy),
+                              make_uint2(((uint32_t)dx & 0xFFFFu) | ((uint32_t)dy << 16), q));
+            }
+            scans += 1024;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    for (uint32_t k = lane; k < n; k += 32) out[k] = L.pay[k];
+    if (lane == 0) counts[v] = (uint8_t)(1u + n);
+    __syncwarp();
+  }
+  if (lane == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
+}
+
 // --------------------------------------------------------------------------------------- the pass kernel
-// CTA shapes.  Throughput kernel: ONE 1024-thread CTA per SM (64 registers per thread), so the metric tables are
+// CTA shapes. Throughput kernel: ONE 1024-thread CTA per SM (64 registers per thread), so the metric tables are
 // staged once per SM and the shared-memory carve-out leaves >= 124 KB of L1 for the offset/meta/point tables that
 // every visit re-reads (2 x 512 threads with map tables took the carve-out to 228 KB and cfg4 ran 1.8x slower).
 // Team kernel: 2 x 512 threads, at most 8 teams (W >= 2) per CTA, one named barrier per team.
@@ -447,6 +658,18 @@ __device__ __forceinline__ uint32_t rs_claim_resolve(const RsDev &J, RsCtrl *ctr
   return __shfl_sync(RS_FULL, v, 0);
 }
 
+// v / J.epoch_len without the division: the estimate from floor(2^32 / len) is exact or one short.
+__device__ __forceinline__ uint32_t rs_epoch_of(const RsDev &J, uint32_t v) {
+  uint32_t q = __umulhi(v, J.epoch_inv);
+  if (v - q * J.epoch_len >= J.epoch_len) q++;
+  return q;
+}
+// t / n for n in [1, 32] and t < 2^16 (a candidate's chunks): multiply by ceil(2^32 / n) kept in constant memory.
+__constant__ uint32_t c_inv32[33] = {
+    0u, 0xFFFFFFFFu, 0x80000000u, 0x55555556u, 0x40000000u, 0x33333334u, 0x2AAAAAABu, 0x24924925u, 0x20000000u, 0x1C71C71Du, 0x1999999Au,
+    0x1745D175u, 0x15555556u, 0x13B13B14u, 0x12492493u, 0x11111112u, 0x10000000u, 0x0F0F0F10u, 0x0E38E38Fu, 0x0D79435Fu, 0x0CCCCCCDu,
+    0x0C30C30Du, 0x0BA2E8BBu, 0x0B21642Du, 0x0AAAAAABu, 0x0A3D70A4u, 0x09D89D8Au, 0x097B425Fu, 0x0924924Au, 0x08D3DCB1u, 0x08888889u,
+    0x08421085u, 0x08000000u};
 // Lane 0: until every visit of the epochs <= epoch_idx - 2 of this pass has completed.  Finishing visits only count
 // themselves (a fire-and-forget reduction); whoever waits moves the watermark over the leading complete epochs.
 __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uint32_t epoch_idx) {
@@ -473,7 +696,7 @@ __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uin
 //
 // (1) One warp: gather the patch of visit v (target point tpos): S.off / S.q / S.aux(meta) and the geometry half of
 // the distance records S.nb[k].{lin,dx,pen}, padded to whole chunks.  Returns K.
-template <bool MAPS, int NB>
+template <int CH, bool MAPS, int NB>
 __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t tpos) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
@@ -547,8 +770,8 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
   __syncwarp();
   {  // geometry half of the distance records, padded to whole chunks with records that cost nothing
     // (whole chunks of the launched kernel's size, and a continuation chunk of the team kernel may start at any k < K)
-    const uint32_t nch = (K + J.chunk - 2u) / J.chunk;
-    const uint32_t kpad = min((uint32_t)WarpScratch<MAPS, NB>::kSlots, max(1u + (nch ? nch : 1u) * J.chunk, K + (uint32_t)RS_CHUNK_MAX));
+    const uint32_t nch = (K + CH - 2u) / CH;  // (CH == J.chunk: a division by a constant)
+    const uint32_t kpad = min((uint32_t)WarpScratch<MAPS, NB>::kSlots, max(1u + (nch ? nch : 1u) * CH, K + (uint32_t)RS_CHUNK_MAX));
     for (uint32_t k = lane; k < kpad; k += 32) {
       RsNb r;
       if (k < K) {
@@ -580,7 +803,10 @@ __device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS
     if (k == 0) r = pass;
     else if (m != RS_CTX_VALUED) {
       if (m < v && m < pass_end) r = pass + 1u;
-      else for (uint32_t p2 = 0; p2 < pass; p2++) r += (m < J.ends[p2]) ? 1u : 0u;
+      else {
+#pragma unroll
+        for (uint32_t p2 = 0; p2 < 5u; p2++) r += (p2 < pass && m < J.ends[p2]) ? 1u : 0u;  // (at most 6 passes)
+      }
     }
     const unsigned long long *wp = J.W + 2 * (size_t)q + (r & 1u);
     unsigned long long w = rs_ld_state(wp);
@@ -611,7 +837,7 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
   //      dropped if outside/masked corpus, if this target index was the last VISIBLE prober of that corpus
   //      point (rs_device.cuh: epochs), or if an earlier neighbour proposes the same point.
   //      The corpus pixel and the three stamp words of a candidate are fetched in one round trip.
-  const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;
+  const uint32_t epoch_idx = rs_epoch_of(J, v), epoch0 = epoch_idx * J.epoch_len;
   const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
   const uint32_t hide_base = tag | hide_from;
   constexpr int NR = NB > 32 ? 2 : 1;  // rounds of 32 neighbours
@@ -646,9 +872,11 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
       if (c != RS_NO_SRC) {
         const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
         uint32_t newest = 0u;
+        const ulonglong2 e01 = rs_ld_state2(J.prober + 4 * a);  // the three arrays' words of one corpus pixel share a sector
+        const unsigned long long e2 = rs_ld_state(J.prober + 4 * a + 2);
 #pragma unroll
         for (int t = 0; t < 3; t++) {
-          const unsigned long long e = rs_ld_state(J.prober[t] + a);
+          const unsigned long long e = t == 0 ? e01.x : (t == 1 ? e01.y : e2);
           const uint32_t h = (uint32_t)(e >> 32);
           newest = max(newest, (h >= hide_base) ? (uint32_t)e : h);
         }
@@ -705,7 +933,7 @@ __device__ __forceinline__ void rs_visit_stamps(const RsDev &J, RsCtrl *ctrl, co
   for (int rnd = 0; rnd < 2; rnd++) {
     if (lane + 32u * rnd < stampEnd) {
       const uint32_t c = rnd ? c1 : c0;
-      unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+      unsigned long long *pp = J.prober + 4 * ((size_t)(c >> 16) * J.cw + (c & 0xFFFFu)) + epoch_idx % 3u;
       unsigned long long old = rs_ld_state(pp);
       while (true) {
         const uint32_t hi = (uint32_t)(old >> 32), lo = (uint32_t)old;
@@ -781,7 +1009,7 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
     }
     for (uint32_t i = lane; i < stampEnd; i += 32) {
       const uint32_t c = candlist[i];
-      unsigned long long *pp = J.prober[epoch_idx % 3u] + (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
+      unsigned long long *pp = J.prober + 4 * ((size_t)(c >> 16) * J.cw + (c & 0xFFFFu)) + epoch_idx % 3u;
       const uint32_t stp = tag | v;
       unsigned long long old = rs_ld_state(pp);
       while (true) {
@@ -938,7 +1166,7 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
   while (v < J.seg_end) {
     {
-      const uint32_t Kv = rs_visit_geometry(J, S, v, tpos);
+      const uint32_t Kv = rs_visit_geometry<CH>(J, S, v, tpos);
       rs_visit_values(J, S, v, Kv);
       rs_visit_candidates<SMEMC>(J, ctrl, S, V, v, Kv, cs);
     }
@@ -952,12 +1180,12 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
     // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
     if (nHeur) {
-      const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = 0xFFFFFFFFu / nch + 1u;
+      const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = c_inv32[nch];
       hsum[lane] = 0u;        // (nHeur <= NB <= 64: two slots per lane cover every candidate)
       if (NB > 32) hsum[lane + 32u] = 0u;
       __syncwarp();
       for (uint32_t t = lane; t < nHeur * nch; t += 32) {
-        const uint32_t ci = __umulhi(t, inv), j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
+        const uint32_t ci = nch > 1u ? __umulhi(t, inv) : t, j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
         atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH, NB, SMEMC>(J, lutc, lutm, S, hcol, K, ci, j, st, cs));
       }
       __syncwarp();
@@ -1033,7 +1261,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       const uint32_t vc = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
       const bool ok = vc < J.seg_end;
       uint32_t Kc = 0;
-      if (ok) Kc = rs_visit_geometry(J, S, vc, __ldg(J.targets + vc));
+      if (ok) Kc = rs_visit_geometry<CH>(J, S, vc, __ldg(J.targets + vc));
       if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = vc; TS.K = Kc; TS.nHeur = 0u; TS.best = ~0ull; TS.win_pt = RS_NO_SRC; }
       for (uint32_t i = lane; i < RS_MAX_NB; i += 32) { TS.hsum[i] = 0u; TS.hcnt[i] = 0u; }
     }
@@ -1069,7 +1297,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
     const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u;
     if (nHeur) {
       for (uint32_t t = tid; t < nHeur * nch; t += T) {
-        const uint32_t ci = t / nch, j = t % nch;
+        const uint32_t ci = nch > 1u ? __umulhi(t, c_inv32[nch]) : t, j = t - ci * nch;
         atomicAdd(&TS.hsum[ci], rs_heur_pair<MAPS, CH, NB>(J, lutc, lutm, S, S.q, K, ci, j, st));
         __threadfence_block();
         // the lane that adds a candidate's last chunk holds its full sum: it enters "first candidate with the minimum
@@ -1141,7 +1369,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       rs_visit_finish<false>(J, ctrl, S, V, bestSum, bestIdx, TS.win_pt, TS.win_col, true);
     } else if (wt == 1) {
       const uint32_t stampEnd = (bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
-      const uint32_t epoch_idx = v / J.epoch_len, epoch0 = epoch_idx * J.epoch_len;  // as in rs_visit_candidates
+      const uint32_t epoch_idx = rs_epoch_of(J, v), epoch0 = epoch_idx * J.epoch_len;  // as in rs_visit_candidates
       rs_visit_stamps(J, ctrl, v, epoch_idx, ((pass + 1u) << 29) | epoch0, epoch_idx ? epoch0 - J.epoch_len : 0u, stampEnd, sc0, sc1);
     }
   }
@@ -1218,10 +1446,10 @@ struct Workspace {
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: work that may run beside the main stream's
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evLater = nullptr;
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
-  DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober0, prober1, prober2, colours,
+  DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, nb_later, nb_later_counts, simg, smask, smask2,
       ord_keys_in, ord_keys_out, ord_vals_in, ord_vals_out, ord_tmp, ord_first, ord_points, ord_flags, ord_raw,
-      cbits, ccounts, cbefore, csamples;
+      cbits, ccounts, cbefore, csamples, ctx_blocks;
   void *pin = nullptr;  // pinned staging (H2D inputs, D2H results)
   size_t pin_cap = 0;
   void *pin_order = nullptr;  // pinned staging of a visit order
@@ -1267,11 +1495,11 @@ static int ws_ensure_pinned(Workspace *w, size_t bytes) {
 static void ws_free(Workspace *w) {
   DeviceGuard guard(w->device);
   DevBuf *all[] = {&w->raw_t, &w->raw_c, &w->corpus, &w->W, &w->meta, &w->tmaps, &w->targets, &w->cpts, &w->offsets,
-                   &w->lut256, &w->lut_rep, &w->prober0, &w->prober1, &w->prober2, &w->colours, &w->sources, &w->ctrl,
+                   &w->lut256, &w->lut_rep, &w->prober, &w->colours, &w->sources, &w->ctrl,
                    &w->sort_keys_in, &w->sort_keys_out, &w->sort_vals_in, &w->sort_tmp, &w->nb_lists, &w->nb_counts, &w->nb_later, &w->nb_later_counts,
                    &w->simg, &w->smask, &w->smask2, &w->ord_keys_in, &w->ord_keys_out, &w->ord_vals_in, &w->ord_vals_out,
                    &w->ord_tmp, &w->ord_first, &w->ord_points, &w->ord_flags, &w->ord_raw, &w->cbits, &w->ccounts, &w->cbefore,
-                   &w->csamples};
+                   &w->csamples, &w->ctx_blocks};
   for (DevBuf *b : all) if (b->p) cudaFree(b->p);
   if (w->pin) cudaFreeHost(w->pin);
   if (w->pin_order) cudaFreeHost(w->pin_order);
@@ -1530,6 +1758,7 @@ struct RsJob {
   uint32_t pass_launches[6] = {0, 0, 0, 0, 0, 0};
   uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
   float ms_synth = 0.f;           // CUDA-event time of the pass kernels alone (after the pass-0 patch gather)
+  int off_w = 0, off_h = 0;       // dimensions of the full offsets table this job reads (0: a caller's partial table)
 };
 
 extern "C" void rs_job_destroy(RsJob *j) {
@@ -1815,7 +2044,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
       (rc = ws_ensure(w->meta, tn * 4)) || (rc = ws_ensure(w->tmaps, j->maps ? tn * 4 : 4)) ||
       (rc = ws_ensure(w->cpts, cap_cpts * 4)) ||
       (rc = ws_ensure(w->lut256, 512 * 4)) || (rc = ws_ensure(w->lut_rep, 2 * RS_LUT_WORDS * 4)) ||
-      (rc = ws_ensure(w->prober0, cn * 8)) || (rc = ws_ensure(w->prober1, cn * 8)) || (rc = ws_ensure(w->prober2, cn * 8)) ||
+      (rc = ws_ensure(w->prober, cn * 32)) ||
       (rc = ws_ensure(w->ctrl, sizeof(RsCtrl))))
     return rc;
   // neighbour offsets: caller-provided table, or built (and kept) on the device
@@ -1969,6 +2198,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     RS_CHECK(cudaMemcpyAsync(w->offsets.p, pin + o_off, sz_off, cudaMemcpyHostToDevice, s));
     w->off_w = w->off_h = 0; w->off_n = 0;  // not a cached full table
     j->nOff = n_offsets;
+    j->off_w = j->off_h = 0;
   } else {
     if (!(w->off_w == ow && w->off_h == oh && w->off_n == full_n)) {
       if ((rc = build_offsets_on_device(w, ow, oh, full_n))) return rc;
@@ -1977,10 +2207,10 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
       while (offset_sort_bits < 32 && (maxd >> offset_sort_bits)) offset_sort_bits++;
     }
     j->nOff = full_n;
+    j->off_w = ow; j->off_h = oh;
   }
-  RS_CHECK(cudaMemsetAsync(w->prober0.p, 0, cn * 8, s));
-  RS_CHECK(cudaMemsetAsync(w->prober1.p, 0, cn * 8, s));
-  RS_CHECK(cudaMemsetAsync(w->prober2.p, 0, cn * 8, s));
+  if ((rc = ws_ensure(w->ctx_blocks, (size_t)((d.tw + 31) / 32) * (size_t)((d.th + 31) / 32) * 4))) return rc;
+  RS_CHECK(cudaMemsetAsync(w->prober.p, 0, cn * 32, s));
   if (!corpus_ready)
     k_canon_corpus<<<(unsigned)((cn + T) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
                                                             d.map_bip, j->maps ? nullptr : (uint32_t *)j->cb.corpus,
@@ -2346,14 +2576,15 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.cbits = j->corpus_bits && !getenv("RS_NO_CORPUS_BITS") ? j->cb.cbits : nullptr;
   D.csamples = j->cb.csamples;
   D.offsets = (const uint32_t *)w->offsets.p; D.lut_rep = (const uint32_t *)w->lut_rep.p;
-  D.prober[0] = (unsigned long long *)w->prober0.p; D.prober[1] = (unsigned long long *)w->prober1.p;
-  D.prober[2] = (unsigned long long *)w->prober2.p;
-  { const uint32_t e = (j->nT + 31u) / 32u; D.epoch_len = e < 64u ? 64u : e; }
+  D.prober = (unsigned long long *)w->prober.p;
+  { const uint32_t e = (j->nT + 31u) / 32u; D.epoch_len = e < 64u ? 64u : e; D.epoch_inv = (uint32_t)(0x100000000ull / D.epoch_len); }
   D.nb_lists = (const uint2 *)w->nb_lists.p; D.nb_counts = (const uint8_t *)w->nb_counts.p;
   D.nb_later = j->later_lists ? (const uint2 *)w->nb_later.p : nullptr;
   D.nb_later_counts = (const uint8_t *)w->nb_later_counts.p;
   D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
   D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch; D.cn = (uint32_t)d.cw * (uint32_t)d.ch;
+  D.ow = j->off_w; D.oh = j->off_h; D.gw = (d.tw + 31) / 32; D.gh = (d.th + 31) / 32;
+  D.ctx_blocks = (const uint32_t *)w->ctx_blocks.p;
   D.nT = j->nT; D.nOff = j->nOff;
   uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;  // the size test follows the append (synthesize.h:222-224)
   D.kmax = kmax > RS_MAX_NB ? RS_MAX_NB : kmax;
@@ -2474,14 +2705,24 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     RsDev D0 = make_dev(j, 0);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
-    RsLine *claims = ((RsCtrl *)w->ctrl.p)->claims;  // [0] coop, [1] warp kernel
-    const uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;  // the long scans: one CTA each
-    RS_CHECK(cudaMemcpyAsync(&claims[1].v, &v1, 4, cudaMemcpyHostToDevice, s));
-    // The two gather kernels write disjoint visits; the cooperative one is a single wave of long scans that leaves
-    // half of every SM idle, so the warp kernel runs beside it on a second stream.
+    RsCtrl *dctrl = (RsCtrl *)w->ctrl.p;
+    RsLine *claims = dctrl->claims;  // [0] search kernel, [1] cooperative scan
+    const uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;  // the first visits: the valued pixels are few and far away
+    // Their patches come from a search over the earlier target points and the context blocks (k_gather_pass0_sparse) when
+    // the job reads the full offsets table; from the cooperative scan otherwise, and for tiled jobs with context.
+    bool sparse = j->off_w > 0 && w->ctx_blocks.p != nullptr;
+    if (const char *e = getenv("RS_SPARSE_GATHER")) sparse = sparse && atoi(e) != 0;
+    if (sparse) {
+      RS_CHECK(cudaMemsetAsync(&dctrl->n_ctx.v, 0, 4, s));
+      k_ctx_blocks<<<sms * 4, 256, 0, s>>>(D0.meta, D0.tw, D0.th, D0.gw, D0.gh, (uint32_t *)w->ctx_blocks.p, &dctrl->n_ctx.v);
+    } else {
+      D0.ctx_blocks = nullptr;
+    }
+    // The gather kernels write disjoint visits; the later visits' short scans run beside the first visits' on a second stream.
     RS_CHECK(cudaEventRecord(w->evFork, s));
     RS_CHECK(cudaStreamWaitEvent(w->stream2, w->evFork, 0));
-    k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, &claims[1].v);
+    if (v1 < j->nT)
+      k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, j->nT);
     RS_CHECK(cudaEventRecord(w->evJoin, w->stream2));
     // (pays off when the meta words of the scan no longer sit in L1/L2 next to everything else: cfg4 98 -> 94 ms, cfg3
     //  59.3 -> 58.2; a 1 Mi-target job loses 3 % to the extra kernel and the streamed lists, so small jobs keep scanning)
@@ -2492,7 +2733,15 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       k_gather_later<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_later.p, (uint8_t *)w->nb_later_counts.p);
       RS_CHECK(cudaEventRecord(w->evLater, w->stream2));
     }
-    k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[0].v);
+    if (sparse) {
+      uint32_t probe = RS_SPARSE_PROBE;
+      if (const char *e = getenv("RS_SPARSE_PROBE")) probe = (uint32_t)strtoul(e, nullptr, 10);  // tests
+      k_gather_pass0_sparse<<<sms * 4, RS_SPARSE_WARPS * 32, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1,
+                                                                      &claims[0].v, probe);
+    }
+    if (!sparse || j->d.htile || j->d.vtile)
+      k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[1].v,
+                                                               sparse ? 1 : 0);
     RS_CHECK(cudaStreamWaitEvent(s, w->evJoin, 0));
   }
   RS_CHECK(cudaEventRecord(w->evG, s));

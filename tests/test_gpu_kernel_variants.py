@@ -51,6 +51,22 @@ def _case(kind):
         m = centered_mask(90, 70, 30, 30)
         return (abi.make_params(0, 0, 2, 0.5, 0.117, 16, 80), 1, 0, False,
                 R.build_pixmap(m, img), R.build_pixmap(255 - m, img))
+    if kind == "heal_tiled":    # context AND tiling: the first visits' patches stay with the cooperative scan
+        img = G(96, 80, 3, 53)
+        m = centered_mask(96, 80, 50, 44)
+        return (abi.make_params(1, 1, 1, 0.5, 0.117, 24, 60), 3, 0, False,
+                R.build_pixmap(m, img), R.build_pixmap(255 - m, img))
+    if kind == "heal64_deep":   # the largest patch (63 neighbours) in a hole whose middle is far from any context
+        img = G(150, 140, 3, 54)
+        m = centered_mask(150, 140, 110, 100)
+        m[20:24, 30:90] = 0     # a strip of context inside the hole, and context that is not usable (ragged mask)
+        return (abi.make_params(0, 0, 1, 0.5, 0.117, 64, 40), 3, 0, False,
+                R.build_pixmap(m, img), R.build_pixmap(255 - m, img))
+    if kind == "texture9_htile":  # wrapped aliases in one direction only, offsets table narrower than the target
+        tgt = np.full((70, 90, 3), 255, np.uint8)
+        cor = G(40, 36, 3, 55)
+        return (abi.make_params(1, 0, 0, 0.5, 0.117, 9, 60), 3, 0, False,
+                R.build_pixmap(np.full((70, 90), 255, np.uint8), tgt), R.build_pixmap(np.full((36, 40), 255, np.uint8), cor))
     raise KeyError(kind)
 
 
@@ -152,6 +168,24 @@ def test_corpus_point_lookup_paths(built_oracle, built_lib, monkeypatch, width):
     monkeypatch.setenv("RS_NO_CORPUS_BITS", "1")
     _check("heal30")
     _check("texture9")
+
+
+@pytest.mark.parametrize("probe", ["0", "64"])
+@pytest.mark.parametrize("kind", KINDS + ["heal_tiled", "heal64_deep", "texture9_htile"])
+def test_pass0_patches_by_search(built_oracle, built_lib, monkeypatch, kind, probe):
+    """k_gather_pass0_sparse: the patches of the first 8192 visits of pass 0 come from a search over the earlier target
+    points (+ their wrapped aliases) and the context blocks instead of a scan of the sorted offsets table
+    (lib/synthesize.h:189-241).  By default a visit searches only when the first 512 table entries do not fill its
+    patch -- never, on jobs this small; RS_SPARSE_PROBE=0 makes every visit search, =64 mixes both."""
+    monkeypatch.setenv("RS_SPARSE_PROBE", probe)
+    _check(kind)
+
+
+@pytest.mark.parametrize("kind", ["heal30", "texture9_tiled", "heal_tiled", "heal64_deep", "texture9_htile"])
+def test_pass0_patches_by_scan(built_oracle, built_lib, monkeypatch, kind):
+    """RS_SPARSE_GATHER=0: the cooperative scan for the first visits, as for jobs with a caller's offsets table."""
+    monkeypatch.setenv("RS_SPARSE_GATHER", "0")
+    _check(kind)
 
 
 @pytest.mark.parametrize("width", [1, 2, 4, 8])
