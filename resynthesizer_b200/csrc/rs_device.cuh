@@ -44,10 +44,6 @@
 #define RS_CHUNK_LARGE 3
 #endif
 #define RS_CHUNK_MAX 8
-// Chunks a surviving candidate runs through per round of the throughput kernel's distance loop (rs_eval_range).
-#ifndef RS_EVAL_CHUNKS_PER_ROUND
-#define RS_EVAL_CHUNKS_PER_ROUND 1
-#endif
 // Latency mode (team kernel): after a probe's first chunk the rest of its patch is walked RS_CHUNK_CONT neighbours at a
 // time -- lanes are plentiful there and what counts is the number of dependent gather rounds, not wasted compares.
 #ifndef RS_CHUNK_CONT
@@ -464,14 +460,6 @@ __device__ __forceinline__ void rs_eval_range(const RsDev &J, unsigned lutc, uns
       if (MAPS && k == 1u) partial += rs_lut3(lutm, __vabsdiffu4(m0, selfmap));  // map terms of the target point itself (synthesize.h:342-355)
       k += CH;
       finished = (k >= K);
-#if RS_EVAL_CHUNKS_PER_ROUND > 1
-      // a candidate that survives its chunk goes on at once instead of through another round of hand-outs and votes
-      if (!finished && !(partial > bestSum || (partial == bestSum && myIdx > bestIdx))) {
-        partial += rs_chunk_sum<MAPS, CH, SMEMC>(J, lutc, lutm, nb, nmap, cx, clin, k, cs);
-        k += CH;
-        finished = (k >= K);
-      }
-#endif
     }
     const bool worse = active && (partial > bestSum || (partial == bestSum && myIdx > bestIdx));
     const bool propose = active && finished && !worse;

@@ -1444,7 +1444,7 @@ struct PassVariant {
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: work that may run beside the main stream's
-  cudaEvent_t evFork = nullptr, evJoin = nullptr, evLater = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoinB = nullptr, evLater = nullptr;
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, nb_later, nb_later_counts, simg, smask, smask2,
@@ -1517,6 +1517,7 @@ static void ws_free(Workspace *w) {
   if (w->evFork) cudaEventDestroy(w->evFork);
   if (w->evJoin) cudaEventDestroy(w->evJoin);
   if (w->evLater) cudaEventDestroy(w->evLater);
+  if (w->evJoinB) cudaEventDestroy(w->evJoinB);
   if (w->stream2) cudaStreamDestroy(w->stream2);
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;
@@ -1595,6 +1596,7 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreateWithFlags(&w->evFork, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evJoin, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evLater, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evJoinB, cudaEventDisableTiming));
   WCHK(cudaEventCreate(&w->ev0));
   WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
@@ -1759,6 +1761,7 @@ struct RsJob {
   uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
   float ms_synth = 0.f;           // CUDA-event time of the pass kernels alone (after the pass-0 patch gather)
   int off_w = 0, off_h = 0;       // dimensions of the full offsets table this job reads (0: a caller's partial table)
+  uint32_t gather_split = 0;      // pass-0 patches of the visits from here on are gathered beside the team segments
 };
 
 extern "C" void rs_job_destroy(RsJob *j) {
@@ -2707,11 +2710,31 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     RsCtrl *dctrl = (RsCtrl *)w->ctrl.p;
     RsLine *claims = dctrl->claims;  // [0] search kernel, [1] cooperative scan
-    const uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;  // the first visits: the valued pixels are few and far away
+    // The first visits: the valued pixels are few and far away.  Up to 8192 of them, fewer in small jobs: a search step costs
+    // about a tenth of a scan step, and visit v scans ~ K n / v table entries where the search looks at v points.
+    uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;
+    // Visits from `split` on are first needed by the throughput segment of pass 0: their (short) scans run beside the team
+    // segments, which are bound by the depth of their dependency chains and leave most issue slots idle.
+    uint32_t split = j->nT;
+    {
+      Segment seg0[4];
+      const int nseg0 = plan_segments(j->nT, j->d.pass_end[0], j->d.ordered_visits, j->d.patch_size, 0, seg0);
+      for (int k = 1; k < nseg0; k++)
+        if (seg0[k].width <= 1) { split = seg0[k - 1].end; break; }
+      if (g_job_slots.load() > 1) split = j->nT;
+      if (const char *e = getenv("RS_GATHER_SPLIT")) { if (atoi(e) == 0) split = j->nT; }
+    }
     // Their patches come from a search over the earlier target points and the context blocks (k_gather_pass0_sparse) when
     // the job reads the full offsets table; from the cooperative scan otherwise, and for tiled jobs with context.
     bool sparse = j->off_w > 0 && w->ctx_blocks.p != nullptr;
     if (const char *e = getenv("RS_SPARSE_GATHER")) sparse = sparse && atoi(e) != 0;
+    if (sparse) {
+      const uint32_t vs = (uint32_t)sqrt(72.0 * (double)j->nT);
+      if (vs < v1) v1 = vs < 256u ? (j->nT < 256u ? j->nT : 256u) : vs;
+    }
+    if (const char *e = getenv("RS_GATHER_FIRST")) { const uint32_t f = (uint32_t)strtoul(e, nullptr, 10); v1 = f < j->nT ? f : j->nT; }  // sweeps
+    if (split < v1) split = v1;
+    j->gather_split = split;
     if (sparse) {
       RS_CHECK(cudaMemsetAsync(&dctrl->n_ctx.v, 0, 4, s));
       k_ctx_blocks<<<sms * 4, 256, 0, s>>>(D0.meta, D0.tw, D0.th, D0.gw, D0.gh, (uint32_t *)w->ctx_blocks.p, &dctrl->n_ctx.v);
@@ -2721,9 +2744,13 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     // The gather kernels write disjoint visits; the later visits' short scans run beside the first visits' on a second stream.
     RS_CHECK(cudaEventRecord(w->evFork, s));
     RS_CHECK(cudaStreamWaitEvent(w->stream2, w->evFork, 0));
-    if (v1 < j->nT)
-      k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, j->nT);
+    if (v1 < split)
+      k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, split);
     RS_CHECK(cudaEventRecord(w->evJoin, w->stream2));
+    if (split < j->nT) {  // half of every SM's threads and registers: one CTA of the team kernel fits beside them
+      k_gather_pass0<<<sms * 4, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, split, j->nT);
+      RS_CHECK(cudaEventRecord(w->evJoinB, w->stream2));
+    }
     // (pays off when the meta words of the scan no longer sit in L1/L2 next to everything else: cfg4 98 -> 94 ms, cfg3
     //  59.3 -> 58.2; a 1 Mi-target job loses 3 % to the extra kernel and the streamed lists, so small jobs keep scanning)
     uint32_t later_min = 1u << 21;
@@ -2745,6 +2772,28 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     RS_CHECK(cudaStreamWaitEvent(s, w->evJoin, 0));
   }
   RS_CHECK(cudaEventRecord(w->evG, s));
+  // RS_L2_PERSIST=1: the canonical corpus (what every patch compare gathers from) is marked persisting in L2 for the pass
+  // kernels of this job; state words, lists and stamps stream past it.
+  bool l2_window = false;
+  if (const char *e = getenv("RS_L2_PERSIST")) {
+    if (atoi(e) != 0) {
+      cudaDeviceProp prop;
+      RS_CHECK(cudaGetDeviceProperties(&prop, w->device));
+      const size_t bytes = ((size_t)j->d.cw * j->d.ch + 1) * (j->maps ? 8 : 4);
+      if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        RS_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+        cudaStreamAttrValue a;
+        memset(&a, 0, sizeof a);
+        a.accessPolicyWindow.base_ptr = j->cb.corpus;
+        a.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)prop.persistingL2CacheMaxSize / (double)a.accessPolicyWindow.num_bytes);
+        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        RS_CHECK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a));
+        l2_window = true;
+      }
+    }
+  }
   uint32_t slot = 0;
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     if (p == 1 && j->later_lists) RS_CHECK(cudaStreamWaitEvent(s, w->evLater, 0));
@@ -2754,6 +2803,8 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     uint32_t begin = 0;
     j->pass_launches[p] = (uint32_t)nseg;
     for (int k = 0; k < nseg; k++) {
+      if (p == 0 && j->gather_split < j->nT && seg[k].end > j->gather_split && begin <= j->gather_split)
+        RS_CHECK(cudaStreamWaitEvent(s, w->evJoinB, 0));  // the patches of the visits from gather_split on
       D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
       const unsigned W = seg[k].width;
       D.chunk = large ? RS_CHUNK_LARGE : RS_CHUNK_SMALL;
@@ -2780,6 +2831,11 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   }
   j->launches = slot;
   RS_CHECK(cudaGetLastError());
+  if (l2_window) {
+    cudaStreamAttrValue a;
+    memset(&a, 0, sizeof a);
+    RS_CHECK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a));
+  }
   RS_CHECK(cudaEventRecord(w->ev1, s));
   k_writeback<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, j->targets_dev, j->nT,
                                                  j->d.tw, j->d.bpp, j->d.n_color, (uint8_t *)w->raw_t.p,
@@ -2838,6 +2894,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   }
   if (tick == nullptr) RS_CHECK(cudaEventSynchronize(w->evDone));  // blocking: the thread sleeps, the driver is left to the others
   RS_CHECK(cudaStreamSynchronize(s));
+  if (l2_window) cudaCtxResetPersistingL2Cache();
   // final, exact replay from the device's own counters: visits [0, pass_visits) of each pass were started
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     const unsigned long long started = w->h_ctrl->pass_visits[p];
