@@ -433,7 +433,8 @@ size_t estimate_targets(const uint8_t *mask0, size_t npx, size_t px_stride) {
 // few thousand target points: B200 sweeps in profiles/); from ~16 k points on a job fills the GPU by itself and more
 // than a few in flight only overlap host work and copies with kernels.
 int cap_slots(int slots, size_t n_est) {
-  const int cap = n_est >= 200000 ? 2 : (n_est >= 16384 ? 4 : 8);
+  int cap = n_est >= 200000 ? 2 : (n_est >= 16384 ? 4 : 8);
+  if (const char *e = getenv("RS_SLOTS_CAP")) { const int c = atoi(e); if (c > 0) cap = c; }  // sweeps
   return slots > cap ? cap : (slots < 1 ? 1 : slots);
 }
 // Jobs in flight on a device each take 1/slots of the SMs.  The alternative -- full-width grids, the jobs in flight only

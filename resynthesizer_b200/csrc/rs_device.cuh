@@ -89,7 +89,7 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   RsLine done_ctas[RS_MAX_LAUNCHES];  // CTAs that have left, per pass-kernel launch
   RsLine epoch_wm[6];       // per pass: number of leading epochs that are complete (what waiters poll)
   RsLine epoch_done[6][RS_MAX_EPOCHS];  // per pass and epoch: visits completed (state word + stamps published)
-  RsLine claims[2];         // work counters of the pass-0 gather kernels
+  RsLine claims[3];         // work counters of the pass-0 gather kernels
   RsLine n_ctx;             // context pixels usable as neighbours in the whole target image (k_ctx_blocks)
 };
 #define RS_CTRL_COPY_BYTES offsetof(RsCtrl, next)
@@ -127,6 +127,8 @@ struct RsDev {              // kernel argument (by value)
   uint32_t chunk;               // CH the launched kernel was instantiated with (patch padding follows it)
   uint32_t epoch_len;       // visits per recentProber epoch: max(64, ceil(nT/32))
   uint32_t epoch_inv;       // floor(2^32 / epoch_len)
+  uint32_t regular_r;       // != 0: passes >= 1 may take the head of the offsets table as the patch of a point that is at least
+                            // this far from a clipping border, provided RsCtrl::n_ctx + nT == tw * th (no unusable pixel)
   uint32_t ends[6];
   int htile, vtile;
   uint32_t sc_slice;        // corpus pixels per CTA slice when the corpus is staged into shared memory (k_synth_pass<..., true>)

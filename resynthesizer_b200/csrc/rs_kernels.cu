@@ -76,6 +76,14 @@ extern "C" unsigned rs_host_cores(void) {
   }();
   return cached;
 }
+// Most threads one staging copy (host buffer <-> pinned memory) is spread over; RS_COPY_THREADS overrides (sweeps).
+static size_t rs_copy_threads_max() {
+  static const size_t cached = []() -> size_t {
+    if (const char *e = getenv("RS_COPY_THREADS")) { const int v = atoi(e); if (v > 0) return (size_t)v; }
+    return 4;
+  }();
+  return cached;
+}
 extern "C" int rs_cuda_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -162,78 +170,70 @@ __global__ void k_writeback(const unsigned long long *__restrict__ W, const uint
 // dependencies at all; the (long, deep-hole) offset scans leave the critical path of the ordered pass.
 // Output per visit: count-1 entries {packed offset, pixel index | target flag << 31}.
 #define RS_TARGET_FLAG 0x80000000u
-__global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__restrict__ lists, uint8_t *__restrict__ counts,
-                                                      const uint32_t v_begin, const uint32_t v_end) {
+// One step of a pass-0 scan by one warp: U table entries per lane from `base` on (all of their loads in flight together),
+// the valued ones appended in table order to out[count - 1 ...]; returns the new count.
+template <int U>
+__device__ __forceinline__ uint32_t rs_scan_step(const RsDev &J, const uint32_t v, const int px, const int py, const uint32_t base,
+                                                 uint32_t count, uint2 *__restrict__ out) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
+  uint32_t o[U], q[U], m[U];
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const uint32_t j = base + 32u * u + lane;
+    o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
+    if (j < J.nOff) {
+      o[u] = __ldg(J.offsets + j);
+      int x = px + rs_off_x(o[u]), y = py + rs_off_y(o[u]);
+      bool in = true;
+      if (x < 0) { if (J.htile) x += J.tw; else in = false; }
+      else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
+      if (y < 0) { if (J.vtile) y += J.th; else in = false; }
+      else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
+      if (in) {
+        q[u] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+        m[u] = __ldg(J.meta + q[u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; u++) {
+    const bool ok = (m[u] == RS_CTX_VALUED) || (m[u] < v);
+    const unsigned b = __ballot_sync(RS_FULL, ok);
+    const uint32_t slot = count + __popc(b & lt);
+    if (ok && slot < J.kmax) out[slot - 1u] = make_uint2(o[u], q[u] | (m[u] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
+    count += __popc(b);
+  }
+  return count;
+}
+#define RS_GATHER_STRIPES 32768u
+__global__ void __launch_bounds__(256) k_gather_pass0(const RsDev J, uint2 *__restrict__ lists, uint8_t *__restrict__ counts,
+                                                      const uint32_t v_begin, const uint32_t v_end, unsigned int *__restrict__ claim) {
+  const unsigned lane = threadIdx.x & 31u;
   const uint32_t stride = J.kmax - 1u;
   unsigned long long scans = 0;
-  // static striding: the long scans of the first visits are not in this range (k_gather_pass0_sparse / _coop), the rest
-  // are short and uniform
-  const uint32_t nwarps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t v = v_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < v_end; v += nwarps) {
+  // The long scans of the first visits are not in this range (k_gather_pass0_sparse / _coop).  The rest is cut into
+  // RS_GATHER_STRIPES stripes -- stripe s = the visits v_begin + s + k * RS_GATHER_STRIPES, the same mix of long and short
+  // scans in each -- that the warps claim one at a time: CTAs that only find room on an SM once the search kernel beside
+  // them has left take fewer stripes, not a fixed share that would finish late.
+  while (true) {
+    uint32_t sidx = 0;
+    if (lane == 0) sidx = atomicAdd(claim, 1u);
+    sidx = __shfl_sync(RS_FULL, sidx, 0);
+    if (sidx >= RS_GATHER_STRIPES) break;
+    for (uint32_t v = v_begin + sidx; v < v_end; v += RS_GATHER_STRIPES) {
     const uint32_t tpos = __ldg(J.targets + v);
     const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
     uint2 *out = lists + (size_t)v * stride;
-    uint32_t count = 1;
-    // Late visits find their patch within the first few dozen offsets: one 32-wide step first, then 128-wide steps.
-    uint32_t base = 1;
-    {
-      const uint32_t j = base + lane;
-      uint32_t o = 0, q = 0, m = RS_NEVER;
-      if (j < J.nOff) {
-        o = __ldg(J.offsets + j);
-        int x = px + rs_off_x(o), y = py + rs_off_y(o);
-        bool in = true;
-        if (x < 0) { if (J.htile) x += J.tw; else in = false; }
-        else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
-        if (y < 0) { if (J.vtile) y += J.th; else in = false; }
-        else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
-        if (in) {
-          q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
-          m = __ldg(J.meta + q);
-        }
-      }
-      const bool ok = (m == RS_CTX_VALUED) || (m < v);
-      const unsigned b = __ballot_sync(RS_FULL, ok);
-      const uint32_t slot = count + __popc(b & lt);
-      if (ok && slot < J.kmax) out[slot - 1u] = make_uint2(o, q | (m == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
-      count += __popc(b);
-      scans += 32;
-      base += 32;
-    }
-    for (; base < J.nOff && count < J.kmax; base += 128) {
-      uint32_t o[4], q[4], m[4];
-      bool ok[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const uint32_t j = base + 32u * u + lane;
-        ok[u] = false; o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
-        if (j < J.nOff) {
-          o[u] = __ldg(J.offsets + j);
-          int x = px + rs_off_x(o[u]), y = py + rs_off_y(o[u]);
-          bool in = true;
-          if (x < 0) { if (J.htile) x += J.tw; else in = false; }
-          else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
-          if (y < 0) { if (J.vtile) y += J.th; else in = false; }
-          else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
-          if (in) {
-            q[u] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
-            m[u] = __ldg(J.meta + q[u]);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        ok[u] = (m[u] == RS_CTX_VALUED) || (m[u] < v);
-        const unsigned b = __ballot_sync(RS_FULL, ok[u]);
-        const uint32_t slot = count + __popc(b & lt);
-        if (ok[u] && slot < J.kmax) out[slot - 1u] = make_uint2(o[u], q[u] | (m[u] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
-        count += __popc(b);
-      }
-      scans += 128;
-    }
+    // The kernel is bound by the L2 sectors of its scattered meta-word loads, so what a step tests beyond the patch is what
+    // it costs: steps of 32, 32 and 64 entries first (the second half of a pass needs fewer than 64), then 128-wide ones.
+    uint32_t count = rs_scan_step<1>(J, v, px, py, 1u, 1u, out), base = 33u;
+    if (count < J.kmax && base < J.nOff) { count = rs_scan_step<1>(J, v, px, py, base, count, out); base += 32u; }
+    if (count < J.kmax && base < J.nOff) { count = rs_scan_step<2>(J, v, px, py, base, count, out); base += 64u; }
+    for (; base < J.nOff && count < J.kmax; base += 128u) count = rs_scan_step<4>(J, v, px, py, base, count, out);
+    scans += base - 1u;
     if (lane == 0) counts[v] = (uint8_t)min(count, J.kmax);
+    }
   }
   if (lane == 0 && scans) atomicAdd(&J.ctrl->offset_scans, scans);
 }
@@ -435,7 +435,6 @@ __global__ void __launch_bounds__(RS_SPARSE_WARPS * 32) k_gather_pass0_sparse(co
                                                                               unsigned int *__restrict__ claim, const uint32_t probe) {
   __shared__ SparseList s_list[RS_SPARSE_WARPS];
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt = (1u << lane) - 1u;
   SparseList &L = s_list[threadIdx.x >> 5];
   const uint32_t K1 = J.kmax - 1u, stride = K1;
   const uint32_t n_ctx = J.ctx_blocks != nullptr ? J.ctrl->n_ctx.v : 0u;
@@ -447,7 +446,8 @@ __global__ void __launch_bounds__(RS_SPARSE_WARPS * 32) k_gather_pass0_sparse(co
     if (lane == 0) v = atomicAdd(claim, 1u);
     v = __shfl_sync(RS_FULL, v, 0);
     if (v >= v_end) break;
-    v = v_end - 1u - v;  // the visits with the most earlier points first
+    v = (v & 1u) ? v_end - 1u - (v >> 1) : (v >> 1);  // the ends first: the fewest earlier points (a far walk to the context
+                                                      // while the list is not full) and the most
     const uint32_t tpos = __ldg(J.targets + v);
     const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
     uint2 *out = lists + (size_t)v * stride;
@@ -455,33 +455,7 @@ __global__ void __launch_bounds__(RS_SPARSE_WARPS * 32) k_gather_pass0_sparse(co
     {
       uint32_t count = 1;
       for (uint32_t base = 1; base < probe && base < J.nOff && count < J.kmax; base += 128) {
-        uint32_t o[4], q[4], m[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const uint32_t j = base + 32u * u + lane;
-          o[u] = 0; q[u] = 0; m[u] = RS_NEVER;
-          if (j < J.nOff) {
-            o[u] = __ldg(J.offsets + j);
-            int x = px + rs_off_x(o[u]), y = py + rs_off_y(o[u]);
-            bool in = true;
-            if (x < 0) { if (J.htile) x += J.tw; else in = false; }
-            else if (x >= J.tw) { if (J.htile) x -= J.tw; else in = false; }
-            if (y < 0) { if (J.vtile) y += J.th; else in = false; }
-            else if (y >= J.th) { if (J.vtile) y -= J.th; else in = false; }
-            if (in) {
-              q[u] = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
-              m[u] = __ldg(J.meta + q[u]);
-            }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const bool ok = (m[u] == RS_CTX_VALUED) || (m[u] < v);
-          const unsigned b = __ballot_sync(RS_FULL, ok);
-          const uint32_t slot = count + __popc(b & lt);
-          if (ok && slot < J.kmax) out[slot - 1u] = make_uint2(o[u], q[u] | (m[u] == RS_CTX_VALUED ? 0u : RS_TARGET_FLAG));
-          count += __popc(b);
-        }
+        count = rs_scan_step<4>(J, v, px, py, base, count, out);
         scans += 128;
       }
       if (count >= J.kmax || (probe >= J.nOff && probe > 1u)) {
@@ -697,7 +671,8 @@ __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uin
 // (1) One warp: gather the patch of visit v (target point tpos): S.off / S.q / S.aux(meta) and the geometry half of
 // the distance records S.nb[k].{lin,dx,pen}, padded to whole chunks.  Returns K.
 template <int CH, bool MAPS, int NB>
-__device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t tpos) {
+__device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t tpos,
+                                                      const bool regular) {
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass;
@@ -721,6 +696,22 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
       S.off[k] = e.x;
       S.q[k] = e.y & ~RS_TARGET_FLAG;
       S.aux[k] = (e.y & RS_TARGET_FLAG) ? 0u : RS_CTX_VALUED;
+    }
+  } else if (pass != 0u && J.regular_r != 0u && regular &&
+             (J.htile || (unsigned)(px - (int)J.regular_r) < (unsigned)(J.tw - 2 * (int)J.regular_r)) &&
+             (J.vtile || (unsigned)(py - (int)J.regular_r) < (unsigned)(J.th - 2 * (int)J.regular_r))) {
+    // Every pixel of the image is usable context or a target point (which all have a value from pass 1 on), and the point
+    // is not near a border that clips: the patch is the head of the offsets table, whatever the pixels hold.
+    count = J.kmax;
+    for (uint32_t k = 1u + lane; k < J.kmax; k += 32) {
+      const uint32_t o = __ldg(J.offsets + k);
+      int x = px + rs_off_x(o), y = py + rs_off_y(o);
+      if (x < 0) x += J.tw; else if (x >= J.tw) x -= J.tw;  // (tiling; a clipping axis was excluded above)
+      if (y < 0) y += J.th; else if (y >= J.th) y -= J.th;
+      const uint32_t q = (uint32_t)y * (uint32_t)J.tw + (uint32_t)x;
+      S.off[k] = o;
+      S.q[k] = q;
+      S.aux[k] = __ldg(J.meta + q);
     }
   } else if (pass != 0u && J.nb_later != nullptr) {
     // gathered once for all later passes by k_gather_later: offset + meta word; the pixel index follows from the offset
@@ -1162,11 +1153,12 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   LaneStats st;
   Visit V;
   if (lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
+  const bool regular = J.regular_r != 0u && ctrl->n_ctx.v + J.nT == (uint32_t)J.tw * (uint32_t)J.th;  // no unusable pixel anywhere
   uint32_t v = stopped ? J.seg_end : rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
   uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
   while (v < J.seg_end) {
     {
-      const uint32_t Kv = rs_visit_geometry<CH>(J, S, v, tpos);
+      const uint32_t Kv = rs_visit_geometry<CH>(J, S, v, tpos, regular);
       rs_visit_values(J, S, v, Kv);
       rs_visit_candidates<SMEMC>(J, ctrl, S, V, v, Kv, cs);
     }
@@ -1253,6 +1245,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
   TeamShared &TS = tshared[team];
   const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
   const uint32_t nPre = min(J.probes, T - 32u);  // probes fetched ahead, one per lane of warps 1..W-1
+  const bool regular = J.regular_r != 0u && ctrl->n_ctx.v + J.nT == (uint32_t)J.tw * (uint32_t)J.th;  // no unusable pixel anywhere
   LaneStats st;
   Visit V;
   if (wt == 0 && lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
@@ -1261,7 +1254,7 @@ __global__ void __launch_bounds__(RS_TEAM_WARPS * 32, 2) k_synth_pass_team(const
       const uint32_t vc = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
       const bool ok = vc < J.seg_end;
       uint32_t Kc = 0;
-      if (ok) Kc = rs_visit_geometry<CH>(J, S, vc, __ldg(J.targets + vc));
+      if (ok) Kc = rs_visit_geometry<CH>(J, S, vc, __ldg(J.targets + vc), regular);
       if (lane == 0) { TS.alive = ok ? 1u : 0u; TS.v = vc; TS.K = Kc; TS.nHeur = 0u; TS.best = ~0ull; TS.win_pt = RS_NO_SRC; }
       for (uint32_t i = lane; i < RS_MAX_NB; i += 32) { TS.hsum[i] = 0u; TS.hcnt[i] = 0u; }
     }
@@ -1444,7 +1437,7 @@ struct PassVariant {
 struct Workspace {
   int device = 0;
   cudaStream_t stream = nullptr, stream2 = nullptr;  // stream2: work that may run beside the main stream's
-  cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoinB = nullptr, evLater = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evLater = nullptr;
   cudaEvent_t ev0 = nullptr, evG = nullptr, ev1 = nullptr, evDone = nullptr;
   DevBuf raw_t, raw_c, corpus, W, meta, tmaps, targets, cpts, offsets, lut256, lut_rep, prober, colours,
       sources, ctrl, sort_keys_in, sort_keys_out, sort_vals_in, sort_tmp, nb_lists, nb_counts, nb_later, nb_later_counts, simg, smask, smask2,
@@ -1517,7 +1510,6 @@ static void ws_free(Workspace *w) {
   if (w->evFork) cudaEventDestroy(w->evFork);
   if (w->evJoin) cudaEventDestroy(w->evJoin);
   if (w->evLater) cudaEventDestroy(w->evLater);
-  if (w->evJoinB) cudaEventDestroy(w->evJoinB);
   if (w->stream2) cudaStreamDestroy(w->stream2);
   if (w->stream) cudaStreamDestroy(w->stream);
   delete w;
@@ -1596,7 +1588,6 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreateWithFlags(&w->evFork, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evJoin, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evLater, cudaEventDisableTiming));
-  WCHK(cudaEventCreateWithFlags(&w->evJoinB, cudaEventDisableTiming));
   WCHK(cudaEventCreate(&w->ev0));
   WCHK(cudaEventCreate(&w->evG));
   WCHK(cudaEventCreate(&w->ev1));
@@ -1761,7 +1752,7 @@ struct RsJob {
   uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
   float ms_synth = 0.f;           // CUDA-event time of the pass kernels alone (after the pass-0 patch gather)
   int off_w = 0, off_h = 0;       // dimensions of the full offsets table this job reads (0: a caller's partial table)
-  uint32_t gather_split = 0;      // pass-0 patches of the visits from here on are gathered beside the team segments
+  bool ctx_counted = false;       // k_ctx_blocks ran for this job: RsCtrl::n_ctx holds the number of usable context pixels
 };
 
 extern "C" void rs_job_destroy(RsJob *j) {
@@ -1982,7 +1973,7 @@ static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t b
     return 0;
   }
   unsigned hw = rs_host_cores();
-  const size_t nt = std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
+  const size_t nt = std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
   for (size_t off = 0; off < bytes; off += PIECE * nt) {
     const size_t len = std::min(bytes - off, PIECE * nt);
     if (nt > 1 && len > PIECE) {
@@ -2007,7 +1998,7 @@ static int stage_rows_to_device(void *dev, uint8_t *pin, const uint8_t *src, siz
                                 cudaStream_t s) {
   if (src_stride == row_len) return stage_to_device(dev, pin, src, rows * row_len, s);
   unsigned hw = rs_host_cores();
-  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
+  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
   auto band = [=](size_t t) {
     const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
     for (size_t y = b; y < e; y++) memcpy(pin + y * row_len, src + y * src_stride, row_len);
@@ -2329,7 +2320,7 @@ extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_byt
   const uint8_t *src = (const uint8_t *)w->pin;
   const uint32_t y0 = j->y_min;
   unsigned hw = rs_host_cores();
-  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
+  const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
   auto band = [=](size_t t) {
     const size_t per = (rows + nt - 1) / nt, b = std::min(rows, t * per), e = std::min(rows, (t + 1) * per);
     for (size_t r = b; r < e; r++) memcpy(img + (size_t)(y0 + r) * img_row_bytes, src + r * row_len, row_len);
@@ -2587,6 +2578,18 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
   D.ctrl = (RsCtrl *)w->ctrl.p; D.host_ticks = w->h_ticks; D.host_cancel = w->h_cancel;
   D.tw = d.tw; D.th = d.th; D.cw = d.cw; D.ch = d.ch; D.cn = (uint32_t)d.cw * (uint32_t)d.ch;
   D.ow = j->off_w; D.oh = j->off_h; D.gw = (d.tw + 31) / 32; D.gh = (d.th + 31) / 32;
+  D.regular_r = 0;
+  if (pass != 0 && j->ctx_counted && j->off_w > 0 && !(getenv("RS_REGULAR") && atoi(getenv("RS_REGULAR")) == 0)) {
+    // largest |component| among the first kmax-1 offsets of the table (ascending distance): floor(sqrt(their largest d^2))
+    uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
+    if (kmax > RS_MAX_NB) kmax = RS_MAX_NB;
+    std::vector<int> d2;
+    for (int y = -9; y <= 9; y++) for (int x = -9; x <= 9; x++) if (x || y) d2.push_back(x * x + y * y);
+    std::sort(d2.begin(), d2.end());
+    int r = 0;
+    while ((r + 1) * (r + 1) <= d2[kmax - 2]) r++;
+    if (j->off_w > r && j->off_h > r && d.tw > 2 * r + 1 && d.th > 2 * r + 1 && j->nOff >= kmax) D.regular_r = (uint32_t)r;
+  }
   D.ctx_blocks = (const uint32_t *)w->ctx_blocks.p;
   D.nT = j->nT; D.nOff = j->nOff;
   uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;  // the size test follows the append (synthesize.h:222-224)
@@ -2609,17 +2612,20 @@ static RsDev make_dev(const RsJob *j, uint32_t pass) {
 // launch each, whose width shrinks as the pass fills in.  Thresholds from sweeps on B200 (profiles/); RS_TEAM_P0 /
 // RS_TEAM_PN force one width for a whole pass, RS_SEG_P0="end:width,end:width,..." forces the pass-0 plan.
 struct Segment { uint32_t end; unsigned width; };
-static unsigned pass_width(uint32_t n, uint32_t p) {
+static unsigned pass_width(uint32_t n, uint32_t p, int slots = 1) {
   if (n <= 32768u) return 8;
-  if (n <= 200000u) return p == 0 ? 8 : 4;
+  // (four or more such jobs side by side on SM shares, a batch: what counts is the visits in flight on the whole device, and
+  //  teams half as wide keep twice as many -- 64 heal jobs 2048^2 / 256^2 hole: 4.17 -> 3.42 ms per job, tools/batch_width_sweep.py)
+  if (n <= 200000u) return slots >= 4 ? (p == 0 ? 4 : 2) : (p == 0 ? 8 : 4);
   if (n <= 600000u) return p == 0 ? 4 : 2;
   return 1;
 }
 static int plan_segments(uint32_t n_targets, uint32_t end, int ordered_visits, int patch_size, uint32_t p, Segment *out /*[4]*/) {
   const char *e = getenv(p == 0 ? "RS_TEAM_P0" : "RS_TEAM_PN");
   if (e) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4 || w == 8) { out[0] = {end, (unsigned)w}; return 1; } }
-  const unsigned base = pass_width(n_targets, p);
-  if (p != 0) { out[0] = {end, base}; return 1; }
+  const int slots = g_job_slots.load();
+  const unsigned base = pass_width(n_targets, p, slots);
+  if (p != 0 || (slots >= 4 && n_targets > 32768u && n_targets <= 200000u)) { out[0] = {end, base}; return 1; }
   if (ordered_visits && !getenv("RS_SEG_P0")) {
     // A spatially sorted order (inwards, outwards, by rows...) keeps pass 0 a narrow dependency front from its first visit
     // to its last: latency mode throughout (1 Mi targets: 11.8 ms at 4 warps per visit, 20.0 with the shuffle's plan).
@@ -2709,21 +2715,10 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     RsCtrl *dctrl = (RsCtrl *)w->ctrl.p;
-    RsLine *claims = dctrl->claims;  // [0] search kernel, [1] cooperative scan
+    RsLine *claims = dctrl->claims;  // [0] search kernel, [1] cooperative scan, [2] the later visits' scans
     // The first visits: the valued pixels are few and far away.  Up to 8192 of them, fewer in small jobs: a search step costs
     // about a tenth of a scan step, and visit v scans ~ K n / v table entries where the search looks at v points.
     uint32_t v1 = j->nT < 8192u ? j->nT : 8192u;
-    // Visits from `split` on are first needed by the throughput segment of pass 0: their (short) scans run beside the team
-    // segments, which are bound by the depth of their dependency chains and leave most issue slots idle.
-    uint32_t split = j->nT;
-    {
-      Segment seg0[4];
-      const int nseg0 = plan_segments(j->nT, j->d.pass_end[0], j->d.ordered_visits, j->d.patch_size, 0, seg0);
-      for (int k = 1; k < nseg0; k++)
-        if (seg0[k].width <= 1) { split = seg0[k - 1].end; break; }
-      if (g_job_slots.load() > 1) split = j->nT;
-      if (const char *e = getenv("RS_GATHER_SPLIT")) { if (atoi(e) == 0) split = j->nT; }
-    }
     // Their patches come from a search over the earlier target points and the context blocks (k_gather_pass0_sparse) when
     // the job reads the full offsets table; from the cooperative scan otherwise, and for tiled jobs with context.
     bool sparse = j->off_w > 0 && w->ctx_blocks.p != nullptr;
@@ -2733,33 +2728,16 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
       if (vs < v1) v1 = vs < 256u ? (j->nT < 256u ? j->nT : 256u) : vs;
     }
     if (const char *e = getenv("RS_GATHER_FIRST")) { const uint32_t f = (uint32_t)strtoul(e, nullptr, 10); v1 = f < j->nT ? f : j->nT; }  // sweeps
-    if (split < v1) split = v1;
-    j->gather_split = split;
-    if (sparse) {
+    j->ctx_counted = w->ctx_blocks.p != nullptr;
+    if (j->ctx_counted) {
       RS_CHECK(cudaMemsetAsync(&dctrl->n_ctx.v, 0, 4, s));
       k_ctx_blocks<<<sms * 4, 256, 0, s>>>(D0.meta, D0.tw, D0.th, D0.gw, D0.gh, (uint32_t *)w->ctx_blocks.p, &dctrl->n_ctx.v);
-    } else {
-      D0.ctx_blocks = nullptr;
     }
-    // The gather kernels write disjoint visits; the later visits' short scans run beside the first visits' on a second stream.
+    if (!sparse) D0.ctx_blocks = nullptr;
+    // The gather kernels write disjoint visits.  The first visits' search goes to the device first (it is short and takes
+    // half of every SM's threads); the later visits' scans fill the other half from a second stream and spread over the
+    // whole SM as the search kernel's CTAs leave.
     RS_CHECK(cudaEventRecord(w->evFork, s));
-    RS_CHECK(cudaStreamWaitEvent(w->stream2, w->evFork, 0));
-    if (v1 < split)
-      k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, split);
-    RS_CHECK(cudaEventRecord(w->evJoin, w->stream2));
-    if (split < j->nT) {  // half of every SM's threads and registers: one CTA of the team kernel fits beside them
-      k_gather_pass0<<<sms * 4, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, split, j->nT);
-      RS_CHECK(cudaEventRecord(w->evJoinB, w->stream2));
-    }
-    // (pays off when the meta words of the scan no longer sit in L1/L2 next to everything else: cfg4 98 -> 94 ms, cfg3
-    //  59.3 -> 58.2; a 1 Mi-target job loses 3 % to the extra kernel and the streamed lists, so small jobs keep scanning)
-    uint32_t later_min = 1u << 21;
-    if (const char *e = getenv("RS_LATER_LISTS_MIN")) later_min = (uint32_t)strtoul(e, nullptr, 10);  // tests, sweeps
-    j->later_lists = j->d.n_passes > 1 && j->nT >= later_min;
-    if (j->later_lists) {  // beside pass 0, needed from pass 1 on
-      k_gather_later<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_later.p, (uint8_t *)w->nb_later_counts.p);
-      RS_CHECK(cudaEventRecord(w->evLater, w->stream2));
-    }
     if (sparse) {
       uint32_t probe = RS_SPARSE_PROBE;
       if (const char *e = getenv("RS_SPARSE_PROBE")) probe = (uint32_t)strtoul(e, nullptr, 10);  // tests
@@ -2769,31 +2747,27 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     if (!sparse || j->d.htile || j->d.vtile)
       k_gather_pass0_coop<<<sms * 2, RS_COOP_THREADS, 0, s>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, &claims[1].v,
                                                                sparse ? 1 : 0);
+    RS_CHECK(cudaStreamWaitEvent(w->stream2, w->evFork, 0));
+    if (v1 < j->nT)
+      k_gather_pass0<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_lists.p, (uint8_t *)w->nb_counts.p, v1, j->nT, &claims[2].v);
+    RS_CHECK(cudaEventRecord(w->evJoin, w->stream2));
+    // (pays off when the meta words of the scan no longer sit in L1/L2 next to everything else: cfg4 98 -> 94 ms, cfg3
+    //  59.3 -> 58.2; a 1 Mi-target job loses 3 % to the extra kernel and the streamed lists, so small jobs keep scanning)
+    uint32_t later_min = 1u << 21;
+    if (const char *e = getenv("RS_LATER_LISTS_MIN")) later_min = (uint32_t)strtoul(e, nullptr, 10);  // tests, sweeps
+    j->later_lists = j->d.n_passes > 1 && j->nT >= later_min;
+    // (a target that is the whole image has no unusable pixel: its later passes take their patches off the head of the
+    //  offsets table, rs_visit_geometry; for patches below 16 neighbours that is as fast as a list -- cfg4 50.8 -> 50.4 ms)
+    if (j->nT == (uint32_t)j->d.tw * (uint32_t)j->d.th && j->d.patch_size < RS_CHUNK_SWITCH_K && j->off_w > 0 &&
+        !getenv("RS_LATER_LISTS_MIN") && !(getenv("RS_REGULAR") && atoi(getenv("RS_REGULAR")) == 0))
+      j->later_lists = false;
+    if (j->later_lists) {  // beside pass 0, needed from pass 1 on
+      k_gather_later<<<sms * 8, 256, 0, w->stream2>>>(D0, (uint2 *)w->nb_later.p, (uint8_t *)w->nb_later_counts.p);
+      RS_CHECK(cudaEventRecord(w->evLater, w->stream2));
+    }
     RS_CHECK(cudaStreamWaitEvent(s, w->evJoin, 0));
   }
   RS_CHECK(cudaEventRecord(w->evG, s));
-  // RS_L2_PERSIST=1: the canonical corpus (what every patch compare gathers from) is marked persisting in L2 for the pass
-  // kernels of this job; state words, lists and stamps stream past it.
-  bool l2_window = false;
-  if (const char *e = getenv("RS_L2_PERSIST")) {
-    if (atoi(e) != 0) {
-      cudaDeviceProp prop;
-      RS_CHECK(cudaGetDeviceProperties(&prop, w->device));
-      const size_t bytes = ((size_t)j->d.cw * j->d.ch + 1) * (j->maps ? 8 : 4);
-      if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
-        RS_CHECK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
-        cudaStreamAttrValue a;
-        memset(&a, 0, sizeof a);
-        a.accessPolicyWindow.base_ptr = j->cb.corpus;
-        a.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)prop.accessPolicyMaxWindowSize);
-        a.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)prop.persistingL2CacheMaxSize / (double)a.accessPolicyWindow.num_bytes);
-        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        RS_CHECK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a));
-        l2_window = true;
-      }
-    }
-  }
   uint32_t slot = 0;
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     if (p == 1 && j->later_lists) RS_CHECK(cudaStreamWaitEvent(s, w->evLater, 0));
@@ -2803,15 +2777,12 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     uint32_t begin = 0;
     j->pass_launches[p] = (uint32_t)nseg;
     for (int k = 0; k < nseg; k++) {
-      if (p == 0 && j->gather_split < j->nT && seg[k].end > j->gather_split && begin <= j->gather_split)
-        RS_CHECK(cudaStreamWaitEvent(s, w->evJoinB, 0));  // the patches of the visits from gather_split on
       D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
       const unsigned W = seg[k].width;
       D.chunk = large ? RS_CHUNK_LARGE : RS_CHUNK_SMALL;
       if (W <= 1 && smemc_ctas) {  // corpus staged into the shared memory of a CTA or of a 2-CTA cluster
         D.sc_slice = smemc_slice;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
+        cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(grid_smemc / smemc_ctas * smemc_ctas), 1, 1);
         cfg.blockDim = dim3(RS_TP_WARPS * 32, 1, 1);
         cfg.dynamicSmemBytes = PV.smemc_base + (size_t)smemc_slice * 4 + 16;
@@ -2831,11 +2802,6 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   }
   j->launches = slot;
   RS_CHECK(cudaGetLastError());
-  if (l2_window) {
-    cudaStreamAttrValue a;
-    memset(&a, 0, sizeof a);
-    RS_CHECK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a));
-  }
   RS_CHECK(cudaEventRecord(w->ev1, s));
   k_writeback<<<(j->nT + 255) / 256, 256, 0, s>>>((const unsigned long long *)w->W.p, j->targets_dev, j->nT,
                                                  j->d.tw, j->d.bpp, j->d.n_color, (uint8_t *)w->raw_t.p,
@@ -2894,7 +2860,6 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
   }
   if (tick == nullptr) RS_CHECK(cudaEventSynchronize(w->evDone));  // blocking: the thread sleeps, the driver is left to the others
   RS_CHECK(cudaStreamSynchronize(s));
-  if (l2_window) cudaCtxResetPersistingL2Cache();
   // final, exact replay from the device's own counters: visits [0, pass_visits) of each pass were started
   for (uint32_t p = 0; p < j->d.n_passes; p++) {
     const unsigned long long started = w->h_ctrl->pass_visits[p];
@@ -2928,7 +2893,7 @@ extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sour
     uint8_t *dst = target_raw_out + (size_t)j->y_min * row_bytes;
     const uint8_t *src = (const uint8_t *)w->pin;
     unsigned hw = rs_host_cores();
-    const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(4, hw > 2 ? hw - 1 : 1);
+    const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
     const size_t per = (rows_bytes + nt - 1) / nt;
     std::vector<std::thread> th;
     for (size_t t = 1; t < nt; t++) {
