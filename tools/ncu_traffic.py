@@ -2,7 +2,7 @@
 """DRAM traffic of the synthesis launches of ONE job, from an ncu launch list, for bench.py's roofline.traffic.
 
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-      -k regex:'k_synth_pass|k_gather' --csv --log-file gpurun_out/traffic_cfg3.csv python tools/ncu_job.py --workload cfg3 --jobs 2
+      -k regex:'k_synth_pass|k_gather|k_ctx' --csv --log-file gpurun_out/traffic_cfg3.csv python tools/ncu_job.py --workload cfg3 --jobs 2
   python tools/ncu_traffic.py gpurun_out/traffic_cfg3.csv cfg3 hbm        -> profiles/traffic_cfg3.json
 
 The last job's launches are taken (the first job also builds the offsets table and warms the workspace).  `bound` is
@@ -30,8 +30,9 @@ def main(path, wname, bound):
                 "nsecond": 1e-6, "msecond": 1.0, "second": 1e3}.get(r[iunit], 1)
         d[r[imetric]] = v * mult
     ids = sorted(launches)
-    # split into jobs at every pass-0 cooperative gather (first synthesis launch of a job)
-    starts = [i for i in ids if "k_gather_pass0_coop" in launches[i]["kernel"]]
+    # split into jobs at the first synthesis launch of a job: the context-block count ahead of the pass-0 patch gathers
+    first = "k_ctx_blocks" if any("k_ctx_blocks" in launches[i]["kernel"] for i in ids) else "k_gather_pass0_coop"
+    starts = [i for i in ids if first in launches[i]["kernel"]]
     last = [i for i in ids if i >= starts[-1]] if starts else ids
     per = [{"kernel": launches[i]["kernel"], "ms": launches[i].get("gpu__time_duration.sum", 0.0),
             "dram_bytes": launches[i].get("dram__bytes_read.sum", 0.0) + launches[i].get("dram__bytes_write.sum", 0.0)} for i in last]

@@ -13,7 +13,7 @@ timeout 600 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $o
 timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
 M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum"
 for w in cfg3 cfg2 cfg5 cfg4 cfg1; do
-  timeout 200 ncu --metrics $M --clock-control none -k regex:'k_synth_pass|k_gather' --csv --log-file $out/${tag}_traffic_$w.csv python tools/ncu_job.py --workload $w --jobs 2 > $out/${tag}_traffic_$w.log 2>&1
+  timeout 200 ncu --metrics $M --clock-control none -k regex:'k_synth_pass|k_gather|k_ctx' --csv --log-file $out/${tag}_traffic_$w.csv python tools/ncu_job.py --workload $w --jobs 2 > $out/${tag}_traffic_$w.log 2>&1
 done
 NCU="ncu --set full --clock-control none --import-source on"
 timeout 300 $NCU -k k_synth_pass -s 7 -c 1 -f -o $out/${tag}_cfg3_pass1 python tools/ncu_job.py --workload cfg3 --jobs 2 > $out/${tag}_ncu_cfg3.log 2>&1
