@@ -613,25 +613,48 @@ __device__ __forceinline__ void rs_stage_tables(const RsDev &J, uint32_t *lutc, 
 // the round trip of the atomic can overlap other work: rs_claim_issue returns lane 0's raw ticket,
 // rs_claim_resolve turns it into the warp-uniform visit index (>= J.seg_end: nothing left) and does the
 // progress tick + cancel poll of the reference (synthesize.h:493-497).
+template <int NV = 1>  // visits per claim: consecutive ones
 __device__ __forceinline__ uint32_t rs_claim_issue(const RsDev &J, RsCtrl *ctrl) {
   uint32_t raw = 0;
-  if ((threadIdx.x & 31u) == 0u) raw = atomicAdd(&ctrl->next[J.slot].v, 1u);
+  if ((threadIdx.x & 31u) == 0u) raw = atomicAdd(&ctrl->next[J.slot].v, (unsigned)NV);
   return raw;
 }
+template <int NV = 1>
 __device__ __forceinline__ uint32_t rs_claim_resolve(const RsDev &J, RsCtrl *ctrl, uint32_t raw) {
   uint32_t v = J.seg_begin + raw;
-  if ((threadIdx.x & 31u) == 0u && v < J.seg_end && (v & 4095u) == 0u) {
-    const uint32_t pass = J.pass;
-    J.host_ticks[pass] = v + 1u;
-    if ((v >> 12) < RS_TIMELINE) ctrl->tick_ns[pass][v >> 12] = rs_globaltimer();
-    if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
-      atomicExch(&ctrl->stop, 1u);
-      atomicAdd(&ctrl->next[J.slot].v, 0x40000000u);
+  if ((threadIdx.x & 31u) == 0u) {
+#pragma unroll
+    for (uint32_t x = 0; x < (uint32_t)NV; x++) {
+      const uint32_t vx = v + x;
+      if (vx < J.seg_end && (vx & 4095u) == 0u) {
+        const uint32_t pass = J.pass;
+        J.host_ticks[pass] = vx + 1u;
+        if ((vx >> 12) < RS_TIMELINE) ctrl->tick_ns[pass][vx >> 12] = rs_globaltimer();
+        if (*J.host_cancel) {  // no further claims succeed; this visit still runs (later ones may wait on it)
+          atomicExch(&ctrl->stop, 1u);
+          atomicAdd(&ctrl->next[J.slot].v, 0x40000000u);
+        }
+      }
     }
   }
   return __shfl_sync(RS_FULL, v, 0);
 }
 
+// A visit is prepared and committed by a GROUP of LW lanes: the whole warp (LW = 32), or one half of it (LW = 16: two
+// visits of small patches side by side in one warp, k_synth_pass<..., 16>).  The two halves run CONVERGED -- one
+// instruction stream, that is the point -- so every vote and barrier is a full-warp one that all 32 lanes reach (loops
+// around them run while ANY group needs them, bodies predicated), and a group reads its own 16 bits of the result.
+template <int LW>
+struct Grp {
+  static __device__ __forceinline__ unsigned lane() { return threadIdx.x & (unsigned)(LW - 1); }
+  static __device__ __forceinline__ unsigned shift() { return LW == 32 ? 0u : (threadIdx.x & 31u & ~(unsigned)(LW - 1)); }
+  static __device__ __forceinline__ unsigned bits(unsigned full) { return LW == 32 ? full : ((full >> shift()) & ((1u << (LW & 31)) - 1u)); }
+  static __device__ __forceinline__ unsigned ballot(bool p) { return bits(__ballot_sync(RS_FULL, p)); }
+  static __device__ __forceinline__ bool any(bool p) { return ballot(p) != 0u; }          // in my group
+  static __device__ __forceinline__ bool any_group(bool p) { return __any_sync(RS_FULL, p) != 0; }  // in any group of the warp
+  static __device__ __forceinline__ unsigned match_any(uint32_t c) { return bits(__match_any_sync(RS_FULL, c)); }
+  static __device__ __forceinline__ void sync() { __syncwarp(); }
+};
 // v / J.epoch_len without the division: the estimate from floor(2^32 / len) is exact or one short.
 __device__ __forceinline__ uint32_t rs_epoch_of(const RsDev &J, uint32_t v) {
   uint32_t q = __umulhi(v, J.epoch_inv);
@@ -670,17 +693,19 @@ __device__ __forceinline__ void rs_wait_epochs(const RsDev &J, RsCtrl *ctrl, uin
 //
 // (1) One warp: gather the patch of visit v (target point tpos): S.off / S.q / S.aux(meta) and the geometry half of
 // the distance records S.nb[k].{lin,dx,pen}, padded to whole chunks.  Returns K.
-template <int CH, bool MAPS, int NB>
+template <int CH, int LW = 32, bool MAPS, int NB>
 __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t tpos,
-                                                      const bool regular) {
-  const unsigned lane = threadIdx.x & 31u;
+                                                      const bool regular, const bool on = true) {
+  typedef Grp<LW> G;
+  const unsigned lane = G::lane();
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass;
   const int px = (int)(tpos & 0xFFFFu), py = (int)(tpos >> 16);
   const uint32_t selfq = (uint32_t)py * (uint32_t)J.tw + (uint32_t)px;
 
   // ---- gather the patch: self + nearest valued pixels (lib/synthesize.h:189-241)
-  if (lane == 0) {
+  // (`on`: this group has a visit; the groups of a warp take the same one of the four ways below)
+  if (lane == 0 && on) {
     S.off[0] = 0u;
     S.q[0] = selfq;
     S.vis.selfq = selfq;
@@ -689,21 +714,21 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
   uint32_t count = 1;
   if (pass == 0u && J.nb_lists != nullptr) {
     // precomputed by k_gather_pass0; aux := 0 (< v+1) marks "target visited before me", else context
-    count = J.nb_counts[v];
+    if (on) count = J.nb_counts[v];
     const uint2 *lst = J.nb_lists + (size_t)v * (J.kmax - 1u);
-    for (uint32_t k = 1u + lane; k < count; k += 32) {
+    for (uint32_t k = 1u + lane; k < count; k += LW) {
       const uint2 e = __ldg(lst + (k - 1u));
       S.off[k] = e.x;
       S.q[k] = e.y & ~RS_TARGET_FLAG;
       S.aux[k] = (e.y & RS_TARGET_FLAG) ? 0u : RS_CTX_VALUED;
     }
   } else if (pass != 0u && J.regular_r != 0u && regular &&
-             (J.htile || (unsigned)(px - (int)J.regular_r) < (unsigned)(J.tw - 2 * (int)J.regular_r)) &&
-             (J.vtile || (unsigned)(py - (int)J.regular_r) < (unsigned)(J.th - 2 * (int)J.regular_r))) {
+             !G::any_group(on && !((J.htile || (unsigned)(px - (int)J.regular_r) < (unsigned)(J.tw - 2 * (int)J.regular_r)) &&
+                                   (J.vtile || (unsigned)(py - (int)J.regular_r) < (unsigned)(J.th - 2 * (int)J.regular_r))))) {
     // Every pixel of the image is usable context or a target point (which all have a value from pass 1 on), and the point
     // is not near a border that clips: the patch is the head of the offsets table, whatever the pixels hold.
-    count = J.kmax;
-    for (uint32_t k = 1u + lane; k < J.kmax; k += 32) {
+    if (on) count = J.kmax;
+    for (uint32_t k = 1u + lane; k < count; k += LW) {
       const uint32_t o = __ldg(J.offsets + k);
       int x = px + rs_off_x(o), y = py + rs_off_y(o);
       if (x < 0) x += J.tw; else if (x >= J.tw) x -= J.tw;  // (tiling; a clipping axis was excluded above)
@@ -715,9 +740,9 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
     }
   } else if (pass != 0u && J.nb_later != nullptr) {
     // gathered once for all later passes by k_gather_later: offset + meta word; the pixel index follows from the offset
-    count = J.nb_later_counts[v];
+    if (on) count = J.nb_later_counts[v];
     const uint2 *lst = J.nb_later + (size_t)v * (J.kmax - 1u);
-    for (uint32_t k = 1u + lane; k < count; k += 32) {
+    for (uint32_t k = 1u + lane; k < count; k += LW) {
       const uint2 e = __ldcs(lst + (k - 1u));  // streamed: read once per pass
       int x = px + rs_off_x(e.x), y = py + rs_off_y(e.x);
       if (x < 0) x += J.tw; else if (x >= J.tw) x -= J.tw;  // only offsets that wrap (tiling) or stay inside were listed
@@ -727,11 +752,13 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
       S.aux[k] = e.y;
     }
   } else {
-    for (uint32_t base = 1; base < J.nOff && count < J.kmax; base += 32) {
+    for (uint32_t base = 1;; base += LW) {
+      const bool go = on && base < J.nOff && count < J.kmax;  // (a group that has its patch idles while another still scans)
+      if (!G::any_group(go)) break;
       const uint32_t j = base + lane;
       bool ok = false;
       uint32_t o = 0, q = 0, m = 0;
-      if (j < J.nOff) {
+      if (go && j < J.nOff) {
         o = __ldg(J.offsets + j);
         int x = px + rs_off_x(o), y = py + rs_off_y(o);
         bool in = true;  // wrap when tiling, else clip (lib/synthesize.h:81-113); |offset| < image size
@@ -746,7 +773,7 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
           ok = (pass == 0u) ? (m == RS_CTX_VALUED || m < v) : (m != RS_NEVER);
         }
       }
-      const unsigned b = __ballot_sync(RS_FULL, ok);
+      const unsigned b = G::ballot(ok);
       const uint32_t slot = count + __popc(b & lt);
       if (ok && slot < J.kmax) {
         S.off[slot] = o;
@@ -754,16 +781,16 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
         S.aux[slot] = m;
       }
       count += __popc(b);
-      if (lane == 0) S.st.scans += min(32u, J.nOff - base);
+      if (lane == 0 && go) S.st.scans += min((uint32_t)LW, J.nOff - base);
     }
   }
-  const uint32_t K = min(count, J.kmax);
-  __syncwarp();
+  const uint32_t K = on ? min(count, J.kmax) : 0u;
+  G::sync();
   {  // geometry half of the distance records, padded to whole chunks with records that cost nothing
     // (whole chunks of the launched kernel's size, and a continuation chunk of the team kernel may start at any k < K)
     const uint32_t nch = (K + CH - 2u) / CH;  // (CH == J.chunk: a division by a constant)
     const uint32_t kpad = min((uint32_t)WarpScratch<MAPS, NB>::kSlots, max(1u + (nch ? nch : 1u) * CH, K + (uint32_t)RS_CHUNK_MAX));
-    for (uint32_t k = lane; k < kpad; k += 32) {
+    for (uint32_t k = lane; on && k < kpad; k += LW) {
       RsNb r;
       if (k < K) {
         const uint32_t o = S.off[k];
@@ -778,17 +805,18 @@ __device__ __forceinline__ uint32_t rs_visit_geometry(const RsDev &J, WarpScratc
       S.nb[k] = r;
     }
   }
-  __syncwarp();
+  G::sync();
   return K;
 }
 
 // (2) One warp: wait for exactly the versions the sequential order would see, then read them (one 64-bit load each):
 // colours into S.nb[k].pix (+ S.map), sources into S.aux.
-template <bool MAPS, int NB>
+template <int LW = 32, bool MAPS, int NB>
 __device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS, NB> &S, const uint32_t v, const uint32_t K) {
-  const unsigned lane = threadIdx.x & 31u;
+  typedef Grp<LW> G;
+  const unsigned lane = G::lane();
   const uint32_t pass = J.pass, pass_end = J.pass_end;
-  for (uint32_t k = lane; k < K; k += 32) {
+  for (uint32_t k = lane; k < K; k += LW) {
     const uint32_t q = S.q[k], m = S.aux[k];
     uint32_t r = 0;
     if (k == 0) r = pass;
@@ -812,14 +840,16 @@ __device__ __forceinline__ void rs_visit_values(const RsDev &J, WarpScratch<MAPS
     if (MAPS) S.map[k] = __ldg(J.tmaps + q);
     S.aux[k] = (uint32_t)(w >> 32);  // source of this neighbour, or RS_NO_SRC
   }
-  __syncwarp();
+  G::sync();
 }
 
 // (3) One warp: the heuristic candidate list S.aux[0..nHeur) of visit v, and what rs_visit_finish needs (S.vis).
-template <bool SMEMC = false, bool MAPS, int NB>
+template <bool SMEMC = false, int LW = 32, bool MAPS, int NB>
 __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS, NB> &S, Visit &V,
-                                                    const uint32_t v, const uint32_t K, const CorpusSmem &cs = CorpusSmem()) {
-  const unsigned lane = threadIdx.x & 31u;
+                                                    const uint32_t v, const uint32_t K, const CorpusSmem &cs = CorpusSmem(),
+                                                    const bool on = true) {  // (a group without a visit comes with K = 0)
+  typedef Grp<LW> G;
+  const unsigned lane = G::lane();
   const unsigned lt = (1u << lane) - 1u;
   const uint32_t pass = J.pass;
   const uint32_t tag = (pass + 1u) << 29;
@@ -831,11 +861,12 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
   const uint32_t epoch_idx = rs_epoch_of(J, v), epoch0 = epoch_idx * J.epoch_len;
   const uint32_t hide_from = epoch_idx ? epoch0 - J.epoch_len : 0u;  // stamps of my pass from here on are hidden
   const uint32_t hide_base = tag | hide_from;
-  constexpr int NR = NB > 32 ? 2 : 1;  // rounds of 32 neighbours
+  constexpr int NR = NB > LW ? 2 : 1;  // rounds of LW neighbours
+  static_assert(NB <= 2 * LW, "a group covers the patch in at most two rounds");
   uint32_t mycand[2];
 #pragma unroll
   for (int rnd = 0; rnd < NR; rnd++) {
-    const uint32_t k = lane + 32u * rnd;
+    const uint32_t k = lane + (unsigned)LW * rnd;
     uint32_t c = RS_NO_SRC;
     if (k < K) {
       const uint32_t src = S.aux[k];
@@ -850,17 +881,18 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
       }
     }
     mycand[rnd] = c;
-    S.q[k] = c;
+    if (on) S.q[k] = c;
   }
-  __syncwarp();
+  G::sync();
   bool pskip[2] = {false, false};
+  bool look = true;  // this group (re)reads the stamps in this attempt
   for (int attempt = 0; attempt < 2; attempt++) {
     bool any = false;
 #pragma unroll
     for (int rnd = 0; rnd < NR; rnd++) {
       const uint32_t c = mycand[rnd];
-      pskip[rnd] = false;
-      if (c != RS_NO_SRC) {
+      if (look) pskip[rnd] = false;
+      if (look && c != RS_NO_SRC) {
         const size_t a = (size_t)(c >> 16) * J.cw + (c & 0xFFFFu);
         uint32_t newest = 0u;
         const ulonglong2 e01 = rs_ld_state2(J.prober + 4 * a);  // the three arrays' words of one corpus pixel share a sector
@@ -875,38 +907,39 @@ __device__ __forceinline__ void rs_visit_candidates(const RsDev &J, RsCtrl *ctrl
         any |= pskip[rnd];
       }
     }
-    if (attempt == 1 || hide_from == 0u || !__any_sync(RS_FULL, any)) break;
-    if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
-    __syncwarp();
+    look = attempt == 0 && hide_from != 0u && G::any(any);  // a skip verdict that the epochs still running could overturn
+    if (!G::any_group(look)) break;
+    if (look && lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
+    G::sync();
   }
   uint32_t nHeur = 0, nSkips = 0;
 #pragma unroll
   for (int rnd = 0; rnd < NR; rnd++) {
-    const uint32_t k = lane + 32u * rnd;
+    const uint32_t k = lane + (unsigned)LW * rnd;
     const uint32_t c = mycand[rnd];
     bool valid = (c != RS_NO_SRC);
     if (rnd == 0) {  // an earlier neighbour proposing the same point: lanes are neighbours here, one MATCH finds them
-      const unsigned same = __match_any_sync(RS_FULL, c);
+      const unsigned same = G::match_any(c);
       if (pskip[0] || (same & lt)) valid = false;
     } else if (valid) {
       bool skip = pskip[rnd];
       for (uint32_t k2 = 0; k2 < k && !skip; k2++) skip = (S.q[k2] == c);
       if (skip) valid = false;
     }
-    const unsigned b = __ballot_sync(RS_FULL, valid);
-    nSkips += __popc(__ballot_sync(RS_FULL, c != RS_NO_SRC)) - __popc(b);
+    const unsigned b = G::ballot(valid);
+    nSkips += __popc(G::ballot(c != RS_NO_SRC)) - __popc(b);
     if (valid) S.aux[nHeur + __popc(b & lt)] = c;  // sources in S.aux are no longer needed (mycand holds mine)
     nHeur += __popc(b);
-    __syncwarp();
+    G::sync();
   }
   V.v = v; V.K = K; V.nHeur = nHeur;
-  if (lane == 0) {
+  if (lane == 0 && on) {
     S.vis.epoch_idx = epoch_idx; S.vis.hide_from = hide_from;
     S.vis.my_base = tag | epoch0;
     S.st.visits++;
     S.st.skips += nSkips;
   }
-  __syncwarp();
+  G::sync();
 }
 
 // One warp: merge the stamps of visit v into the recentProber array of its epoch (c0/c1: this lane's candidates
@@ -947,18 +980,19 @@ __device__ __forceinline__ void rs_visit_stamps(const RsDev &J, RsCtrl *ctrl, co
 // hcol[i] = colour of heuristic candidate i (fetched with its first chunk).  For a winning probe: win_pt = its corpus
 // point if the distance phase tracked it (else RS_NO_SRC: looked up from the probe's index), win_col = its colour if
 // have_col (else fetched here).
-template <bool STAMPS = true, bool SMEMC = false, bool MAPS, int NB>
+template <bool STAMPS = true, bool SMEMC = false, int LW = 32, bool MAPS, int NB>
 __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, WarpScratch<MAPS, NB> &S, const Visit &V,
                                                 uint32_t bestSum, int bestIdx, uint32_t win_pt, uint32_t win_col,
-                                                bool have_col, const CorpusSmem &cs = CorpusSmem()) {
-  const unsigned lane = threadIdx.x & 31u;
-  const uint32_t pass = J.pass, v = V.v, nHeur = V.nHeur;
+                                                bool have_col, const CorpusSmem &cs = CorpusSmem(), const bool on = true) {
+  typedef Grp<LW> G;
+  const unsigned lane = G::lane();
+  const uint32_t pass = J.pass, v = V.v, nHeur = on ? V.nHeur : 0u;
   const uint32_t *candlist = S.aux, *hcol = S.q;
   const uint32_t epoch_idx = S.vis.epoch_idx, my_base = S.vis.my_base;
   const bool bettered = bestIdx != 0x7FFFFFFF;
   const uint32_t total = nHeur + J.probes;
   const uint32_t seq_evals = !bettered ? 0u : (bestSum == 0u ? (uint32_t)bestIdx + 1u : total);
-  if (lane == 0) {  // new colour + source only if the source changed; the new version is always published
+  if (lane == 0 && on) {  // new colour + source only if the source changed; the new version is always published
     const unsigned long long selfw = S.vis.selfw;
     uint32_t colour = (uint32_t)selfw & 0xFFFFFFu, src = (uint32_t)(selfw >> 32);
     if (bettered) {
@@ -994,11 +1028,12 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
     // ---- heuristic 2 bookkeeping: stamp the evaluated heuristic candidates before the perfect one, if any
     const uint32_t tag = (pass + 1u) << 29;
     const uint32_t stampEnd = (bettered && bestSum == 0u && (uint32_t)bestIdx < nHeur) ? (uint32_t)bestIdx : nHeur;
-    if (stampEnd > 0u && S.vis.hide_from > 0u) {  // one writing epoch per array: epochs <= e-2 must be complete
-      if (lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
-      __syncwarp();
+    const bool wait = on && stampEnd > 0u && S.vis.hide_from > 0u;  // one writing epoch per array: epochs <= e-2 must be complete
+    if (G::any_group(wait)) {
+      if (wait && lane == 0) rs_wait_epochs(J, ctrl, epoch_idx);
+      G::sync();
     }
-    for (uint32_t i = lane; i < stampEnd; i += 32) {
+    for (uint32_t i = lane; i < stampEnd; i += LW) {
       const uint32_t c = candlist[i];
       unsigned long long *pp = J.prober + 4 * ((size_t)(c >> 16) * J.cw + (c & 0xFFFFu)) + epoch_idx % 3u;
       const uint32_t stp = tag | v;
@@ -1013,13 +1048,27 @@ __device__ __forceinline__ void rs_visit_finish(const RsDev &J, RsCtrl *ctrl, Wa
         old = prev;
       }
     }
-    __syncwarp();
+    G::sync();
     // publish: this visit is complete (its stamps were merged by CAS operations that have returned)
-    if (lane == 0)
+    if (lane == 0 && on)
       asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(&ctrl->epoch_done[pass][epoch_idx].v) : "memory");
   }
 }
 
+// One lane: the counters a scratch has collected, into the job's.
+__device__ __forceinline__ void rs_flush_warp_stats(const RsDev &J, RsCtrl *ctrl, const WarpStats *ws) {
+  if (!ws->visits) return;
+  const uint32_t pass = J.pass;
+  atomicAdd(&ctrl->visits, (unsigned long long)ws->visits);
+  atomicAdd(&ctrl->pass_visits[pass], (unsigned long long)ws->visits);
+  atomicAdd(&ctrl->evals, ws->evals);
+  atomicAdd(&ctrl->offset_scans, (unsigned long long)ws->scans);
+  atomicAdd(&ctrl->heur_evals, (unsigned long long)ws->heur);
+  atomicAdd(&ctrl->heur_skips, (unsigned long long)ws->skips);
+  atomicAdd(&ctrl->perfect, (unsigned long long)ws->perfect);
+  atomicAdd(&ctrl->sum_best[pass], ws->sumbest);
+  atomicAdd(&ctrl->betters[pass], ws->betters);
+}
 // Whole CTA, at kernel end: flush the per-warp counters; the last CTA out decides whether later passes run
 // (lib/refiner.h:111): (float)betters/n < 0.1.
 __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, LaneStats &ls, const WarpStats *ws) {
@@ -1031,17 +1080,7 @@ __device__ __forceinline__ void rs_pass_epilogue(const RsDev &J, RsCtrl *ctrl, L
     atomicAdd(&ctrl->evals_issued, (unsigned long long)ls.issued);
     atomicAdd(&ctrl->compares, (unsigned long long)ls.compares);
   }
-  if (lane == 0 && ws != nullptr && ws->visits) {  // ws: the counters of the warp that prepared and committed visits
-    atomicAdd(&ctrl->visits, (unsigned long long)ws->visits);
-    atomicAdd(&ctrl->pass_visits[pass], (unsigned long long)ws->visits);
-    atomicAdd(&ctrl->evals, ws->evals);
-    atomicAdd(&ctrl->offset_scans, (unsigned long long)ws->scans);
-    atomicAdd(&ctrl->heur_evals, (unsigned long long)ws->heur);
-    atomicAdd(&ctrl->heur_skips, (unsigned long long)ws->skips);
-    atomicAdd(&ctrl->perfect, (unsigned long long)ws->perfect);
-    atomicAdd(&ctrl->sum_best[pass], ws->sumbest);
-    atomicAdd(&ctrl->betters[pass], ws->betters);
-  }
+  if (lane == 0 && ws != nullptr) rs_flush_warp_stats(J, ctrl, ws);  // ws: the counters of the warp that prepared and committed visits
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -1115,20 +1154,26 @@ __device__ __forceinline__ PassSmem rs_pass_smem(const RsDev &J, unsigned char *
 // ---- throughput mode: one warp per visit -------------------------------------------------------------------
 // SMEMC: the corpus (no map channels) lives in the shared memory of the CTA, or of the two CTAs of its cluster; the launch
 // passes the slice length in J.sc_slice (pixels per CTA, a multiple of 4) and sizes the dynamic shared memory for it.
-template <bool MAPS, int CH, int NB, bool SMEMC>
+// LW: lanes that prepare and commit a visit.  32 = one visit per warp.  16 (patches of at most 16 neighbours) = TWO visits per
+// warp, consecutive ones, side by side in its halves through geometry, values, candidates and commit -- the steps that
+// leave most lanes of a warp idle when a patch has 9 neighbours -- and one after the other, with all 32 lanes, through
+// the distance loop.  Should the second visit's patch hold the first visit's pixel it runs after it instead of beside it.
+template <bool MAPS, int CH, int NB, bool SMEMC, int LW>
 __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass(const RsDev J) {
+  constexpr int NV = 32 / LW;  // visits a warp works on at once
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
   const bool stopped = rs_ld_u32_relaxed(&ctrl->stop) != 0u;
   if (!SMEMC && stopped) return;  // (a cluster leaves together: both CTAs go through the two cluster barriers below)
-  const PassSmem P = rs_pass_smem<MAPS, NB, RS_TP_WARPS>(J, smem_raw);
+  const PassSmem P = rs_pass_smem<MAPS, NB, RS_TP_WARPS * NV>(J, smem_raw);
   const unsigned lutc = P.lutc, lutm = P.lutm;
-  WarpScratch<MAPS, NB> &S = reinterpret_cast<WarpScratch<MAPS, NB> *>(P.scratch)[threadIdx.x >> 5];
-  const unsigned lane = threadIdx.x & 31u;
+  WarpScratch<MAPS, NB> *Sw = reinterpret_cast<WarpScratch<MAPS, NB> *>(P.scratch) + (threadIdx.x >> 5) * NV;  // this warp's scratches
+  const unsigned lane = threadIdx.x & 31u, grp = NV == 1 ? 0u : lane / (unsigned)LW;
+  WarpScratch<MAPS, NB> &Sg = Sw[grp];  // my group's
   CorpusSmem cs;
   if (SMEMC) {
     // this CTA's slice of the canonical corpus (sentinel pixel included) -> shared memory, by TMA bulk copies
-    uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw + ((pass_smem_bytes<MAPS, NB>(RS_TP_WARPS) + 127u) & ~127u));
+    uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw + ((pass_smem_bytes<MAPS, NB>(RS_TP_WARPS * NV) + 127u) & ~127u));
     const unsigned rank = rs_cluster_ctarank(), nr = rs_cluster_nctarank();
     const uint32_t first = rank * J.sc_slice, total = J.cn + 1u;
     const uint32_t count = first < total ? min(J.sc_slice, total - first) : 0u;
@@ -1151,56 +1196,79 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
     cs.split = nr > 1u ? J.sc_slice : 0xFFFFFFFFu;
   }
   LaneStats st;
-  Visit V;
-  if (lane == 0) S.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
+  if (Grp<LW>::lane() == 0) Sg.st = WarpStats{0ull, 0ull, 0u, 0u, 0u, 0u, 0u, 0u};
   const bool regular = J.regular_r != 0u && ctrl->n_ctx.v + J.nT == (uint32_t)J.tw * (uint32_t)J.th;  // no unusable pixel anywhere
-  uint32_t v = stopped ? J.seg_end : rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
-  uint32_t tpos = (v < J.seg_end) ? __ldg(J.targets + v) : 0u;
-  while (v < J.seg_end) {
-    {
-      const uint32_t Kv = rs_visit_geometry<CH>(J, S, v, tpos, regular);
-      rs_visit_values(J, S, v, Kv);
-      rs_visit_candidates<SMEMC>(J, ctrl, S, V, v, Kv, cs);
-    }
-    // ---- evaluate: heuristic candidates first, then the random probes (lib/synthesize.h:583-604)
-    uint32_t bestSum = 0xFFFFFFFFu, bestLin = RS_NO_SRC;
-    int bestIdx = 0x7FFFFFFF, bestCx = 0;
-    uint32_t *hsum = S.off;  // offsets are dead by now (WarpScratch)
-    uint32_t *hcol = S.q;    // so are the per-neighbour candidates: colour of each heuristic candidate
-    const uint32_t nHeur = V.nHeur, pass = J.pass, seed = J.seed, nC = ctrl->n_corpus, K = V.K;
-    const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
-    // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
-    // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
-    if (nHeur) {
-      const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = c_inv32[nch];
-      hsum[lane] = 0u;        // (nHeur <= NB <= 64: two slots per lane cover every candidate)
-      if (NB > 32) hsum[lane + 32u] = 0u;
+  const uint32_t pass = J.pass, seed = J.seed, nC = ctrl->n_corpus;
+  uint32_t v0 = stopped ? J.seg_end : rs_claim_resolve<NV>(J, ctrl, rs_claim_issue<NV>(J, ctrl));
+  while (v0 < J.seg_end) {
+    const uint32_t vg = v0 + grp;  // my group's visit
+    const bool valid = vg < J.seg_end;
+    const uint32_t Kg = rs_visit_geometry<CH, LW>(J, Sg, vg, valid ? __ldg(J.targets + vg) : 0u, regular, valid);
+    bool dep = false;
+    if (NV > 1) {  // does the second visit read the pixel of the first?  (then it has to see its new value)
       __syncwarp();
-      for (uint32_t t = lane; t < nHeur * nch; t += 32) {
-        const uint32_t ci = nch > 1u ? __umulhi(t, inv) : t, j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
-        atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH, NB, SMEMC>(J, lutc, lutm, S, hcol, K, ci, j, st, cs));
+      const unsigned k = Grp<LW>::lane();
+      dep = __any_sync(RS_FULL, grp == 1u && valid && k >= 1u && k < Kg && Sg.q[k] == Sw[0].vis.selfq);
+    }
+    for (unsigned round = 0; round < (dep ? 2u : 1u); round++) {
+      const bool act = valid && (NV == 1 || !dep || grp == round);
+      Visit V;
+      V.v = vg; V.K = Kg; V.nHeur = 0u;
+      rs_visit_values<LW>(J, Sg, vg, act ? Kg : 0u);
+      rs_visit_candidates<SMEMC, LW>(J, ctrl, Sg, V, vg, act ? Kg : 0u, cs, act);
+      V.K = Kg;
+      // ---- evaluate, all 32 lanes on one visit at a time: heuristic candidates first, then the random probes
+      //      (lib/synthesize.h:583-604)
+      uint32_t gSum = 0xFFFFFFFFu, gWin = RS_NO_SRC;
+      int gIdx = 0x7FFFFFFF;
+#pragma unroll 1
+      for (unsigned x = 0; x < (unsigned)NV; x++) {
+        if (NV > 1 && !__shfl_sync(RS_FULL, (int)act, (int)(x * LW))) continue;
+        WarpScratch<MAPS, NB> &S = Sw[x];
+        const uint32_t v = v0 + x;
+        const uint32_t K = NV == 1 ? Kg : __shfl_sync(RS_FULL, Kg, (int)(x * LW));
+        const uint32_t nHeur = NV == 1 ? V.nHeur : __shfl_sync(RS_FULL, V.nHeur, (int)(x * LW));
+        uint32_t bestSum = 0xFFFFFFFFu, bestLin = RS_NO_SRC;
+        int bestIdx = 0x7FFFFFFF, bestCx = 0;
+        uint32_t *hsum = S.off;  // offsets are dead by now (WarpScratch)
+        uint32_t *hcol = S.q;    // so are the per-neighbour candidates: colour of each heuristic candidate
+        const uint32_t hv = rs_probe_hash_visit(seed, pass, v);  // the two visit-constant rounds of rs_probe_hash
+        // Heuristic candidates (few, and the likely winners): every (candidate, chunk) pair gets a lane, so all lanes
+        // work instead of nHeur of them; full sums, then "first candidate with the minimum sum" as ever.
+        if (nHeur) {
+          const uint32_t nchr = (K + CH - 2u) / CH, nch = nchr ? nchr : 1u, inv = c_inv32[nch];
+          hsum[lane] = 0u;        // (nHeur <= NB <= 64: two slots per lane cover every candidate)
+          if (NB > 32) hsum[lane + 32u] = 0u;
+          __syncwarp();
+          for (uint32_t t = lane; t < nHeur * nch; t += 32) {
+            const uint32_t ci = nch > 1u ? __umulhi(t, inv) : t, j = t - ci * nch;  // t / nch, exact while t * nch < 2^32
+            atomicAdd(&hsum[ci], rs_heur_pair<MAPS, CH, NB, SMEMC>(J, lutc, lutm, S, hcol, K, ci, j, st, cs));
+          }
+          __syncwarp();
+          const uint32_t h0 = lane < nHeur ? hsum[lane] : 0xFFFFFFFFu, h1 = (NB > 32 && lane + 32u < nHeur) ? hsum[lane + 32u] : 0xFFFFFFFFu;
+          const uint32_t msum = __reduce_min_sync(RS_FULL, min(h0, h1));
+          const int midx = __reduce_min_sync(RS_FULL, (h0 == msum) ? (int)lane : ((h1 == msum) ? (int)lane + 32 : 0x7FFFFFFF));
+          bestSum = msum;
+          bestIdx = midx;
+        }
+        if (bestSum != 0u)
+          rs_eval_range<MAPS, CH, SMEMC>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
+                              [&](int i) { return rs_corpus_point(J, nC, rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
+                              bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued, cs);
+        if (NV == 1 || grp == x) {
+          gSum = bestSum;
+          gIdx = bestIdx;
+          gWin = bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC;
+        }
       }
-      __syncwarp();
-      const uint32_t h0 = lane < nHeur ? hsum[lane] : 0xFFFFFFFFu, h1 = (NB > 32 && lane + 32u < nHeur) ? hsum[lane + 32u] : 0xFFFFFFFFu;
-      const uint32_t msum = __reduce_min_sync(RS_FULL, min(h0, h1));
-      const int midx = __reduce_min_sync(RS_FULL, (h0 == msum) ? (int)lane : ((h1 == msum) ? (int)lane + 32 : 0x7FFFFFFF));
-      bestSum = msum;
-      bestIdx = midx;
+      rs_visit_finish<true, SMEMC, LW>(J, ctrl, Sg, V, gSum, gIdx, gWin, 0u, false, cs, act);
+      if (NV > 1) __syncwarp();
     }
-    if (bestSum != 0u)
-      rs_eval_range<MAPS, CH, SMEMC>(J, lutc, lutm, S.nb, S.map, K, (int)nHeur, (int)(nHeur + J.probes),
-                          [&](int i) { return rs_corpus_point(J, nC, rs_range(rs_mix32(hv + ((uint32_t)i - nHeur) * 0xC2B2AE35u), nC)); },
-                          bestSum, bestIdx, bestLin, bestCx, st.compares, st.issued, cs);
-    rs_visit_finish<true, SMEMC>(J, ctrl, S, V, bestSum, bestIdx,
-                          bestLin != RS_NO_SRC ? ((uint32_t)bestCx | (((bestLin - (uint32_t)bestCx) / (uint32_t)J.cw) << 16)) : RS_NO_SRC,
-                          0u, false, cs);
-    const uint32_t v_next = rs_claim_resolve(J, ctrl, rs_claim_issue(J, ctrl));
-    const uint32_t tpos_next = (v_next < J.seg_end) ? __ldg(J.targets + v_next) : 0u;
-    v = v_next;
-    tpos = tpos_next;
+    v0 = rs_claim_resolve<NV>(J, ctrl, rs_claim_issue<NV>(J, ctrl));
   }
   __syncwarp();
-  if (!SMEMC || !stopped) rs_pass_epilogue(J, ctrl, st, &S.st);
+  if (NV > 1 && (!SMEMC || !stopped) && lane == 0) rs_flush_warp_stats(J, ctrl, &Sw[1].st);
+  if (!SMEMC || !stopped) rs_pass_epilogue(J, ctrl, st, &Sw[0].st);
   if (SMEMC) rs_cluster_sync();  // nobody leaves while its peer may still read its slice
 }
 
@@ -1433,6 +1501,11 @@ struct PassVariant {
   void (*tp_smemc)(const RsDev) = nullptr;              // k_synth_pass<false, chunk, nb, true>: corpus in shared memory
   size_t smemc_base = 0;                                // dynamic shared memory before the corpus slice
   uint32_t smemc_slice_max = 0;                         // pixels a CTA's slice can hold
+  // two visits per warp (patches of at most RS_NB_SMALL neighbours): k_synth_pass<..., 16>
+  void (*tp_pair)(const RsDev) = nullptr;
+  void (*tp_pair_smemc)(const RsDev) = nullptr;
+  size_t smem_tp_pair = 0, smemc_base_pair = 0;
+  uint32_t smemc_slice_max_pair = 0;
 };
 struct Workspace {
   int device = 0;
@@ -1521,14 +1594,41 @@ static size_t pass_smem(bool maps, int scratch_slots, bool nb_full = true) {
 }
 // The instantiations of the two pass kernels: map channels x chunk size x scratch size (index = rs_variant()).
 static int rs_variant(bool maps, bool chunk_large, bool nb_full) { return (maps ? 4 : 0) + (chunk_large ? 2 : 0) + (nb_full ? 1 : 0); }
+template <int CH, int NB>
+static int configure_pair_smemc(PassVariant &V, size_t smem_max) {
+  V.tp_pair_smemc = k_synth_pass<false, CH, NB, true, 16>;
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<false, CH, NB, true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  return 0;
+}
+// The two-visits-per-warp instantiations exist for the small-patch scratch only (a half warp covers 16 neighbours).
+template <bool MAPS, int CH, int NB>
+static typename std::enable_if<(NB > 16), int>::type configure_pair_kernel(Workspace *, PassVariant &, size_t) { return 0; }
+template <bool MAPS, int CH, int NB>
+static typename std::enable_if<(NB <= 16), int>::type configure_pair_kernel(Workspace *w, PassVariant &V, size_t sm_max) {
+  const size_t smem = pass_smem(MAPS, RS_TP_WARPS * 2, false);
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int carve = (int)std::min<size_t>(100, ((smem + 1024) * 100 + sm_max - 1) / sm_max);
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+  V.tp_pair = k_synth_pass<MAPS, CH, NB, false, 16>;
+  V.smem_tp_pair = smem;
+  if (!MAPS) {
+    const size_t smem_max = 232448;  // 227 KB per CTA on sm_100
+    const size_t base = (smem + 127) & ~(size_t)127;
+    configure_pair_smemc<CH, NB>(V, smem_max);
+    V.smemc_base_pair = base;
+    V.smemc_slice_max_pair = (uint32_t)(((smem_max - base) / 4) & ~(size_t)3);
+  }
+  (void)w;
+  return 0;
+}
 template <bool MAPS, int CH, int NB>
 static int configure_pass_kernel(Workspace *w) {
   const bool full = NB == RS_NB_FULL;
   const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS, full), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS, full);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
   int per_sm = 0, per_sm_team = 0, sms = 0;
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB, false>, RS_TP_WARPS * 32, smem_tp));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB, false, 32>, RS_TP_WARPS * 32, smem_tp));
   RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS, CH, NB>, RS_TEAM_WARPS * 32, smem_team));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
   if (per_sm < 1 || per_sm_team < 1) { g_err = "the pass kernels do not fit on an SM"; return 100; }
@@ -1537,10 +1637,10 @@ static int configure_pass_kernel(Workspace *w) {
   const size_t sm_max = 233472;
   const int carve_tp = (int)std::min<size_t>(100, ((smem_tp + 1024) * per_sm * 100 + sm_max - 1) / sm_max);
   const int carve_team = (int)std::min<size_t>(100, ((smem_team + 1024) * per_sm_team * 100 + sm_max - 1) / sm_max);
-  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_tp));
+  RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_tp));
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_team));
   PassVariant &V = w->variant[rs_variant(MAPS, CH == RS_CHUNK_LARGE, full)];
-  V.tp = k_synth_pass<MAPS, CH, NB, false>;
+  V.tp = k_synth_pass<MAPS, CH, NB, false, 32>;
   V.team = k_synth_pass_team<MAPS, CH, NB>;
   V.smem_tp = smem_tp; V.smem_team = smem_team;
   V.grid = per_sm * sms; V.grid_team = per_sm_team * sms;
@@ -1548,11 +1648,12 @@ static int configure_pass_kernel(Workspace *w) {
   if (!MAPS) {  // the corpus-in-shared-memory instantiation: one CTA per SM, everything the SM has left goes to the slice
     const size_t smem_max = 232448;  // 227 KB per CTA on sm_100
     const size_t base = (smem_tp + 127) & ~(size_t)127;
-    V.tp_smemc = k_synth_pass<false, CH, NB, true>;
+    V.tp_smemc = k_synth_pass<false, CH, NB, true, 32>;
     V.smemc_base = base;
     V.smemc_slice_max = (uint32_t)(((smem_max - base) / 4) & ~(size_t)3);
-    RS_CHECK(cudaFuncSetAttribute(k_synth_pass<false, CH, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    RS_CHECK(cudaFuncSetAttribute(k_synth_pass<false, CH, NB, true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   }
+  if (int rc = configure_pair_kernel<MAPS, CH, NB>(w, V, sm_max)) return rc;
   return 0;
 }
 
@@ -2692,14 +2793,24 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     }
     if (const char *e = getenv("RS_GRID_CAP")) { const int c = atoi(e); if (c > 0 && c < grid) grid = c; if (c > 0 && c < grid_team) grid_team = c; }
   }
-  const size_t smem_tp = PV.smem_tp, smem_team = PV.smem_team;
+  // Patches of at most RS_NB_SMALL neighbours in a shuffled order: two visits per warp (k_synth_pass<..., 16>).  A spatially
+  // sorted order puts consecutive visits next to each other -- the second of a pair would wait for the first every time.
+  bool pair = !nb_full && PV.tp_pair != nullptr && !j->d.ordered_visits;
+  if (const char *e = getenv("RS_PAIR")) {  // 0: one visit per warp; 2: pairs for sorted orders too (tests: every pair is dependent)
+    const int f = atoi(e);
+    pair = f == 2 ? (!nb_full && PV.tp_pair != nullptr) : (pair && f != 0);
+  }
+  uint32_t pair_from = 262144u;
+  if (const char *e = getenv("RS_PAIR_FROM")) pair_from = (uint32_t)strtoul(e, nullptr, 10);  // sweeps
+  const size_t smem_team = PV.smem_team;
   // Corpus on chip (throughput kernel, no map channels): whole in one CTA's shared memory when it fits, else split over the
   // two CTAs of a cluster.  RS_SMEM_CORPUS=0 keeps it in L2; =1/2 forces the cluster size (tests).
   int smemc_ctas = 0, grid_smemc = grid < PV.sms ? grid : PV.sms;
   uint32_t smemc_slice = 0;
   if (!j->maps && PV.tp_smemc != nullptr) {
     const uint32_t total = (uint32_t)j->d.cw * (uint32_t)j->d.ch + 1u;  // pixels + the sentinel
-    int want = total <= PV.smemc_slice_max ? 1 : (total <= 2u * PV.smemc_slice_max ? 2 : 0);
+    const uint32_t slice_max = pair ? PV.smemc_slice_max_pair : PV.smemc_slice_max;
+    int want = total <= slice_max ? 1 : (total <= 2u * slice_max ? 2 : 0);
     if (const char *e = getenv("RS_SMEM_CORPUS")) {
       const int f = atoi(e);
       if (f == 0) want = 0;
@@ -2774,31 +2885,47 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     RsDev D = make_dev(j, p);
     Segment seg[4];
     const int nseg = plan_segments(j->nT, j->d.pass_end[p], j->d.ordered_visits, j->d.patch_size, p, seg);
-    uint32_t begin = 0;
-    j->pass_launches[p] = (uint32_t)nseg;
-    for (int k = 0; k < nseg; k++) {
-      D.seg_begin = begin; D.seg_end = seg[k].end; D.slot = slot++; D.last_seg = (k == nseg - 1) ? 1u : 0u;
-      const unsigned W = seg[k].width;
+    uint32_t begin = 0, n_launched = 0;
+    // one launch: the visits [b, e) of the pass at W warps per visit (W <= 1: the throughput kernel, one visit per warp or two)
+    auto launch = [&](uint32_t b, uint32_t e, unsigned W, bool two, bool last) -> int {
+      D.seg_begin = b; D.seg_end = e; D.slot = slot++; D.last_seg = last ? 1u : 0u;
       D.chunk = large ? RS_CHUNK_LARGE : RS_CHUNK_SMALL;
+      n_launched++;
       if (W <= 1 && smemc_ctas) {  // corpus staged into the shared memory of a CTA or of a 2-CTA cluster
         D.sc_slice = smemc_slice;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(grid_smemc / smemc_ctas * smemc_ctas), 1, 1);
         cfg.blockDim = dim3(RS_TP_WARPS * 32, 1, 1);
-        cfg.dynamicSmemBytes = PV.smemc_base + (size_t)smemc_slice * 4 + 16;
+        cfg.dynamicSmemBytes = (two ? PV.smemc_base_pair : PV.smemc_base) + (size_t)smemc_slice * 4 + 16;
         cfg.stream = s;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)smemc_ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        RS_CHECK(cudaLaunchKernelEx(&cfg, PV.tp_smemc, D));
+        RS_CHECK(cudaLaunchKernelEx(&cfg, two ? PV.tp_pair_smemc : PV.tp_smemc, D));
       } else if (W <= 1) {
-        PV.tp<<<grid, RS_TP_WARPS * 32, smem_tp, s>>>(D);
+        (two ? PV.tp_pair : PV.tp)<<<grid, RS_TP_WARPS * 32, two ? PV.smem_tp_pair : PV.smem_tp, s>>>(D);
       } else {
         PV.team<<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
       }
+      return 0;
+    };
+    for (int k = 0; k < nseg; k++) {
+      const unsigned W = seg[k].width;
+      const bool last = k == nseg - 1;
+      // Two visits per warp double the visits in flight; while pass 0 is young a visit's neighbours are often among them,
+      // and a warp then waits with both of its visits (cfg2: pass 0 2.00 -> 2.13 ms with pairs throughout).  Pairs from
+      // visit pair_from on, where a neighbour in flight has become rare.
+      if (W <= 1 && pair && p == 0 && begin < pair_from) {
+        const uint32_t mid = seg[k].end < pair_from ? seg[k].end : pair_from;
+        if (int rc = launch(begin, mid, W, false, last && mid == seg[k].end)) return rc;
+        if (mid < seg[k].end) { if (int rc = launch(mid, seg[k].end, W, true, last)) return rc; }
+      } else {
+        if (int rc = launch(begin, seg[k].end, W, pair, last)) return rc;
+      }
       begin = seg[k].end;
     }
+    j->pass_launches[p] = n_launched;
   }
   j->launches = slot;
   RS_CHECK(cudaGetLastError());

@@ -188,6 +188,21 @@ def test_pass0_patches_by_scan(built_oracle, built_lib, monkeypatch, kind):
     _check(kind)
 
 
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("kind", ["texture9", "texture9_tiled", "maps9", "texture9_htile", "gray16"])
+def test_two_visits_per_warp(built_oracle, built_lib, monkeypatch, kind, mode):
+    """k_synth_pass<..., 16>: patches of at most 16 neighbours run TWO consecutive visits per warp, side by side in its
+    halves through geometry / values / candidates / commit and one after the other through the distance loop; a second
+    visit whose patch holds the first one's pixel runs after it.  RS_PAIR=0: one visit per warp; 1: the default; 2: pairs
+    for spatially sorted orders too (gray16 visits by rows... every second visit then depends on the first)."""
+    monkeypatch.setenv("RS_PAIR", mode)
+    monkeypatch.setenv("RS_TEAM_P0", "1")
+    monkeypatch.setenv("RS_TEAM_PN", "1")
+    _check(kind)
+    monkeypatch.setenv("RS_SMEM_CORPUS", "2")
+    _check(kind)
+
+
 @pytest.mark.parametrize("width", [1, 2, 4, 8])
 def test_later_lists_with_every_width(built_oracle, built_lib, monkeypatch, width):
     monkeypatch.setenv("RS_LATER_LISTS_MIN", "1")
