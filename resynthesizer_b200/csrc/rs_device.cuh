@@ -339,9 +339,9 @@ __device__ __forceinline__ uint32_t rs_lut3(unsigned col, uint32_t d) {
 // The two halves of a chunk, usable apart: the gathers need only the patch GEOMETRY (lin, dx of the records), the
 // table lookups need the neighbour colours.  The team kernel issues the gathers of a visit's probes while the visit
 // is still waiting for its neighbours to be synthesised.
-template <bool MAPS, int CH>
+template <bool MAPS, int CH, bool SMEMC = false>
 __device__ __forceinline__ void rs_chunk_gather(const RsDev &J, const RsNb *nb, int cx, uint32_t clin, uint32_t k0,
-                                                uint32_t (&cp)[CH], uint32_t (&cm)[CH]) {
+                                                uint32_t (&cp)[CH], uint32_t (&cm)[CH], const CorpusSmem &cs = CorpusSmem()) {
 #pragma unroll
   for (int u = 0; u < CH; u++) {
     const int2 g = *reinterpret_cast<const int2 *>(&nb[k0 + u]);  // lin, dx
@@ -353,7 +353,7 @@ __device__ __forceinline__ void rs_chunk_gather(const RsDev &J, const RsNb *nb, 
       cp[u] = t.x;
       cm[u] = t.y;
     } else {
-      cp[u] = __ldg(J.corpus4 + a);
+      cp[u] = rs_corpus4<SMEMC>(J, cs, a);
       cm[u] = 0u;
     }
   }
