@@ -552,6 +552,20 @@ __global__ void __launch_bounds__(RS_SPARSE_WARPS * 32) k_gather_pass0_sparse(co
 #ifndef RS_TP_MIN_CTAS
 #define RS_TP_MIN_CTAS 1
 #endif
+// The instantiation for large patches without map channels (the heal / inpaint jobs) compiles to 48 registers without a
+// spill, so TWO CTAs of 20 warps fit an SM: 40 warps to hide the gathers' latency behind instead of 32 (cfg3 48.7 -> 45.8
+// ms).  Not for the others: with map channels a second CTA doubles 64 KB of tables and takes the L1 with it (cfg4 46.5 ->
+// 61.3), the small-patch kernels lose the same way (cfg2 3.49 -> 4.53), a corpus slice leaves room for one CTA only, and
+// 2 x 24 warps at 40 registers spill (cfg3 56.1).
+#ifndef RS_TP_SPLIT_WARPS
+#define RS_TP_SPLIT_WARPS 20
+#endif
+template <bool MAPS, int NB, bool SMEMC, int LW>
+struct TpShape {
+  static constexpr bool split = !MAPS && NB > 16 && !SMEMC && LW == 32 && RS_TP_WARPS == 32 && RS_TP_MIN_CTAS == 1;
+  static constexpr int warps = split ? RS_TP_SPLIT_WARPS : RS_TP_WARPS;
+  static constexpr int ctas = split ? 2 : RS_TP_MIN_CTAS;
+};
 #define RS_TEAM_WARPS 16
 #define RS_TEAM_SLOTS 8
 #define RS_BF_WARPS 16
@@ -1159,13 +1173,14 @@ __device__ __forceinline__ PassSmem rs_pass_smem(const RsDev &J, unsigned char *
 // leave most lanes of a warp idle when a patch has 9 neighbours -- and one after the other, with all 32 lanes, through
 // the distance loop.  Should the second visit's patch hold the first visit's pixel it runs after it instead of beside it.
 template <bool MAPS, int CH, int NB, bool SMEMC, int LW>
-__global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass(const RsDev J) {
+__global__ void __launch_bounds__(TpShape<MAPS, NB, SMEMC, LW>::warps * 32, TpShape<MAPS, NB, SMEMC, LW>::ctas) k_synth_pass(const RsDev J) {
   constexpr int NV = 32 / LW;  // visits a warp works on at once
+  constexpr int TPW = TpShape<MAPS, NB, SMEMC, LW>::warps;  // warps of this CTA
   extern __shared__ __align__(128) unsigned char smem_raw[];
   RsCtrl *ctrl = J.ctrl;
   const bool stopped = rs_ld_u32_relaxed(&ctrl->stop) != 0u;
   if (!SMEMC && stopped) return;  // (a cluster leaves together: both CTAs go through the two cluster barriers below)
-  const PassSmem P = rs_pass_smem<MAPS, NB, RS_TP_WARPS * NV>(J, smem_raw);
+  const PassSmem P = rs_pass_smem<MAPS, NB, TPW * NV>(J, smem_raw);
   const unsigned lutc = P.lutc, lutm = P.lutm;
   WarpScratch<MAPS, NB> *Sw = reinterpret_cast<WarpScratch<MAPS, NB> *>(P.scratch) + (threadIdx.x >> 5) * NV;  // this warp's scratches
   const unsigned lane = threadIdx.x & 31u, grp = NV == 1 ? 0u : lane / (unsigned)LW;
@@ -1173,7 +1188,7 @@ __global__ void __launch_bounds__(RS_TP_WARPS * 32, RS_TP_MIN_CTAS) k_synth_pass
   CorpusSmem cs;
   if (SMEMC) {
     // this CTA's slice of the canonical corpus (sentinel pixel included) -> shared memory, by TMA bulk copies
-    uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw + ((pass_smem_bytes<MAPS, NB>(RS_TP_WARPS * NV) + 127u) & ~127u));
+    uint32_t *slice = reinterpret_cast<uint32_t *>(smem_raw + ((pass_smem_bytes<MAPS, NB>(TPW * NV) + 127u) & ~127u));
     const unsigned rank = rs_cluster_ctarank(), nr = rs_cluster_nctarank();
     const uint32_t first = rank * J.sc_slice, total = J.cn + 1u;
     const uint32_t count = first < total ? min(J.sc_slice, total - first) : 0u;
@@ -1496,6 +1511,7 @@ struct PassVariant {
   void (*tp)(const RsDev) = nullptr;                    // k_synth_pass<maps, chunk, nb>
   void (*team)(const RsDev, const unsigned) = nullptr;  // k_synth_pass_team<maps, chunk, nb>
   size_t smem_tp = 0, smem_team = 0;
+  int tp_threads = RS_TP_WARPS * 32;                    // threads of a CTA of `tp` (TpShape)
   int grid = 0, grid_team = 0;                          // persistent grids: resident CTAs per SM x SMs
   int sms = 0;
   void (*tp_smemc)(const RsDev) = nullptr;              // k_synth_pass<false, chunk, nb, true>: corpus in shared memory
@@ -1624,11 +1640,12 @@ static typename std::enable_if<(NB <= 16), int>::type configure_pair_kernel(Work
 template <bool MAPS, int CH, int NB>
 static int configure_pass_kernel(Workspace *w) {
   const bool full = NB == RS_NB_FULL;
-  const size_t smem_tp = pass_smem(MAPS, RS_TP_WARPS, full), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS, full);
+  constexpr int tp_warps = TpShape<MAPS, NB, false, 32>::warps;
+  const size_t smem_tp = pass_smem(MAPS, tp_warps, full), smem_team = pass_smem(MAPS, RS_TEAM_SLOTS, full);
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass<MAPS, CH, NB, false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tp));
   RS_CHECK(cudaFuncSetAttribute(k_synth_pass_team<MAPS, CH, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_team));
   int per_sm = 0, per_sm_team = 0, sms = 0;
-  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB, false, 32>, RS_TP_WARPS * 32, smem_tp));
+  RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_synth_pass<MAPS, CH, NB, false, 32>, tp_warps * 32, smem_tp));
   RS_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_team, k_synth_pass_team<MAPS, CH, NB>, RS_TEAM_WARPS * 32, smem_team));
   RS_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device));
   if (per_sm < 1 || per_sm_team < 1) { g_err = "the pass kernels do not fit on an SM"; return 100; }
@@ -1643,11 +1660,12 @@ static int configure_pass_kernel(Workspace *w) {
   V.tp = k_synth_pass<MAPS, CH, NB, false, 32>;
   V.team = k_synth_pass_team<MAPS, CH, NB>;
   V.smem_tp = smem_tp; V.smem_team = smem_team;
+  V.tp_threads = tp_warps * 32;
   V.grid = per_sm * sms; V.grid_team = per_sm_team * sms;
   V.sms = sms;
   if (!MAPS) {  // the corpus-in-shared-memory instantiation: one CTA per SM, everything the SM has left goes to the slice
     const size_t smem_max = 232448;  // 227 KB per CTA on sm_100
-    const size_t base = (smem_tp + 127) & ~(size_t)127;
+    const size_t base = (pass_smem(false, RS_TP_WARPS, full) + 127) & ~(size_t)127;  // (this instantiation: RS_TP_WARPS warps, one CTA)
     V.tp_smemc = k_synth_pass<false, CH, NB, true, 32>;
     V.smemc_base = base;
     V.smemc_slice_max = (uint32_t)(((smem_max - base) / 4) & ~(size_t)3);
@@ -2904,7 +2922,8 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
         cfg.attrs = attr; cfg.numAttrs = 1;
         RS_CHECK(cudaLaunchKernelEx(&cfg, two ? PV.tp_pair_smemc : PV.tp_smemc, D));
       } else if (W <= 1) {
-        (two ? PV.tp_pair : PV.tp)<<<grid, RS_TP_WARPS * 32, two ? PV.smem_tp_pair : PV.smem_tp, s>>>(D);
+        if (two) PV.tp_pair<<<grid, RS_TP_WARPS * 32, PV.smem_tp_pair, s>>>(D);
+        else PV.tp<<<grid, PV.tp_threads, PV.smem_tp, s>>>(D);
       } else {
         PV.team<<<grid_team, RS_TEAM_WARPS * 32, smem_team, s>>>(D, W);
       }
