@@ -1,12 +1,12 @@
 // sm_100a kernels of the synthesis engine and the thin C-ABI over them (include/rs_cuda.h).
 //
 // A pass is one or a few persistent launches (segments of shrinking team width, see plan_segments).  Every warp -- or
-// team of 2/4/8 warps -- claims target visits IN ORDER (atomic counter), so a visit can only ever wait on visits
+// team of 2/4/8 warps, or half of a warp for small patches -- claims target visits IN ORDER (atomic counter), so a visit can only ever wait on visits
 // claimed before it by warps that are already running: the dependency wavefront of the reference's sequential loop
 // (lib/synthesize.h:480-640) is respected exactly, with no barrier between "waves".  A visit waits only for the
 // neighbours it actually reads (RAW); write-after-read hazards are removed by the two version slots of the state word
-// (rs_device.cuh).  File order: init kernels, pass-0 / later-pass patch gathers, visit steps (geometry, values,
-// candidates, finish), the two pass kernels, best-fit test kernel, workspaces, visit-order machinery (digest, cache,
+// (rs_device.cuh).  File order: init kernels, pass-0 / later-pass patch gathers (scan, and search for the first visits),
+// visit steps (geometry, values, candidates, finish; templated on the lanes that work on a visit), the two pass kernels, best-fit test kernel, workspaces, visit-order machinery (digest, cache,
 // exact device shuffle, pair sort), staging / upload, rs_job_run, download, counters.
 #include <cstdio>
 #include <cstdlib>
