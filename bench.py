@@ -353,24 +353,39 @@ class Runner:
     engine changes nothing else), so that the bench itself moves as little host memory as possible between the timed
     calls -- at 8 ranks on one host, copying whole 64 MB images per step would compete with the other ranks' staging."""
 
-    def __init__(self, api, torch, w, fi):
+    def __init__(self, api, torch, w, fi, pinned=True):
+        """pinned: the caller's buffers are page-locked (the bench contract's "inputs in pinned host memory"): the engine
+        hands them to the copy engine as they are; False: malloc'ed numpy buffers like the reference's callers'
+        (lib/imageBuffer.h), which the engine stages through its own pinned workspace."""
         self.api, self.torch, self.w, self.fi = api, torch, w, fi
+        self.pinned, self._keep = pinned, []
         self.n = int((w["tmask"] != 0).sum())
+        self.tmask = self._host(w["tmask"])
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
         rows = np.flatnonzero(w["tmask"].any(axis=1))
         cols = np.flatnonzero(w["tmask"].any(axis=0))
         self.box = (slice(int(rows[0]), int(rows[-1]) + 1), slice(int(cols[0]), int(cols[-1]) + 1))
         n_rows = int(rows[-1] - rows[0] + 1)
         if "simple" in w:
-            self.img = w["tgt"].copy()
+            self.img = self._host(w["tgt"])
             self.pristine = w["tgt"][self.box].copy()
             self.h2d = w["tgt"].nbytes + w["tmask"].nbytes + 4 * self.n      # image + mask planes and the PRNG draws of the order
             self.d2h = n_rows * w["tmask"].shape[1] * (w["bpp"] - 1)          # the rows that hold target points
         else:
-            self.tp, self.cp = pixmaps(w)
+            self.tp, self.cp = (self._host(x) for x in pixmaps(w))
             self.pristine = self.tp[self.box].copy()
             self.h2d = self.tp.nbytes + self.cp.nbytes + 4 * self.n
             self.d2h = n_rows * w["tmask"].shape[1] * w["bpp"]
+
+    def _host(self, a):
+        """A private copy of `a` for the calls: page-locked (a numpy view of a pinned torch tensor) or malloc'ed."""
+        if not self.pinned:
+            return a.copy()
+        t = self.torch.empty(a.shape, dtype=self.torch.uint8, pin_memory=True)
+        self._keep.append(t)
+        v = t.numpy()
+        v[...] = a
+        return v
 
     def step(self):
         api, w = self.api, self.w
@@ -380,7 +395,7 @@ class Runner:
             self.flush.fill_(1)
             self.torch.cuda.synchronize()
             t0 = time.perf_counter()
-            err = api.image_synth(self.img, w["tmask"], w["simple"], w["params"])
+            err = api.image_synth(self.img, self.tmask, w["simple"], w["params"])
             wall = time.perf_counter() - t0
         else:
             self.tp[self.box] = self.pristine
@@ -413,6 +428,11 @@ def sub_record(api, torch, wname, steps, warmup):
             "ms_e2e_steps": [round(1000.0 * x, 3) for x in walls],
             "ms_prep": float(np.mean([s["ms_prep"] for s in stats])), "ms_h2d": float(np.mean([s["ms_h2d"] for s in stats])),
             "ms_d2h": float(np.mean([s["ms_d2h"] for s in stats])),
+            "e2e_pageable": ({"value": world * n / float(np.mean(pageable_walls)), "unit": UNIT,
+                              "ms_call": 1000.0 * float(np.mean(pageable_walls)),
+                              "what": "same call with malloc'ed caller buffers (rank 0's mean over %d jobs x %d ranks): staged "
+                                      "through the workspace's pinned memory by host threads" % (len(pageable_walls), world)}
+                             if pageable_walls else None),
             "ms_pass": [float(np.mean([s["ms_pass"][p] for s in stats])) for p in range(6)],
             "passes_run": stats[-1]["passes_run"], "visits_per_px": visits / r.n, "evals_per_visit": evals / max(visits, 1),
             "visits_per_s": steps * visits / kern_s, "evals_per_s": steps * evals / kern_s,
@@ -429,8 +449,12 @@ def cfg5_batch_record(api, torch, dist, rank, local, world, n_jobs, probe_list, 
     m = centered_mask(2048, 2048, 256, 256)
     with ThreadPoolExecutor(4) as ex:
         pristine = list(ex.map(lambda k: G(2048, 2048, 3, 100 + k), mine))
-    work = [p.copy() for p in pristine]
-    masks = [m] * len(mine)
+    # the caller's images and mask in page-locked memory (one allocation, a view per job): copied from and to directly
+    pin = torch.empty((max(len(mine), 1), 2048, 2048, 3), dtype=torch.uint8, pin_memory=True).numpy()
+    pin_m = torch.empty((2048, 2048), dtype=torch.uint8, pin_memory=True).numpy()
+    pin_m[...] = m
+    work = [pin[i] for i in range(len(mine))]
+    masks = [pin_m] * len(mine)
     n_px = int((m != 0).sum())
 
     def barrier():
@@ -459,7 +483,7 @@ def cfg5_batch_record(api, torch, dist, rank, local, world, n_jobs, probe_list, 
                             "ms_batch": 1000.0 * t_all, "every_image_healed": bool(ok)}
     api.order_cache(False)
     return {"workload": "cfg5: %d heal jobs 2048x2048 RGB, 256x256 hole, ctx1, patch 30, dealt round robin over %d GPU(s)" % (n_jobs, world),
-            "api": "rs_image_synth_batch() = imageSynth() per image; host buffers in and out; visit-order cache on",
+            "api": "rs_image_synth_batch() = imageSynth() per image; page-locked host buffers in and out; visit-order cache on",
             "jobs": n_jobs, "jobs_per_rank": [len(sharding.deal_round_robin(n_jobs, world, r)) for r in range(world)],
             "slots_per_gpu": slots, "scaling": "strong", "unit": UNIT, "timing": "wall clock between barriers, max over ranks",
             "h2d_bytes_per_job": int(pristine[0].nbytes + m.nbytes) if pristine else 0,
@@ -548,6 +572,19 @@ def run_ours(a):
     n_launches = api.total_kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
 
+    # the same call from malloc'ed buffers, as the reference's callers hold them (lib/imageBuffer.h): the engine stages
+    # them through its own pinned workspace with host threads (rank 0's figure is reported; every rank runs it so that the
+    # staging threads compete for the host as they would)
+    pageable_walls = []
+    if not a.quick:
+        pr = Runner(api, torch, w, fi, pinned=False)
+        pr.step()
+        barrier()
+        for i in range(max(3, a.steps // 4)):
+            pageable_walls.append(pr.step()[0])
+        barrier()
+        del pr
+
     # the same job stream with the order cache on (what a batch of same-shaped jobs or the frames of a clip see)
     cached_walls = []
     if not a.quick:
@@ -619,11 +656,18 @@ def run_ours(a):
             "visits_per_s": world * visits / kern_s, "evals_per_s": world * evals / kern_s,
             "evals_issued_per_s": world * issued / kern_s, "compares_per_s": world * compares / kern_s,
             "compares_per_eval_issued": compares / max(issued, 1),
-            "e2e": {"value": total_px / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(runner.h2d), "d2h_bytes_per_step": int(runner.d2h),
+            "e2e": {"value": total_px / e2e_s, "unit": UNIT,
+                    "host_buffers": "page-locked (pinned torch tensors handed to the C-ABI call; copied from and to directly)",
+                    "h2d_bytes_per_step": int(runner.h2d), "d2h_bytes_per_step": int(runner.d2h),
                     "visits_per_s": world * visits / e2e_s, "evals_per_s": world * evals / e2e_s,
                     "ms_call": 1000.0 * e2e_s / a.steps,
                     "ms_prep": float(np.mean([s["ms_prep"] for s in stats])), "ms_h2d": float(np.mean([s["ms_h2d"] for s in stats])),
                     "ms_kernels": float(np.mean([s["ms_kernels"] for s in stats])), "ms_d2h": float(np.mean([s["ms_d2h"] for s in stats]))},
+            "e2e_pageable": ({"value": world * n / float(np.mean(pageable_walls)), "unit": UNIT,
+                              "ms_call": 1000.0 * float(np.mean(pageable_walls)),
+                              "what": "same call with malloc'ed caller buffers (rank 0's mean over %d jobs x %d ranks): staged "
+                                      "through the workspace's pinned memory by host threads" % (len(pageable_walls), world)}
+                             if pageable_walls else None),
             "ms_pass": [float(np.mean([s["ms_pass"][p] for s in stats])) for p in range(6)],
             "e2e_order_cached": ({"value": n / float(np.mean(cached_walls)), "unit": UNIT,
                                   "what": "same call with the visit-order cache on (rank 0, %d jobs): the target order of an "

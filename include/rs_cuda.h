@@ -164,6 +164,13 @@ int rs_job_run(RsJob *job, RsTickFn tick, void *tick_ctx);
  * each target point in visit order, 0xFFFFFFFF if none. */
 int rs_job_download(RsJob *job, uint8_t *target_raw_out, uint32_t *sources_out);
 void rs_job_want_sources(RsJob *job, int yes);
+/* Page-locked caller buffers (cudaHostAlloc / cudaHostRegister; a pinned torch tensor) are copied from and to directly,
+ * without the staging copy through the workspace's pinned memory (the reference's callers pass malloc'ed ImageBuffers,
+ * lib/imageBuffer.h: those are staged).  rs_cuda_host_is_pinned: 1 if `p` is such memory.  rs_job_result_direct(job, 1)
+ * before rs_job_run: the result rows are not staged; rs_job_download / rs_job_download_simple then copy them from the
+ * device into the (page-locked) destination they are given. */
+int rs_cuda_host_is_pinned(const void *p);
+void rs_job_result_direct(RsJob *job, int yes);
 int rs_job_counters(RsJob *job, RsJobCounters *out);
 void rs_job_destroy(RsJob *job);
 /* Throughput profile of a pass of the last run: out_ns[i] = ns from the start of the pass to the claim of visit

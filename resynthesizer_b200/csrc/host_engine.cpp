@@ -340,7 +340,9 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   dbg("after order");
   const double t2b = now_ms();
   TickState ts{progressCallback, contextInfo, cancelFlag, 0u, estimated, 0u};
-  if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rc = rs_job_run(job, t_quiet ? nullptr : on_tick, &ts); }
+  // a page-locked destination gets its rows straight from the device (decided before the run: the staged copy is skipped)
+  const bool direct = !t_keep_result && rs_cuda_host_is_pinned(src.simple() ? (const void *)src.img->data : (const void *)src.tpix) != 0;
+  if (!rc) { rs_job_want_sources(job, t_keep_result ? 1 : 0); rs_job_result_direct(job, direct ? 1 : 0); rc = rs_job_run(job, t_quiet ? nullptr : on_tick, &ts); }
   const double t3 = now_ms();
   if (!rc) {
     // engine() mutates the colour bytes of targetMap in place (lib/synthesize.h:403-419); alpha and maps untouched

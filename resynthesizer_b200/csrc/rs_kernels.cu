@@ -1871,6 +1871,7 @@ struct RsJob {
   uint32_t upload_launches = 0;   // kernels launched by the upload (init, offsets, compaction)
   float ms_synth = 0.f;           // CUDA-event time of the pass kernels alone (after the pass-0 patch gather)
   int off_w = 0, off_h = 0;       // dimensions of the full offsets table this job reads (0: a caller's partial table)
+  bool result_direct = false;     // the caller's result buffer is page-locked: the rows go there straight from the device (download)
   bool ctx_counted = false;       // k_ctx_blocks ran for this job: RsCtrl::n_ctx holds the number of usable context pixels
 };
 
@@ -2084,7 +2085,19 @@ __global__ void k_extract_simple(const uint8_t *__restrict__ raw_t, uint32_t fir
 
 // Host copy into pinned staging followed by the H2D copy, in pieces: a piece goes to the device while the next one is
 // being copied, and large images are copied by several cores (a single core moves ~9 GB/s, PCIe 5 takes 25+).
+// A caller's buffer that is page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): the copy engine
+// reads and writes it directly, no staging copy through the workspace's pinned memory.
+extern "C" int rs_cuda_host_is_pinned(const void *p) {
+  if (p == nullptr || getenv("RS_NO_DIRECT_COPY")) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
 static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t bytes, cudaStream_t s) {
+  if (rs_cuda_host_is_pinned(src)) {
+    RS_CHECK(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
   const size_t PIECE = (size_t)4 << 20;
   if (bytes <= PIECE) {
     memcpy(pin, src, bytes);
@@ -2116,6 +2129,10 @@ static int stage_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t b
 static int stage_rows_to_device(void *dev, uint8_t *pin, const uint8_t *src, size_t rows, size_t row_len, size_t src_stride,
                                 cudaStream_t s) {
   if (src_stride == row_len) return stage_to_device(dev, pin, src, rows * row_len, s);
+  if (rs_cuda_host_is_pinned(src)) {
+    RS_CHECK(cudaMemcpy2DAsync(dev, row_len, src, src_stride, row_len, rows, cudaMemcpyHostToDevice, s));
+    return 0;
+  }
   unsigned hw = rs_host_cores();
   const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
   auto band = [=](size_t t) {
@@ -2438,6 +2455,12 @@ extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_byt
   const size_t row_len = (size_t)j->d.tw * (j->d.bpp - 1), rows = j->y_max - j->y_min + 1;
   const uint8_t *src = (const uint8_t *)w->pin;
   const uint32_t y0 = j->y_min;
+  if (j->result_direct) {  // device -> the caller's page-locked image, rows in place
+    RS_CHECK(cudaSetDevice(w->device));
+    RS_CHECK(cudaMemcpy2DAsync(img + (size_t)y0 * img_row_bytes, img_row_bytes, w->simg.p, row_len, row_len, rows, cudaMemcpyDeviceToHost, w->stream));
+    RS_CHECK(cudaStreamSynchronize(w->stream));
+    return 0;
+  }
   unsigned hw = rs_host_cores();
   const size_t nt = rows * row_len < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
   auto band = [=](size_t t) {
@@ -2959,8 +2982,8 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
     const uint32_t npx = (j->y_max - j->y_min + 1) * (uint32_t)j->d.tw;
     k_extract_simple<<<(npx + 255) / 256, 256, 0, s>>>((const uint8_t *)w->raw_t.p, j->y_min * (uint32_t)j->d.tw, npx, nc,
                                                        (uint8_t *)w->simg.p);
-    RS_CHECK(cudaMemcpyAsync(w->pin, w->simg.p, (size_t)npx * nc, cudaMemcpyDeviceToHost, s));
-  } else {
+    if (!j->result_direct) RS_CHECK(cudaMemcpyAsync(w->pin, w->simg.p, (size_t)npx * nc, cudaMemcpyDeviceToHost, s));
+  } else if (!j->result_direct) {
     RS_CHECK(cudaMemcpyAsync(w->pin, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes, rows_bytes,
                              cudaMemcpyDeviceToHost, s));
   }
@@ -3030,6 +3053,7 @@ extern "C" int rs_job_run(RsJob *j, RsTickFn tick, void *tick_ctx) {
 }
 
 extern "C" void rs_job_want_sources(RsJob *j, int yes) { j->want_sources = yes != 0; }
+extern "C" void rs_job_result_direct(RsJob *j, int yes) { j->result_direct = yes != 0; }
 
 extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sources_out) {
   const Workspace *w = j->ws;  // rs_job_run left the rows (and sources) in pinned memory
@@ -3037,17 +3061,23 @@ extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sour
   if (target_raw_out) {
     if (j->simple) { g_err = "rs_job_download: a job staged by rs_job_stage_simple returns its rows through rs_job_download_simple"; return 100; }
     uint8_t *dst = target_raw_out + (size_t)j->y_min * row_bytes;
-    const uint8_t *src = (const uint8_t *)w->pin;
-    unsigned hw = rs_host_cores();
-    const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
-    const size_t per = (rows_bytes + nt - 1) / nt;
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < nt; t++) {
-      const size_t b = std::min(rows_bytes, t * per), e = std::min(rows_bytes, (t + 1) * per);
-      if (e > b) th.emplace_back([=]() { memcpy(dst + b, src + b, e - b); });
+    if (j->result_direct) {  // device -> the caller's page-locked pixmap
+      RS_CHECK(cudaSetDevice(w->device));
+      RS_CHECK(cudaMemcpyAsync(dst, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes, rows_bytes, cudaMemcpyDeviceToHost, w->stream));
+      RS_CHECK(cudaStreamSynchronize(w->stream));
+    } else {
+      const uint8_t *src = (const uint8_t *)w->pin;
+      unsigned hw = rs_host_cores();
+      const size_t nt = rows_bytes < ((size_t)4 << 20) ? 1 : std::min<size_t>(rs_copy_threads_max(), hw > 2 ? hw - 1 : 1);
+      const size_t per = (rows_bytes + nt - 1) / nt;
+      std::vector<std::thread> th;
+      for (size_t t = 1; t < nt; t++) {
+        const size_t b = std::min(rows_bytes, t * per), e = std::min(rows_bytes, (t + 1) * per);
+        if (e > b) th.emplace_back([=]() { memcpy(dst + b, src + b, e - b); });
+      }
+      memcpy(dst, src, std::min(rows_bytes, per));
+      for (auto &x : th) x.join();
     }
-    memcpy(dst, src, std::min(rows_bytes, per));
-    for (auto &x : th) x.join();
   }
   if (sources_out) {
     if (!j->want_sources) { g_err = "rs_job_download: sources were not requested before rs_job_run"; return 100; }

@@ -146,3 +146,55 @@ def test_reference_testsynth_binary_runs_on_this_library(built_lib):
         assert norm(expect) == norm(result), (name, expect, result)
         checked += 1
     assert checked == 3
+
+
+def _pinned_like(a):
+    """A copy of `a` in page-locked host memory (a numpy view of a pinned torch tensor)."""
+    import torch
+    t = torch.empty(a.shape, dtype=torch.uint8, pin_memory=True)
+    v = t.numpy()
+    v[...] = a
+    return t, v
+
+
+def test_page_locked_buffers_are_copied_directly(built_lib):
+    """A caller's page-locked image / mask / pixmaps are read by the copy engine and written back in place, without the
+    staging copy through the workspace (rs_cuda_host_is_pinned, rs_job_result_direct): same result as from malloc'ed
+    buffers (the reference's ImageBuffer, lib/imageBuffer.h), padded rows included, and nothing is written on cancel."""
+    L = api.lib()
+    L.rs_cuda_host_is_pinned.argtypes = [C.c_void_p]
+    img = G(200, 160, 3, 77)
+    m = centered_mask(200, 160, 70, 60)
+    p = abi.make_params(0, 0, 1, 0.5, 0.117, 16, 60)
+    want = img.copy()
+    assert api.image_synth(want, m, abi.T_RGB, p) == 0
+    keep_i, pimg = _pinned_like(img)
+    keep_m, pm = _pinned_like(m)
+    assert L.rs_cuda_host_is_pinned(pimg.ctypes.data) == 1 and L.rs_cuda_host_is_pinned(img.ctypes.data) == 0
+    assert api.image_synth(pimg, pm, abi.T_RGB, p) == 0
+    assert (pimg == want).all() and (pimg != img).any()
+    # rows wider than the image (ImageBuffer.rowBytes), page-locked: a strided copy in, a strided copy out
+    wide = np.zeros((160, 640), np.uint8)
+    keep_w, pw = _pinned_like(wide)
+    pw[:, :600] = img.reshape(160, 600)
+    pw[:, 600:] = 0xAB
+    ib, _a = abi.image_buffer_padded(pw.reshape(-1), 200, 160, 640)
+    mb, _b = abi.image_buffer_padded(pm.reshape(-1), 200, 160, 200)
+    cancel = C.c_int(0)
+    cb = abi.PROGRESS_CB(lambda pc, c: None)
+    assert L.imageSynth(C.byref(ib), C.byref(mb), abi.T_RGB, C.byref(p), cb, None, C.byref(cancel)) == 0
+    assert (pw[:, :600].reshape(160, 200, 3) == want).all() and (pw[:, 600:] == 0xAB).all()
+    # engine(): page-locked pixmaps
+    tp = R.build_pixmap(m, img)
+    cp = R.build_pixmap(255 - m, img)
+    fi = api.format_indices(3)
+    want_t = tp.copy()
+    assert api.engine(p, fi, want_t, cp) == 0
+    keep_t, ptp = _pinned_like(tp)
+    keep_c, pcp = _pinned_like(cp)
+    assert api.engine(p, fi, ptp, pcp) == 0
+    assert (ptp == want_t).all()
+    # cancelled: the page-locked image stays as it was
+    pimg[...] = img
+    err = api.image_synth(pimg, pm, abi.T_RGB, p, cancel_after=1)
+    assert (pimg == img).all()
