@@ -369,12 +369,12 @@ class Runner:
         if "simple" in w:
             self.img = self._host(w["tgt"])
             self.pristine = w["tgt"][self.box].copy()
-            self.h2d = w["tgt"].nbytes + w["tmask"].nbytes + 4 * self.n      # image + mask planes and the PRNG draws of the order
+            self.h2d = w["tgt"].nbytes + w["tmask"].nbytes      # image + mask planes (the PRNG stream of the order is made on the device)
             self.d2h = n_rows * w["tmask"].shape[1] * (w["bpp"] - 1)          # the rows that hold target points
         else:
             self.tp, self.cp = (self._host(x) for x in pixmaps(w))
             self.pristine = self.tp[self.box].copy()
-            self.h2d = self.tp.nbytes + self.cp.nbytes + 4 * self.n
+            self.h2d = self.tp.nbytes + self.cp.nbytes
             self.d2h = n_rows * w["tmask"].shape[1] * w["bpp"]
 
     def _host(self, a):
@@ -428,11 +428,6 @@ def sub_record(api, torch, wname, steps, warmup):
             "ms_e2e_steps": [round(1000.0 * x, 3) for x in walls],
             "ms_prep": float(np.mean([s["ms_prep"] for s in stats])), "ms_h2d": float(np.mean([s["ms_h2d"] for s in stats])),
             "ms_d2h": float(np.mean([s["ms_d2h"] for s in stats])),
-            "e2e_pageable": ({"value": world * n / float(np.mean(pageable_walls)), "unit": UNIT,
-                              "ms_call": 1000.0 * float(np.mean(pageable_walls)),
-                              "what": "same call with malloc'ed caller buffers (rank 0's mean over %d jobs x %d ranks): staged "
-                                      "through the workspace's pinned memory by host threads" % (len(pageable_walls), world)}
-                             if pageable_walls else None),
             "ms_pass": [float(np.mean([s["ms_pass"][p] for s in stats])) for p in range(6)],
             "passes_run": stats[-1]["passes_run"], "visits_per_px": visits / r.n, "evals_per_visit": evals / max(visits, 1),
             "visits_per_s": steps * visits / kern_s, "evals_per_s": steps * evals / kern_s,

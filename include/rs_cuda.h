@@ -150,6 +150,13 @@ int rs_job_shuffle_order(RsJob *job, const uint32_t *draws, const RsOrderKey *ke
  * survive, the job is flagged faulty and rs_job_run returns an error. */
 uint32_t *rs_job_raw_buffer(RsJob *job, size_t n_words);
 int rs_job_shuffle_order_raw(RsJob *job, uint32_t n_raw, const RsOrderKey *key, uint32_t *ordered_out);
+/* The same with the PRNG stream made on the device as well: the raw words of GLib's GRand (MT19937, g_rand_new_with_seed /
+ * g_rand_int; the reference seeds it in lib/engine.c and draws in lib/orderTarget.h:38-53) come from one CTA beside the
+ * image upload; nothing of the order is computed on or copied from the host.  The whole pipeline of the three
+ * rs_job_shuffle_order* calls runs on the job's side stream from the moment the selection is on the device.
+ * rs_cuda_mt19937_raw (test entry): the first n_words words of the stream of `seed`, made on the device, to the host. */
+int rs_job_shuffle_order_seed(RsJob *job, uint32_t seed, const RsOrderKey *key, uint32_t *ordered_out);
+int rs_cuda_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t *out_host);
 /* Stable ascending radix sort of n (key, value) pairs on the low key_bits bits of the keys, host buffers in place, on a
  * side stream of the job (it runs beside the staging).  The sort step of the target orderings 2-8. */
 int rs_job_sort_pairs(RsJob *job, uint32_t *keys, uint32_t *vals, uint32_t n, int key_bits);

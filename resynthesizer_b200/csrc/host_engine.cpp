@@ -247,8 +247,9 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
 
   // Stage the images (asynchronous: host -> device, state init, corpus points, offsets table) and get the digest of
   // the target selection back: number of target points, their rows, and the key of the visit-order cache.
-  // The shuffling orders need one PRNG draw per target point.  The raw words of the stream depend on the seed only, so a
-  // producer thread starts making them now, while the images are staged and counted (rejection rate < n / 2^32).
+  // The shuffling orders need one PRNG draw per target point.  By default the device makes the stream itself
+  // (rs_job_shuffle_order_seed).  RS_HOST_PRNG=1 keeps the host's producer: the raw words of the stream depend on the seed
+  // only, so a producer thread starts making them now, while the images are staged and counted (rejection rate < n / 2^32).
   RsJob *job = nullptr;
   dbg("before create");
   if (rs_job_create(&desc, &job)) { t_err = rs_cuda_last_error(); return RS_ERROR_CUDA; }
@@ -257,7 +258,8 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   const size_t npx = (size_t)tw * th, raw_cap = npx + npx / 32 + 65536;
   std::unique_ptr<rs::RawStream> raw;
   bool raw_pinned = false;
-  if (prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26) &&
+  const bool host_prng = std::getenv("RS_HOST_PRNG") != nullptr || std::getenv("RS_NO_RAW_STREAM") != nullptr;
+  if (host_prng && prm.matchContextType <= 1 && npx >= g_device_shuffle_min.load() * 4 && npx <= ((size_t)1 << 26) &&
       !std::getenv("RS_NO_RAW_STREAM")) {  // (the switch lets the tests take the host-reduced path below)
     uint32_t *pinned = rs_job_raw_buffer(job, raw_cap);  // the producer writes where the H2D copy will read
     raw_pinned = pinned != nullptr;
@@ -293,28 +295,31 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   if (hit == 0) {
     if (t_keep_result) hit = rs_job_bind_order(job, &dg, nullptr) == 100 ? 100 : 0;  // sizes only; the order is wanted on the host
     if (hit == 0 && prm.matchContextType <= 1 && n >= g_device_shuffle_min.load()) {
-      // miss, shuffling order: the host only makes the draws (the reference's PRNG stream); the device compacts the
-      // target points and resolves the chain of swaps (rs_job_shuffle_order)
+      // miss, shuffling order: the device compacts the target points and resolves the chain of swaps from the draws of
+      // the reference's PRNG stream (rs_job_shuffle_order*)
       static thread_local std::vector<uint32_t> draws;
-      if (!(raw && raw_pinned)) draws.resize(n);
-      if (raw && raw_pinned) {
+      uint32_t *ordered = nullptr;
+      if (t_keep_result) { targets.resize(n); ordered = targets.data(); }
+      const RsOrderKey *ckey = t_keep_result ? nullptr : &key;
+      if (!host_prng) {
+        // the PRNG stream, the rejection rule, the modulo and the chain of swaps all on the device
+        rc = rs_job_shuffle_order_seed(job, t_seed, ckey, ordered);
+      } else if (raw && raw_pinned) {
         // raw words straight from the producer's pinned buffer; rejection rule and modulo applied on the device
         const size_t n_raw = std::min(raw_cap, (size_t)n + n / 32 + 65536);
         raw->wait_ready(n_raw);
-        if (t_keep_result) targets.resize(n);
-        rc = rs_job_shuffle_order_raw(job, (uint32_t)n_raw, t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
-        hit = 2;
-      } else if (raw) {
-        raw->reduce(n, draws.data(), n);
+        rc = rs_job_shuffle_order_raw(job, (uint32_t)n_raw, ckey, ordered);
       } else {
-        rs::GRandMT prng(t_seed);
-        prng.fill_int_range(n, draws.data(), n);
+        draws.resize(n);
+        if (raw) {
+          raw->reduce(n, draws.data(), n);
+        } else {
+          rs::GRandMT prng(t_seed);
+          prng.fill_int_range(n, draws.data(), n);
+        }
+        rc = rs_job_shuffle_order(job, draws.data(), ckey, ordered);
       }
-      if (hit != 2) {
-        if (t_keep_result) targets.resize(n);
-        rc = rs_job_shuffle_order(job, draws.data(), t_keep_result ? nullptr : &key, t_keep_result ? targets.data() : nullptr);
-        hit = 2;
-      }
+      hit = 2;
     }
     if (hit == 0) {  // miss: collect and order the points on the host (the reference's PRNG stream) while the device stages
       const uint8_t *mask0 = src.simple() ? src.mask->data : src.tpix;

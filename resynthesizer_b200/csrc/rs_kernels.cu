@@ -1542,6 +1542,7 @@ struct Workspace {
   size_t pin_raw_cap = 0;
   RsTargetDigest *h_digest = nullptr;  // pinned
   cudaEvent_t evDigest = nullptr;
+  cudaEvent_t evSel = nullptr, evOrder = nullptr;  // the selection (mask plane / target pixmap) is on the device; the visit order is made
   unsigned int *h_ticks = nullptr;
   int *h_cancel = nullptr;
   RsCtrl *h_ctrl = nullptr;
@@ -1589,6 +1590,8 @@ static void ws_free(Workspace *w) {
   if (w->pin_raw) cudaFreeHost(w->pin_raw);
   if (w->h_digest) cudaFreeHost(w->h_digest);
   if (w->evDigest) cudaEventDestroy(w->evDigest);
+  if (w->evSel) cudaEventDestroy(w->evSel);
+  if (w->evOrder) cudaEventDestroy(w->evOrder);
   if (w->h_ticks) cudaFreeHost(w->h_ticks);
   if (w->h_cancel) cudaFreeHost(w->h_cancel);
   if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
@@ -1712,6 +1715,8 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreate(&w->ev1));
   WCHK(cudaEventCreateWithFlags(&w->evDone, cudaEventDisableTiming | cudaEventBlockingSync));
   WCHK(cudaEventCreateWithFlags(&w->evDigest, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evSel, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evOrder, cudaEventDisableTiming));
   WCHK(cudaHostAlloc(&w->h_digest, sizeof(RsTargetDigest), cudaHostAllocDefault));
   WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
   WCHK(cudaHostAlloc(&w->h_cancel, sizeof(int), cudaHostAllocMapped));
@@ -2210,6 +2215,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     if ((rc = ws_ensure(w->simg, sz_img)) || (rc = ws_ensure(w->smask, tn)) || (rc = ws_ensure(w->smask2, simple->mask2 ? tn : 4)))
       return rc;
     if ((rc = stage_rows_to_device(w->smask.p, pin + o_t + sz_img, simple->mask, d.th, d.tw, simple->mask_rb, s))) return rc;
+    RS_CHECK(cudaEventRecord(w->evSel, s));  // what the order pipeline reads (shuffle_order_impl, on the side stream) is up
     if (digest && (rc = enqueue_digest((const uint8_t *)w->smask.p, 1))) return rc;  // the selection IS the mask plane
     if ((rc = stage_rows_to_device(w->simg.p, pin + o_t, simple->img, d.th, (size_t)d.tw * simple->nc, simple->img_rb, s))) return rc;
     if (simple->mask2 && (rc = stage_rows_to_device(w->smask2.p, pin + o_c, simple->mask2, d.th, d.tw, simple->mask2_rb, s))) return rc;
@@ -2219,6 +2225,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     j->upload_launches += 1u;
   } else {
     if ((rc = stage_to_device(w->raw_t.p, pin + o_t, target_raw, sz_t, s))) return rc;
+    RS_CHECK(cudaEventRecord(w->evSel, s));
     if (digest && (rc = enqueue_digest((const uint8_t *)w->raw_t.p, d.bpp))) return rc;
   }
   memcpy(pin + o_lut, color_lut256, 256 * 4);
@@ -2565,10 +2572,69 @@ __global__ void k_reduce_draws(uint32_t *__restrict__ draws, const unsigned int 
   if (i < n) draws[i] %= n;
 }
 
+// The PRNG stream itself on the device: the first n_words raw 32-bit words of GLib's GRand seeded with `seed` (MT19937 with
+// init_genrand seeding -- g_rand_new_with_seed / g_rand_int, what the reference draws its visit order from,
+// lib/engine.c:643, lib/orderTarget.h:38-53).  Word i of the stream is x[i] = x[i-227] ^ twist(x[i-624], x[i-623]): 227
+// words at a time are independent of each other, and a step needs nothing younger than two steps back except x[i-227],
+// which the same lane made in the step before (a register).  One CTA of 227 threads, the state in a ring in shared
+// memory, two steps (454 words) per barrier.  4.4 M words (cfg3) take ~0.6 ms of one SM, beside the image upload, where
+// the host's AVX2 producer takes 3-4 ms of a core and the words another 17 MB of PCIe traffic.
+__global__ void __launch_bounds__(227, 1) k_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t *__restrict__ out) {
+  __shared__ uint32_t ring[2048];  // word i of the stream lives at ring[(i + 624) & 2047]; words -624..-1 = the seeded state
+  const uint32_t t = threadIdx.x;
+  if (t == 0) {
+    uint32_t x = seed;
+    ring[0] = x;
+    for (uint32_t i = 1; i < 624; i++) { x = 1812433253u * (x ^ (x >> 30)) + i; ring[i] = x; }
+  }
+  __syncthreads();
+  auto twist = [](uint32_t a, uint32_t b, uint32_t c) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return c ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+  };
+  auto temper = [](uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    return y ^ (y >> 18);
+  };
+  uint32_t c = ring[397 + t];  // x[t - 227]
+  for (uint32_t base = 0; base < n_words; base += 454u) {
+    const uint32_t i0 = base + t, i1 = i0 + 227u;
+    const uint32_t a0 = ring[i0 & 2047u], b0 = ring[(i0 + 1u) & 2047u];
+    const uint32_t a1 = ring[i1 & 2047u], b1 = ring[(i1 + 1u) & 2047u];
+    const uint32_t v0 = twist(a0, b0, c), v1 = twist(a1, b1, v0);
+    c = v1;
+    ring[(i0 + 624u) & 2047u] = v0;
+    ring[(i1 + 624u) & 2047u] = v1;
+    if (i0 < n_words) out[i0] = temper(v0);
+    if (i1 < n_words) out[i1] = temper(v1);
+    __syncthreads();
+  }
+}
+// Test entry: the first n_words words of the stream of `seed`, made on the current device, into host memory.
+extern "C" int rs_cuda_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t *out_host) {
+  if (n_words == 0) return 0;
+  uint32_t *d = nullptr;
+  RS_CHECK(cudaMalloc(&d, (size_t)n_words * 4));
+  k_mt19937_raw<<<1, 227>>>(seed, n_words, d);
+  cudaError_t e = cudaMemcpy(out_host, d, (size_t)n_words * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  RS_CHECK(e);
+  return 0;
+}
+
 static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *raw_pinned, uint32_t n_raw, const RsOrderKey *key,
-                              uint32_t *ordered_out);
+                              uint32_t *ordered_out, bool raw_on_device = false, uint32_t seed = 0);
 extern "C" int rs_job_shuffle_order(RsJob *j, const uint32_t *draws, const RsOrderKey *key, uint32_t *ordered_out) {
   return shuffle_order_impl(j, draws, nullptr, 0, key, ordered_out);
+}
+// The same with the PRNG stream made on the device too (k_mt19937_raw): nothing of the order comes from the host.
+extern "C" int rs_job_shuffle_order_seed(RsJob *j, uint32_t seed, const RsOrderKey *key, uint32_t *ordered_out) {
+  const uint32_t n = j->nT;
+  const uint64_t n_raw = (uint64_t)n + n / 32u + 65536u;  // room for the rejections (probability n / 2^32 per word)
+  if (n_raw > 0xFFFFFFFFull) { g_err = "rs_job_shuffle_order_seed: too many target points"; return 100; }
+  return shuffle_order_impl(j, nullptr, nullptr, (uint32_t)n_raw, key, ordered_out, true, seed);
 }
 // The same from RAW words of the PRNG stream (the first n_raw of them, in the pinned buffer rs_job_raw_buffer returned):
 // the device applies the rejection rule and the modulo itself.  n_raw must leave room for the rejections (probability
@@ -2590,16 +2656,21 @@ extern "C" uint32_t *rs_job_raw_buffer(RsJob *j, size_t n_words) {
   return (uint32_t *)w->pin_raw;
 }
 static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *raw_pinned, uint32_t n_raw, const RsOrderKey *key,
-                              uint32_t *ordered_out) {
+                              uint32_t *ordered_out, bool raw_on_device, uint32_t seed) {
   Workspace *w = j->ws;
   RS_CHECK(cudaSetDevice(w->device));
   const RsJobDesc &d = j->d;
   const uint32_t n = j->nT;
   const size_t bytes = (size_t)n * 4, tn = (size_t)d.tw * d.th;
-  cudaStream_t s = w->stream;
+  // The whole pipeline reads the selection only (the mask plane of the simple API, the target pixmap of the full one):
+  // it runs on the SIDE stream from the moment that is on the device (evSel), beside the upload of the image and the
+  // kernels that build the job's state on the main stream, which joins it (evOrder) before the order is scattered.
+  cudaStream_t s = w->stream2, s_main = w->stream;
+  RS_CHECK(cudaStreamWaitEvent(s, w->evSel, 0));
+  const bool raw_words = raw_pinned || raw_on_device;
   int rc = 0;
-  if (raw_pinned && n_raw < n) { g_err = "rs_job_shuffle_order_raw: fewer raw words than target points"; return 100; }
-  if (raw_pinned && (rc = ws_ensure(w->ord_raw, (size_t)n_raw * 4))) return rc;
+  if (raw_words && n_raw < n) { g_err = "rs_job_shuffle_order_raw: fewer raw words than target points"; return 100; }
+  if (raw_words && (rc = ws_ensure(w->ord_raw, (size_t)n_raw * 4))) return rc;
   if ((rc = ws_ensure(w->ord_keys_in, bytes)) || (rc = ws_ensure(w->ord_keys_out, bytes)) || (rc = ws_ensure(w->ord_vals_in, bytes)) ||
       (rc = ws_ensure(w->ord_vals_out, bytes)) || (rc = ws_ensure(w->ord_first, bytes)) || (rc = ws_ensure(w->ord_points, bytes + 4)) ||
       (rc = ws_ensure(w->ord_flags, tn)))
@@ -2624,13 +2695,18 @@ static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *r
   j->targets_dev = dst;
   const int T = 256;
   size_t tmp3 = 0;
-  if (raw_pinned) {  // raw words up (already pinned), accepted ones compacted into the draw array, then reduced mod n
+  if (raw_words) {  // raw words made here or sent up (already pinned), accepted ones compacted into the draw array, then reduced mod n
     uint32_t leftover = (0x80000000u % n) * 2u;
     if (leftover >= n) leftover -= n;
     const RsAccept acc{(n <= 0x80000000u) ? 0xffffffffu - leftover : n - 1u};
     // (the draw array takes up to n_raw words here; only the first n are used afterwards)
     if ((rc = ws_ensure(w->ord_keys_in, (size_t)n_raw * 4))) return rc;
-    RS_CHECK(cudaMemcpyAsync(w->ord_raw.p, raw_pinned, (size_t)n_raw * 4, cudaMemcpyHostToDevice, s));
+    if (raw_on_device) {
+      k_mt19937_raw<<<1, 227, 0, s>>>(seed, n_raw, (uint32_t *)w->ord_raw.p);
+      j->upload_launches += 1u;
+    } else {
+      RS_CHECK(cudaMemcpyAsync(w->ord_raw.p, raw_pinned, (size_t)n_raw * 4, cudaMemcpyHostToDevice, s));
+    }
     unsigned int *d_acc = &((RsCtrl *)w->ctrl.p)->dg_acc;
     RS_CHECK(cub::DeviceSelect::If(nullptr, tmp3, (const uint32_t *)w->ord_raw.p, (uint32_t *)w->ord_keys_in.p, d_acc, (int)n_raw, acc, s));
     if ((rc = ws_ensure(w->ord_tmp, tmp3))) return rc;
@@ -2641,7 +2717,9 @@ static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *r
     memcpy(w->pin_order, draws, bytes);
     RS_CHECK(cudaMemcpyAsync(w->ord_keys_in.p, w->pin_order, bytes, cudaMemcpyHostToDevice, s));
   }
-  k_target_flags<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>((const uint8_t *)w->raw_t.p, (uint32_t)tn, d.bpp, (uint8_t *)w->ord_flags.p);
+  // (a job of the simple API: the target pixmap is still being built on the main stream; its mask plane is the selection)
+  k_target_flags<<<(unsigned)((tn + T - 1) / T), T, 0, s>>>(j->simple ? (const uint8_t *)w->smask.p : (const uint8_t *)w->raw_t.p, (uint32_t)tn,
+                                                          j->simple ? 1 : d.bpp, (uint8_t *)w->ord_flags.p);
   thrust::counting_iterator<uint32_t> idx(0);
   unsigned int *d_cnt = &((RsCtrl *)w->ctrl.p)->dg_sel;
   size_t tmp = 0, tmp2 = 0;
@@ -2667,8 +2745,10 @@ static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *r
     RS_CHECK(cudaEventRecord(entry->ready, s));
     order_cache_publish(entry);
   }
+  RS_CHECK(cudaEventRecord(w->evOrder, s));
+  RS_CHECK(cudaStreamWaitEvent(s_main, w->evOrder, 0));  // the join: meta[] (k_init_target, main stream) takes the visit indices
   j->upload_launches += 1u;
-  k_scatter_order<<<(n + 255) / 256, 256, 0, s>>>(dst, n, d.tw, (uint32_t *)w->meta.p);
+  k_scatter_order<<<(n + 255) / 256, 256, 0, s_main>>>(dst, n, d.tw, (uint32_t *)w->meta.p);
   RS_CHECK(cudaGetLastError());
   if (ordered_out) {
     RS_CHECK(cudaMemcpyAsync(w->pin_order, dst, bytes, cudaMemcpyDeviceToHost, s));

@@ -141,11 +141,31 @@ def test_device_shuffle_equals_host_shuffle(mode, hole):
         api.order_cache(True)
 
 
-@pytest.mark.parametrize("raw", [True, False])
-def test_device_shuffle_large(raw, monkeypatch):
-    """200 k target points: the device-resolved shuffle (from raw PRNG words reduced on the device, or from draws reduced
-    on the host) orders them exactly as the host's swap loop does."""
-    if not raw:
+@pytest.mark.parametrize("seed", [1198472, 0, 1, 0xFFFFFFFF, 20241017])
+def test_device_prng_stream_is_glib_mt19937(seed):
+    """k_mt19937_raw: the raw 32-bit words of g_rand_new_with_seed(seed) / g_rand_int (MT19937, init_genrand seeding -- the
+    stream the reference draws its visit order from, lib/orderTarget.h:38-53), made on the device, equal numpy's legacy
+    MT19937 word for word; lengths around the kernel's steps of 227 / 454 words and the state size."""
+    import ctypes as C
+    L = api.lib()
+    L.rs_cuda_mt19937_raw.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+    api.set_device(0)
+    want = np.random.RandomState(seed).randint(0, 2 ** 32, 1200000, dtype=np.uint32)
+    for n in (1, 226, 227, 228, 453, 454, 455, 623, 624, 625, 1247, 100000, 1200000):
+        got = np.zeros(n + 8, np.uint32)
+        got[n:] = 0xDEADBEEF
+        assert L.rs_cuda_mt19937_raw(seed, n, got.ctypes.data) == 0
+        assert (got[:n] == want[:n]).all(), (seed, n)
+        assert (got[n:] == 0xDEADBEEF).all()
+
+
+@pytest.mark.parametrize("prng", ["device", "host_raw", "host_draws"])
+def test_device_shuffle_large(prng, monkeypatch):
+    """200 k target points: the device-resolved shuffle (PRNG stream made on the device; raw words of the host's producer
+    reduced on the device; draws reduced on the host) orders them exactly as the host's swap loop does."""
+    if prng == "host_raw":
+        monkeypatch.setenv("RS_HOST_PRNG", "1")
+    if prng == "host_draws":
         monkeypatch.setenv("RS_NO_RAW_STREAM", "1")
     api.order_cache(False)
     api.keep_result(True)
