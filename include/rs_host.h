@@ -19,6 +19,10 @@ int rs_host_order_targets(int match_context_type, int32_t *xy, uint32_t n, uint3
  * or through the early-started raw-word producer the engine uses (1).  Must be identical. */
 void rs_host_draws(uint32_t seed, uint32_t n, uint32_t count, uint32_t *out, int via_raw_stream);
 uint32_t rs_host_pass_schedule(uint32_t n_targets, uint32_t *ends6);
+/* MT19937 jump-ahead (csrc/host_prep.h: mt_jump_poly): the positions of the set bits of z^(q * jump_words) mod phi(z),
+ * ascending, into idx (room for 19937 entries); returns their number.  The state of the generator after q * jump_words
+ * words is the XOR of the windows of the untempered stream that start at those positions. */
+uint32_t rs_host_mt_jump_poly(uint32_t q, uint32_t jump_words, uint16_t *idx);
 #ifdef __cplusplus
 }
 #endif

@@ -689,3 +689,8 @@ extern "C" void rs_host_draws(uint32_t seed, uint32_t n, uint32_t count, uint32_
   }
 }
 extern "C" uint32_t rs_host_pass_schedule(uint32_t n, uint32_t *ends6) { return rs::pass_schedule(n, ends6); }
+extern "C" uint32_t rs_host_mt_jump_poly(uint32_t q, uint32_t jump_words, uint16_t *idx) {
+  const std::vector<uint16_t> &v = rs::mt_jump_poly(q, jump_words);
+  if (idx) std::memcpy(idx, v.data(), v.size() * sizeof(uint16_t));
+  return (uint32_t)v.size();
+}

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <mutex>
+#include <memory>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -253,6 +255,121 @@ void GRandMT::fill_raw(uint32_t *out, size_t count) {
     mti_ += (int)take;
     i += take;
   }
+}
+
+// ------------------------------------------------------------------------------------------- MT19937 jump-ahead
+namespace {
+constexpr size_t kPolyWords = (kMtDegree + 64) / 64;  // bits 0..19937 (phi has bit 19937 set)
+using Poly = std::vector<uint64_t>;                    // bit k = coefficient of z^k
+
+inline bool poly_bit(const Poly &p, size_t k) { return (p[k >> 6] >> (k & 63)) & 1u; }
+// dst ^= src << shift (whole words of src; dst is long enough)
+void xor_shl(uint64_t *dst, const uint64_t *src, size_t src_words, size_t shift) {
+  const size_t ws = shift >> 6, bs = shift & 63;
+  if (bs == 0) {
+    for (size_t i = 0; i < src_words; i++) dst[i + ws] ^= src[i];
+  } else {
+    uint64_t carry = 0;
+    for (size_t i = 0; i < src_words; i++) {
+      dst[i + ws] ^= (src[i] << bs) | carry;
+      carry = src[i] >> (64 - bs);
+    }
+    dst[src_words + ws] ^= carry;
+  }
+}
+
+// The characteristic polynomial: Berlekamp-Massey over GF(2) on 2 * 19937 successive values of one state bit (bit 0 of
+// the untempered words; phi is irreducible, so every non-zero bit stream of the generator has it as minimal polynomial).
+Poly mt_characteristic_polynomial() {
+  const size_t N = kMtDegree, T = 2 * N;
+  std::vector<uint32_t> x(624 + T);
+  x[0] = 5489u;  // any non-zero state does
+  for (size_t i = 1; i < 624; i++) x[i] = 1812433253u * (x[i - 1] ^ (x[i - 1] >> 30)) + (uint32_t)i;
+  for (size_t i = 624; i < x.size(); i++) {
+    const uint32_t y = (x[i - 624] & 0x80000000u) | (x[i - 623] & 0x7fffffffu);
+    x[i] = x[i - 227] ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+  }
+  const size_t W = kPolyWords + 1;
+  Poly C(W, 0), B(W, 0), R(W, 0), Tmp(W, 0);
+  C[0] = 1; B[0] = 1;
+  size_t L = 0, m = 1;
+  for (size_t i = 0; i < T; i++) {
+    // R: bit j = s[i - j]
+    uint64_t carry = x[624 + i] & 1u;
+    for (size_t w = 0; w < W; w++) { const uint64_t nc = R[w] >> 63; R[w] = (R[w] << 1) | carry; carry = nc; }
+    uint64_t acc = 0;
+    for (size_t w = 0; w <= (L >> 6); w++) acc ^= C[w] & R[w];
+    if (__builtin_parityll(acc)) {
+      const bool grow = 2 * L <= i;
+      if (grow) Tmp = C;
+      // C ^= z^m B: deg(z^m B) <= the new L <= N, so the words of B whose image would leave C are zero
+      const size_t ws = m >> 6;
+      if (ws + 1 < W) xor_shl(C.data(), B.data(), W - ws - 1, m);
+      if (grow) { L = i + 1 - L; B.swap(Tmp); m = 1; } else { m++; }
+    } else {
+      m++;
+    }
+  }
+  Poly phi(kPolyWords, 0);
+  if (L != N) return phi;  // (cannot happen)
+  for (size_t k = 0; k <= N; k++)
+    if (poly_bit(C, N - k)) phi[k >> 6] |= (uint64_t)1 << (k & 63);
+  return phi;
+}
+
+// a * b mod phi; a, b of degree < 19937
+Poly poly_mulmod(const Poly &a, const Poly &b, const Poly &phi) {
+  std::vector<uint64_t> acc(2 * kPolyWords + 2, 0);
+  for (size_t w = 0; w < kPolyWords; w++) {
+    uint64_t bits = b[w];
+    while (bits) {
+      const int k = __builtin_ctzll(bits);
+      bits &= bits - 1;
+      xor_shl(acc.data(), a.data(), kPolyWords, w * 64 + (size_t)k);
+    }
+  }
+  for (size_t i = 2 * (size_t)kMtDegree; i-- > kMtDegree;)
+    if ((acc[i >> 6] >> (i & 63)) & 1u) xor_shl(acc.data(), phi.data(), kPolyWords, i - kMtDegree);
+  Poly r(acc.begin(), acc.begin() + kPolyWords);
+  r[kPolyWords - 1] &= ((uint64_t)1 << (kMtDegree & 63)) - 1u;  // (bit 19937 and above are zero after the reduction)
+  return r;
+}
+
+struct JumpTable {
+  std::mutex mu;
+  Poly phi;
+  uint32_t jump = 0;
+  Poly g1;                                                  // z^jump mod phi
+  Poly last;                                                // z^(q * jump) mod phi of the newest entry
+  std::vector<std::unique_ptr<std::vector<uint16_t>>> idx;  // idx[q - 1]
+};
+JumpTable g_jump;
+}  // namespace
+
+const std::vector<uint16_t> &mt_jump_poly(uint32_t q, uint32_t jump_words) {
+  static const std::vector<uint16_t> none;
+  if (q == 0 || jump_words == 0) return none;
+  std::lock_guard<std::mutex> lk(g_jump.mu);
+  if (g_jump.phi.empty()) g_jump.phi = mt_characteristic_polynomial();
+  if (g_jump.jump != jump_words) {  // z^jump by square and multiply
+    g_jump.idx.clear();
+    Poly r(kPolyWords, 0), base(kPolyWords, 0);
+    r[0] = 1; base[0] = 2;
+    for (uint32_t e = jump_words; e; e >>= 1) {
+      if (e & 1u) r = poly_mulmod(r, base, g_jump.phi);
+      if (e > 1u) base = poly_mulmod(base, base, g_jump.phi);
+    }
+    g_jump.g1 = r;
+    g_jump.jump = jump_words;
+  }
+  while (g_jump.idx.size() < q) {
+    g_jump.last = g_jump.idx.empty() ? g_jump.g1 : poly_mulmod(g_jump.last, g_jump.g1, g_jump.phi);
+    std::unique_ptr<std::vector<uint16_t>> v(new std::vector<uint16_t>());
+    for (size_t k = 0; k < kMtDegree; k++)
+      if (poly_bit(g_jump.last, k)) v->push_back((uint16_t)k);
+    g_jump.idx.push_back(std::move(v));
+  }
+  return *g_jump.idx[q - 1];
 }
 
 RawStream::RawStream(uint32_t seed, size_t max_words, uint32_t *external) : cap_(max_words), seed_(seed) {

@@ -54,6 +54,16 @@ class RawStream {
   std::thread th_;
 };
 
+// Jump-ahead of MT19937, so that the device makes the PRNG stream of a large job on many SMs at once (k_mt19937_raw in
+// csrc/rs_kernels.cu).  The generator is linear over GF(2): with phi(z) its characteristic polynomial (degree 19937) and
+// g(z) = z^J mod phi(z), the untempered word stream x obeys x[J + j] = XOR over the set bits k of g of x[k + j].
+// mt_jump_poly(q, jump) = the positions of the set bits of z^(q * jump) mod phi, ascending: the state after q * jump words
+// is that combination of the first 19937 + 624 words.  phi comes from Berlekamp-Massey on one output bit (computed once
+// per process, ~20 ms); the polynomials of q = 1, 2, ... are built on demand, each from the one before (~10 ms), and kept.
+// Thread-safe; the reference returned stays valid.
+constexpr uint32_t kMtDegree = 19937;
+const std::vector<uint16_t> &mt_jump_poly(uint32_t q, uint32_t jump_words);
+
 // lib/matchWeighting.h:142-204.  Tables over the signed difference, index 256+d, like the reference.
 void build_metric_tables(double sensitivity, double map_weight, uint16_t color512[512], uint32_t map512[512]);
 

@@ -28,6 +28,11 @@
 #include "../../include/rs_cuda.h"
 #include "rs_device.cuh"
 
+namespace rs {
+// csrc/host_prep.cpp: set-bit positions of z^(q * jump_words) mod MT19937's characteristic polynomial (jump-ahead)
+const std::vector<uint16_t> &mt_jump_poly(uint32_t q, uint32_t jump_words);
+}
+
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
 #define RS_CHECK(call)                                                                        \
@@ -2574,52 +2579,191 @@ __global__ void k_reduce_draws(uint32_t *__restrict__ draws, const unsigned int 
 
 // The PRNG stream itself on the device: the first n_words raw 32-bit words of GLib's GRand seeded with `seed` (MT19937 with
 // init_genrand seeding -- g_rand_new_with_seed / g_rand_int, what the reference draws its visit order from,
-// lib/engine.c:643, lib/orderTarget.h:38-53).  Word i of the stream is x[i] = x[i-227] ^ twist(x[i-624], x[i-623]): 227
-// words at a time are independent of each other, and a step needs nothing younger than two steps back except x[i-227],
-// which the same lane made in the step before (a register).  One CTA of 227 threads, the state in a ring in shared
-// memory, two steps (454 words) per barrier.  4.4 M words (cfg3) take ~0.6 ms of one SM, beside the image upload, where
-// the host's AVX2 producer takes 3-4 ms of a core and the words another 17 MB of PCIe traffic.
-__global__ void __launch_bounds__(227, 1) k_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t *__restrict__ out) {
-  __shared__ uint32_t ring[2048];  // word i of the stream lives at ring[(i + 624) & 2047]; words -624..-1 = the seeded state
-  const uint32_t t = threadIdx.x;
+// lib/engine.c:643, lib/orderTarget.h:38-53).
+//
+// One CTA (rs_mt_rounds).  Word i of the stream is x[i] = x[i-227] ^ f(x[i-624], x[i-623]): every f of a round of 623
+// consecutive words reads words older than the round, and the x[i-227] chain is one XOR per word that stays inside a lane
+// -- lane t of the 227 MAKER threads makes words t, t + 227 and (t < 169) t + 454 of the round.  The state lives in a
+// ring in shared memory, one barrier per round; warps 8-19 temper the words of the round before and write them out, so
+// that a makers' round is the dependency chain and nothing else (loads, f, XORs, stores, barrier).  Shapes measured on
+// B200 with tools/microbench/mt_bench.cu (4.39 M words, cfg3): this one 1.54 ms; rounds of 454 words 1.71 (makers store) /
+// 1.95 (256 writers); fewer, wider lanes 2.4-10 ms -- a round is latency (shared-memory round trip + barrier with its
+// store drain), so lanes beat words per lane.
+//
+// Many CTAs (k_mt19937_raw, grid > 1).  The generator is linear over GF(2), so CTA q can start RS_MT_JUMP * q words into
+// the stream without making them: with g_q(z) = z^(q * RS_MT_JUMP) mod the characteristic polynomial (host_prep.cpp:
+// mt_jump_poly, set-bit positions in a device table), its state is the XOR over the set bits k of g_q of the windows
+// x[k .. k + 624) of the untempered stream -- 19936 words that every CTA makes itself from the seed (32 rounds, 7 us),
+// combined by one thread per state word (~10 k shared-memory loads each), after which it runs its own 2^18 words.
+// cfg3's 4.39 M words: 17 CTAs on 17 SMs, ~0.2 ms beside the image upload; the host's AVX2 producer takes 3-4 ms of a
+// core for the same words, and the words another 17 MB of PCIe traffic.
+#define RS_MT_WRITERS 384
+#define RS_MT_THREADS (256 + RS_MT_WRITERS)
+#define RS_MT_JUMP (1u << 18)        // words per CTA of a multi-CTA launch
+#define RS_MT_MAX_CTAS 512u          // above that many (134 M words) one CTA makes the whole stream
+#define RS_MT_IDX_STRIDE 19968u      // entries per polynomial in the device table (at most 19937 set bits)
+#define RS_MT_X_PAD (624u + 19936u)  // index of 624 zero words behind the stream: what the padding of an index list selects
+#define RS_MT_X_WORDS (RS_MT_X_PAD + 624u)
+__device__ __forceinline__ uint32_t rs_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void rs_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// n_words words from the state in ring[0..623] (= words -624..-1), tempered into out[0..n_words).  TO_X: the untempered
+// words go to X[624 + i] instead and nothing is written out.  Every thread of the CTA calls it (one barrier per round,
+// the same instruction for makers and writers).
+template <bool TO_X>
+__device__ __forceinline__ void rs_mt_rounds(const uint32_t sb, const uint32_t t, const uint32_t n_words, uint32_t *__restrict__ out,
+                                             uint32_t *__restrict__ X) {
+  const uint32_t rounds = (n_words + 622u) / 623u;
+  auto f = [](uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
+  };
+  const bool maker = t < 227u, third = t < 169u, writer = t >= 256u;  // (lanes 227..255 only keep the barrier count)
+  const uint32_t u = t - 256u;
+  constexpr int K = (623 + RS_MT_WRITERS - 1) / RS_MT_WRITERS;
+  uint32_t pb = t * 4u;  // makers: byte offset in the ring of x[i0 - 624], i0 = 623 r + t
+  for (uint32_t r = 0; r <= rounds; r++) {
+    if (maker) {
+      if (r < rounds) {
+        const uint32_t c = rs_lds32(sb + ((pb + 1588u) & 8188u));  // x[i0 - 227]
+        const uint32_t a0 = rs_lds32(sb + pb), b0 = rs_lds32(sb + ((pb + 4u) & 8188u));
+        const uint32_t a1 = rs_lds32(sb + ((pb + 908u) & 8188u)), b1 = rs_lds32(sb + ((pb + 912u) & 8188u));
+        uint32_t a2 = 0, b2 = 0;
+        if (third) { a2 = rs_lds32(sb + ((pb + 1816u) & 8188u)); b2 = rs_lds32(sb + ((pb + 1820u) & 8188u)); }
+        const uint32_t v0 = c ^ f(a0, b0), v1 = v0 ^ f(a1, b1), v2 = v1 ^ f(a2, b2);
+        rs_sts32(sb + ((pb + 2496u) & 8188u), v0);
+        rs_sts32(sb + ((pb + 3404u) & 8188u), v1);
+        if (third) rs_sts32(sb + ((pb + 4312u) & 8188u), v2);
+        if (TO_X) {
+          const uint32_t i0 = 624u + r * 623u + t;
+          X[i0] = v0;
+          X[i0 + 227u] = v1;
+          if (third) X[i0 + 454u] = v2;
+        }
+        pb = (pb + 2492u) & 8188u;
+      }
+    } else if (writer && !TO_X && r > 0) {
+      // the 623 words of round r - 1 (still in the ring: a position is reused 2048 words later), tempered
+      const uint32_t base = (r - 1u) * 623u;
+      uint32_t y[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) { const uint32_t o = u + k * RS_MT_WRITERS; y[k] = o < 623u ? rs_lds32(sb + (((base + o + 624u) & 2047u) << 2)) : 0u; }
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const uint32_t o = u + k * RS_MT_WRITERS, i = base + o;
+        if (o < 623u && i < n_words) {
+          uint32_t z = y[k];
+          z ^= z >> 11;
+          z ^= (z << 7) & 0x9d2c5680u;
+          z ^= (z << 15) & 0xefc60000u;
+          out[i] = z ^ (z >> 18);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+// CTA q makes words [q * jump, min((q + 1) * jump, n_words)).  grid 1: jump >= n_words, no table, no dynamic shared memory.
+__global__ void __launch_bounds__(RS_MT_THREADS, 1) k_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t jump, uint32_t *__restrict__ out,
+                                                                  const uint16_t *__restrict__ jump_idx, const uint32_t *__restrict__ jump_cnt) {
+  extern __shared__ uint32_t mt_x[];               // CTAs q > 0: the untempered words -624 .. 19935 of the stream
+  __shared__ __align__(16) uint32_t ring[2048];    // word i of the stream lives at ring[(i + 624) & 2047]; words -624..-1 = the state
+  const uint32_t sb = (uint32_t)__cvta_generic_to_shared(ring);
+  const uint32_t t = threadIdx.x, q = blockIdx.x;
+  const unsigned long long first = (unsigned long long)q * jump;
+  if (first >= n_words) return;
+  const uint32_t count = (uint32_t)min((unsigned long long)jump, (unsigned long long)n_words - first);
   if (t == 0) {
     uint32_t x = seed;
     ring[0] = x;
     for (uint32_t i = 1; i < 624; i++) { x = 1812433253u * (x ^ (x >> 30)) + i; ring[i] = x; }
   }
   __syncthreads();
-  auto twist = [](uint32_t a, uint32_t b, uint32_t c) {
-    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-    return c ^ (y >> 1) ^ ((0u - (y & 1u)) & 0x9908b0dfu);
-  };
-  auto temper = [](uint32_t y) {
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    return y ^ (y >> 18);
-  };
-  uint32_t c = ring[397 + t];  // x[t - 227]
-  for (uint32_t base = 0; base < n_words; base += 454u) {
-    const uint32_t i0 = base + t, i1 = i0 + 227u;
-    const uint32_t a0 = ring[i0 & 2047u], b0 = ring[(i0 + 1u) & 2047u];
-    const uint32_t a1 = ring[i1 & 2047u], b1 = ring[(i1 + 1u) & 2047u];
-    const uint32_t v0 = twist(a0, b0, c), v1 = twist(a1, b1, v0);
-    c = v1;
-    ring[(i0 + 624u) & 2047u] = v0;
-    ring[(i1 + 624u) & 2047u] = v1;
-    if (i0 < n_words) out[i0] = temper(v0);
-    if (i1 < n_words) out[i1] = temper(v1);
+  if (q > 0) {
+    if (t < 624u) { mt_x[t] = ring[t]; mt_x[RS_MT_X_PAD + t] = 0u; }
+    rs_mt_rounds<true>(sb, t, 19936u, nullptr, mt_x);
+    __syncthreads();
+    // eight positions per 16-byte load (the list is padded to a multiple of eight with RS_MT_X_PAD); the loop is bound by
+    // the shared-memory loads of the windows: 624 x ~10 k words
+    const uint4 *__restrict__ idx8 = reinterpret_cast<const uint4 *>(jump_idx + (size_t)(q - 1u) * RS_MT_IDX_STRIDE);
+    const uint32_t cnt8 = (__ldg(jump_cnt + (q - 1u)) + 7u) / 8u;
+    uint32_t acc = 0;
+    if (t < 624u) {
+      const uint32_t *__restrict__ xt = mt_x + t;
+#pragma unroll 2
+      for (uint32_t e = 0; e < cnt8; e++) {
+        const uint4 p = __ldg(idx8 + e);
+        acc ^= xt[p.x & 0xFFFFu] ^ xt[p.x >> 16] ^ xt[p.y & 0xFFFFu] ^ xt[p.y >> 16] ^ xt[p.z & 0xFFFFu] ^ xt[p.z >> 16] ^
+               xt[p.w & 0xFFFFu] ^ xt[p.w >> 16];
+      }
+    }
+    __syncthreads();
+    if (t < 624u) ring[t] = acc;  // (of word -624 only the top bit is state, and only that bit is right)
     __syncthreads();
   }
+  rs_mt_rounds<false>(sb, t, count, out + first, nullptr);
+}
+// The jump polynomials of a device: built on the host on demand (mt_jump_poly), kept for the life of the process.
+struct MtJumpDev {
+  uint16_t *idx = nullptr;
+  uint32_t *cnt = nullptr;
+  uint32_t have = 0, cap = 0;
+};
+static std::mutex g_mtj_mutex;
+static MtJumpDev g_mtj[64];
+// Launches the stream kernel on `s` of the current device (the launch happens under the table's mutex: a table that
+// grows is freed only after the kernels that read it have run).
+static int mt19937_launch(uint32_t seed, uint32_t n_words, uint32_t *out, cudaStream_t s) {
+  if (n_words == 0) return 0;
+  uint32_t ctas = (n_words + RS_MT_JUMP - 1u) / RS_MT_JUMP;
+  if (ctas <= 1u || ctas > RS_MT_MAX_CTAS || getenv("RS_MT_ONE_CTA")) {
+    k_mt19937_raw<<<1, RS_MT_THREADS, 0, s>>>(seed, n_words, 0xFFFFFFFFu, out, nullptr, nullptr);
+    RS_CHECK(cudaGetLastError());
+    return 0;
+  }
+  int device = 0;
+  RS_CHECK(cudaGetDevice(&device));
+  if (device < 0 || device >= 64) { g_err = "mt19937_launch: device ordinal out of range"; return 100; }
+  std::lock_guard<std::mutex> lk(g_mtj_mutex);
+  MtJumpDev &T = g_mtj[device];
+  const uint32_t need = ctas - 1u;
+  if (need > T.cap) {
+    const uint32_t cap = std::max(need, std::max(2u * T.cap, 32u));
+    uint16_t *idx = nullptr;
+    uint32_t *cnt = nullptr;
+    RS_CHECK(cudaMalloc(&idx, (size_t)cap * RS_MT_IDX_STRIDE * sizeof(uint16_t)));
+    RS_CHECK(cudaMalloc(&cnt, (size_t)cap * sizeof(uint32_t)));
+    if (T.have) {
+      RS_CHECK(cudaMemcpy(idx, T.idx, (size_t)T.have * RS_MT_IDX_STRIDE * sizeof(uint16_t), cudaMemcpyDeviceToDevice));
+      RS_CHECK(cudaMemcpy(cnt, T.cnt, (size_t)T.have * sizeof(uint32_t), cudaMemcpyDeviceToDevice));
+    }
+    if (T.idx) cudaFree(T.idx);  // (cudaFree waits for the kernels in flight)
+    if (T.cnt) cudaFree(T.cnt);
+    T.idx = idx; T.cnt = cnt; T.cap = cap;
+  }
+  for (uint32_t q = T.have + 1u; q <= need; q++) {
+    const std::vector<uint16_t> &v = rs::mt_jump_poly(q, RS_MT_JUMP);
+    const uint32_t c = (uint32_t)v.size();
+    if (c == 0 || c + 8u > RS_MT_IDX_STRIDE) { g_err = "mt19937_launch: bad jump polynomial"; return 100; }
+    std::vector<uint16_t> padded(v);
+    while (padded.size() % 8u) padded.push_back((uint16_t)RS_MT_X_PAD);
+    RS_CHECK(cudaMemcpy(T.idx + (size_t)(q - 1u) * RS_MT_IDX_STRIDE, padded.data(), padded.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    RS_CHECK(cudaMemcpy(T.cnt + (q - 1u), &c, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    T.have = q;
+  }
+  RS_CHECK(cudaFuncSetAttribute(k_mt19937_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RS_MT_X_WORDS * 4u)));
+  k_mt19937_raw<<<ctas, RS_MT_THREADS, RS_MT_X_WORDS * 4u, s>>>(seed, n_words, RS_MT_JUMP, out, T.idx, T.cnt);
+  RS_CHECK(cudaGetLastError());
+  return 0;
 }
 // Test entry: the first n_words words of the stream of `seed`, made on the current device, into host memory.
 extern "C" int rs_cuda_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t *out_host) {
   if (n_words == 0) return 0;
   uint32_t *d = nullptr;
   RS_CHECK(cudaMalloc(&d, (size_t)n_words * 4));
-  k_mt19937_raw<<<1, 227>>>(seed, n_words, d);
-  cudaError_t e = cudaMemcpy(out_host, d, (size_t)n_words * 4, cudaMemcpyDeviceToHost);
+  int rc = mt19937_launch(seed, n_words, d, nullptr);
+  cudaError_t e = rc ? cudaSuccess : cudaMemcpy(out_host, d, (size_t)n_words * 4, cudaMemcpyDeviceToHost);
   cudaFree(d);
+  if (rc) return rc;
   RS_CHECK(e);
   return 0;
 }
@@ -2702,7 +2846,7 @@ static int shuffle_order_impl(RsJob *j, const uint32_t *draws, const uint32_t *r
     // (the draw array takes up to n_raw words here; only the first n are used afterwards)
     if ((rc = ws_ensure(w->ord_keys_in, (size_t)n_raw * 4))) return rc;
     if (raw_on_device) {
-      k_mt19937_raw<<<1, 227, 0, s>>>(seed, n_raw, (uint32_t *)w->ord_raw.p);
+      if ((rc = mt19937_launch(seed, n_raw, (uint32_t *)w->ord_raw.p, s))) return rc;
       j->upload_launches += 1u;
     } else {
       RS_CHECK(cudaMemcpyAsync(w->ord_raw.p, raw_pinned, (size_t)n_raw * 4, cudaMemcpyHostToDevice, s));

@@ -145,13 +145,15 @@ def test_device_shuffle_equals_host_shuffle(mode, hole):
 def test_device_prng_stream_is_glib_mt19937(seed):
     """k_mt19937_raw: the raw 32-bit words of g_rand_new_with_seed(seed) / g_rand_int (MT19937, init_genrand seeding -- the
     stream the reference draws its visit order from, lib/orderTarget.h:38-53), made on the device, equal numpy's legacy
-    MT19937 word for word; lengths around the kernel's steps of 227 / 454 words and the state size."""
+    MT19937 word for word; lengths around the kernel's rounds of 623 words, the state size, and the 2^18 words of a CTA."""
     import ctypes as C
     L = api.lib()
     L.rs_cuda_mt19937_raw.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
     api.set_device(0)
-    want = np.random.RandomState(seed).randint(0, 2 ** 32, 1200000, dtype=np.uint32)
-    for n in (1, 226, 227, 228, 453, 454, 455, 623, 624, 625, 1247, 100000, 1200000):
+    want = np.random.RandomState(seed).randint(0, 2 ** 32, 4400000, dtype=np.uint32)
+    # up to 2^18 words: one CTA; above: CTA q starts q * 2^18 words into the stream by jump-ahead (1.2 M words: 5 CTAs,
+    # 4.4 M, the order of a 4 Mi-point job: 17)
+    for n in (1, 226, 227, 228, 453, 454, 455, 622, 623, 624, 625, 1246, 1247, 100000, 262144, 262145, 524288 + 5, 1200000, 4400000):
         got = np.zeros(n + 8, np.uint32)
         got[n:] = 0xDEADBEEF
         assert L.rs_cuda_mt19937_raw(seed, n, got.ctypes.data) == 0
