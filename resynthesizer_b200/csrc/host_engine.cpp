@@ -209,12 +209,16 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
   if (prm.patchSize > 64) return IMAGE_SYNTH_ERROR_PATCH_SIZE_EXCEEDED;  // lib/engine.c:591
   const int tw = src.tw, th = src.th, cw = src.cw, ch = src.ch, bpp = src.bpp;
 
-  // Empty target / corpus and the context-type range are detected on the host, before CUDA is touched
-  // (lib/engine.c:605-610, 620-627, 645-647); everything else about the points happens on the device.
-  if (!any_target(src)) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;
-  if (!any_corpus(src, *fi)) return IMAGE_SYNTH_ERROR_EMPTY_CORPUS;
-  if (prm.matchContextType < 0 || prm.matchContextType > 8)
-    return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;  // orderTargetPoints' default case
+  // Empty target / corpus and the context-type range, in the reference's order (lib/engine.c:605-610, 620-627, 645-647).
+  // Without a device they are detected on the host before CUDA is touched.  With one, the empty-target scan -- megabytes of
+  // mask above a centred hole, 0.3 ms of a 50 ms call -- is left to the device: the selection digest that every job waits
+  // for counts the target points anyway (an empty target then costs a staged job instead of a scan: the error path).
+  // The host scans only where the answer decides which error comes first.
+  const bool ctx_ok = prm.matchContextType >= 0 && prm.matchContextType <= 8;
+  const bool count_on_device = ctx_ok && !std::getenv("RS_HOST_TARGET_SCAN") && (t_device_chosen || rs_cuda_device_count() > 0);
+  if (!count_on_device && !any_target(src)) return IMAGE_SYNTH_ERROR_EMPTY_TARGET;
+  if (!any_corpus(src, *fi)) return (count_on_device && !any_target(src)) ? IMAGE_SYNTH_ERROR_EMPTY_TARGET : IMAGE_SYNTH_ERROR_EMPTY_CORPUS;
+  if (!ctx_ok) return IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE;  // orderTargetPoints' default case
 
   if (tw > 32767 || th > 32767 || cw > 32767 || ch > 32767) {
     t_err = "image dimensions above 32767 are not supported by the packed device layout";
@@ -279,6 +283,11 @@ int synth_core(TImageSynthParameters prm, TFormatIndices *fi, const PixelSource 
     return RS_ERROR_CUDA;
   }
   dbg("after stage+digest");
+  if (dg.n == 0) {  // (count_on_device: no host scan was made)
+    raw.reset();
+    rs_job_destroy(job);
+    return IMAGE_SYNTH_ERROR_EMPTY_TARGET;
+  }
   const uint32_t n = dg.n;
   uint32_t pass_end[6];
   const uint32_t estimated = rs::pass_schedule(n, pass_end);

@@ -1548,6 +1548,7 @@ struct Workspace {
   RsTargetDigest *h_digest = nullptr;  // pinned
   cudaEvent_t evDigest = nullptr;
   cudaEvent_t evSel = nullptr, evOrder = nullptr;  // the selection (mask plane / target pixmap) is on the device; the visit order is made
+  cudaEvent_t evAux = nullptr;                     // input-independent setup queued on the side stream (prober memset) is done
   unsigned int *h_ticks = nullptr;
   int *h_cancel = nullptr;
   RsCtrl *h_ctrl = nullptr;
@@ -1597,6 +1598,7 @@ static void ws_free(Workspace *w) {
   if (w->evDigest) cudaEventDestroy(w->evDigest);
   if (w->evSel) cudaEventDestroy(w->evSel);
   if (w->evOrder) cudaEventDestroy(w->evOrder);
+  if (w->evAux) cudaEventDestroy(w->evAux);
   if (w->h_ticks) cudaFreeHost(w->h_ticks);
   if (w->h_cancel) cudaFreeHost(w->h_cancel);
   if (w->h_ctrl) cudaFreeHost(w->h_ctrl);
@@ -1722,6 +1724,7 @@ static int ws_acquire(Workspace **out) {
   WCHK(cudaEventCreateWithFlags(&w->evDigest, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evSel, cudaEventDisableTiming));
   WCHK(cudaEventCreateWithFlags(&w->evOrder, cudaEventDisableTiming));
+  WCHK(cudaEventCreateWithFlags(&w->evAux, cudaEventDisableTiming));
   WCHK(cudaHostAlloc(&w->h_digest, sizeof(RsTargetDigest), cudaHostAllocDefault));
   WCHK(cudaHostAlloc(&w->h_ticks, 6 * sizeof(unsigned int), cudaHostAllocMapped));
   WCHK(cudaHostAlloc(&w->h_cancel, sizeof(int), cudaHostAllocMapped));
@@ -2200,6 +2203,10 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
   if ((rc = ws_ensure_pinned(w, need_pin))) return rc;
   uint8_t *pin = (uint8_t *)w->pin;
   RS_CHECK(cudaMemsetAsync(w->ctrl.p, 0, sizeof(RsCtrl), s));
+  // the recentProber words depend on no input: cleared on the side stream while the images are on their way (32 bytes per
+  // corpus pixel: half a gigabyte for a 4096x4096 image), joined below
+  RS_CHECK(cudaMemsetAsync(w->prober.p, 0, cn * 32, w->stream2));
+  RS_CHECK(cudaEventRecord(w->evAux, w->stream2));
   const int T = 256;
   j->upload_launches = 0;
   auto enqueue_digest = [&](const uint8_t *mask_bytes, int stride) -> int {
@@ -2352,7 +2359,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     j->off_w = ow; j->off_h = oh;
   }
   if ((rc = ws_ensure(w->ctx_blocks, (size_t)((d.tw + 31) / 32) * (size_t)((d.th + 31) / 32) * 4))) return rc;
-  RS_CHECK(cudaMemsetAsync(w->prober.p, 0, cn * 32, s));
+  RS_CHECK(cudaStreamWaitEvent(s, w->evAux, 0));
   if (!corpus_ready)
     k_canon_corpus<<<(unsigned)((cn + T) / T), T, 0, s>>>((const uint8_t *)w->raw_c.p, (int)cn, d.bpp, d.n_color, d.n_map,
                                                             d.map_bip, j->maps ? nullptr : (uint32_t *)j->cb.corpus,

@@ -198,3 +198,47 @@ def test_page_locked_buffers_are_copied_directly(built_lib):
     pimg[...] = img
     err = api.image_synth(pimg, pm, abi.T_RGB, p, cancel_after=1)
     assert (pimg == img).all()
+
+
+def test_empty_target_counted_on_the_device(built_lib, monkeypatch):
+    """With a device the empty-target scan of the mask is left to the selection digest (host_engine.cpp: count_on_device);
+    error codes and their precedence stay the reference's (lib/engine.c:605-647): empty target before empty corpus before
+    the context-type range; padding bytes of a mask with rowBytes > width do not count; an unchanged image on error."""
+    L = api.lib()
+    img = G(40, 24, 3, 5)
+    zero = np.zeros((24, 40), np.uint8)
+    p = abi.make_params(0, 0, 1, 0.5, 0.117, 16, 60)
+    for force_host in (False, True):
+        if force_host:
+            monkeypatch.setenv("RS_HOST_TARGET_SCAN", "1")
+        work = img.copy()
+        assert api_err(lambda: api.image_synth(work, zero, abi.T_RGB, p)) == abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+        assert (work == img).all()
+        # all selected: nothing left for the corpus
+        assert api_err(lambda: api.image_synth(work, np.full((24, 40), 255, np.uint8), abi.T_RGB, p)) == abi.IMAGE_SYNTH_ERROR_EMPTY_CORPUS
+        # empty target AND a bad context type: the target error comes first; a non-empty one reports the range
+        bad = abi.make_params(0, 0, 9, 0.5, 0.117, 16, 60)
+        assert api_err(lambda: api.image_synth(work, zero, abi.T_RGB, bad)) == abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+        one = zero.copy(); one[3, 7] = 1
+        assert api_err(lambda: api.image_synth(work, one, abi.T_RGB, bad)) == abi.IMAGE_SYNTH_ERROR_MATCH_CONTEXT_TYPE_RANGE
+        # full API: empty target pixmap, and empty target + fully transparent corpus (both empty: target first)
+        fi = api.format_indices(3)
+        tp = R.build_pixmap(zero, img); cp = R.build_pixmap(255 - zero, img)
+        assert api_err(lambda: api.engine(p, fi, tp, cp)) == abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+        cp0 = R.build_pixmap(zero, img)
+        assert api_err(lambda: api.engine(p, fi, tp, cp0)) == abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+        # a padded mask whose padding is non-zero is still empty
+        wide = np.zeros((24, 64), np.uint8); wide[:, 40:] = 0xFF
+        ib, _a = abi.image_buffer_padded(work.reshape(-1), 40, 24, 120)
+        mb, _b = abi.image_buffer_padded(wide.reshape(-1), 40, 24, 64)
+        cancel = C.c_int(0)
+        cb = abi.PROGRESS_CB(lambda pc, c: None)
+        assert L.imageSynth(C.byref(ib), C.byref(mb), abi.T_RGB, C.byref(p), cb, None, C.byref(cancel)) == abi.IMAGE_SYNTH_ERROR_EMPTY_TARGET
+        # and a job after the errors runs as before
+        m = centered_mask(40, 24, 10, 8)
+        assert api.image_synth(work, m, abi.T_RGB, p) == 0 and (work != img).any()
+
+
+def api_err(call):
+    """The error code of a call through resynthesizer_b200.api (which raises only for the CUDA layer's code 100)."""
+    return call()
