@@ -2601,8 +2601,8 @@ __global__ void k_reduce_draws(uint32_t *__restrict__ draws, const unsigned int 
 // the stream without making them: with g_q(z) = z^(q * RS_MT_JUMP) mod the characteristic polynomial (host_prep.cpp:
 // mt_jump_poly, set-bit positions in a device table), its state is the XOR over the set bits k of g_q of the windows
 // x[k .. k + 624) of the untempered stream -- 19936 words that every CTA makes itself from the seed (32 rounds, 7 us),
-// combined by one thread per state word (~10 k shared-memory loads each), after which it runs its own 2^18 words.
-// cfg3's 4.39 M words: 17 CTAs on 17 SMs, ~0.2 ms beside the image upload; the host's AVX2 producer takes 3-4 ms of a
+// combined by one thread per state word (~10 k shared-memory loads each; the index list staged in shared memory), after
+// which it runs its own 2^18 words.  cfg3's 4.39 M words: 17 CTAs on 17 SMs, 0.26 ms beside the image upload; the host's AVX2 producer takes 3-4 ms of a
 // core for the same words, and the words another 17 MB of PCIe traffic.
 #define RS_MT_WRITERS 384
 #define RS_MT_THREADS (256 + RS_MT_WRITERS)
@@ -2611,6 +2611,7 @@ __global__ void k_reduce_draws(uint32_t *__restrict__ draws, const unsigned int 
 #define RS_MT_IDX_STRIDE 19968u      // entries per polynomial in the device table (at most 19937 set bits)
 #define RS_MT_X_PAD (624u + 19936u)  // index of 624 zero words behind the stream: what the padding of an index list selects
 #define RS_MT_X_WORDS (RS_MT_X_PAD + 624u)
+#define RS_MT_SMEM_BYTES (RS_MT_X_WORDS * 4u + RS_MT_IDX_STRIDE * 2u)  // the words, then the CTA's index list
 __device__ __forceinline__ uint32_t rs_lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void rs_sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 // n_words words from the state in ring[0..623] (= words -624..-1), tempered into out[0..n_words).  TO_X: the untempered
@@ -2672,7 +2673,7 @@ __device__ __forceinline__ void rs_mt_rounds(const uint32_t sb, const uint32_t t
 // CTA q makes words [q * jump, min((q + 1) * jump, n_words)).  grid 1: jump >= n_words, no table, no dynamic shared memory.
 __global__ void __launch_bounds__(RS_MT_THREADS, 1) k_mt19937_raw(uint32_t seed, uint32_t n_words, uint32_t jump, uint32_t *__restrict__ out,
                                                                   const uint16_t *__restrict__ jump_idx, const uint32_t *__restrict__ jump_cnt) {
-  extern __shared__ uint32_t mt_x[];               // CTAs q > 0: the untempered words -624 .. 19935 of the stream
+  extern __shared__ __align__(16) uint32_t mt_x[];  // CTAs q > 0: the untempered words -624 .. 19935 of the stream, then the index list
   __shared__ __align__(16) uint32_t ring[2048];    // word i of the stream lives at ring[(i + 624) & 2047]; words -624..-1 = the state
   const uint32_t sb = (uint32_t)__cvta_generic_to_shared(ring);
   const uint32_t t = threadIdx.x, q = blockIdx.x;
@@ -2687,18 +2688,23 @@ __global__ void __launch_bounds__(RS_MT_THREADS, 1) k_mt19937_raw(uint32_t seed,
   __syncthreads();
   if (q > 0) {
     if (t < 624u) { mt_x[t] = ring[t]; mt_x[RS_MT_X_PAD + t] = 0u; }
+    // the CTA's index list into shared memory (coalesced, once), eight positions per 16-byte word; the list is padded to
+    // a multiple of eight with RS_MT_X_PAD.  Read from global memory in the loop, every second iteration waited for a sector.
+    const uint32_t cnt8 = (__ldg(jump_cnt + (q - 1u)) + 7u) / 8u;
+    uint4 *idx_s = reinterpret_cast<uint4 *>(mt_x + RS_MT_X_WORDS);
+    {
+      const uint4 *__restrict__ idx_g = reinterpret_cast<const uint4 *>(jump_idx + (size_t)(q - 1u) * RS_MT_IDX_STRIDE);
+      for (uint32_t e = t; e < cnt8; e += RS_MT_THREADS) idx_s[e] = __ldg(idx_g + e);
+    }
     rs_mt_rounds<true>(sb, t, 19936u, nullptr, mt_x);
     __syncthreads();
-    // eight positions per 16-byte load (the list is padded to a multiple of eight with RS_MT_X_PAD); the loop is bound by
-    // the shared-memory loads of the windows: 624 x ~10 k words
-    const uint4 *__restrict__ idx8 = reinterpret_cast<const uint4 *>(jump_idx + (size_t)(q - 1u) * RS_MT_IDX_STRIDE);
-    const uint32_t cnt8 = (__ldg(jump_cnt + (q - 1u)) + 7u) / 8u;
+    // the loop is bound by the shared-memory loads of the windows: 624 x ~10 k words
     uint32_t acc = 0;
     if (t < 624u) {
       const uint32_t *__restrict__ xt = mt_x + t;
 #pragma unroll 2
       for (uint32_t e = 0; e < cnt8; e++) {
-        const uint4 p = __ldg(idx8 + e);
+        const uint4 p = idx_s[e];
         acc ^= xt[p.x & 0xFFFFu] ^ xt[p.x >> 16] ^ xt[p.y & 0xFFFFu] ^ xt[p.y >> 16] ^ xt[p.z & 0xFFFFu] ^ xt[p.z >> 16] ^
                xt[p.w & 0xFFFFu] ^ xt[p.w >> 16];
       }
@@ -2757,8 +2763,8 @@ static int mt19937_launch(uint32_t seed, uint32_t n_words, uint32_t *out, cudaSt
     RS_CHECK(cudaMemcpy(T.cnt + (q - 1u), &c, sizeof(uint32_t), cudaMemcpyHostToDevice));
     T.have = q;
   }
-  RS_CHECK(cudaFuncSetAttribute(k_mt19937_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RS_MT_X_WORDS * 4u)));
-  k_mt19937_raw<<<ctas, RS_MT_THREADS, RS_MT_X_WORDS * 4u, s>>>(seed, n_words, RS_MT_JUMP, out, T.idx, T.cnt);
+  RS_CHECK(cudaFuncSetAttribute(k_mt19937_raw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_MT_SMEM_BYTES));
+  k_mt19937_raw<<<ctas, RS_MT_THREADS, RS_MT_SMEM_BYTES, s>>>(seed, n_words, RS_MT_JUMP, out, T.idx, T.cnt);
   RS_CHECK(cudaGetLastError());
   return 0;
 }
