@@ -366,16 +366,18 @@ class Runner:
         cols = np.flatnonzero(w["tmask"].any(axis=0))
         self.box = (slice(int(rows[0]), int(rows[-1]) + 1), slice(int(cols[0]), int(cols[-1]) + 1))
         n_rows = int(rows[-1] - rows[0] + 1)
+        n_cols = int(cols[-1] - cols[0] + 1)
         if "simple" in w:
             self.img = self._host(w["tgt"])
             self.pristine = w["tgt"][self.box].copy()
             self.h2d = w["tgt"].nbytes + w["tmask"].nbytes      # image + mask planes (the PRNG stream of the order is made on the device)
-            self.d2h = n_rows * w["tmask"].shape[1] * (w["bpp"] - 1)          # the rows that hold target points
+            # what comes back: the box that holds target points (page-locked buffers), their whole rows (staged)
+            self.d2h = n_rows * (n_cols if pinned else w["tmask"].shape[1]) * (w["bpp"] - 1)
         else:
             self.tp, self.cp = (self._host(x) for x in pixmaps(w))
             self.pristine = self.tp[self.box].copy()
             self.h2d = self.tp.nbytes + self.cp.nbytes
-            self.d2h = n_rows * w["tmask"].shape[1] * w["bpp"]
+            self.d2h = n_rows * (n_cols if pinned else w["tmask"].shape[1]) * w["bpp"]
 
     def _host(self, a):
         """A private copy of `a` for the calls: page-locked (a numpy view of a pinned torch tensor) or malloc'ed."""

@@ -63,7 +63,7 @@ typedef struct {
 /* The target selection (mask byte != 0) as the device sees it: count, first/last row, 128-bit digest. */
 typedef struct {
   uint64_t h1, h2;
-  uint32_t n, ymin, ymax, pad;
+  uint32_t n, ymin, ymax, xmin, xmax, pad; /* number of target points, the rows and the columns that hold them */
 } RsTargetDigest;
 /* What a visit order is a function of (lib/orderTarget.h): the selection, the image size, matchContextType and the
  * seed of the ordering PRNG stream. */

@@ -77,7 +77,7 @@ struct RsCtrl {             // device-resident control block of one job (zeroed 
   unsigned int passes_run;
   unsigned int fault;       // set by a warp whose wait for another visit outlived RS_SPIN_LIMIT_NS: the job is invalid
   unsigned long long dg_h1, dg_h2;        // digest of the target selection (k_target_digest), layout = RsTargetDigest
-  unsigned int dg_n, dg_ymin, dg_ymax, dg_pad;
+  unsigned int dg_n, dg_ymin, dg_ymax, dg_xmin, dg_xmax, dg_pad;  // count, rows and columns that hold target points
   unsigned int dg_sel;      // scratch counter of the target-point compaction (rs_job_shuffle_order)
   unsigned int dg_acc;      // number of raw PRNG words the rejection rule accepted (rs_job_shuffle_order_raw)
   unsigned long long visits, evals, evals_issued, compares, offset_scans, heur_evals, heur_skips, perfect;

@@ -1871,6 +1871,7 @@ struct RsJob {
   bool maps = false;
   uint32_t nT = 0, nC = 0, nOff = 0, penalty = 0;
   uint32_t y_min = 0, y_max = 0;  // rows of the target image that hold target points
+  uint32_t x_min = 0, x_max = 0;  // columns likewise (the whole width unless the selection digest narrowed them)
   size_t out_bytes = 0;           // pinned bytes the results need (rows with target points + sources)
   std::shared_ptr<OrderEntry> order;     // cached visit order this job reads, if any
   const uint32_t *targets_dev = nullptr;  // the visit order on the device (cache entry or the workspace's buffer)
@@ -1992,7 +1993,7 @@ __device__ __forceinline__ unsigned long long rs_mix64(unsigned long long x) {
 __global__ void __launch_bounds__(256) k_target_digest(const uint8_t *__restrict__ raw, uint32_t n_px, int bpp, int tw,
                                                        RsCtrl *__restrict__ ctrl) {
   unsigned long long h1 = 0, h2 = 0;
-  uint32_t cnt = 0, ymin = 0xFFFFFFFFu, ymax = 0;
+  uint32_t cnt = 0, ymin = 0xFFFFFFFFu, ymax = 0, xmin = 0xFFFFFFFFu, xmax = 0;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_round = (n_px + 31u) & ~31u;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
@@ -2004,8 +2005,12 @@ __global__ void __launch_bounds__(256) k_target_digest(const uint8_t *__restrict
       h2 += rs_mix64((((unsigned long long)w << 32) | wi) ^ 0x9E3779B97F4A7C15ull);
       cnt += __popc(w);
       const uint32_t first = i + (__ffs(w) - 1), last = i + (31 - __clz(w));
-      ymin = min(ymin, first / (uint32_t)tw);
-      ymax = max(ymax, last / (uint32_t)tw);
+      const uint32_t y0 = first / (uint32_t)tw, y1 = last / (uint32_t)tw;
+      ymin = min(ymin, y0);
+      ymax = max(ymax, y1);
+      // columns: exact where the 32 pixels of the word lie in one row, the whole width where they straddle rows
+      xmin = min(xmin, y0 == y1 ? first - y0 * (uint32_t)tw : 0u);
+      xmax = max(xmax, y0 == y1 ? last - y1 * (uint32_t)tw : (uint32_t)tw - 1u);
     }
   }
   if (lane == 0 && cnt) {
@@ -2014,6 +2019,8 @@ __global__ void __launch_bounds__(256) k_target_digest(const uint8_t *__restrict
     atomicAdd(&ctrl->dg_n, cnt);
     atomicMin(&ctrl->dg_ymin, ymin);
     atomicMax(&ctrl->dg_ymax, ymax);
+    atomicMin(&ctrl->dg_xmin, xmin);
+    atomicMax(&ctrl->dg_xmax, xmax);
   }
 }
 static std::mutex g_order_mutex;
@@ -2216,6 +2223,7 @@ static int stage_images(RsJob *j, const uint8_t *target_raw, const uint8_t *corp
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     const uint32_t ymin_init = 0xFFFFFFFFu;
     RS_CHECK(cudaMemcpyAsync(&((RsCtrl *)w->ctrl.p)->dg_ymin, &ymin_init, 4, cudaMemcpyHostToDevice, s));
+    RS_CHECK(cudaMemcpyAsync(&((RsCtrl *)w->ctrl.p)->dg_xmin, &ymin_init, 4, cudaMemcpyHostToDevice, s));
     k_target_digest<<<sms * 8, 256, 0, s>>>(mask_bytes, (uint32_t)tn, stride, d.tw, (RsCtrl *)w->ctrl.p);
     RS_CHECK(cudaMemcpyAsync(w->h_digest, &((RsCtrl *)w->ctrl.p)->dg_h1, sizeof(RsTargetDigest), cudaMemcpyDeviceToHost, s));
     RS_CHECK(cudaEventRecord(w->evDigest, s));
@@ -2387,6 +2395,7 @@ static int set_targets(RsJob *j, uint32_t n_targets, uint32_t y_min, uint32_t y_
     return 100;
   }
   j->nT = n_targets; j->y_min = y_min; j->y_max = y_max;
+  j->x_min = 0; j->x_max = (uint32_t)d.tw - 1u;
   uint32_t kmax = d.patch_size < 2 ? 2 : d.patch_size;
   if (kmax > RS_MAX_NB) kmax = RS_MAX_NB;
   int rc = 0;
@@ -2474,9 +2483,11 @@ extern "C" int rs_job_download_simple(RsJob *j, uint8_t *img, size_t img_row_byt
   const size_t row_len = (size_t)j->d.tw * (j->d.bpp - 1), rows = j->y_max - j->y_min + 1;
   const uint8_t *src = (const uint8_t *)w->pin;
   const uint32_t y0 = j->y_min;
-  if (j->result_direct) {  // device -> the caller's page-locked image, rows in place
+  if (j->result_direct) {  // device -> the caller's page-locked image, in place: the box that holds the target points
     RS_CHECK(cudaSetDevice(w->device));
-    RS_CHECK(cudaMemcpy2DAsync(img + (size_t)y0 * img_row_bytes, img_row_bytes, w->simg.p, row_len, row_len, rows, cudaMemcpyDeviceToHost, w->stream));
+    const size_t nc = (size_t)j->d.bpp - 1, x0 = (size_t)j->x_min * nc, box_len = ((size_t)j->x_max - j->x_min + 1) * nc;
+    RS_CHECK(cudaMemcpy2DAsync(img + (size_t)y0 * img_row_bytes + x0, img_row_bytes, (const uint8_t *)w->simg.p + x0, row_len, box_len, rows,
+                               cudaMemcpyDeviceToHost, w->stream));
     RS_CHECK(cudaStreamSynchronize(w->stream));
     return 0;
   }
@@ -2507,6 +2518,7 @@ extern "C" int rs_job_bind_order(RsJob *j, const RsTargetDigest *dg, const RsOrd
   // the staging copies are not all done yet: the pinned buffer must not move now (idle = false); it already holds the
   // whole input, which is at least as large as the rows that come back
   if (int rc = set_targets(j, dg->n, dg->ymin, dg->ymax, false)) return rc;
+  if (dg->xmin <= dg->xmax && dg->xmax < (uint32_t)j->d.tw) { j->x_min = dg->xmin; j->x_max = dg->xmax; }
   if (j->out_bytes > w->pin_cap) {  // (cannot happen for same-sized in/out images; be safe)
     RS_CHECK(cudaStreamSynchronize(w->stream));
     if (int rc = ws_ensure_pinned(w, j->out_bytes)) return rc;
@@ -3298,9 +3310,11 @@ extern "C" int rs_job_download(RsJob *j, uint8_t *target_raw_out, uint32_t *sour
   if (target_raw_out) {
     if (j->simple) { g_err = "rs_job_download: a job staged by rs_job_stage_simple returns its rows through rs_job_download_simple"; return 100; }
     uint8_t *dst = target_raw_out + (size_t)j->y_min * row_bytes;
-    if (j->result_direct) {  // device -> the caller's page-locked pixmap
+    if (j->result_direct) {  // device -> the caller's page-locked pixmap: the box that holds the target points
       RS_CHECK(cudaSetDevice(w->device));
-      RS_CHECK(cudaMemcpyAsync(dst, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes, rows_bytes, cudaMemcpyDeviceToHost, w->stream));
+      const size_t x0 = (size_t)j->x_min * j->d.bpp, box_len = ((size_t)j->x_max - j->x_min + 1) * j->d.bpp;
+      RS_CHECK(cudaMemcpy2DAsync(dst + x0, row_bytes, (const uint8_t *)w->raw_t.p + (size_t)j->y_min * row_bytes + x0, row_bytes, box_len,
+                                 (size_t)(j->y_max - j->y_min + 1), cudaMemcpyDeviceToHost, w->stream));
       RS_CHECK(cudaStreamSynchronize(w->stream));
     } else {
       const uint8_t *src = (const uint8_t *)w->pin;

@@ -242,3 +242,32 @@ def test_empty_target_counted_on_the_device(built_lib, monkeypatch):
 def api_err(call):
     """The error code of a call through resynthesizer_b200.api (which raises only for the CUDA layer's code 100)."""
     return call()
+
+
+@pytest.mark.parametrize("w,h", [(200, 160), (97, 83)])
+def test_page_locked_read_back_is_the_target_box(built_lib, w, h):
+    """Page-locked caller buffers get back the BOX that holds target points (columns from the selection digest, exact per
+    32-pixel word, the whole width where a word straddles rows): selections off centre, at the image edges, in two pieces,
+    widths that are no multiple of 32 -- same images as from malloc'ed buffers, through imageSynth() and engine()."""
+    img = G(w, h, 3, 91)
+    p = abi.make_params(0, 0, 1, 0.5, 0.117, 12, 40)
+    masks = []
+    m = np.zeros((h, w), np.uint8); m[5:20, w - 14:w] = 255; masks.append(m)                 # right edge, top
+    m = np.zeros((h, w), np.uint8); m[h - 9:h, 0:11] = 255; masks.append(m)                  # left edge, bottom
+    m = np.zeros((h, w), np.uint8); m[10:22, 8:20] = 255; m[h - 30:h - 20, w - 40:w - 31] = 255; masks.append(m)   # two pieces
+    m = np.zeros((h, w), np.uint8); m[h // 2, 31:34] = 255; masks.append(m)                  # three pixels across a word boundary
+    fi = api.format_indices(3)
+    for m in masks:
+        want = img.copy()
+        assert api.image_synth(want, m, abi.T_RGB, p) == 0
+        keep_i, pimg = _pinned_like(img)
+        keep_m, pm = _pinned_like(m)
+        assert api.image_synth(pimg, pm, abi.T_RGB, p) == 0
+        assert (pimg == want).all() and (pimg != img).any()
+        tp = R.build_pixmap(m, img); cp = R.build_pixmap(255 - m, img)
+        want_t = tp.copy()
+        assert api.engine(p, fi, want_t, cp) == 0
+        keep_t, ptp = _pinned_like(tp)
+        keep_c, pcp = _pinned_like(cp)
+        assert api.engine(p, fi, ptp, pcp) == 0
+        assert (ptp == want_t).all()
