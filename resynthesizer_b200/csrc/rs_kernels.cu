@@ -2701,7 +2701,8 @@ __global__ void __launch_bounds__(RS_MT_THREADS, 1) k_mt19937_raw(uint32_t seed,
   if (q > 0) {
     if (t < 624u) { mt_x[t] = ring[t]; mt_x[RS_MT_X_PAD + t] = 0u; }
     // the CTA's index list into shared memory (coalesced, once), eight positions per 16-byte word; the list is padded to
-    // a multiple of eight with RS_MT_X_PAD.  Read from global memory in the loop, every second iteration waited for a sector.
+    // a multiple of eight with RS_MT_X_PAD.  (Read from global memory inside the loop, every second iteration waited for
+    // a new sector: 0.35 instead of 0.26 ms for the kernel.)
     const uint32_t cnt8 = (__ldg(jump_cnt + (q - 1u)) + 7u) / 8u;
     uint4 *idx_s = reinterpret_cast<uint4 *>(mt_x + RS_MT_X_WORDS);
     {
